@@ -1,0 +1,189 @@
+"""B200 drop-ins for MONAI's DiffusionInferer / LatentDiffusionInferer:
+
+    inferer = LatentDiffusionInferer(scheduler, scale_factor=1.0)            3d_ldm/inference.py:85
+    inferer.sample(input_noise=..., autoencoder_model=..., diffusion_model=..., scheduler=...)   :94-99
+    inferer.sample(..., conditioning=latents, mode="concat")                 3d_ldm/train_diffusion.py:326-333
+    inferer(inputs=..., noise=..., timesteps=..., condition=..., mode="concat")  3d_ldm/train_diffusion.py:197-205
+
+`sample` is the hot path.  When the models are b200ldm modules it runs the fused loop: the latent
+stays in NDHWC on the device (fp32 master + a compute-dtype copy inside the UNet input buffer),
+time-embedding projections for every step are tabulated once, and ONE CUDA graph
+(select temb row -> UNet -> fused scheduler update -> counter++) is replayed per step; per-step
+coefficients / temb rows / noise slabs are indexed by a device-side step counter.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import ops
+from .nets import AutoencoderKL, DiffusionModelUNet, _PREC, _pad64
+
+USE_GRAPH = os.environ.get("B200LDM_CUDA_GRAPH", "1") != "0"
+
+
+class SamplingLoop:
+    """Device-resident state + (optionally graph-captured) body of one denoising step."""
+
+    def __init__(self, unet: DiffusionModelUNet, scheduler, input_noise: torch.Tensor, conditioning, mode: str,
+                 step_noise=None, seed: int = 0, use_graph: bool = True):
+        dev = input_noise.device
+        self.unet, self.scheduler = unet, scheduler
+        self.dtype = _PREC[unet.precision]
+        N, self.c_lat = input_noise.shape[:2]
+        self.spatial = tuple(input_noise.shape[2:])
+        c_in = self.c_lat + (conditioning.shape[1] if mode == "concat" else 0)
+        if c_in != unet.in_channels:
+            raise ValueError(f"UNet expects {unet.in_channels} input channels, sampling provides {c_in}")
+        if self.c_lat % 4:
+            raise ValueError("latent channel count must be a multiple of 4")
+        self.n_steps = len(scheduler.timesteps)
+        # state
+        self.x_t = ops.to_ndhwc(input_noise, self.c_lat, torch.float32)            # fp32 master [N,D,H,W,C]
+        self.x_model = ops.to_ndhwc(input_noise, _pad64(c_in), self.dtype)          # UNet input buffer
+        if mode == "concat":
+            ops.to_ndhwc(conditioning, _pad64(c_in), self.dtype, out=self.x_model, c_offset=self.c_lat)
+        ts = torch.as_tensor([float(t) for t in scheduler.timesteps], dtype=torch.float32, device=dev)
+        self.temb_table = unet.time_embedding_table(ts)                            # [n_steps, total]
+        self.temb_cur = torch.empty((1, self.temb_table.shape[1]), dtype=torch.float32, device=dev)
+        self.coef = scheduler.coef_table(dev)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.seed = seed
+        self.noise, self.noise_stride = None, 0
+        if step_noise is not None:
+            if step_noise.shape[0] != self.n_steps or tuple(step_noise.shape[1:]) != tuple(input_noise.shape):
+                raise ValueError("step_noise must be [n_steps, *input_noise.shape]")
+            sn = step_noise.to(dev).reshape((self.n_steps * N,) + tuple(input_noise.shape[1:]))
+            self.noise = ops.to_ndhwc(sn, self.c_lat, torch.float32)
+            self.noise_stride = self.noise.numel() // self.n_steps
+        self.graph = None
+        self.use_graph = use_graph and USE_GRAPH
+
+    def _body(self):
+        ops.select_row(self.temb_table, self.counter, self.temb_cur)
+        eps = self.unet.forward_ndhwc(self.x_model, self.temb_cur, 0)
+        ops.scheduler_step(eps, self.x_t, self.coef, self.counter, self.c_lat, noise=self.noise,
+                           noise_step_stride=self.noise_stride, x_model=self.x_model, seed=self.seed)
+        ops.counter_add(self.counter, 1)
+
+    def _capture(self):
+        # warm-up (weight repack, cudaFuncSetAttribute, allocator) on a scratch copy of the state
+        keep_x, keep_m = self.x_t.clone(), self.x_model.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._body()
+        torch.cuda.current_stream().wait_stream(s)
+        self.x_t.copy_(keep_x)
+        self.x_model.copy_(keep_m)
+        self.counter.zero_()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._body()
+        self.x_t.copy_(keep_x)
+        self.x_model.copy_(keep_m)
+        self.counter.zero_()
+        self.graph = g
+
+    def step(self):
+        if self.use_graph:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+        else:
+            self._body()
+
+    def latent_ncdhw(self) -> torch.Tensor:
+        return ops.to_ncdhw(self.x_t, self.c_lat)
+
+
+class DiffusionInferer:
+    def __init__(self, scheduler):
+        self.scheduler = scheduler
+
+    @torch.no_grad()
+    def sample(self, input_noise, diffusion_model, scheduler=None, save_intermediates=False, intermediate_steps=100,
+               conditioning=None, mode="crossattn", verbose=True, seg=None, step_noise=None, seed=None,
+               _return_loop=False):
+        if mode not in ("crossattn", "concat"):
+            raise NotImplementedError(f"{mode} condition is not supported")
+        if mode == "concat" and conditioning is None:
+            raise ValueError("Conditioning must be supplied for if condition mode is concat.")
+        if mode == "crossattn" and conditioning is not None:
+            raise ValueError("model should have with_conditioning = True if context is provided")
+        scheduler = scheduler or self.scheduler
+        if not isinstance(diffusion_model, DiffusionModelUNet):
+            raise TypeError("b200ldm inferers drive b200ldm.DiffusionModelUNet (there is no generic / CPU fallback)")
+        if not input_noise.is_cuda:
+            raise RuntimeError("b200ldm sampling needs CUDA tensors (there is no CPU fallback)")
+        if seed is None:
+            seed = int(torch.initial_seed()) & (2 ** 63 - 1)
+        loop = SamplingLoop(diffusion_model, scheduler, input_noise, conditioning, mode, step_noise=step_noise,
+                            seed=seed, use_graph=len(scheduler.timesteps) > 2)
+        intermediates = []
+        for t in scheduler.timesteps:
+            loop.step()
+            if save_intermediates and int(t) % intermediate_steps == 0:
+                intermediates.append(loop.latent_ncdhw())
+        image = loop.latent_ncdhw()
+        if _return_loop:
+            return image, intermediates, loop
+        return (image, intermediates) if save_intermediates else image
+
+    @torch.no_grad()
+    def __call__(self, inputs, diffusion_model, noise, timesteps, condition=None, mode="crossattn", seg=None):
+        if mode not in ("crossattn", "concat"):
+            raise NotImplementedError(f"{mode} condition is not supported")
+        noisy = self.scheduler.add_noise(original_samples=inputs, noise=noise, timesteps=timesteps)
+        if mode == "concat":
+            if condition is None:
+                raise ValueError("Conditioning is required for concat condition")
+            noisy = torch.cat([noisy, condition.to(noisy.dtype)], dim=1)
+            condition = None
+        return diffusion_model(x=noisy, timesteps=timesteps, context=condition)
+
+
+class LatentDiffusionInferer(DiffusionInferer):
+    def __init__(self, scheduler, scale_factor: float = 1.0, ldm_latent_shape=None, autoencoder_latent_shape=None):
+        super().__init__(scheduler)
+        self.scale_factor = scale_factor
+        if (ldm_latent_shape is None) ^ (autoencoder_latent_shape is None):
+            raise ValueError("If ldm_latent_shape is None, autoencoder_latent_shape must be None, and vice versa.")
+        if ldm_latent_shape is not None:
+            raise NotImplementedError("latent resizing (ldm_latent_shape) is not used by the reference")
+
+    @torch.no_grad()
+    def sample(self, input_noise, autoencoder_model, diffusion_model, scheduler=None, save_intermediates=False,
+               intermediate_steps=100, conditioning=None, mode="crossattn", verbose=True, seg=None, step_noise=None,
+               seed=None, return_latent=False):
+        if not isinstance(autoencoder_model, AutoencoderKL):
+            raise TypeError("b200ldm inferers drive b200ldm.AutoencoderKL (there is no generic / CPU fallback)")
+        latent, lat_inter, loop = super().sample(
+            input_noise, diffusion_model, scheduler, save_intermediates, intermediate_steps, conditioning, mode,
+            verbose, seg, step_noise=step_noise, seed=seed, _return_loop=True)
+        image = self._decode(autoencoder_model, loop)
+        if save_intermediates:
+            inter = [autoencoder_model.decode_stage_2_outputs(l / self.scale_factor) for l in lat_inter]
+            return image, inter
+        if return_latent:
+            return image, latent
+        return image
+
+    def _decode(self, ae: AutoencoderKL, loop: SamplingLoop) -> torch.Tensor:
+        """decode(x_0 / scale_factor) straight from the device-resident NDHWC latent."""
+        lat = loop.latent_ncdhw()
+        if self.scale_factor != 1.0:
+            inv = torch.full((lat.shape[0],), 1.0 / float(self.scale_factor), dtype=torch.float32, device=lat.device)
+            zero = torch.zeros_like(inv)
+            lat = ops.add_noise(lat, lat, inv, zero)  # lat * (1/scale) on our own kernel
+        return ae.decode_stage_2_outputs(lat)
+
+    @torch.no_grad()
+    def __call__(self, inputs, autoencoder_model, diffusion_model, noise, timesteps, condition=None, mode="crossattn",
+                 seg=None, encode_noise=None):
+        latent = autoencoder_model.encode_stage_2_inputs(inputs, noise=encode_noise)
+        if self.scale_factor != 1.0:
+            sf = torch.full((latent.shape[0],), float(self.scale_factor), dtype=torch.float32, device=latent.device)
+            latent = ops.add_noise(latent, latent, sf, torch.zeros_like(sf))
+        return super().__call__(latent, diffusion_model, noise, timesteps, condition, mode, seg)

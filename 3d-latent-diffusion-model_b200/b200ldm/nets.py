@@ -1,0 +1,639 @@
+"""B200 drop-ins for the two MONAI networks the reference instantiates by `_target_`
+(3d_ldm/config/config_train_32g.json:8,41 through 3d_ldm/utils.py:243-246):
+
+    DiffusionModelUNet(...).forward(x, timesteps, context=None, ...)        3d_ldm/inference.py:75
+    AutoencoderKL(...).encode / sampling / decode / decode_stage_2_outputs  3d_ldm/inference.py:71
+
+Same constructor kwargs, forward signatures and state_dict key names as MONAI >= 1.4
+(SURVEY.md App. A, B, E), so `load_state_dict(torch.load("diffusion_unet.pt"))`
+(3d_ldm/inference.py:72-77) works unchanged.  Parameters are kept in PyTorch layout (fp32);
+on first use they are repacked once per dtype into the kernels' [tap][Cout][Cin] layout.
+All arithmetic runs in libb200ldm (ops.py); activations are NDHWC internally and NCDHW fp32
+at the module boundary.  `precision` = "bf16" (tcgen05 path) or "fp32" (validation path).
+"""
+from __future__ import annotations
+
+import os
+from typing import Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+_PREC = {"bf16": torch.bfloat16, "fp32": torch.float32}
+FUSE_GN_STATS = os.environ.get("B200LDM_FUSE_GN_STATS", "1") != "0"
+
+
+def default_precision() -> str:
+    return os.environ.get("B200LDM_PRECISION", "bf16")
+
+
+def _pad64(c: int) -> int:
+    return ops.round_up(c, 64)
+
+
+class PackedCache:
+    """Per-module cache of repacked weights keyed by (dtype, device, parameter versions)."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, key, params, build):
+        ver = tuple((p._version, p.data_ptr()) for p in params)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        val = build()
+        self._store[key] = (ver, val)
+        return val
+
+
+class Conv(nn.Module):
+    """Leaf that owns `weight` [Cout,Cin,k,k,k] + `bias` like nn.Conv3d and runs the conv3d kernel."""
+
+    def __init__(self, cin: int, cout: int, ksize: int = 3, stride: int = 1, pad_lo: int = 1, pad_hi: int | None = None,
+                 terminal: bool = False):
+        super().__init__()
+        self.cin, self.cout, self.ksize, self.stride = cin, cout, ksize, stride
+        self.pad_lo, self.pad_hi = pad_lo, pad_lo if pad_hi is None else pad_hi
+        self.weight = nn.Parameter(torch.empty(cout, cin, ksize, ksize, ksize))
+        self.bias = nn.Parameter(torch.empty(cout))
+        nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
+        bound = 1.0 / (cin * ksize ** 3) ** 0.5
+        nn.init.uniform_(self.bias, -bound, bound)
+        # physical (padded) output channels: feeds another conv -> multiple of 64, else multiple of 16
+        self.cout_phys = ops.round_up(cout, 16) if terminal else _pad64(cout)
+        self._cache = PackedCache()
+
+    def packed(self, dtype, c1: int | None = None, c1_phys: int | None = None, cin_phys: int | None = None):
+        """(weights [k^3][cout_phys][cin_phys], bias fp32 [cout_phys]); c1/c1_phys describe a concat split."""
+        if cin_phys is None:
+            cin_phys = _pad64(self.cin) if c1 is None else c1_phys + _pad64(self.cin - c1)
+
+        def build():
+            w = ops.repack_conv_weight(self.weight, self.cout_phys, cin_phys, dtype, c1, c1_phys)
+            b = torch.zeros(self.cout_phys, dtype=torch.float32, device=self.weight.device)
+            b[: self.cout] = self.bias.detach().float()
+            return w, b
+
+        return self._cache.get((dtype, c1, c1_phys, cin_phys), (self.weight, self.bias), build)
+
+    def run(self, x, x2=None, c1: int | None = None, temb=None, temb_stride: int = 0, residual=None, gn_stats=None,
+            gn_groups: int = 0, out_f32: bool = False):
+        if x2 is None:
+            w, b = self.packed(x.dtype, cin_phys=x.shape[-1])
+        else:
+            w, b = self.packed(x.dtype, c1=c1, c1_phys=x.shape[-1], cin_phys=x.shape[-1] + x2.shape[-1])
+        return ops.conv3d(x, w, b, self.cout_phys, self.ksize, self.stride, self.pad_lo, self.pad_hi, x2=x2, temb=temb,
+                          temb_stride=temb_stride, residual=residual, gn_stats=gn_stats, gn_groups=gn_groups,
+                          out_f32=out_f32)
+
+
+class ConvOnly(nn.Module):
+    """MONAI `Convolution(conv_only=True)`: container with a single child `.conv` (key `*.conv.weight`)."""
+
+    def __init__(self, cin, cout, ksize=3, stride=1, pad_lo=1, pad_hi=None, terminal=False):
+        super().__init__()
+        self.conv = Conv(cin, cout, ksize, stride, pad_lo, pad_hi, terminal)
+
+    def run(self, *a, **k):
+        return self.conv.run(*a, **k)
+
+
+class Linear(nn.Module):
+    """nn.Linear-shaped parameters; runs as a 1x1x1 conv (GEMM) in fp32 or bf16."""
+
+    def __init__(self, cin: int, cout: int):
+        super().__init__()
+        self.cin, self.cout = cin, cout
+        self.weight = nn.Parameter(torch.empty(cout, cin))
+        self.bias = nn.Parameter(torch.empty(cout))
+        nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
+        nn.init.uniform_(self.bias, -1.0 / cin ** 0.5, 1.0 / cin ** 0.5)
+        self._cache = PackedCache()
+
+    def packed(self, dtype):
+        def build():
+            w = ops.repack_conv_weight(self.weight, ops.round_up(self.cout, 16), self.cin, dtype)
+            b = torch.zeros(ops.round_up(self.cout, 16), dtype=torch.float32, device=self.weight.device)
+            b[: self.cout] = self.bias.detach().float()
+            return w, b
+
+        return self._cache.get(dtype, (self.weight, self.bias), build)
+
+
+class GroupNorm(nn.Module):
+    def __init__(self, groups: int, channels: int, eps: float):
+        super().__init__()
+        self.groups, self.channels, self.eps = groups, channels, eps
+        self.weight = nn.Parameter(torch.ones(channels))
+        self.bias = nn.Parameter(torch.zeros(channels))
+
+    def run(self, x, silu: bool, x2=None, stats=None):
+        return ops.groupnorm(x, self.weight.detach(), self.bias.detach(), self.groups, self.eps, silu, x2=x2,
+                             stats=stats)
+
+
+def zero_module(m: nn.Module) -> nn.Module:
+    for p in m.parameters():
+        nn.init.zeros_(p)
+    return m
+
+
+# ------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------
+class SABlock(nn.Module):
+    """Separate to_q/to_k/to_v/out_proj linears (MONAI key names); executed as one fused QKV GEMM."""
+
+    def __init__(self, hidden: int, heads: int):
+        super().__init__()
+        if hidden % heads:
+            raise ValueError("hidden size should be divisible by num_heads.")
+        self.hidden, self.heads, self.head_dim = hidden, heads, hidden // heads
+        self.scale = self.head_dim ** -0.5
+        self.to_q, self.to_k, self.to_v = Linear(hidden, hidden), Linear(hidden, hidden), Linear(hidden, hidden)
+        self.out_proj = Linear(hidden, hidden)
+        self._cache = PackedCache()
+
+    def packed_qkv(self, dtype):
+        ps = [self.to_q.weight, self.to_k.weight, self.to_v.weight, self.to_q.bias, self.to_k.bias, self.to_v.bias]
+
+        def build():
+            w = torch.cat([self.to_q.weight, self.to_k.weight, self.to_v.weight], dim=0).detach()
+            b = torch.cat([self.to_q.bias, self.to_k.bias, self.to_v.bias], dim=0).detach().float().contiguous()
+            return ops.repack_conv_weight(w, 3 * self.hidden, self.hidden, dtype), b
+
+        return self._cache.get(dtype, ps, build)
+
+    def run(self, xn, residual):
+        """xn: normalised tokens [B, D,H,W, C]; residual: same shape; returns out_proj(att) + residual."""
+        shp = xn.shape
+        B, Cc = shp[0], shp[-1]
+        L = xn.numel() // (B * Cc)
+        wqkv, bqkv = self.packed_qkv(xn.dtype)
+        qkv = ops.linear(xn.reshape(B * L, Cc), wqkv, bqkv, 3 * Cc)
+        att = ops.attention(qkv.reshape(B, L, 3 * Cc), self.heads, self.head_dim, self.scale)
+        wo, bo = self.out_proj.packed(xn.dtype)
+        y = ops.linear(att.reshape(B * L, Cc), wo, bo, Cc, residual=residual.reshape(B * L, Cc))
+        return y.reshape(shp)
+
+
+class SpatialAttentionBlock(nn.Module):
+    def __init__(self, channels: int, num_head_channels: int | None, groups: int, eps: float):
+        super().__init__()
+        self.norm = GroupNorm(groups, channels, eps)
+        heads = channels // num_head_channels if num_head_channels else 1
+        self.attn = SABlock(channels, heads)
+
+    def run(self, x):
+        return self.attn.run(self.norm.run(x, silu=False), x)
+
+
+class NearestUp(nn.Module):
+    """UpSample(mode="nontrainable", nearest x2) + post conv; children `upsample_non_trainable`, `postconv`."""
+
+    def __init__(self, ch: int):
+        super().__init__()
+        self.upsample_non_trainable = nn.Identity()
+        self.postconv = ConvOnly(ch, ch, 3, 1, 1)
+
+    def run(self, x):
+        return self.postconv.run(ops.upsample_nearest2x(x))
+
+
+# ------------------------------------------------------------------------------------------
+# DiffusionModelUNet
+# ------------------------------------------------------------------------------------------
+class UNetResBlock(nn.Module):
+    def __init__(self, cin, cout, temb_ch, groups, eps):
+        super().__init__()
+        self.cin, self.cout, self.groups = cin, cout, groups
+        self.norm1 = GroupNorm(groups, cin, eps)
+        self.conv1 = ConvOnly(cin, cout)
+        self.time_emb_proj = Linear(temb_ch, cout)
+        self.norm2 = GroupNorm(groups, cout, eps)
+        self.conv2 = zero_module(ConvOnly(cout, cout))
+        self.skip_connection = nn.Identity() if cin == cout else ConvOnly(cin, cout, 1, 1, 0)
+
+    def run(self, x, temb, temb_stride, x2=None):
+        """x (and optional skip x2, concatenated on channels); temb: fp32 view [n_t, cout] for this block."""
+        h = self.norm1.run(x, silu=True, x2=x2)
+        stats = None
+        cpg = self.cout // self.groups
+        if FUSE_GN_STATS and cpg >= 2 and (cpg & (cpg - 1)) == 0:
+            stats = ops.zeros_f64(x.shape[0] * self.groups * 2, x.device)
+        h = self.conv1.run(h, temb=temb, temb_stride=temb_stride, gn_stats=stats, gn_groups=self.groups)
+        h = self.norm2.run(h, silu=True, stats=stats)
+        if isinstance(self.skip_connection, nn.Identity):
+            res = x
+        else:
+            res = self.skip_connection.run(x, x2=x2, c1=None if x2 is None else x.shape[-1])
+        return self.conv2.run(h, residual=res)
+
+
+class _DownOp(nn.Module):
+    def __init__(self, ch):
+        super().__init__()
+        self.op = ConvOnly(ch, ch, 3, 2, 1)
+
+
+class _UNetUp(nn.Module):
+    def __init__(self, ch):
+        super().__init__()
+        self.upsample = NearestUp(ch)
+
+
+class _DownBlock(nn.Module):
+    def __init__(self, cin, cout, temb, n_res, groups, eps, add_down, attn, head_ch):
+        super().__init__()
+        self.resnets = nn.ModuleList([UNetResBlock(cin if j == 0 else cout, cout, temb, groups, eps)
+                                      for j in range(n_res)])
+        if attn:
+            self.attentions = nn.ModuleList([SpatialAttentionBlock(cout, head_ch, groups, eps) for _ in range(n_res)])
+        self.has_attn = attn
+        self.downsampler = _DownOp(cout) if add_down else None
+
+
+class _MidBlock(nn.Module):
+    def __init__(self, ch, temb, groups, eps, head_ch):
+        super().__init__()
+        self.resnet_1 = UNetResBlock(ch, ch, temb, groups, eps)
+        self.attention = SpatialAttentionBlock(ch, head_ch, groups, eps)
+        self.resnet_2 = UNetResBlock(ch, ch, temb, groups, eps)
+
+
+class _UpBlock(nn.Module):
+    def __init__(self, cin, prev, cout, temb, n_res, groups, eps, add_up, attn, head_ch):
+        super().__init__()
+        blocks = []
+        for j in range(n_res):
+            skip_ch = cin if j == n_res - 1 else cout
+            res_in = prev if j == 0 else cout
+            blocks.append(UNetResBlock(res_in + skip_ch, cout, temb, groups, eps))
+        self.resnets = nn.ModuleList(blocks)
+        if attn:
+            self.attentions = nn.ModuleList([SpatialAttentionBlock(cout, head_ch, groups, eps) for _ in range(n_res)])
+        self.has_attn = attn
+        self.upsampler = _UNetUp(cout) if add_up else None
+
+
+def _per_level(v, n):
+    return list(v) if isinstance(v, (list, tuple)) else [v] * n
+
+
+class DiffusionModelUNet(nn.Module):
+    def __init__(
+        self,
+        spatial_dims: int,
+        in_channels: int,
+        out_channels: int,
+        num_res_blocks: Sequence[int] | int = (2, 2, 2, 2),
+        channels: Sequence[int] = (32, 64, 64, 64),
+        attention_levels: Sequence[bool] = (False, False, True, True),
+        norm_num_groups: int = 32,
+        norm_eps: float = 1e-6,
+        resblock_updown: bool = False,
+        num_head_channels: int | Sequence[int] = 8,
+        with_conditioning: bool = False,
+        transformer_num_layers: int = 1,
+        cross_attention_dim: int | None = None,
+        num_class_embeds: int | None = None,
+        upcast_attention: bool = False,
+        dropout_cattn: float = 0.0,
+        include_fc: bool = True,
+        use_combined_linear: bool = False,
+        use_flash_attention: bool = False,
+        precision: str | None = None,
+    ):
+        super().__init__()
+        if spatial_dims != 3:
+            raise ValueError("b200ldm implements the 3-D hot path only (spatial_dims=3)")
+        if with_conditioning or cross_attention_dim is not None:
+            raise NotImplementedError("cross-attention conditioning is not on the reference's hot path (SURVEY.md 8f)")
+        if resblock_updown or num_class_embeds is not None:
+            raise NotImplementedError("resblock_updown / class embeddings are not used by any reference config")
+        if any(c % norm_num_groups for c in channels):
+            raise ValueError("DiffusionModelUNet expects all channels being multiple of norm_num_groups")
+        if len(channels) != len(attention_levels):
+            raise ValueError("DiffusionModelUNet expects channels being same size of attention_levels")
+        if any(c % 64 for c in channels):
+            raise NotImplementedError("b200ldm UNet needs channel counts that are multiples of 64 (128-byte TMA rows)")
+        L = len(channels)
+        head, nres = _per_level(num_head_channels, L), _per_level(num_res_blocks, L)
+        if len(head) != L:
+            raise ValueError("num_head_channels should have the same length as attention_levels.")
+        if len(nres) != L:
+            raise ValueError("`num_res_blocks` should be a single integer or a tuple of integers with the same length "
+                             "as `channels`.")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.block_out_channels = list(channels)
+        self.with_conditioning = with_conditioning
+        self.precision = precision or default_precision()
+        temb = channels[0] * 4
+
+        self.conv_in = ConvOnly(in_channels, channels[0])
+        self.time_embed = nn.Sequential(Linear(channels[0], temb), nn.SiLU(), Linear(temb, temb))
+        self.down_blocks = nn.ModuleList()
+        cout = channels[0]
+        for i in range(L):
+            cin, cout = cout, channels[i]
+            self.down_blocks.append(_DownBlock(cin, cout, temb, nres[i], norm_num_groups, norm_eps, i != L - 1,
+                                               bool(attention_levels[i]), head[i]))
+        self.middle_block = _MidBlock(channels[-1], temb, norm_num_groups, norm_eps, head[-1])
+        self.up_blocks = nn.ModuleList()
+        rc, rn = list(reversed(channels)), list(reversed(nres))
+        ra, rh = list(reversed(attention_levels)), list(reversed(head))
+        cout = rc[0]
+        for i in range(L):
+            prev, cout = cout, rc[i]
+            cin = rc[min(i + 1, L - 1)]
+            self.up_blocks.append(_UpBlock(cin, prev, cout, temb, rn[i] + 1, norm_num_groups, norm_eps, i != L - 1,
+                                           bool(ra[i]), rh[i]))
+        self.out = nn.Sequential(GroupNorm(norm_num_groups, channels[0], norm_eps), nn.SiLU(),
+                                 zero_module(ConvOnly(channels[0], out_channels, terminal=True)))
+        self._cache = PackedCache()
+
+    # ---- time embedding (always fp32: tiny M, and it keeps t-conditioning exact in both modes)
+    def resblocks(self):
+        out = []
+        for b in self.down_blocks:
+            out += list(b.resnets)
+        out += [self.middle_block.resnet_1, self.middle_block.resnet_2]
+        for b in self.up_blocks:
+            out += list(b.resnets)
+        return out
+
+    def _temb_layout(self):
+        offs, o = [], 0
+        for r in self.resblocks():
+            offs.append(o)
+            o += r.cout
+        return offs, o
+
+    def time_embedding_table(self, timesteps: torch.Tensor) -> torch.Tensor:
+        """[n_t] -> fp32 [n_t, sum(C_out over ResNet blocks)]: time_emb_proj_i(SiLU(time_embed(sincos(t)))) for every
+        block i, computed by one fused GEMM (the 19 M=1 GEMVs are independent of x)."""
+        rbs = self.resblocks()
+        params = [p for r in rbs for p in (r.time_emb_proj.weight, r.time_emb_proj.bias)]
+
+        def build():
+            w = torch.cat([r.time_emb_proj.weight for r in rbs], dim=0).detach()
+            b = torch.cat([r.time_emb_proj.bias for r in rbs], dim=0).detach().float().contiguous()
+            return ops.repack_conv_weight(w, ops.round_up(w.shape[0], 16), w.shape[1], torch.float32), b, w.shape[0]
+
+        wall, ball, total = self._cache.get("temb_proj", params, build)
+        t_emb = ops.timestep_embedding(timesteps, self.block_out_channels[0])
+        l0, l2 = self.time_embed[0], self.time_embed[2]
+        w0, b0 = l0.packed(torch.float32)
+        w2, b2 = l2.packed(torch.float32)
+        h = ops.linear(t_emb, w0, b0, l0.cout)
+        h = ops.linear(ops.silu_f32(h), w2, b2, l2.cout)
+        return ops.linear(ops.silu_f32(h), wall, ball, total)
+
+    # ---- NDHWC core
+    def forward_ndhwc(self, x, temb_all, temb_stride: int):
+        """x: [N,D,H,W,pad64(in_channels)] (bf16|fp32); temb_all: fp32 [n_t, total] rows (n_t = 1 -> stride 0).
+        Returns eps [N,D,H,W,round16(out_channels)]."""
+        offs, _ = self._temb_layout()
+        it = iter(range(len(offs)))
+
+        def temb_for():
+            i = next(it)
+            return temb_all[:, offs[i]:]  # pointer offset only; the kernel strides rows by temb_stride
+
+        h = self.conv_in.run(x)
+        skips = [h]
+        for blk in self.down_blocks:
+            for j, r in enumerate(blk.resnets):
+                h = r.run(h, temb_for(), temb_stride)
+                if blk.has_attn:
+                    h = blk.attentions[j].run(h)
+                skips.append(h)
+            if blk.downsampler is not None:
+                h = blk.downsampler.op.run(h)
+                skips.append(h)
+        mb = self.middle_block
+        h = mb.resnet_1.run(h, temb_for(), temb_stride)
+        h = mb.attention.run(h)
+        h = mb.resnet_2.run(h, temb_for(), temb_stride)
+        for blk in self.up_blocks:
+            for j, r in enumerate(blk.resnets):
+                h = r.run(h, temb_for(), temb_stride, x2=skips.pop())
+                if blk.has_attn:
+                    h = blk.attentions[j].run(h)
+            if blk.upsampler is not None:
+                h = blk.upsampler.upsample.run(h)
+        h = self.out[0].run(h, silu=True)
+        return self.out[2].run(h)
+
+    def forward(self, x, timesteps, context=None, class_labels=None, down_block_additional_residuals=None,
+                mid_block_additional_residual=None):
+        if context is not None and not self.with_conditioning:
+            raise ValueError("model should have with_conditioning = True if context is provided")
+        if class_labels is not None or down_block_additional_residuals is not None \
+                or mid_block_additional_residual is not None:
+            raise NotImplementedError("class labels / ControlNet residuals are not on the reference's hot path")
+        if x.ndim != 5 or x.shape[1] != self.in_channels:
+            raise ValueError(f"expected [B,{self.in_channels},D,H,W], got {tuple(x.shape)}")
+        if timesteps.ndim != 1:
+            raise ValueError("Timesteps should be a 1d-array")
+        if timesteps.numel() not in (1, x.shape[0]):
+            raise ValueError("timesteps must have 1 or batch elements")
+        with torch.no_grad():
+            dt = _PREC[self.precision]
+            xa = ops.to_ndhwc(x, _pad64(self.in_channels), dt)
+            temb_all = self.time_embedding_table(timesteps.to(x.device))
+            stride = 0 if timesteps.numel() == 1 else temb_all.shape[1]
+            eps = self.forward_ndhwc(xa, temb_all, stride)
+            return ops.to_ncdhw(eps, self.out_channels)
+
+
+# ------------------------------------------------------------------------------------------
+# AutoencoderKL
+# ------------------------------------------------------------------------------------------
+class AEResBlock(nn.Module):
+    def __init__(self, cin, cout, groups, eps):
+        super().__init__()
+        self.cout, self.groups = cout, groups
+        self.norm1 = GroupNorm(groups, cin, eps)
+        self.conv1 = ConvOnly(cin, cout)
+        self.norm2 = GroupNorm(groups, cout, eps)
+        self.conv2 = ConvOnly(cout, cout)
+        self.nin_shortcut = nn.Identity() if cin == cout else ConvOnly(cin, cout, 1, 1, 0)
+
+    def run(self, x):
+        h = self.norm1.run(x, silu=True)
+        stats = None
+        cpg = self.cout // self.groups
+        if FUSE_GN_STATS and cpg >= 2 and (cpg & (cpg - 1)) == 0:
+            stats = ops.zeros_f64(x.shape[0] * self.groups * 2, x.device)
+        h = self.conv1.run(h, gn_stats=stats, gn_groups=self.groups)
+        h = self.norm2.run(h, silu=True, stats=stats)
+        res = x if isinstance(self.nin_shortcut, nn.Identity) else self.nin_shortcut.run(x)
+        return self.conv2.run(h, residual=res)
+
+
+class AEDownsample(nn.Module):
+    """F.pad(x, (0,1)*3) then conv3 stride 2 pad 0 == conv with pad_lo 0, pad_hi 1 (zero fill by TMA)."""
+
+    def __init__(self, ch):
+        super().__init__()
+        self.conv = ConvOnly(ch, ch, 3, 2, 0, 1)
+
+    def run(self, x):
+        return self.conv.run(x)
+
+
+class _AEStack(nn.Module):
+    def run(self, x):
+        for b in self.blocks:
+            if isinstance(b, GroupNorm):
+                x = b.run(x, silu=False)
+            else:
+                x = b.run(x)
+        return x
+
+
+class Encoder(_AEStack):
+    def __init__(self, in_channels, channels, out_channels, num_res_blocks, groups, eps, attention_levels,
+                 with_nonlocal_attn):
+        super().__init__()
+        blocks: list[nn.Module] = [ConvOnly(in_channels, channels[0])]
+        cout = channels[0]
+        for i, ch in enumerate(channels):
+            cin, cout = cout, ch
+            for _ in range(num_res_blocks[i]):
+                blocks.append(AEResBlock(cin, cout, groups, eps))
+                cin = cout
+                if attention_levels[i]:
+                    blocks.append(SpatialAttentionBlock(cin, None, groups, eps))
+            if i != len(channels) - 1:
+                blocks.append(AEDownsample(cin))
+        if with_nonlocal_attn:
+            blocks += [AEResBlock(channels[-1], channels[-1], groups, eps),
+                       SpatialAttentionBlock(channels[-1], None, groups, eps),
+                       AEResBlock(channels[-1], channels[-1], groups, eps)]
+        blocks.append(GroupNorm(groups, channels[-1], eps))
+        blocks.append(ConvOnly(channels[-1], out_channels))
+        self.blocks = nn.ModuleList(blocks)
+
+
+class Decoder(_AEStack):
+    def __init__(self, channels, in_channels, out_channels, num_res_blocks, groups, eps, attention_levels,
+                 with_nonlocal_attn):
+        super().__init__()
+        rc = list(reversed(channels))
+        ra, rn = list(reversed(attention_levels)), list(reversed(num_res_blocks))
+        blocks: list[nn.Module] = [ConvOnly(in_channels, rc[0])]
+        if with_nonlocal_attn:
+            blocks += [AEResBlock(rc[0], rc[0], groups, eps), SpatialAttentionBlock(rc[0], None, groups, eps),
+                       AEResBlock(rc[0], rc[0], groups, eps)]
+        cout = rc[0]
+        for i, ch in enumerate(rc):
+            cin, cout = cout, ch
+            for _ in range(rn[i]):
+                blocks.append(AEResBlock(cin, cout, groups, eps))
+                cin = cout
+                if ra[i]:
+                    blocks.append(SpatialAttentionBlock(cin, None, groups, eps))
+            if i != len(rc) - 1:
+                blocks.append(NearestUp(cin))
+        blocks.append(GroupNorm(groups, cin, eps))
+        blocks.append(ConvOnly(cin, out_channels, terminal=True))
+        self.blocks = nn.ModuleList(blocks)
+
+
+class AutoencoderKL(nn.Module):
+    def __init__(
+        self,
+        spatial_dims: int,
+        in_channels: int = 1,
+        out_channels: int = 1,
+        num_res_blocks: Sequence[int] | int = (2, 2, 2, 2),
+        channels: Sequence[int] = (32, 64, 64, 64),
+        attention_levels: Sequence[bool] = (False, False, True, True),
+        latent_channels: int = 3,
+        norm_num_groups: int = 32,
+        norm_eps: float = 1e-6,
+        with_encoder_nonlocal_attn: bool = True,
+        with_decoder_nonlocal_attn: bool = True,
+        use_checkpoint: bool = False,
+        use_convtranspose: bool = False,
+        include_fc: bool = True,
+        use_combined_linear: bool = False,
+        use_flash_attention: bool = False,
+        precision: str | None = None,
+    ):
+        super().__init__()
+        if spatial_dims != 3:
+            raise ValueError("b200ldm implements the 3-D hot path only (spatial_dims=3)")
+        if use_convtranspose:
+            raise NotImplementedError("use_convtranspose is not used by any reference config")
+        if any(c % norm_num_groups for c in channels):
+            raise ValueError("AutoencoderKL expects all channels being multiple of norm_num_groups")
+        if len(channels) != len(attention_levels):
+            raise ValueError("AutoencoderKL expects channels being same size of attention_levels")
+        if any(c % 64 for c in channels):
+            raise NotImplementedError("b200ldm AutoencoderKL needs channel counts that are multiples of 64")
+        nres = _per_level(num_res_blocks, len(channels))
+        if len(nres) != len(channels):
+            raise ValueError("`num_res_blocks` should be a single integer or a tuple of integers with the same length "
+                             "as `channels`.")
+        self.in_channels, self.out_channels, self.latent_channels = in_channels, out_channels, latent_channels
+        self.precision = precision or default_precision()
+        self.encoder = Encoder(in_channels, channels, latent_channels, nres, norm_num_groups, norm_eps,
+                               attention_levels, with_encoder_nonlocal_attn)
+        self.decoder = Decoder(channels, latent_channels, out_channels, nres, norm_num_groups, norm_eps,
+                               attention_levels, with_decoder_nonlocal_attn)
+        self.quant_conv_mu = ConvOnly(latent_channels, latent_channels, 1, 1, 0, terminal=True)
+        self.quant_conv_log_sigma = ConvOnly(latent_channels, latent_channels, 1, 1, 0, terminal=True)
+        self.post_quant_conv = ConvOnly(latent_channels, latent_channels, 1, 1, 0)
+
+    # ---- NDHWC cores
+    def decode_ndhwc(self, z):
+        """z: [N,d,h,w,pad64(latent)] -> [N,4d,4h,4w,round16(out_channels)]"""
+        return self.decoder.run(self.post_quant_conv.run(z))
+
+    def encode_ndhwc(self, x):
+        h = self.encoder.run(x)
+        return self.quant_conv_mu.run(h), self.quant_conv_log_sigma.run(h)
+
+    # ---- MONAI surface (NCDHW fp32)
+    @torch.no_grad()
+    def encode(self, x):
+        dt = _PREC[self.precision]
+        mu, logvar = self.encode_ndhwc(ops.to_ndhwc(x, _pad64(self.in_channels), dt))
+        z, sigma = ops.ae_sampling(mu, logvar, None)  # z == mu (fp32), sigma = exp(clamp(logvar)/2)
+        return ops.to_ncdhw(z, self.latent_channels), ops.to_ncdhw(sigma, self.latent_channels)
+
+    @torch.no_grad()
+    def sampling(self, z_mu, z_sigma, noise=None):
+        """z = mu + sigma * eps.  `noise` (optional, parity tests) replaces the internally drawn eps."""
+        if noise is None:
+            n = z_mu.numel()
+            noise = ops.philox_normal(n, int(torch.randint(0, 2 ** 31 - 1, (1,)).item()), 0, z_mu.device)
+            noise = noise.reshape(z_mu.shape)
+        return ops.mul_add_f32(z_mu, z_sigma, noise)
+
+    @torch.no_grad()
+    def decode(self, z):
+        dt = _PREC[self.precision]
+        y = self.decode_ndhwc(ops.to_ndhwc(z, _pad64(self.latent_channels), dt))
+        return ops.to_ncdhw(y, self.out_channels)
+
+    def reconstruct(self, x):
+        return self.decode(self.encode(x)[0])
+
+    def forward(self, x):
+        z_mu, z_sigma = self.encode(x)
+        return self.decode(self.sampling(z_mu, z_sigma)), z_mu, z_sigma
+
+    def encode_stage_2_inputs(self, x, noise=None):
+        z_mu, z_sigma = self.encode(x)
+        return self.sampling(z_mu, z_sigma, noise)
+
+    def decode_stage_2_outputs(self, z):
+        return self.decode(z)
+

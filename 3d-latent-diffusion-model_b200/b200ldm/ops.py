@@ -1,0 +1,250 @@
+"""Thin tensor-level wrappers over the C ABI (include/b200ldm.h).
+
+PyTorch is used for device memory (torch.empty), the current stream and nothing else:
+every arithmetic op below is a libb200ldm kernel.  Activations are NDHWC tensors
+`[N, D, H, W, C]`, contiguous, bf16 (tensor-core path) or fp32 (validation path).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05  # noqa: F401
+
+
+def dtype_code(t: torch.dtype) -> int:
+    if t == torch.bfloat16:
+        return BF16
+    if t == torch.float32:
+        return F32
+    raise TypeError(f"b200ldm supports bf16 / fp32 activations, got {t}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("b200ldm kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def conv_out_extent(n: int, k: int, stride: int, pad_lo: int, pad_hi: int) -> int:
+    return (n + pad_lo + pad_hi - k) // stride + 1
+
+
+def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo: int = 1, pad_hi: int | None = None,
+           x2=None, temb=None, temb_stride: int = 0, residual=None, gn_stats=None, gn_groups: int = 0,
+           out_f32: bool = False, engine: int = ENGINE_AUTO):
+    """y = conv3d(cat(x, x2)) + bias (+ temb) (+ residual); x: [N,D,H,W,C1] NDHWC."""
+    _need_cuda(x, x2, w_packed, bias, temb, residual)
+    lib = _lib.load()
+    N, D, H, W, C1 = x.shape
+    C2 = 0 if x2 is None else x2.shape[-1]
+    if pad_hi is None:
+        pad_hi = pad_lo
+    Do, Ho, Wo = (conv_out_extent(v, ksize, stride, pad_lo, pad_hi) for v in (D, H, W))
+    odt = torch.float32 if out_f32 else x.dtype
+    y = torch.empty((N, Do, Ho, Wo, cout), dtype=odt, device=x.device)
+    p = _lib.ConvParams(
+        x=_ptr(x), x2=_ptr(x2), w=_ptr(w_packed), bias=_ptr(bias), temb=_ptr(temb), residual=_ptr(residual),
+        y=_ptr(y), gn_stats=_ptr(gn_stats), N=N, D=D, H=H, W=W, C1=C1, C2=C2, Cout=cout, Do=Do, Ho=Ho, Wo=Wo,
+        ksize=ksize, stride=stride, pad_lo=pad_lo, temb_stride=temb_stride, gn_groups=gn_groups,
+        dtype=dtype_code(x.dtype), engine=engine, out_f32=int(out_f32))
+    assert x.is_contiguous() and (x2 is None or x2.is_contiguous())
+    assert residual is None or (residual.is_contiguous() and residual.shape == y.shape and residual.dtype == odt)
+    _lib.check(lib.b200ldm_conv3d(C.byref(p), _stream()), "conv3d")
+    return y
+
+
+def linear(x2d, w_packed, bias, cout: int, residual=None, out_f32: bool = False, engine: int = ENGINE_AUTO):
+    """[M, K] @ W^T (+bias) (+residual) as a 1x1x1 conv over a [1,1,1,M,K] view."""
+    M, K = x2d.shape
+    r = None if residual is None else residual.reshape(1, 1, 1, M, cout)
+    y = conv3d(x2d.reshape(1, 1, 1, M, K), w_packed, bias, cout, ksize=1, stride=1, pad_lo=0, residual=r,
+               out_f32=out_f32, engine=engine)
+    return y.reshape(M, cout)
+
+
+def repack_conv_weight(w: torch.Tensor, cout_pad: int, cin_pad: int, dtype: torch.dtype, cin_split: int | None = None,
+                       cin_split_pad: int | None = None):
+    """fp32 [Cout,Cin,k,k,k] (or [Cout,Cin] for linears) -> packed [k^3][cout_pad][cin_pad]."""
+    _need_cuda(w)
+    lib = _lib.load()
+    w = w.detach().to(torch.float32).contiguous()
+    cout, cin = w.shape[0], w.shape[1]
+    ksize = w.shape[2] if w.ndim == 5 else 1
+    if cin_split is None:
+        cin_split, cin_split_pad = cin, cin_pad
+    out = torch.empty((ksize ** 3, cout_pad, cin_pad), dtype=dtype, device=w.device)
+    _lib.check(lib.b200ldm_repack_conv_weight(w.data_ptr(), out.data_ptr(), cout, cin, ksize, cout_pad, cin_pad,
+                                              cin_split, cin_split_pad, dtype_code(dtype), _stream()), "repack")
+    return out
+
+
+def zeros_f64(n: int, device) -> torch.Tensor:
+    t = torch.empty((n,), dtype=torch.float64, device=device)
+    _lib.check(_lib.load().b200ldm_fill_zero(t.data_ptr(), n * 8, _stream()), "fill_zero")
+    return t
+
+
+def groupnorm(x, gamma, beta, groups: int, eps: float, silu: bool, x2=None, stats=None):
+    """GroupNorm(+SiLU) over cat(x, x2) channels; `stats` may come pre-accumulated from a conv epilogue."""
+    _need_cuda(x, x2, gamma, beta)
+    lib = _lib.load()
+    N = x.shape[0]
+    C1 = x.shape[-1]
+    C2 = 0 if x2 is None else x2.shape[-1]
+    S = x.numel() // (N * C1)
+    dt = dtype_code(x.dtype)
+    if stats is None:
+        stats = zeros_f64(N * groups * 2, x.device)
+        _lib.check(lib.b200ldm_groupnorm_stats(_ptr(x), _ptr(x2), stats.data_ptr(), N, S, C1, C2, groups, dt,
+                                               _stream()), "groupnorm_stats")
+    y = torch.empty(x.shape[:-1] + (C1 + C2,), dtype=x.dtype, device=x.device)
+    _lib.check(lib.b200ldm_groupnorm_apply(_ptr(x), _ptr(x2), y.data_ptr(), stats.data_ptr(), gamma.data_ptr(),
+                                           beta.data_ptr(), N, S, C1, C2, groups, float(eps), int(silu), dt,
+                                           _stream()), "groupnorm_apply")
+    return y
+
+
+def attention(qkv, heads: int, head_dim: int, scale: float, engine: int = ENGINE_AUTO):
+    """qkv: [B, L, 3*H*d] fused projections -> [B, L, H*d]."""
+    _need_cuda(qkv)
+    lib = _lib.load()
+    B, L, C3 = qkv.shape
+    Cc = heads * head_dim
+    assert C3 == 3 * Cc and qkv.is_contiguous()
+    o = torch.empty((B, L, Cc), dtype=qkv.dtype, device=qkv.device)
+    es = qkv.element_size()
+    base = qkv.data_ptr()
+    _lib.check(lib.b200ldm_attention(base, base + Cc * es, base + 2 * Cc * es, o.data_ptr(), B, heads, L, head_dim,
+                                     C3, float(scale), dtype_code(qkv.dtype), engine, _stream()), "attention")
+    return o
+
+
+def upsample_nearest2x(x):
+    _need_cuda(x)
+    N, D, H, W, Cc = x.shape
+    y = torch.empty((N, 2 * D, 2 * H, 2 * W, Cc), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.load().b200ldm_upsample_nearest2x(x.data_ptr(), y.data_ptr(), N, D, H, W, Cc,
+                                                      dtype_code(x.dtype), _stream()), "upsample")
+    return y
+
+
+def to_ndhwc(src: torch.Tensor, c_dst: int, dtype: torch.dtype, out: torch.Tensor | None = None, c_offset: int = 0):
+    """NCDHW fp32 -> NDHWC `dtype`, channels [c_offset, c_offset+C) of a c_dst-wide (zero padded) buffer."""
+    _need_cuda(src)
+    src = src.to(torch.float32).contiguous()
+    N, Cc = src.shape[:2]
+    sp = tuple(src.shape[2:])
+    S = src.numel() // (N * Cc)
+    if out is None:
+        out = torch.empty((N,) + sp + (c_dst,), dtype=dtype, device=src.device)
+        if c_dst != Cc:
+            _lib.check(_lib.load().b200ldm_fill_zero(out.data_ptr(), out.numel() * out.element_size(), _stream()),
+                       "fill_zero")
+    _lib.check(_lib.load().b200ldm_ncdhw_to_ndhwc(src.data_ptr(), out.data_ptr(), N, Cc, S, c_dst, c_offset,
+                                                  dtype_code(out.dtype), _stream()), "ncdhw_to_ndhwc")
+    return out
+
+
+def to_ncdhw(src: torch.Tensor, channels: int) -> torch.Tensor:
+    """NDHWC (bf16|fp32, possibly channel padded) -> NCDHW fp32 with the first `channels` channels."""
+    _need_cuda(src)
+    N = src.shape[0]
+    sp = tuple(src.shape[1:-1])
+    c_src = src.shape[-1]
+    S = src.numel() // (N * c_src)
+    out = torch.empty((N, channels) + sp, dtype=torch.float32, device=src.device)
+    _lib.check(_lib.load().b200ldm_ndhwc_to_ncdhw(src.data_ptr(), out.data_ptr(), N, channels, S, c_src,
+                                                  dtype_code(src.dtype), _stream()), "ndhwc_to_ncdhw")
+    return out
+
+
+def silu_f32(x):
+    _need_cuda(x)
+    y = torch.empty_like(x)
+    _lib.check(_lib.load().b200ldm_silu_f32(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "silu")
+    return y
+
+
+def timestep_embedding(timesteps: torch.Tensor, dim: int, max_period: float = 10000.0):
+    _need_cuda(timesteps)
+    ts = timesteps.to(torch.float32).contiguous()
+    out = torch.empty((ts.numel(), dim), dtype=torch.float32, device=ts.device)
+    _lib.check(_lib.load().b200ldm_timestep_embedding(ts.data_ptr(), out.data_ptr(), ts.numel(), dim,
+                                                      float(max_period), _stream()), "timestep_embedding")
+    return out
+
+
+def select_row(table, counter, dst):
+    _lib.check(_lib.load().b200ldm_select_row(table.data_ptr(), counter.data_ptr(), dst.data_ptr(), dst.numel(),
+                                              _stream()), "select_row")
+
+
+def counter_add(counter, delta: int = 1):
+    _lib.check(_lib.load().b200ldm_counter_add(counter.data_ptr(), delta, _stream()), "counter_add")
+
+
+def scheduler_step(eps, x_t, coef, counter, c: int, noise=None, noise_step_stride: int = 0, x0_out=None, x_model=None,
+                   seed: int = 0):
+    """In-place x_t <- step(eps, x_t); eps [.., C_eps] NDHWC, x_t fp32 [.., C] NDHWC."""
+    _need_cuda(eps, x_t, coef, noise, x_model)
+    n_vox = x_t.numel() // c
+    p = _lib.SchedParams(
+        eps=_ptr(eps), x_t=_ptr(x_t), noise=_ptr(noise), x0_out=_ptr(x0_out), x_model=_ptr(x_model), coef=_ptr(coef),
+        counter=_ptr(counter), n_vox=n_vox, noise_step_stride=noise_step_stride, C=c, C_eps=eps.shape[-1],
+        C_model=0 if x_model is None else x_model.shape[-1], dtype=dtype_code(eps.dtype), seed=seed)
+    _lib.check(_lib.load().b200ldm_scheduler_step(C.byref(p), _stream()), "scheduler_step")
+
+
+def philox_normal(n: int, seed: int, step: int, device) -> torch.Tensor:
+    out = torch.empty((n,), dtype=torch.float32, device=device)
+    _lib.check(_lib.load().b200ldm_philox_normal(out.data_ptr(), n, seed, step, _stream()), "philox_normal")
+    return out
+
+
+def ae_sampling(mu, logvar, noise):
+    _need_cuda(mu, logvar, noise)
+    z = torch.empty(mu.shape, dtype=torch.float32, device=mu.device)
+    sig = torch.empty(mu.shape, dtype=torch.float32, device=mu.device)
+    _lib.check(_lib.load().b200ldm_ae_sampling(mu.data_ptr(), logvar.data_ptr(), _ptr(noise), z.data_ptr(),
+                                               sig.data_ptr(), mu.numel(), dtype_code(mu.dtype), _stream()),
+               "ae_sampling")
+    return z, sig
+
+
+def add_noise(x0, noise, sqrt_acp, sqrt_1m_acp):
+    _need_cuda(x0, noise, sqrt_acp, sqrt_1m_acp)
+    out = torch.empty_like(x0)
+    N = x0.shape[0]
+    _lib.check(_lib.load().b200ldm_add_noise(x0.data_ptr(), noise.data_ptr(), sqrt_acp.data_ptr(),
+                                             sqrt_1m_acp.data_ptr(), out.data_ptr(), N, x0.numel() // N, _stream()),
+               "add_noise")
+    return out
+
+
+def mul_add_f32(a, b, c):
+    """a + b * c elementwise, fp32 (AutoencoderKL.sampling: mu + sigma * eps)."""
+    _need_cuda(a, b, c)
+    a, b, c = (t.to(torch.float32).contiguous() for t in (a, b, c))
+    out = torch.empty_like(a)
+    _lib.check(_lib.load().b200ldm_mul_add_f32(a.data_ptr(), b.data_ptr(), c.data_ptr(), out.data_ptr(), a.numel(),
+                                               _stream()), "mul_add_f32")
+    return out
+
+
+def launch_count() -> int:
+    return int(_lib.load().b200ldm_launch_count())

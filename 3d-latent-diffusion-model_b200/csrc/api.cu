@@ -1,0 +1,56 @@
+// api.cu - library-wide C ABI plumbing: version, thread-local error text, device check.
+#include "common.cuh"
+
+namespace b200ldm {
+
+static thread_local char t_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+}  // namespace b200ldm
+
+extern "C" {
+
+int b200ldm_version(void) { return B200LDM_VERSION; }
+
+int b200ldm_last_error(char* buf, size_t n) {
+  if (!buf || n == 0) return (int)strlen(b200ldm::t_err);
+  strncpy(buf, b200ldm::t_err, n - 1);
+  buf[n - 1] = 0;
+  return (int)strlen(buf);
+}
+
+uint64_t b200ldm_launch_count(void) { return b200ldm::g_launches.load(); }
+
+int b200ldm_check_device(void) {
+  int dev = 0;
+  B2_CHECK_CUDA(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  B2_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  B2_CHECK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10)
+    return b200ldm::fail(B200LDM_UNSUPPORTED_ARCH, "device %d is sm_%d%d; libb200ldm is sm_100a only", dev,
+                         major, minor);
+  return B200LDM_OK;
+}
+
+int b200ldm_fill_zero(void* p, size_t bytes, b200ldm_stream stream) {
+  B2_CHECK_CUDA(cudaMemsetAsync(p, 0, bytes, (cudaStream_t)stream));
+  return B200LDM_OK;
+}
+
+}  // extern "C"

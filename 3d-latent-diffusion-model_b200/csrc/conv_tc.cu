@@ -1,0 +1,448 @@
+// conv_tc.cu - Conv3d (k=1|3, stride 1|2) as an implicit GEMM on tcgen05 tensor cores.
+//
+//   M = output voxels (a TMA box of tn x td x th x tw <= 128 voxels of the NDHWC tensor)
+//   N = Cout tile (BN <= 256), K = taps x (C1 + C2) walked in 64-channel (128-byte) chunks.
+//
+// No im2col buffer exists: for every (tap, 64-channel chunk) the producer issues one 5-D TMA box
+// load of the *shifted* activation window (out-of-bounds rows are zero-filled by the TMA unit =
+// the conv zero padding) plus one 3-D box load of the matching [BN x 64] weight slab.  Both land
+// in SWIZZLE_128B K-major layout, which is exactly the canonical UMMA operand layout, so one
+// elected thread issues 4 x tcgen05.mma (K=16 each) per stage into a 128 x BN fp32 TMEM tile.
+// Stride-2 convs use 8 parity-subsampled tensor maps (one per (d,h,w) parity of the tap offset);
+// the UNet skip concat / concat conditioning is read in place as a second K range (x2).
+// Epilogue warps read TMEM (one accumulator row per thread), add bias / time-embedding /
+// residual in fp32, optionally accumulate GroupNorm partial sums, and store bf16 (or fp32).
+//
+// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace b200ldm {
+
+struct ConvTcMaps {
+  CUtensorMap a[8];  // stride 1: a[0] = x, a[1] = x2;  stride 2: a[pd*4+ph*2+pw]
+  CUtensorMap w;     // [taps][Cout_pad][Cin_total]
+};
+
+struct ConvTcArgs {
+  int tn, td, th, tw;      // voxel box of one M tile
+  int nb_d, nb_h, nb_w;    // tiles per spatial dim (tiles over N = gridDim.x / (nb_d*nb_h*nb_w))
+  int N, Do, Ho, Wo, Cout;
+  int nchunk1, nchunk2;    // 64-channel chunks in x / x2
+  int ksize, stride, pad_lo;
+  int rows_box;            // tn*td*th*tw
+  int temb_stride, out_f32, gn_groups;
+  const float* bias;
+  const float* temb;
+  const void* residual;
+  void* y;
+  double* gn_stats;
+};
+
+constexpr int kConvThreads = 192;
+constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
+
+template <int BN>
+struct ConvTcCfg {
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
+  using Cfg = ConvTcCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
+  // barriers: full[s] @ +8s, empty[s] @ +8(STAGES+s), tmem_full @ +16*STAGES, tmem slot after it
+  const uint32_t tmem_full_bar = bar_base + 16 * STAGES;
+  const uint32_t tmem_slot = tmem_full_bar + 8;
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  int mt = blockIdx.x;
+  const int bw = mt % a.nb_w; mt /= a.nb_w;
+  const int bh = mt % a.nb_h; mt /= a.nb_h;
+  const int bd = mt % a.nb_d; mt /= a.nb_d;
+  const int n0 = mt * a.tn, d0 = bd * a.td, h0 = bh * a.th, w0 = bw * a.tw;
+  const int co0 = blockIdx.y * BN;
+
+  const int taps = a.ksize * a.ksize * a.ksize;
+  const int nchunks = a.nchunk1 + a.nchunk2;
+  const int iters = taps * nchunks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&maps.w);
+    ptx::prefetch_tmap(&maps.a[0]);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(bar_base + 8 * s, 1);
+      ptx::mbar_init(bar_base + 8 * (STAGES + s), 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)a.rows_box * 128u + (uint32_t)Cfg::kBBytes;
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        ptx::mbar_wait(bar_base + 8 * (STAGES + s), ph ^ 1u, 0);
+        const int tap = it / nchunks;
+        const int chunk = it - tap * nchunks;
+        int kd = 0, kh = 0, kw = 0;
+        if (a.ksize == 3) { kd = tap / 9; kh = (tap / 3) % 3; kw = tap % 3; }
+        const uint32_t full = bar_base + 8 * s;
+        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+        const uint32_t sb = sa + kABytes;
+        ptx::mbar_expect_tx(full, tx_bytes);
+        if (a.stride == 1) {
+          const bool second = chunk >= a.nchunk1;
+          const CUtensorMap* m = second ? &maps.a[1] : &maps.a[0];
+          const int c0 = (second ? chunk - a.nchunk1 : chunk) * 64;
+          ptx::tma_load_5d(sa, m, full, c0, w0 + kw - a.pad_lo, h0 + kh - a.pad_lo, d0 + kd - a.pad_lo, n0);
+        } else {
+          // input coord = 2*o + k - pad_lo  ->  parity grid (k-pad_lo)&1 at index o + floor((k-pad_lo)/2)
+          const int od = kd - a.pad_lo, oh = kh - a.pad_lo, ow = kw - a.pad_lo;
+          const int pd = od & 1, ph2 = oh & 1, pw = ow & 1;
+          const CUtensorMap* m = &maps.a[pd * 4 + ph2 * 2 + pw];
+          ptx::tma_load_5d(sa, m, full, chunk * 64, w0 + ((ow - pw) >> 1), h0 + ((oh - ph2) >> 1),
+                           d0 + ((od - pd) >> 1), n0);
+        }
+        ptx::tma_load_3d(sb, &maps.w, full, chunk * 64, co0, tap);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        ptx::mbar_wait(bar_base + 8 * s, ph, 1);
+        ptx::tc_fence_after();
+        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+        const uint32_t sb = sa + kABytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = ptx::umma_desc_k_sw128(sa + k * 32);
+          const uint64_t db = ptx::umma_desc_k_sw128(sb + k * 32);
+          ptx::umma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        ptx::umma_commit(bar_base + 8 * (STAGES + s));  // frees the smem stage when the MMAs retire
+      }
+      ptx::umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // =========================== epilogue ===========================
+    const int q = warp & 3;            // TMEM lane quarter this warp may touch
+    const int row = q * 32 + lane;     // accumulator row == voxel slot in the box
+    int t = row;
+    const int rw = t % a.tw; t /= a.tw;
+    const int rh = t % a.th; t /= a.th;
+    const int rd = t % a.td; t /= a.td;
+    const int rn = t;
+    const int n = n0 + rn, d = d0 + rd, h = h0 + rh, w = w0 + rw;
+    const bool valid = row < a.rows_box && n < a.N && d < a.Do && h < a.Ho && w < a.Wo;
+    const size_t vox = (((size_t)n * a.Do + d) * a.Ho + h) * a.Wo + w;
+    const size_t obase = vox * (size_t)a.Cout;
+    const float* temb_row = a.temb ? a.temb + (size_t)(a.temb_stride ? n : 0) * a.temb_stride : nullptr;
+    const int cpg = a.gn_stats ? a.Cout / a.gn_groups : 1;
+
+    ptx::mbar_wait(tmem_full_bar, 0, 2);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      uint32_t r[16];
+      ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+      ptx::tmem_ld_wait();
+      const int co = co0 + c;
+      if (co >= a.Cout) continue;  // warp-uniform
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+      const int ncol = min(16, a.Cout - co);  // Cout % 8 == 0 -> 8 or 16
+      if (a.bias) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < ncol) v[j] += __ldg(a.bias + co + j);
+      }
+      if (temb_row && valid) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < ncol) v[j] += __ldg(temb_row + co + j);
+      }
+      if (a.residual && valid) {
+        if (a.out_f32) {
+          const float* rp = reinterpret_cast<const float*>(a.residual) + obase + co;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            if (j < ncol) {
+              float4 f = *reinterpret_cast<const float4*>(rp + j);
+              v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
+            }
+        } else {
+          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(a.residual) + obase + co;
+#pragma unroll
+          for (int j = 0; j < 16; j += 8)
+            if (j < ncol) {
+              float f[8];
+              Vec8<__nv_bfloat16>::load(rp + j, f);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[j + e] += f[e];
+            }
+        }
+      }
+      if (valid) {
+        if (a.out_f32) {
+          float* yp = reinterpret_cast<float*>(a.y) + obase + co;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            if (j < ncol) *reinterpret_cast<float4*>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + obase + co;
+#pragma unroll
+          for (int j = 0; j < 16; j += 8)
+            if (j < ncol) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = v[j + e];
+              Vec8<__nv_bfloat16>::store(yp + j, f);
+            }
+        }
+      }
+      if (a.gn_stats) {
+        // GroupNorm partials of the tensor just produced: (sum, sumsq) per (sample, group).
+        // Statistics use the values as stored (bf16-rounded when the output is bf16).
+        // cpg in {2,4,8,16,32,...}: a 16-column chunk covers 16/cpg groups or part of one.
+        const int gmask = (cpg >= 16 ? 16 : cpg) - 1;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (j < ncol && valid) {
+            const float x = a.out_f32 ? v[j] : __bfloat162float(__float2bfloat16_rn(v[j]));
+            s1 += x; s2 += x * x;
+          }
+          if (((j + 1) & gmask) == 0 && j < ncol) {  // warp-uniform: end of a group span
+            const int g = (co + j) / cpg;
+            // rows of one warp belong to different samples only when tn > 1
+            if (a.tn == 1) {
+              const float t1 = warp_sum(s1), t2 = warp_sum(s2);
+              if (lane == 0) {
+                atomicAdd(a.gn_stats + ((size_t)n0 * a.gn_groups + g) * 2, (double)t1);
+                atomicAdd(a.gn_stats + ((size_t)n0 * a.gn_groups + g) * 2 + 1, (double)t2);
+              }
+            } else if (valid) {
+              atomicAdd(a.gn_stats + ((size_t)n * a.gn_groups + g) * 2, (double)s1);
+              atomicAdd(a.gn_stats + ((size_t)n * a.gn_groups + g) * 2 + 1, (double)s2);
+            }
+            s1 = 0.f; s2 = 0.f;
+          }
+        }
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+// 5-D bf16 activation map: dims (C, W, H, D, N) innermost first
+static int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int D, int N, uint64_t sW,
+                        uint64_t sH, uint64_t sD, uint64_t sN, int tw, int th, int td, int tn) {
+  auto enc = get_encode_fn();
+  if (!enc) return fail(B200LDM_CUDA_ERROR, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t strides[4] = {sW * 2, sH * 2, sD * 2, sN * 2};  // bytes
+  cuuint32_t box[5] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)td, (cuuint32_t)tn};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(B200LDM_BAD_SHAPE,
+                "cuTensorMapEncodeTiled(act) failed: %d dims=(%d,%d,%d,%d,%d) box=(64,%d,%d,%d,%d)", (int)r, C, W,
+                H, D, N, tw, th, td, tn);
+  return B200LDM_OK;
+}
+
+static int make_weight_map(CUtensorMap* m, const void* base, int Cin, int Cout_rows, int taps, int bn) {
+  auto enc = get_encode_fn();
+  if (!enc) return fail(B200LDM_CUDA_ERROR, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout_rows, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * Cout_rows * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)bn, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(B200LDM_BAD_SHAPE, "cuTensorMapEncodeTiled(weight) failed: %d Cin=%d Cout=%d taps=%d bn=%d", (int)r,
+                Cin, Cout_rows, taps, bn);
+  return B200LDM_OK;
+}
+
+// Pick the voxel box (tn,td,th,tw), product <= 128, that covers the output with the fewest tiles.
+void choose_conv_tile(int N, int Do, int Ho, int Wo, int* tn, int* td, int* th, int* tw) {
+  long best_tiles = -1;
+  int b[4] = {1, 1, 1, 1};
+  for (int w = 1; w <= Wo && w <= 128; ++w) {
+    for (int h = 1; h <= Ho && w * h <= 128; ++h) {
+      for (int d = 1; d <= Do && w * h * d <= 128; ++d) {
+        int nmax = (w == Wo && h == Ho && d == Do) ? 128 / (w * h * d) : 1;
+        if (nmax > N) nmax = N;
+        for (int n = 1; n <= nmax; ++n) {
+          long tiles = (long)ceil_div(N, n) * ceil_div(Do, d) * ceil_div(Ho, h) * ceil_div(Wo, w);
+          bool better = best_tiles < 0 || tiles < best_tiles ||
+                        (tiles == best_tiles && (w > b[3] || (w == b[3] && h > b[2])));
+          if (better) { best_tiles = tiles; b[0] = n; b[1] = d; b[2] = h; b[3] = w; }
+        }
+      }
+    }
+  }
+  *tn = b[0]; *td = b[1]; *th = b[2]; *tw = b[3];
+}
+
+template <int BN>
+static int launch_conv_tc(const ConvTcMaps& maps, const ConvTcArgs& args, dim3 grid, cudaStream_t st) {
+  using Cfg = ConvTcCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  conv3d_tc_kernel<BN><<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(maps, args);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
+  B2_REQUIRE(p->dtype == B200LDM_BF16, B200LDM_BAD_ARG, "tcgen05 conv needs bf16 activations");
+  B2_REQUIRE(p->ksize == 1 || p->ksize == 3, B200LDM_BAD_SHAPE, "ksize must be 1 or 3 (got %d)", p->ksize);
+  B2_REQUIRE(p->stride == 1 || p->stride == 2, B200LDM_BAD_SHAPE, "stride must be 1 or 2 (got %d)", p->stride);
+  B2_REQUIRE(p->C1 > 0 && p->C1 % 64 == 0 && p->C2 >= 0 && p->C2 % 64 == 0, B200LDM_BAD_SHAPE,
+             "tcgen05 conv needs C1, C2 multiples of 64 (got %d, %d)", p->C1, p->C2);
+  B2_REQUIRE(p->Cout > 0 && p->Cout % 8 == 0, B200LDM_BAD_SHAPE, "Cout must be a multiple of 8 (got %d)", p->Cout);
+  B2_REQUIRE(!(p->stride == 2 && p->C2 > 0), B200LDM_BAD_SHAPE, "stride-2 conv takes a single source");
+  B2_REQUIRE(p->stride == 1 || (p->D >= 2 && p->H >= 2 && p->W >= 2), B200LDM_BAD_SHAPE,
+             "stride-2 conv needs extents >= 2");
+  B2_REQUIRE(aligned16(p->x) && aligned16(p->w) && aligned16(p->y) && (!p->x2 || aligned16(p->x2)) &&
+                 (!p->residual || aligned16(p->residual)),
+             B200LDM_BAD_ALIGN, "conv3d pointers must be 16-byte aligned");
+  B2_REQUIRE((p->C2 > 0) == (p->x2 != nullptr), B200LDM_BAD_ARG, "x2 / C2 mismatch");
+  if (p->gn_stats) {
+    B2_REQUIRE(p->gn_groups > 0 && p->Cout % p->gn_groups == 0, B200LDM_BAD_SHAPE, "bad gn_groups");
+    const int cpg = p->Cout / p->gn_groups;
+    B2_REQUIRE((cpg & (cpg - 1)) == 0 && cpg >= 2, B200LDM_BAD_SHAPE,
+               "fused GroupNorm partials need channels/group a power of two >= 2 (got %d)", cpg);
+  }
+
+  const int taps = p->ksize * p->ksize * p->ksize;
+  const int Cin = p->C1 + p->C2;
+  int bn;
+  if (p->Cout % 256 == 0) bn = 256;
+  else if (p->Cout % 128 == 0) bn = 128;
+  else if (p->Cout % 64 == 0) bn = 64;
+  else if (p->Cout <= 16) bn = 16;
+  else if (p->Cout <= 64) bn = 64;
+  else if (p->Cout <= 128) bn = 128;
+  else bn = 256;
+  const int n_tiles = ceil_div(p->Cout, bn);
+
+  ConvTcArgs a{};
+  choose_conv_tile(p->N, p->Do, p->Ho, p->Wo, &a.tn, &a.td, &a.th, &a.tw);
+  a.nb_d = ceil_div(p->Do, a.td); a.nb_h = ceil_div(p->Ho, a.th); a.nb_w = ceil_div(p->Wo, a.tw);
+  const int nb_n = ceil_div(p->N, a.tn);
+  a.N = p->N; a.Do = p->Do; a.Ho = p->Ho; a.Wo = p->Wo; a.Cout = p->Cout;
+  a.nchunk1 = p->C1 / 64; a.nchunk2 = p->C2 / 64;
+  a.ksize = p->ksize; a.stride = p->stride; a.pad_lo = p->pad_lo;
+  a.rows_box = a.tn * a.td * a.th * a.tw;
+  a.temb_stride = p->temb_stride; a.out_f32 = p->out_f32; a.gn_groups = p->gn_groups;
+  a.bias = p->bias; a.temb = p->temb; a.residual = p->residual; a.y = p->y; a.gn_stats = p->gn_stats;
+
+  ConvTcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const uint64_t W = p->W, H = p->H, D = p->D;
+  int rc;
+  if (p->stride == 1) {
+    const uint64_t C = p->C1;
+    rc = make_act_map(&maps.a[0], p->x, p->C1, p->W, p->H, p->D, p->N, C, W * C, H * W * C, D * H * W * C, a.tw,
+                      a.th, a.td, a.tn);
+    if (rc) return rc;
+    if (p->C2 > 0) {
+      const uint64_t C2 = p->C2;
+      rc = make_act_map(&maps.a[1], p->x2, p->C2, p->W, p->H, p->D, p->N, C2, W * C2, H * W * C2, D * H * W * C2,
+                        a.tw, a.th, a.td, a.tn);
+      if (rc) return rc;
+    } else {
+      maps.a[1] = maps.a[0];
+    }
+  } else {
+    const uint64_t C = p->C1;
+    for (int pd = 0; pd < 2; ++pd)
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+          const __nv_bfloat16* base =
+              reinterpret_cast<const __nv_bfloat16*>(p->x) + ((uint64_t)(pd * H + ph) * W + pw) * C;
+          rc = make_act_map(&maps.a[pd * 4 + ph * 2 + pw], base, p->C1, (p->W - pw + 1) / 2, (p->H - ph + 1) / 2,
+                            (p->D - pd + 1) / 2, p->N, 2 * C, 2 * W * C, 2 * H * W * C, D * H * W * C, a.tw, a.th,
+                            a.td, a.tn);
+          if (rc) return rc;
+        }
+  }
+  // weight rows are padded by the packer to a multiple of 16 so small-Cout tiles stay in bounds
+  const int cout_rows = (p->Cout + 15) / 16 * 16;
+  rc = make_weight_map(&maps.w, p->w, Cin, cout_rows, taps, bn);
+  if (rc) return rc;
+
+  dim3 grid((unsigned)(nb_n * a.nb_d * a.nb_h * a.nb_w), (unsigned)n_tiles, 1);
+  switch (bn) {
+    case 256: return launch_conv_tc<256>(maps, a, grid, st);
+    case 128: return launch_conv_tc<128>(maps, a, grid, st);
+    case 64: return launch_conv_tc<64>(maps, a, grid, st);
+    default: return launch_conv_tc<16>(maps, a, grid, st);
+  }
+}
+
+}  // namespace b200ldm

@@ -1,0 +1,397 @@
+// elementwise.cu - the memory-bound odds and ends of the hot path: weight repack, layout
+// bridges (NCDHW fp32 <-> NDHWC), nearest x2 upsample, timestep embedding, per-step row select,
+// the fused scheduler update (DDPM / DDIM, Philox noise in-kernel) and AE sampling / add_noise.
+#include "common.cuh"
+
+namespace b200ldm {
+
+constexpr int kEwThreads = 256;
+static inline unsigned ew_blocks(long long n, int per_block = kEwThreads) {
+  long long b = (n + per_block - 1) / per_block;
+  const long long cap = 148LL * 32;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ------------------------------------------------------------------ weight repack
+template <typename T>
+__global__ void repack_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, int Cout, int Cin, int taps,
+                                     int Cout_pad, int Cin_pad, int cin_split, int cin_split_pad) {
+  const long long total = (long long)taps * Cout_pad * Cin_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci_d = (int)(i % Cin_pad);
+    long long t = i / Cin_pad;
+    const int co = (int)(t % Cout_pad);
+    const int tap = (int)(t / Cout_pad);
+    int ci = -1;
+    if (ci_d < cin_split) ci = ci_d;
+    else if (ci_d >= cin_split_pad && ci_d - cin_split_pad + cin_split < Cin) ci = ci_d - cin_split_pad + cin_split;
+    float v = 0.f;
+    if (co < Cout && ci >= 0 && ci < Cin) v = src[((size_t)co * Cin + ci) * taps + tap];
+    dst[i] = from_f32<T>(v);
+  }
+}
+
+// ------------------------------------------------------------------ layout bridges
+template <typename T>
+__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int C, long long S,
+                                      int C_dst, int c_offset) {
+  const long long total = (long long)N * S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / S, s = i - n * S;
+    for (int c = 0; c < C; ++c) dst[(size_t)i * C_dst + c_offset + c] = from_f32<T>(src[((size_t)n * C + c) * S + s]);
+  }
+}
+template <typename T>
+__global__ void ndhwc_to_ncdhw_kernel(const T* __restrict__ src, float* __restrict__ dst, int N, int C, long long S,
+                                      int C_src) {
+  const long long total = (long long)N * S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / S, s = i - n * S;
+    for (int c = 0; c < C; ++c) dst[((size_t)n * C + c) * S + s] = to_f32<T>(src[(size_t)i * C_src + c]);
+  }
+}
+
+// ------------------------------------------------------------------ nearest x2 upsample
+template <typename T>
+__global__ void upsample2x_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int D, int H, int W, int C) {
+  const int vecs = C >> 3;
+  const long long total = (long long)N * 8 * D * H * W * vecs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % vecs);
+    long long t = i / vecs;
+    const int wo = (int)(t % (2 * W)); t /= 2 * W;
+    const int ho = (int)(t % (2 * H)); t /= 2 * H;
+    const int dd = (int)(t % (2 * D));
+    const int n = (int)(t / (2 * D));
+    const size_t in = ((((size_t)n * D + (dd >> 1)) * H + (ho >> 1)) * W + (wo >> 1)) * C + (size_t)cv * 8;
+    if (sizeof(T) == 2) {
+      *reinterpret_cast<uint4*>(y + (size_t)i * 8) = *reinterpret_cast<const uint4*>(x + in);
+    } else {
+      const uint4* s = reinterpret_cast<const uint4*>(x + in);
+      uint4* o = reinterpret_cast<uint4*>(y + (size_t)i * 8);
+      o[0] = s[0]; o[1] = s[1];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ time embedding helpers
+__global__ void silu_f32_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    y[i] = v / (1.0f + expf(-v));
+  }
+}
+// cos first, then sin; freqs = exp(-ln(max_period) * j / half).  The
+// frequency and the trig are evaluated in fp64 and rounded once, so the fp32 validation mode
+// is not limited by device-vs-host libm differences on arguments as large as 999.
+__global__ void timestep_embedding_kernel(const float* __restrict__ ts, float* __restrict__ out, int n_t, int dim,
+                                          float max_period) {
+  const int half = dim / 2;
+  const int total = n_t * dim;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int t = i / dim, j = i - t * dim;
+    float v = 0.f;
+    if (j < 2 * half) {
+      const int jj = j < half ? j : j - half;
+      const float freq = (float)exp(-log((double)max_period) * (double)jj / (double)half);
+      const float arg = ts[t] * freq;
+      v = (float)(j < half ? cos((double)arg) : sin((double)arg));
+    }
+    out[i] = v;
+  }
+}
+__global__ void select_row_kernel(const float* __restrict__ table, const int* __restrict__ counter,
+                                  float* __restrict__ dst, int width) {
+  const size_t row = (size_t)counter[0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < width; i += gridDim.x * blockDim.x)
+    dst[i] = table[row * width + i];
+}
+__global__ void counter_add_kernel(int* counter, int delta) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) counter[0] += delta;
+}
+
+// ------------------------------------------------------------------ Philox4x32-10 + Box-Muller
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// 4 standard normals for the 4-element group `quad` of stream (seed, step)
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t step, uint64_t quad, float (&z)[4]) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)quad, (uint32_t)(quad >> 32), step, 0x5eedu, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const float u1 = ((float)r[2 * p] + 0.5f) * k;
+    const float u2 = ((float)r[2 * p + 1] + 0.5f) * k;
+    const float rad = sqrtf(-2.0f * logf(fminf(fmaxf(u1, 1e-12f), 1.0f)));
+    float s, c;
+    sincosf(6.283185307179586f * u2, &s, &c);
+    z[2 * p] = rad * c;
+    z[2 * p + 1] = rad * s;
+  }
+}
+__global__ void philox_normal_kernel(float* __restrict__ out, long long n, uint64_t seed, int step) {
+  const long long quads = (n + 3) / 4;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < quads;
+       q += (long long)gridDim.x * blockDim.x) {
+    float z[4];
+    philox_normal4(seed, (uint32_t)step, (uint64_t)q, z);
+    for (int e = 0; e < 4; ++e)
+      if (q * 4 + e < n) out[q * 4 + e] = z[e];
+  }
+}
+
+// ------------------------------------------------------------------ scheduler update
+template <typename T>
+__global__ void scheduler_step_kernel(const b200ldm_sched_params p) {
+  const int step = p.counter ? p.counter[0] : 0;
+  const float* cf = p.coef + (size_t)step * 8;
+  const float inv_sqrt_acp = cf[0], sqrt_1m = cf[1], c_x0 = cf[2], c_xt = cf[3], c_eps = cf[4], sigma = cf[5],
+              lo = cf[6], hi = cf[7];
+  const int qpv = p.C >> 2;  // 4-channel groups per voxel
+  const long long quads = p.n_vox * qpv;
+  const T* eps = reinterpret_cast<const T*>(p.eps);
+  T* xm = reinterpret_cast<T*>(p.x_model);
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < quads;
+       q += (long long)gridDim.x * blockDim.x) {
+    const long long vox = q / qpv;
+    const int c = (int)(q - vox * qpv) * 4;
+    const size_t xi = (size_t)vox * p.C + c;
+    const float4 xt = *reinterpret_cast<const float4*>(p.x_t + xi);
+    float e[4], x[4] = {xt.x, xt.y, xt.z, xt.w}, z[4] = {0.f, 0.f, 0.f, 0.f}, o[4], x0[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) e[j] = to_f32<T>(eps[(size_t)vox * p.C_eps + c + j]);
+    if (sigma != 0.f) {
+      if (p.noise) {
+        const float4 nz = *reinterpret_cast<const float4*>(p.noise + (size_t)step * p.noise_step_stride + xi);
+        z[0] = nz.x; z[1] = nz.y; z[2] = nz.z; z[3] = nz.w;
+      } else {
+        philox_normal4(p.seed, (uint32_t)step, (uint64_t)q, z);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      x0[j] = fminf(fmaxf((x[j] - sqrt_1m * e[j]) * inv_sqrt_acp, lo), hi);
+      o[j] = c_x0 * x0[j] + c_xt * x[j] + c_eps * e[j] + sigma * z[j];
+    }
+    *reinterpret_cast<float4*>(p.x_t + xi) = make_float4(o[0], o[1], o[2], o[3]);
+    if (p.x0_out) *reinterpret_cast<float4*>(p.x0_out + xi) = make_float4(x0[0], x0[1], x0[2], x0[3]);
+    if (xm) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xm[(size_t)vox * p.C_model + c + j] = from_f32<T>(o[j]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void ae_sampling_kernel(const T* __restrict__ mu, const T* __restrict__ logvar,
+                                   const float* __restrict__ noise, float* __restrict__ z, float* __restrict__ sig,
+                                   long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float lv = fminf(fmaxf(to_f32<T>(logvar[i]), -30.f), 20.f);
+    const float s = expf(0.5f * lv);
+    if (sig) sig[i] = s;
+    z[i] = to_f32<T>(mu[i]) + s * (noise ? noise[i] : 0.f);
+  }
+}
+
+__global__ void mul_add_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                               float* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = fmaf(b[i], c[i], a[i]);
+}
+
+__global__ void add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                 const float* __restrict__ sa, const float* __restrict__ sb, float* __restrict__ out,
+                                 int N, long long per) {
+  const long long total = (long long)N * per;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / per);
+    out[i] = sa[n] * x0[i] + sb[n] * noise[i];
+  }
+}
+
+}  // namespace b200ldm
+
+extern "C" {
+using namespace b200ldm;
+
+int b200ldm_repack_conv_weight(const float* src, void* dst, int32_t Cout, int32_t Cin, int32_t ksize,
+                               int32_t Cout_pad, int32_t Cin_pad, int32_t cin_split, int32_t cin_split_pad,
+                               int32_t dtype, b200ldm_stream stream) {
+  B2_REQUIRE(src && dst && Cout > 0 && Cin > 0 && Cout_pad >= Cout && Cin_pad >= Cin, B200LDM_BAD_ARG,
+             "repack_conv_weight: bad arguments");
+  B2_REQUIRE(ksize == 1 || ksize == 3, B200LDM_BAD_SHAPE, "ksize must be 1 or 3");
+  B2_REQUIRE(cin_split >= 0 && cin_split <= Cin && cin_split_pad >= cin_split &&
+                 cin_split_pad + (Cin - cin_split) <= Cin_pad,
+             B200LDM_BAD_SHAPE, "repack_conv_weight: bad channel split");
+  const int taps = ksize * ksize * ksize;
+  const long long total = (long long)taps * Cout_pad * Cin_pad;
+  if (dtype == B200LDM_BF16)
+    repack_weight_kernel<__nv_bfloat16><<<ew_blocks(total), kEwThreads, 0, (cudaStream_t)stream>>>(
+        src, (__nv_bfloat16*)dst, Cout, Cin, taps, Cout_pad, Cin_pad, cin_split, cin_split_pad);
+  else if (dtype == B200LDM_F32)
+    repack_weight_kernel<float><<<ew_blocks(total), kEwThreads, 0, (cudaStream_t)stream>>>(
+        src, (float*)dst, Cout, Cin, taps, Cout_pad, Cin_pad, cin_split, cin_split_pad);
+  else
+    return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+int b200ldm_ncdhw_to_ndhwc(const float* src, void* dst, int32_t N, int32_t C, int64_t S, int32_t C_dst,
+                           int32_t c_offset, int32_t dtype, b200ldm_stream stream) {
+  B2_REQUIRE(src && dst && N > 0 && C > 0 && S > 0 && c_offset >= 0 && c_offset + C <= C_dst, B200LDM_BAD_ARG,
+             "ncdhw_to_ndhwc: bad arguments");
+  const long long total = (long long)N * S;
+  if (dtype == B200LDM_BF16)
+    ncdhw_to_ndhwc_kernel<__nv_bfloat16><<<ew_blocks(total), kEwThreads, 0, (cudaStream_t)stream>>>(
+        src, (__nv_bfloat16*)dst, N, C, S, C_dst, c_offset);
+  else if (dtype == B200LDM_F32)
+    ncdhw_to_ndhwc_kernel<float><<<ew_blocks(total), kEwThreads, 0, (cudaStream_t)stream>>>(src, (float*)dst, N, C, S,
+                                                                                            C_dst, c_offset);
+  else
+    return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+int b200ldm_ndhwc_to_ncdhw(const void* src, float* dst, int32_t N, int32_t C, int64_t S, int32_t C_src,
+                           int32_t dtype, b200ldm_stream stream) {
+  B2_REQUIRE(src && dst && N > 0 && C > 0 && S > 0 && C <= C_src, B200LDM_BAD_ARG, "ndhwc_to_ncdhw: bad arguments");
+  const long long total = (long long)N * S;
+  if (dtype == B200LDM_BF16)
+    ndhwc_to_ncdhw_kernel<__nv_bfloat16><<<ew_blocks(total), kEwThreads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)src, dst, N, C, S, C_src);
+  else if (dtype == B200LDM_F32)
+    ndhwc_to_ncdhw_kernel<float><<<ew_blocks(total), kEwThreads, 0, (cudaStream_t)stream>>>((const float*)src, dst, N,
+                                                                                            C, S, C_src);
+  else
+    return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+int b200ldm_upsample_nearest2x(const void* x, void* y, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C,
+                               int32_t dtype, b200ldm_stream stream) {
+  B2_REQUIRE(x && y && N > 0 && D > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, B200LDM_BAD_SHAPE,
+             "upsample_nearest2x: bad arguments (C must be a multiple of 8)");
+  B2_REQUIRE(aligned16(x) && aligned16(y), B200LDM_BAD_ALIGN, "upsample_nearest2x: pointers must be 16-byte aligned");
+  const long long total = (long long)N * 8 * D * H * W * (C / 8);
+  if (dtype == B200LDM_BF16)
+    upsample2x_kernel<__nv_bfloat16><<<ew_blocks(total), kEwThreads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, D, H, W, C);
+  else if (dtype == B200LDM_F32)
+    upsample2x_kernel<float><<<ew_blocks(total), kEwThreads, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, N,
+                                                                                        D, H, W, C);
+  else
+    return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+int b200ldm_silu_f32(const float* x, float* y, int64_t n, b200ldm_stream stream) {
+  B2_REQUIRE(x && y && n > 0, B200LDM_BAD_ARG, "silu_f32: bad arguments");
+  silu_f32_kernel<<<ew_blocks(n), kEwThreads, 0, (cudaStream_t)stream>>>(x, y, n);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+int b200ldm_timestep_embedding(const float* timesteps, float* out, int32_t n_t, int32_t dim, float max_period,
+                               b200ldm_stream stream) {
+  B2_REQUIRE(timesteps && out && n_t > 0 && dim > 1, B200LDM_BAD_ARG, "timestep_embedding: bad arguments");
+  timestep_embedding_kernel<<<ew_blocks((long long)n_t * dim), kEwThreads, 0, (cudaStream_t)stream>>>(
+      timesteps, out, n_t, dim, max_period);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+int b200ldm_select_row(const float* table, const int32_t* counter, float* dst, int32_t width,
+                       b200ldm_stream stream) {
+  B2_REQUIRE(table && counter && dst && width > 0, B200LDM_BAD_ARG, "select_row: bad arguments");
+  select_row_kernel<<<ew_blocks(width), kEwThreads, 0, (cudaStream_t)stream>>>(table, counter, dst, width);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+int b200ldm_counter_add(int32_t* counter, int32_t delta, b200ldm_stream stream) {
+  B2_REQUIRE(counter, B200LDM_BAD_ARG, "counter_add: null counter");
+  counter_add_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter, delta);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+int b200ldm_scheduler_step(const b200ldm_sched_params* p, b200ldm_stream stream) {
+  B2_REQUIRE(p && p->eps && p->x_t && p->coef, B200LDM_BAD_ARG, "scheduler_step: null eps / x_t / coef");
+  B2_REQUIRE(p->n_vox > 0 && p->C > 0 && p->C % 4 == 0 && p->C_eps >= p->C, B200LDM_BAD_SHAPE,
+             "scheduler_step: C must be a positive multiple of 4 and <= C_eps");
+  B2_REQUIRE(!p->x_model || p->C_model >= p->C, B200LDM_BAD_SHAPE, "scheduler_step: C_model < C");
+  B2_REQUIRE(aligned16(p->x_t) && aligned16(p->noise) && aligned16(p->x0_out) && p->noise_step_stride % 4 == 0,
+             B200LDM_BAD_ALIGN, "scheduler_step: fp32 buffers must be 16-byte aligned");
+  const long long quads = p->n_vox * (p->C / 4);
+  if (p->dtype == B200LDM_BF16)
+    scheduler_step_kernel<__nv_bfloat16><<<ew_blocks(quads), kEwThreads, 0, (cudaStream_t)stream>>>(*p);
+  else if (p->dtype == B200LDM_F32)
+    scheduler_step_kernel<float><<<ew_blocks(quads), kEwThreads, 0, (cudaStream_t)stream>>>(*p);
+  else
+    return fail(B200LDM_BAD_ARG, "bad dtype %d", p->dtype);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+int b200ldm_philox_normal(float* out, int64_t n, uint64_t seed, int32_t step, b200ldm_stream stream) {
+  B2_REQUIRE(out && n > 0, B200LDM_BAD_ARG, "philox_normal: bad arguments");
+  philox_normal_kernel<<<ew_blocks((n + 3) / 4), kEwThreads, 0, (cudaStream_t)stream>>>(out, n, seed, step);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+int b200ldm_ae_sampling(const void* mu, const void* logvar, const float* noise, float* z, float* sigma_out, int64_t n,
+                        int32_t dtype, b200ldm_stream stream) {
+  B2_REQUIRE(mu && logvar && z && n > 0, B200LDM_BAD_ARG, "ae_sampling: bad arguments");
+  if (dtype == B200LDM_BF16)
+    ae_sampling_kernel<__nv_bfloat16><<<ew_blocks(n), kEwThreads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)mu, (const __nv_bfloat16*)logvar, noise, z, sigma_out, n);
+  else if (dtype == B200LDM_F32)
+    ae_sampling_kernel<float><<<ew_blocks(n), kEwThreads, 0, (cudaStream_t)stream>>>((const float*)mu,
+                                                                                     (const float*)logvar, noise, z,
+                                                                                     sigma_out, n);
+  else
+    return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+int b200ldm_mul_add_f32(const float* a, const float* b, const float* c, float* out, int64_t n,
+                        b200ldm_stream stream) {
+  B2_REQUIRE(a && b && c && out && n > 0, B200LDM_BAD_ARG, "mul_add_f32: bad arguments");
+  mul_add_kernel<<<ew_blocks(n), kEwThreads, 0, (cudaStream_t)stream>>>(a, b, c, out, n);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+int b200ldm_add_noise(const float* x0, const float* noise, const float* sqrt_acp, const float* sqrt_1m_acp,
+                      float* out, int32_t N, int64_t per_sample, b200ldm_stream stream) {
+  B2_REQUIRE(x0 && noise && sqrt_acp && sqrt_1m_acp && out && N > 0 && per_sample > 0, B200LDM_BAD_ARG,
+             "add_noise: bad arguments");
+  add_noise_kernel<<<ew_blocks((long long)N * per_sample), kEwThreads, 0, (cudaStream_t)stream>>>(
+      x0, noise, sqrt_acp, sqrt_1m_acp, out, N, per_sample);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+// norm.cu - GroupNorm (+SiLU) on NDHWC activations: HBM-bound, vectorised (8 channels =
+// one 16-byte bf16 load per thread), statistics in fp32 per thread -> fp32 shared atomics per
+// block -> fp64 global atomics (so E[x^2]-mean^2 survives eps = 1e-6).
+//   stats pass : 1 read;  apply pass : 1 read + 1 write  (algorithmic bytes)
+// Thread mapping: a thread owns one 8-channel vector position `cv` for its whole life, so its
+// group ids, gamma/beta and mean/rstd are loop invariant; it strides over voxels.
+#include "common.cuh"
+
+namespace b200ldm {
+
+constexpr int kNormThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ x2, double* __restrict__ stats, long long S,
+                int C1, int C2, int G, int vox_per_block) {
+  extern __shared__ float sh[];  // [2*G]
+  const int n = blockIdx.y;
+  const int C = C1 + C2;
+  const int vecs = C >> 3;
+  const int cpg = C / G;
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int vpp = blockDim.x / vecs;  // voxels per pass (>= 1)
+  const int cv = threadIdx.x % vecs;
+  const int vslot = threadIdx.x / vecs;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
+  if (vslot < vpp) {
+    const long long v0 = (long long)blockIdx.x * vox_per_block;
+    const long long v1 = min(v0 + vox_per_block, S);
+    const bool second = cv * 8 >= C1;
+    const int Cs = second ? C2 : C1;
+    const T* base = (second ? x2 : x) + ((size_t)n * S) * Cs + (size_t)(second ? cv * 8 - C1 : cv * 8);
+    for (long long v = v0 + vslot; v < v1; v += vpp) {
+      float f[8];
+      Vec8<T>::load(base + (size_t)v * Cs, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s1[e] += f[e]; s2[e] += f[e] * f[e]; }
+    }
+    // fold the 8 lanes into their groups (cpg >= 8: all one group; else 8/cpg groups)
+    if (cpg % 8 == 0) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { a += s1[e]; b += s2[e]; }
+      const int g = (cv * 8) / cpg;
+      atomicAdd(&sh[2 * g], a);
+      atomicAdd(&sh[2 * g + 1], b);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int g = (cv * 8 + e) / cpg;
+        atomicAdd(&sh[2 * g], s1[e]);
+        atomicAdd(&sh[2 * g + 1], s2[e]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x)
+    atomicAdd(stats + (size_t)n * 2 * G + i, (double)sh[i]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict__ y,
+                const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                long long S, int C1, int C2, int G, float eps, int silu, int vox_per_block) {
+  const int n = blockIdx.y;
+  const int C = C1 + C2;
+  const int vecs = C >> 3;
+  const int cpg = C / G;
+  const int vpp = blockDim.x / vecs;
+  const int cv = threadIdx.x % vecs;
+  const int vslot = threadIdx.x / vecs;
+  if (vslot >= vpp) return;
+  float sc[8], sf[8];
+  const double cnt = (double)S * (double)cpg;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = cv * 8 + e;
+    const int g = c / cpg;
+    const double m = stats[((size_t)n * G + g) * 2] / cnt;
+    double var = stats[((size_t)n * G + g) * 2 + 1] / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float ga = gamma[c], be = beta[c];
+    sc[e] = rstd * ga;
+    sf[e] = be - (float)m * rstd * ga;
+  }
+  const long long v0 = (long long)blockIdx.x * vox_per_block;
+  const long long v1 = min(v0 + vox_per_block, S);
+  const size_t off = ((size_t)n * S) * C + (size_t)cv * 8;
+  const bool second = cv * 8 >= C1;
+  const int Cs = second ? C2 : C1;
+  const T* src = (second ? x2 : x) + ((size_t)n * S) * Cs + (size_t)(second ? cv * 8 - C1 : cv * 8);
+  for (long long v = v0 + vslot; v < v1; v += vpp) {
+    float f[8];
+    Vec8<T>::load(src + (size_t)v * Cs, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float t = fmaf(f[e], sc[e], sf[e]);
+      f[e] = silu ? silu_f(t) : t;
+    }
+    Vec8<T>::store(y + off + (size_t)v * C, f);
+  }
+}
+
+static int norm_geometry(int N, long long S, int C, int G, int* vox_per_block, dim3* grid) {
+  B2_REQUIRE(C % 8 == 0 && C / 8 <= kNormThreads, B200LDM_BAD_SHAPE, "GroupNorm needs C %% 8 == 0 and C <= %d (got %d)",
+             8 * kNormThreads, C);
+  B2_REQUIRE(G > 0 && C % G == 0 && G <= 1024, B200LDM_BAD_SHAPE, "bad group count %d for C=%d", G, C);
+  const int vpp = kNormThreads / (C / 8);
+  // ~8 blocks per SM across the batch; each block at least 4 passes
+  long long want_blocks = (148LL * 8 + N - 1) / N;
+  long long vpb = (S + want_blocks - 1) / want_blocks;
+  if (vpb < 4LL * vpp) vpb = 4LL * vpp;
+  vpb = (vpb + vpp - 1) / vpp * vpp;
+  *vox_per_block = (int)vpb;
+  *grid = dim3((unsigned)((S + vpb - 1) / vpb), (unsigned)N, 1);
+  return B200LDM_OK;
+}
+
+}  // namespace b200ldm
+
+extern "C" {
+
+int b200ldm_groupnorm_stats(const void* x, const void* x2, double* stats, int32_t N, int64_t S, int32_t C1,
+                            int32_t C2, int32_t G, int32_t dtype, b200ldm_stream stream) {
+  using namespace b200ldm;
+  B2_REQUIRE(x && stats && N > 0 && S > 0, B200LDM_BAD_ARG, "groupnorm_stats: bad arguments");
+  B2_REQUIRE(aligned16(x) && aligned16(x2), B200LDM_BAD_ALIGN, "groupnorm_stats: x must be 16-byte aligned");
+  B2_REQUIRE(C1 > 0 && C1 % 8 == 0 && C2 >= 0 && C2 % 8 == 0 && ((C2 > 0) == (x2 != nullptr)), B200LDM_BAD_SHAPE,
+             "groupnorm_stats: C1/C2 must be multiples of 8 and match x2");
+  int vpb; dim3 grid;
+  int rc = norm_geometry(N, S, C1 + C2, G, &vpb, &grid);
+  if (rc) return rc;
+  const size_t sh = 2 * G * sizeof(float);
+  if (dtype == B200LDM_BF16)
+    gn_stats_kernel<__nv_bfloat16><<<grid, kNormThreads, sh, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)x2, stats, S, C1, C2, G, vpb);
+  else if (dtype == B200LDM_F32)
+    gn_stats_kernel<float><<<grid, kNormThreads, sh, (cudaStream_t)stream>>>((const float*)x, (const float*)x2, stats,
+                                                                             S, C1, C2, G, vpb);
+  else
+    return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+int b200ldm_groupnorm_apply(const void* x, const void* x2, void* y, const double* stats, const float* gamma,
+                            const float* beta, int32_t N, int64_t S, int32_t C1, int32_t C2, int32_t G, float eps,
+                            int32_t silu, int32_t dtype, b200ldm_stream stream) {
+  using namespace b200ldm;
+  B2_REQUIRE(x && y && stats && gamma && beta && N > 0 && S > 0, B200LDM_BAD_ARG, "groupnorm_apply: bad arguments");
+  B2_REQUIRE(aligned16(x) && aligned16(y) && aligned16(x2), B200LDM_BAD_ALIGN,
+             "groupnorm_apply: x/y must be 16-byte aligned");
+  B2_REQUIRE(C1 > 0 && C1 % 8 == 0 && C2 >= 0 && C2 % 8 == 0 && ((C2 > 0) == (x2 != nullptr)), B200LDM_BAD_SHAPE,
+             "groupnorm_apply: C1/C2 must be multiples of 8 and match x2");
+  int vpb; dim3 grid;
+  int rc = norm_geometry(N, S, C1 + C2, G, &vpb, &grid);
+  if (rc) return rc;
+  if (dtype == B200LDM_BF16)
+    gn_apply_kernel<__nv_bfloat16><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)x2, (__nv_bfloat16*)y, stats, gamma, beta, S, C1, C2, G, eps,
+        silu, vpb);
+  else if (dtype == B200LDM_F32)
+    gn_apply_kernel<float><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(
+        (const float*)x, (const float*)x2, (float*)y, stats, gamma, beta, S, C1, C2, G, eps, silu, vpb);
+  else
+    return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,193 @@
+/*
+ * b200ldm.h - C ABI of libb200ldm.so: the B200 (sm_100a) kernels behind the latent
+ * sampling hot path (UNet noise prediction x scheduler steps -> AutoencoderKL decode).
+ *
+ * Every entry point replaces an ATen/cuDNN/cuBLAS dispatch that MONAI performs for the
+ * reference's hot path; the reference itself owns no kernels, so the
+ * "interface replaced" is cited as the reference call site that reaches the op:
+ *   3d_ldm/inference.py:94-99   inferer.sample(...)            -> everything below
+ *   3d_ldm/inference.py:75      DiffusionModelUNet.forward      -> conv3d / groupnorm / attention / linear
+ *   3d_ldm/inference.py:79-84   DDPMScheduler(...).step          -> b200ldm_scheduler_step
+ *   3d_ldm/inference.py:71      AutoencoderKL.decode_stage_2_outputs -> conv3d / groupnorm / attention / upsample
+ *   3d_ldm/inference.py:72-77   load_state_dict                  -> b200ldm_repack_conv_weight
+ *
+ * Conventions:
+ *   - plain pointers + sizes; all pointers are DEVICE pointers unless stated otherwise;
+ *   - activations are NDHWC ("channels last"), dtype B200LDM_BF16 or B200LDM_F32;
+ *   - the caller (PyTorch) owns every buffer; the library never allocates device memory;
+ *   - every call is asynchronous on `stream`, capture-safe (no sync, no allocation,
+ *     no host read of device data) and returns 0 on success or a b200ldm_status;
+ *     the message is available from b200ldm_last_error() (thread-local);
+ *   - no C++ exception crosses the ABI; there is no CPU fallback.
+ */
+#ifndef B200LDM_H
+#define B200LDM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  B200LDM_OK = 0,
+  B200LDM_BAD_SHAPE = 1,
+  B200LDM_BAD_ALIGN = 2,
+  B200LDM_UNSUPPORTED_ARCH = 3,
+  B200LDM_CUDA_ERROR = 4,
+  B200LDM_BAD_ARG = 5
+} b200ldm_status;
+
+typedef enum { B200LDM_F32 = 0, B200LDM_BF16 = 1 } b200ldm_dtype;
+
+/* which conv engine ran / should run */
+typedef enum {
+  B200LDM_ENGINE_AUTO = 0,  /* bf16 -> tcgen05 implicit GEMM, f32 -> SIMT validation kernel */
+  B200LDM_ENGINE_TCGEN05 = 1,
+  B200LDM_ENGINE_SIMT = 2
+} b200ldm_engine;
+
+typedef void* b200ldm_stream; /* cudaStream_t */
+
+#define B200LDM_VERSION 100
+
+int b200ldm_version(void);
+/* copies the calling thread's last error message (NUL terminated) into buf; returns its length */
+int b200ldm_last_error(char* buf, size_t n);
+/* 0 if the current device is sm_100 (B200), else B200LDM_UNSUPPORTED_ARCH / CUDA_ERROR */
+int b200ldm_check_device(void);
+/* number of kernels this library has launched from the calling process (bench.py gpu_launches) */
+uint64_t b200ldm_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Conv3d, NDHWC, k in {1,3}, stride in {1,2}; replaces F.conv3d reached from
+ * DiffusionModelUNet / AutoencoderKL (a2.2, a2.4, a4) and, with k=1 on a
+ * [1,1,1,M,K] view, every nn.Linear on the path (a2.1, a2.3).
+ *   y[n,do,ho,wo,co] = bias[co] + temb[n*temb_stride + co] + residual[n,do,ho,wo,co]
+ *                    + sum_{tap,ci} w[tap][co][ci] * xcat[n, do*s+kd-pad_lo, ..., ci]
+ * xcat = channel concat of x (C1 channels) and x2 (C2 channels; NULL if C2 == 0): the skip
+ * concat of the UNet up path and mode="concat" conditioning are read in place.
+ * Weights are packed [k^3][Cout][C1+C2] in the activation dtype (b200ldm_repack_conv_weight).
+ * Out-of-range taps read zeros; pad_hi is implied by (Do,Ho,Wo).
+ * bf16/TCGEN05 requirements: C1 % 64 == 0, C2 % 64 == 0, Cout % 8 == 0, 16-byte aligned pointers.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* x;
+  const void* x2;
+  const void* w;
+  const float* bias;     /* [Cout] or NULL */
+  const float* temb;     /* [N or 1][Cout] fp32 or NULL */
+  const void* residual;  /* same shape/dtype as y, or NULL */
+  void* y;
+  double* gn_stats;      /* optional [N][gn_groups][2] (sum, sumsq) accumulated from y; or NULL */
+  int32_t N, D, H, W;    /* input extents */
+  int32_t C1, C2, Cout;
+  int32_t Do, Ho, Wo;    /* output extents */
+  int32_t ksize, stride, pad_lo;
+  int32_t temb_stride;   /* elements between per-sample temb rows; 0: one row broadcast over N */
+  int32_t gn_groups;     /* groups of the following GroupNorm when gn_stats != NULL */
+  int32_t dtype;         /* b200ldm_dtype of x, x2, w, residual, y */
+  int32_t engine;        /* b200ldm_engine */
+  int32_t out_f32;       /* 1: y (and residual) are fp32 even when dtype is bf16 */
+} b200ldm_conv3d_params;
+
+int b200ldm_conv3d(const b200ldm_conv3d_params* p, b200ldm_stream stream);
+
+/* src: fp32 [Cout][Cin][k][k][k] (PyTorch layout) -> dst: [k^3][Cout_pad][Cin_pad] in `dtype`,
+ * zero padded; cin_offset lets a weight be split across padded concat sources:
+ * channels [0,cin_split) go to dst columns [0,cin_split), the rest start at column cin_split_pad. */
+int b200ldm_repack_conv_weight(const float* src, void* dst, int32_t Cout, int32_t Cin, int32_t ksize,
+                               int32_t Cout_pad, int32_t Cin_pad, int32_t cin_split, int32_t cin_split_pad,
+                               int32_t dtype, b200ldm_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GroupNorm (+ optional SiLU), NDHWC; replaces F.group_norm + F.silu.
+ * x: [N][S][C1], optional x2: [N][S][C2] = channel concat read in place (the UNet up path norms
+ * cat([h, skip]) whose groups straddle the two tensors); y: [N][S][C1+C2] (S = D*H*W).
+ * stats: [N][G][2] doubles (sum, sumsq).
+ *   b200ldm_groupnorm_stats  zero-fills nothing: caller zeroes `stats` (b200ldm_fill_zero) unless
+ *                            a conv epilogue already accumulated them.
+ *   b200ldm_groupnorm_apply  y = (x-mean)*rstd*gamma+beta, then SiLU if silu != 0.
+ * ------------------------------------------------------------------------------------------ */
+int b200ldm_groupnorm_stats(const void* x, const void* x2, double* stats, int32_t N, int64_t S, int32_t C1,
+                            int32_t C2, int32_t G, int32_t dtype, b200ldm_stream stream);
+int b200ldm_groupnorm_apply(const void* x, const void* x2, void* y, const double* stats, const float* gamma,
+                            const float* beta, int32_t N, int64_t S, int32_t C1, int32_t C2, int32_t G, float eps,
+                            int32_t silu, int32_t dtype, b200ldm_stream stream);
+int b200ldm_fill_zero(void* p, size_t bytes, b200ldm_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-head self attention core over flattened D*H*W tokens; replaces the two einsum/bmm
+ * + softmax of MONAI SABlock.  q,k,v: token-major with row stride
+ * `ld` elements, head h at columns [h*d,(h+1)*d); o: [B][L][H*d] dense (ldo = H*d).
+ *   o = softmax(q k^T * scale) v ; O(L) memory (never materialises L x L).
+ * ------------------------------------------------------------------------------------------ */
+int b200ldm_attention(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t H,
+                      int32_t L, int32_t d, int64_t ld, float scale, int32_t dtype, int32_t engine,
+                      b200ldm_stream stream);
+
+/* nearest x2 up-sampling, NDHWC: [N][D][H][W][C] -> [N][2D][2H][2W][C] */
+int b200ldm_upsample_nearest2x(const void* x, void* y, int32_t N, int32_t D, int32_t H, int32_t W,
+                               int32_t C, int32_t dtype, b200ldm_stream stream);
+
+/* layout bridges between the MONAI surface (NCDHW fp32) and the engine (NDHWC, channel padded) */
+int b200ldm_ncdhw_to_ndhwc(const float* src, void* dst, int32_t N, int32_t C, int64_t S, int32_t C_dst,
+                           int32_t c_offset, int32_t dtype, b200ldm_stream stream);
+int b200ldm_ndhwc_to_ncdhw(const void* src, float* dst, int32_t N, int32_t C, int64_t S, int32_t C_src,
+                           int32_t dtype, b200ldm_stream stream);
+
+/* y = silu(x), fp32, n elements (time embedding MLP) */
+int b200ldm_silu_f32(const float* x, float* y, int64_t n, b200ldm_stream stream);
+/* sinusoidal timestep embedding, cos first: out [n_t][dim] fp32 */
+int b200ldm_timestep_embedding(const float* timesteps, float* out, int32_t n_t, int32_t dim,
+                               float max_period, b200ldm_stream stream);
+/* dst[0:width] = table[counter[0]][0:width] (fp32): per-step row select for graph replay */
+int b200ldm_select_row(const float* table, const int32_t* counter, float* dst, int32_t width,
+                       b200ldm_stream stream);
+int b200ldm_counter_add(int32_t* counter, int32_t delta, b200ldm_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Scheduler update; replaces DDPMScheduler.step / DDIMScheduler.step.
+ * coef: device table [n_steps][8] fp32 rows
+ *     {inv_sqrt_acp, sqrt_1m_acp, c_x0, c_xt, c_eps, sigma, clip_lo, clip_hi}
+ *   x0   = clamp((x_t - sqrt_1m_acp*eps) * inv_sqrt_acp, clip_lo, clip_hi)   (epsilon prediction)
+ *   x'   = c_x0*x0 + c_xt*x_t + c_eps*eps + sigma*noise
+ * (DDPM: c_eps = 0; DDIM: c_xt = 0.)  Row index = counter[0] (device) so one CUDA graph replays
+ * for every step.  eps: [N][S][C_eps] `dtype` (first C channels used); x_t: fp32 [N][S][C]
+ * master copy updated in place; noise: fp32 [N][S][C] (slab counter[0]*noise_step_stride of a
+ * pre-generated stack) or NULL -> Philox4x32-10 + Box-Muller keyed by (seed, counter[0], element).  x_model (optional): the UNet input buffer
+ * [N][S][C_model] `dtype`, channels [0,C) are refreshed with x'.  x0_out optional fp32.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* eps;
+  float* x_t;
+  const float* noise;
+  float* x0_out;
+  void* x_model;
+  const float* coef;
+  const int32_t* counter;
+  int64_t n_vox;       /* N*S */
+  int64_t noise_step_stride; /* elements between per-step noise slabs (0: `noise` is this step's slab) */
+  int32_t C, C_eps, C_model;
+  int32_t dtype;
+  uint64_t seed;
+} b200ldm_sched_params;
+int b200ldm_scheduler_step(const b200ldm_sched_params* p, b200ldm_stream stream);
+/* standalone Philox normal stream identical to the one scheduler_step draws (parity tests) */
+int b200ldm_philox_normal(float* out, int64_t n, uint64_t seed, int32_t step, b200ldm_stream stream);
+
+/* z = mu + sigma * noise with sigma = exp(clamp(logvar,-30,20)/2): AutoencoderKL.sampling (a5) */
+int b200ldm_ae_sampling(const void* mu, const void* logvar, const float* noise, float* z, float* sigma_out,
+                        int64_t n, int32_t dtype, b200ldm_stream stream);
+/* out = a + b*c, fp32, n elements: AutoencoderKL.sampling(z_mu, z_sigma) with caller-supplied eps (a5) */
+int b200ldm_mul_add_f32(const float* a, const float* b, const float* c, float* out, int64_t n,
+                        b200ldm_stream stream);
+/* add_noise: out = sqrt_acp[t_n]*x0 + sqrt_1m_acp[t_n]*noise, per-sample coefficients (8f rank 1) */
+int b200ldm_add_noise(const float* x0, const float* noise, const float* sqrt_acp, const float* sqrt_1m_acp,
+                      float* out, int32_t N, int64_t per_sample, b200ldm_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LDM_H */
