@@ -58,6 +58,7 @@ class SamplingLoop:
             self.noise = ops.to_ndhwc(sn, self.c_lat, torch.float32)
             self.noise_stride = self.noise.numel() // self.n_steps
         self.graph = None
+        self.launches_per_step = 0
         self.use_graph = use_graph and USE_GRAPH
 
     def _body(self):
@@ -79,8 +80,10 @@ class SamplingLoop:
         self.x_model.copy_(keep_m)
         self.counter.zero_()
         g = torch.cuda.CUDAGraph()
+        l0 = ops.launch_count()
         with torch.cuda.graph(g):
             self._body()
+        self.launches_per_step = ops.launch_count() - l0
         self.x_t.copy_(keep_x)
         self.x_model.copy_(keep_m)
         self.counter.zero_()

@@ -14,6 +14,39 @@ from . import _lib
 from ._lib import BF16, F32, ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05  # noqa: F401
 
 
+class KernelProfiler:
+    """CUDA-event timer around individual kernel launches on the launching stream (bench.py roofline leg).
+    Enabled by setting `ops.PROFILER = KernelProfiler()`; eager mode only (events are not graph-capturable)."""
+
+    def __init__(self):
+        self.records = []  # (kind, tag, work, start_event, stop_event)
+
+    def start(self):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream())
+        return ev
+
+    def stop(self, kind, tag, work, ev0):
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record(torch.cuda.current_stream())
+        self.records.append((kind, tag, work, ev0, ev1))
+
+    def summary(self):
+        """kind -> dict(launches, ms, work); per (kind, tag) too.  Call after torch.cuda.synchronize()."""
+        out, by_tag = {}, {}
+        for kind, tag, work, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            for d, k in ((out, kind), (by_tag, (kind, tag))):
+                s = d.setdefault(k, {"launches": 0, "ms": 0.0, "work": 0.0})
+                s["launches"] += 1
+                s["ms"] += ms
+                s["work"] += work
+        return out, by_tag
+
+
+PROFILER: KernelProfiler | None = None
+
+
 def dtype_code(t: torch.dtype) -> int:
     if t == torch.bfloat16:
         return BF16
@@ -64,7 +97,12 @@ def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo
         dtype=dtype_code(x.dtype), engine=engine, out_f32=int(out_f32))
     assert x.is_contiguous() and (x2 is None or x2.is_contiguous())
     assert residual is None or (residual.is_contiguous() and residual.shape == y.shape and residual.dtype == odt)
+    ev = PROFILER.start() if PROFILER is not None else None
     _lib.check(lib.b200ldm_conv3d(C.byref(p), _stream()), "conv3d")
+    if ev is not None:
+        # algorithmic FLOPs of the (padded) problem the kernel ran: 2*M*Cout*Cin*k^3
+        PROFILER.stop("conv3d", f"{C1 + C2}->{cout} k{ksize}s{stride} @{N}x{Do}x{Ho}x{Wo}",
+                      2.0 * N * Do * Ho * Wo * cout * (C1 + C2) * ksize ** 3, ev)
     return y
 
 
@@ -108,14 +146,21 @@ def groupnorm(x, gamma, beta, groups: int, eps: float, silu: bool, x2=None, stat
     C2 = 0 if x2 is None else x2.shape[-1]
     S = x.numel() // (N * C1)
     dt = dtype_code(x.dtype)
+    nbytes = float(N * S * (C1 + C2) * x.element_size())
     if stats is None:
         stats = zeros_f64(N * groups * 2, x.device)
+        ev = PROFILER.start() if PROFILER is not None else None
         _lib.check(lib.b200ldm_groupnorm_stats(_ptr(x), _ptr(x2), stats.data_ptr(), N, S, C1, C2, groups, dt,
                                                _stream()), "groupnorm_stats")
+        if ev is not None:
+            PROFILER.stop("gn_stats", f"C{C1 + C2} S{S}", nbytes, ev)  # one read
     y = torch.empty(x.shape[:-1] + (C1 + C2,), dtype=x.dtype, device=x.device)
+    ev = PROFILER.start() if PROFILER is not None else None
     _lib.check(lib.b200ldm_groupnorm_apply(_ptr(x), _ptr(x2), y.data_ptr(), stats.data_ptr(), gamma.data_ptr(),
                                            beta.data_ptr(), N, S, C1, C2, groups, float(eps), int(silu), dt,
                                            _stream()), "groupnorm_apply")
+    if ev is not None:
+        PROFILER.stop("gn_apply", f"C{C1 + C2} S{S}", 2.0 * nbytes, ev)  # one read + one write
     return y
 
 
@@ -129,8 +174,11 @@ def attention(qkv, heads: int, head_dim: int, scale: float, engine: int = ENGINE
     o = torch.empty((B, L, Cc), dtype=qkv.dtype, device=qkv.device)
     es = qkv.element_size()
     base = qkv.data_ptr()
+    ev = PROFILER.start() if PROFILER is not None else None
     _lib.check(lib.b200ldm_attention(base, base + Cc * es, base + 2 * Cc * es, o.data_ptr(), B, heads, L, head_dim,
                                      C3, float(scale), dtype_code(qkv.dtype), engine, _stream()), "attention")
+    if ev is not None:
+        PROFILER.stop("attention", f"B{B} H{heads} L{L} d{head_dim}", 4.0 * B * heads * L * L * head_dim, ev)
     return o
 
 

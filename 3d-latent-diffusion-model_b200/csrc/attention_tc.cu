@@ -1,9 +1,340 @@
-// attention_tc.cu - tcgen05 flash attention (placeholder until the kernel lands; AUTO routes to SIMT).
+// attention_tc.cu - fused flash attention on tcgen05 / TMEM for the SpatialAttentionBlock core
+// (softmax(Q K^T * scale) V over D*H*W tokens; never materialises the L x L matrix).
+//
+// One CTA = 128 queries of one (batch, head).  Per KV tile of BN keys:
+//   MMA warp   : S = Q K^T          (A = Q smem K-major, B = K smem K-major)  -> TMEM S[j%2]
+//   softmax WG : S -> regs (1 row / thread), online max (lazy rescale), P = exp2(.) -> bf16 -> smem
+//                (hand-swizzled into the SWIZZLE_128B K-major UMMA layout), O rescale in TMEM if needed
+//   MMA warp   : O += P V           (A = P smem K-major, B = V smem MN-major as landed by TMA) -> TMEM O
+// Q/K/V tiles arrive through 3-D TMA maps (cols, L, B) over the fused [B, L, 3C] projection buffer, so
+// rows past L are zero-filled; S double-buffered so QK^T of tile j+1 overlaps the softmax of tile j.
+// Warp roles (192 threads): warp0 TMA, warp1 MMA + TMEM owner, warps 2..5 softmax / correction / epilogue.
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
 #include "common.cuh"
+#include "tc_ptx.cuh"
+
 namespace b200ldm {
-bool attention_tcgen05_supported(int d) { (void)d; return false; }
-int attention_tcgen05(const void*, const void*, const void*, void*, int, int, int, int, long long, float,
-                      cudaStream_t) {
-  return fail(B200LDM_BAD_ARG, "tcgen05 attention not built");
+
+struct AttnMaps {
+  CUtensorMap q, k, v;  // dims (H*d, L, B), box (64, 128|BN, 1), SWIZZLE_128B
+};
+
+struct AttnArgs {
+  int H, L, d;
+  float scale_log2;  // softmax scale * log2(e)
+  __nv_bfloat16* o;  // [B][L][H*d]
+};
+
+constexpr int kAttnThreads = 192;
+
+template <int D, int BN>
+struct AttnCfg {
+  static constexpr int kStages = (D == 64) ? 3 : 2;
+  static constexpr int kQBytes = (D / 64) * 16384;
+  static constexpr int kKVSub = BN * 128;             // one 64-column sub-tile of K or V
+  static constexpr int kKVBytes = (D / 64) * kKVSub;  // K (or V) tile
+  static constexpr int kPBytes = (BN / 64) * 16384;
+  static constexpr int kSmem = kQBytes + kStages * 2 * kKVBytes + kPBytes + 1024 + 256;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kSCol0 = 0;        // S buffers at columns [0, 2*BN)
+  static constexpr int kOCol = 2 * BN;    // O at [2*BN, 2*BN + D)
+  static_assert(2 * BN + D <= 512, "TMEM budget");
+};
+
+// MN-major SWIZZLE_128B operand (V as landed by TMA: rows = keys (K dim), 64 head-dim columns per 128-byte row).
+// LBO = byte distance between 64-column blocks, SBO = distance between 8-key groups (1024).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
 }
+
+template <int D, int BN>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
+  using Cfg = AttnCfg<D, BN>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = smem_base;
+  const uint32_t kv_smem = q_smem + Cfg::kQBytes;                  // stage s: K at +s*2*kKVBytes, V after K
+  const uint32_t p_smem = kv_smem + STAGES * 2 * Cfg::kKVBytes;
+  const uint32_t bar = p_smem + Cfg::kPBytes;
+  // barrier map (8 bytes each)
+  const uint32_t q_full = bar;
+  const uint32_t kv_full = bar + 8;                  // [STAGES]
+  const uint32_t kv_empty = kv_full + 8 * STAGES;    // [STAGES]
+  const uint32_t s_full = kv_empty + 8 * STAGES;     // [2]
+  const uint32_t s_empty = s_full + 16;              // [2]
+  const uint32_t p_full = s_empty + 16;
+  const uint32_t pv_done = p_full + 8;
+  const uint32_t tmem_slot = pv_done + 8;
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int ntiles = (a.L + BN - 1) / BN;
+  const int col0 = h * D;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&maps.q); ptx::prefetch_tmap(&maps.k); ptx::prefetch_tmap(&maps.v);
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(kv_full + 8 * s, 1); ptx::mbar_init(kv_empty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(s_full + 8 * s, 1); ptx::mbar_init(s_empty + 8 * s, 128); }
+    ptx::mbar_init(p_full, 128);
+    ptx::mbar_init(pv_done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      ptx::mbar_expect_tx(q_full, Cfg::kQBytes);
+#pragma unroll
+      for (int sub = 0; sub < D / 64; ++sub)
+        ptx::tma_load_3d(q_smem + sub * 16384, &maps.q, q_full, col0 + sub * 64, q0, b);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % STAGES;
+        const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
+        ptx::mbar_wait(kv_empty + 8 * s, ph ^ 1u, 10);
+        const uint32_t ks = kv_smem + s * 2 * Cfg::kKVBytes, vs = ks + Cfg::kKVBytes;
+        ptx::mbar_expect_tx(kv_full + 8 * s, 2 * Cfg::kKVBytes);
+#pragma unroll
+        for (int sub = 0; sub < D / 64; ++sub) {
+          ptx::tma_load_3d(ks + sub * Cfg::kKVSub, &maps.k, kv_full + 8 * s, col0 + sub * 64, j * BN, b);
+          ptx::tma_load_3d(vs + sub * Cfg::kKVSub, &maps.v, kv_full + 8 * s, col0 + sub * 64, j * BN, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, BN);
+      constexpr uint32_t idesc_o = ptx::umma_idesc_bf16_bmn(128, D);
+      auto issue_s = [&](int j) {
+        const int s = j % STAGES;
+        ptx::mbar_wait(kv_full + 8 * s, (uint32_t)(j / STAGES) & 1u, 11);
+        if (j >= 2) ptx::mbar_wait(s_empty + 8 * (j & 1), (uint32_t)((j >> 1) - 1) & 1u, 12);
+        ptx::tc_fence_after();
+        const uint32_t ks = kv_smem + s * 2 * Cfg::kKVBytes;
+        const uint32_t tS = tmem + Cfg::kSCol0 + (j & 1) * BN;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint64_t da = ptx::umma_desc_k_sw128(q_smem + (kk >> 2) * 16384 + (kk & 3) * 32);
+          const uint64_t db = ptx::umma_desc_k_sw128(ks + (kk >> 2) * Cfg::kKVSub + (kk & 3) * 32);
+          ptx::umma_bf16(tS, da, db, idesc_s, kk > 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(s_full + 8 * (j & 1));
+      };
+      ptx::mbar_wait(q_full, 0, 13);
+      issue_s(0);
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) issue_s(j + 1);
+        const int s = j % STAGES;
+        ptx::mbar_wait(p_full, (uint32_t)j & 1u, 14);
+        ptx::tc_fence_after();
+        const uint32_t vs = kv_smem + s * 2 * Cfg::kKVBytes + Cfg::kKVBytes;
+        const uint32_t tO = tmem + Cfg::kOCol;
+#pragma unroll
+        for (int kk = 0; kk < BN / 16; ++kk) {
+          const uint64_t da = ptx::umma_desc_k_sw128(p_smem + (kk >> 2) * 16384 + (kk & 3) * 32);
+          const uint64_t db = umma_desc_mn_sw128(vs + kk * 2048, Cfg::kKVSub, 1024);
+          ptx::umma_bf16(tO, da, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        ptx::umma_commit(kv_empty + 8 * s);  // K/V stage reusable once S_j and PV_j retired
+        ptx::umma_commit(pv_done);
+      }
+    }
+  } else {
+    // =========================== softmax / correction / epilogue ===========================
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    float m_used = -INFINITY;  // reference max (log2 domain) the running sums are expressed against
+    float l_sum = 0.f;
+    uint8_t* p_gen = smem_gen + (p_smem - smem_base);
+
+    for (int j = 0; j < ntiles; ++j) {
+      ptx::mbar_wait(s_full + 8 * (j & 1), (uint32_t)(j >> 1) & 1u, 20);
+      ptx::tc_fence_after();
+      const uint32_t tS = tmem + lane_off + Cfg::kSCol0 + (j & 1) * BN;
+      float sv[BN];
+#pragma unroll
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld32(tS + c, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sv[c + i] = __uint_as_float(r[i]) * a.scale_log2;
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(s_empty + 8 * (j & 1));  // S buffer may be overwritten by tile j+2
+
+      const int kvalid = a.L - j * BN;  // keys in this tile that exist
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < BN; ++i) {
+        if (i >= kvalid) sv[i] = -INFINITY;
+        mx = fmaxf(mx, sv[i]);
+      }
+      // lazy rescale: keep the old reference unless the max grew by more than 2^8 (warp-uniform decision)
+      const bool need = mx > m_used + 8.0f;
+      const bool any_need = __any_sync(0xffffffffu, need);
+      float alpha = 1.0f;
+      if (j > 0) ptx::mbar_wait(pv_done, (uint32_t)(j - 1) & 1u, 21);  // PV_{j-1} retired: O and P buffer are ours
+      if (any_need) {
+        if (need) {
+          alpha = exp2f(m_used - mx);  // 0 on the first tile (m_used = -inf)
+          m_used = mx;
+          l_sum *= alpha;
+        }
+        if (j > 0) {
+          ptx::tc_fence_after();
+          const uint32_t tO = tmem + lane_off + Cfg::kOCol;
+#pragma unroll
+          for (int c = 0; c < D; c += 16) {
+            uint32_t r[16];
+            ptx::tmem_ld16(tO + c, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            ptx::tmem_st16(tO + c, r);
+          }
+          ptx::tmem_st_wait();
+        }
+      }
+      // P = exp2(s - m_used) -> bf16, written in the SWIZZLE_128B K-major layout (16-byte chunk c of row r
+      // lives at r*128 + ((c ^ (r & 7)) << 4) inside each [128 x 64-key] sub-tile)
+      float psum = 0.f;
+#pragma unroll
+      for (int c8 = 0; c8 < BN / 8; ++c8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p0 = exp2f(sv[c8 * 8 + 2 * e] - m_used);
+          const float p1 = exp2f(sv[c8 * 8 + 2 * e + 1] - m_used);
+          const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+          // the row sum uses the rounded values that the tensor core will actually multiply
+          psum += __low2float(hb) + __high2float(hb);
+          pk[e] = *reinterpret_cast<const uint32_t*>(&hb);
+        }
+        const int sub = c8 >> 3, cc = c8 & 7;
+        uint4* dst = reinterpret_cast<uint4*>(p_gen + sub * 16384 + row * 128 + ((cc ^ (row & 7)) << 4));
+        *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      l_sum += psum;
+      ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the UMMA (async proxy)
+      ptx::tc_fence_before();     // orders the TMEM rescale stores before the MMA warp's next PV
+      ptx::mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> bf16 -> global
+    ptx::mbar_wait(pv_done, (uint32_t)(ntiles - 1) & 1u, 22);
+    ptx::tc_fence_after();
+    const int qi = q0 + row;
+    const float inv = 1.0f / l_sum;
+    __nv_bfloat16* orow = a.o + ((size_t)b * a.L + (qi < a.L ? qi : 0)) * ((size_t)a.H * D) + col0;
+    const uint32_t tO = tmem + lane_off + Cfg::kOCol;
+#pragma unroll
+    for (int c = 0; c < D; c += 16) {
+      uint32_t r[16];
+      ptx::tmem_ld16(tO + c, r);
+      ptx::tmem_ld_wait();
+      if (qi < a.L) {
+        float f[8];
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[hlf * 8 + e]) * inv;
+          Vec8<__nv_bfloat16>::store(orow + c + hlf * 8, f);
+        }
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<Cfg::kTmemCols>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+static PFN_cuTensorMapEncodeTiled_v12000 attn_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+static int make_qkv_map(CUtensorMap* m, const void* base, int cols, int L, int B, long long ld, int box_rows) {
+  auto enc = attn_encode_fn();
+  if (!enc) return fail(B200LDM_CUDA_ERROR, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)L, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)L};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(B200LDM_BAD_SHAPE, "cuTensorMapEncodeTiled(qkv) failed: %d cols=%d L=%d B=%d ld=%lld", (int)r, cols, L, B,
+                ld);
+  return B200LDM_OK;
+}
+
+template <int D, int BN>
+static int launch_attention_tc(const void* q, const void* k, const void* v, void* o, int B, int H, int L, long long ld,
+                               float scale, cudaStream_t st) {
+  using Cfg = AttnCfg<D, BN>;
+  AttnMaps maps;
+  int rc;
+  if ((rc = make_qkv_map(&maps.q, q, H * D, L, B, ld, 128))) return rc;
+  if ((rc = make_qkv_map(&maps.k, k, H * D, L, B, ld, BN))) return rc;
+  if ((rc = make_qkv_map(&maps.v, v, H * D, L, B, ld, BN))) return rc;
+  AttnArgs a{H, L, D, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o)};
+  static bool attr_done = false;
+  if (!attr_done) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmem));
+    attr_done = true;
+  }
+  dim3 grid((unsigned)ceil_div(L, 128), (unsigned)H, (unsigned)B);
+  attention_tc_kernel<D, BN><<<grid, kAttnThreads, Cfg::kSmem, st>>>(maps, a);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+bool attention_tcgen05_supported(int d) { return d == 64 || d == 128 || d == 256; }
+
+int attention_tcgen05(const void* q, const void* k, const void* v, void* o, int B, int H, int L, int d, long long ld,
+                      float scale, cudaStream_t st) {
+  B2_REQUIRE(attention_tcgen05_supported(d), B200LDM_BAD_SHAPE, "tcgen05 attention supports head dim 64/128/256 (got %d)",
+             d);
+  B2_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && ld % 8 == 0, B200LDM_BAD_ALIGN,
+             "attention: pointers / row stride must be 16-byte aligned");
+  if (d == 64) return launch_attention_tc<64, 128>(q, k, v, o, B, H, L, ld, scale, st);
+  if (d == 128) return launch_attention_tc<128, 128>(q, k, v, o, B, H, L, ld, scale, st);
+  return launch_attention_tc<256, 64>(q, k, v, o, B, H, L, ld, scale, st);
+}
+
 }  // namespace b200ldm

@@ -177,6 +177,8 @@ extern "C" int b200ldm_conv3d(const b200ldm_conv3d_params* p, b200ldm_stream str
   B2_REQUIRE(p->N > 0 && p->D > 0 && p->H > 0 && p->W > 0 && p->Do > 0 && p->Ho > 0 && p->Wo > 0,
              B200LDM_BAD_SHAPE, "non-positive extent");
   B2_REQUIRE(p->dtype == B200LDM_F32 || p->dtype == B200LDM_BF16, B200LDM_BAD_ARG, "bad dtype %d", p->dtype);
+  B2_REQUIRE(p->ksize == 1 || p->ksize == 3, B200LDM_BAD_SHAPE, "ksize must be 1 or 3 (got %d)", p->ksize);
+  B2_REQUIRE(p->stride == 1 || p->stride == 2, B200LDM_BAD_SHAPE, "stride must be 1 or 2 (got %d)", p->stride);
   // output extents must agree with (k, stride, pad_lo) and a pad_hi in {0,1}
   for (int i = 0; i < 3; ++i) {
     const int in = i == 0 ? p->D : (i == 1 ? p->H : p->W);

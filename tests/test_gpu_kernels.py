@@ -1,0 +1,335 @@
+"""GPU parity tests of every kernel behind the C ABI against plain fp32 torch math (the oracle's
+building blocks: F.conv3d / F.group_norm / softmax / the oracle schedulers), on the same seeded inputs.
+
+Tolerances: max|a-b| / max|b| <= 1e-4 for the fp32 validation engine and <= 2e-2 for the
+bf16 tensor-core engine.  For bf16 the reference is evaluated in fp64 on the bf16-ROUNDED operands, so
+the only differences left are accumulation order and the final bf16 rounding (tight 1e-2 bound).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import golden_cases as gc
+import oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = {torch.float32: 1e-4, torch.bfloat16: 1e-2}
+
+
+def relerr(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def rnd(shape, seed, scale=1.0):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+def q(t, dtype):
+    """round to the activation dtype and come back to fp32 (what the kernel actually sees)"""
+    return t.to(dtype).float()
+
+
+def to_act(t_ncdhw, dtype, cpad=None):
+    from b200ldm import ops
+    c = t_ncdhw.shape[1]
+    return ops.to_ndhwc(t_ncdhw.to(DEV), cpad or c, dtype)
+
+
+def from_act(a, c):
+    from b200ldm import ops
+    return ops.to_ncdhw(a, c).cpu()
+
+
+# ------------------------------------------------------------------------------------------
+# conv3d
+# ------------------------------------------------------------------------------------------
+CONV_CASES = [
+    # name,            N, (D,H,W),     C1,  C2, Cout, k, s, pad_lo, pad_hi, temb, resid
+    ("k3_basic",       1, (8, 8, 8),    64,   0,  64, 3, 1, 1, 1, False, False),
+    ("k3_fused_epi",   2, (6, 8, 4),   128,   0, 256, 3, 1, 1, 1, True, True),
+    ("k3_two_source",  1, (5, 5, 5),    64, 128,  64, 3, 1, 1, 1, False, True),
+    ("k1_linear",      1, (1, 1, 300), 256,   0, 768, 1, 1, 0, 0, False, True),
+    ("k1_two_source",  2, (4, 4, 4),   128,  64, 128, 1, 1, 0, 0, False, False),
+    ("k3_s2_even",     1, (8, 8, 8),    64,   0,  64, 3, 2, 1, 1, False, False),
+    ("k3_s2_odd",      2, (9, 7, 6),    64,   0, 128, 3, 2, 1, 1, False, False),
+    ("ae_down_even",   1, (8, 8, 8),    64,   0,  64, 3, 2, 0, 1, False, False),
+    ("ae_down_odd",    1, (7, 9, 6),   128,   0, 128, 3, 2, 0, 1, False, False),
+    ("cout16",         1, (6, 6, 6),    64,   0,  16, 3, 1, 1, 1, False, False),
+    ("batch_in_tile",  8, (4, 4, 4),   256,   0, 256, 3, 1, 1, 1, True, False),
+    ("deep_k",         2, (4, 4, 4),   512, 512, 512, 3, 1, 1, 1, False, False),
+    ("odd_36_44_28",   1, (9, 11, 7),  256,   0, 512, 3, 1, 1, 1, False, False),
+    ("wide_n_tiles",   1, (4, 6, 10),   64,   0, 1024, 3, 1, 1, 1, False, False),
+]
+
+
+def _conv_case(case, dtype, engine, with_stats=False):
+    from b200ldm import ops
+    name, N, (D, H, W), C1, C2, Cout, k, s, pl, phi, use_temb, use_res = case
+    Cin = C1 + C2
+    x = q(rnd((N, Cin, D, H, W), 1), dtype)
+    w = q(rnd((Cout, Cin, k, k, k), 2, 1.0 / math.sqrt(Cin * k ** 3)), dtype)
+    b = rnd((Cout,), 3, 0.1)
+    xp = F.pad(x.double(), (pl, phi, pl, phi, pl, phi))
+    ref = F.conv3d(xp, w.double(), b.double(), stride=s)
+    temb = None
+    if use_temb:
+        temb = rnd((N, Cout), 4)
+        ref = ref + temb.double()[:, :, None, None, None]
+    res = None
+    if use_res:
+        res = q(rnd(tuple(ref.shape), 5), dtype)
+        ref = ref + res.double()
+    cout_rows = ops.round_up(Cout, 16)
+    wp = ops.repack_conv_weight(w.to(DEV), cout_rows, Cin, dtype)
+    xa = to_act(x[:, :C1], dtype)
+    x2a = to_act(x[:, C1:], dtype) if C2 else None
+    resa = to_act(res, dtype) if use_res else None
+    G = 32
+    stats = ops.zeros_f64(N * G * 2, DEV) if with_stats else None
+    y = ops.conv3d(xa, wp, b.to(DEV), Cout, k, s, pl, phi, x2=x2a, temb=None if temb is None else temb.to(DEV),
+                   temb_stride=Cout if use_temb else 0, residual=resa, gn_stats=stats, gn_groups=G if with_stats else 0,
+                   engine=engine)
+    torch.cuda.synchronize()
+    out = from_act(y, Cout)
+    assert out.shape == ref.shape, (out.shape, ref.shape)
+    return out, ref.float(), (stats.cpu() if with_stats else None), y
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv3d_simt_fp32(case):
+    from b200ldm import ops
+    out, ref, _, _ = _conv_case(case, torch.float32, ops.ENGINE_SIMT)
+    assert relerr(out, ref) <= 1e-4, relerr(out, ref)
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv3d_tcgen05_bf16(case):
+    from b200ldm import ops
+    out, ref, _, _ = _conv_case(case, torch.bfloat16, ops.ENGINE_TCGEN05)
+    e = relerr(out, ref)
+    assert e <= 1e-2, f"{case[0]}: relerr {e}"
+
+
+@pytest.mark.parametrize("case", [CONV_CASES[1], CONV_CASES[10], CONV_CASES[12]], ids=["fused", "batch_tile", "odd"])
+@pytest.mark.parametrize("engine_dtype", ["simt_f32", "tc_bf16"])
+def test_conv3d_fused_groupnorm_partials(case, engine_dtype):
+    from b200ldm import ops
+    dtype, engine = (torch.float32, ops.ENGINE_SIMT) if engine_dtype == "simt_f32" else (torch.bfloat16, ops.ENGINE_TCGEN05)
+    out, ref, stats, y = _conv_case(case, dtype, engine, with_stats=True)
+    N, Cout, G = out.shape[0], out.shape[1], 32
+    yy = out.double().reshape(N, G, -1)  # stats are taken over the values as stored
+    want = torch.stack([yy.sum(-1), (yy * yy).sum(-1)], dim=-1).reshape(-1)
+    assert relerr(stats, want) <= 1e-4, relerr(stats, want)
+
+
+def test_conv3d_rejects_bad_arguments():
+    from b200ldm import ops
+    x = torch.zeros((1, 4, 4, 4, 48), dtype=torch.bfloat16, device=DEV)
+    w = torch.zeros((27, 64, 48), dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(RuntimeError, match="multiples of 64"):
+        ops.conv3d(x, w, None, 64)
+    x = torch.zeros((1, 4, 4, 4, 64), dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(RuntimeError, match="ksize"):
+        ops.conv3d(x, w, None, 64, ksize=5, pad_lo=2)
+    with pytest.raises(RuntimeError, match="inconsistent"):
+        ops.conv3d(x, w, None, 64, ksize=3, pad_lo=1, pad_hi=3)
+
+
+# ------------------------------------------------------------------------------------------
+# GroupNorm (+SiLU)
+# ------------------------------------------------------------------------------------------
+GN_CASES = [(2, (4, 6, 5), 64, 0), (1, (8, 8, 8), 256, 0), (2, (3, 5, 7), 512, 256), (1, (4, 4, 4), 1024, 1024),
+            (3, (2, 3, 5), 1024, 512), (1, (16, 16, 16), 128, 0)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("silu", [True, False])
+@pytest.mark.parametrize("case", GN_CASES, ids=[f"N{c[0]}_C{c[2]}+{c[3]}" for c in GN_CASES])
+def test_groupnorm(case, silu, dtype):
+    from b200ldm import ops
+    N, sp, C1, C2 = case
+    C = C1 + C2
+    x = q(rnd((N, C) + sp, 11) * 2.0 + 0.7, dtype)
+    gamma, beta = 1.0 + 0.1 * rnd((C,), 12), 0.1 * rnd((C,), 13)
+    ref = F.group_norm(x.double(), 32, gamma.double(), beta.double(), eps=1e-6)
+    if silu:
+        ref = F.silu(ref)
+    xa = to_act(x[:, :C1], dtype)
+    x2a = to_act(x[:, C1:], dtype) if C2 else None
+    y = ops.groupnorm(xa, gamma.to(DEV), beta.to(DEV), 32, 1e-6, silu, x2=x2a)
+    e = relerr(from_act(y, C), ref)
+    assert e <= (1e-5 if dtype == torch.float32 else 6e-3), e
+
+
+# ------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------
+ATT_CASES = [(2, 2, 100, 64), (1, 4, 693, 64), (1, 1, 300, 256), (2, 1, 129, 128), (1, 8, 512, 64), (1, 2, 64, 32)]
+
+
+def _att_ref(qkv, H, d):
+    B, L, _ = qkv.shape
+    qq, kk, vv = (t.reshape(B, L, H, d).permute(0, 2, 1, 3).double() for t in qkv.chunk(3, dim=-1))
+    att = torch.softmax(qq @ kk.transpose(-1, -2) * d ** -0.5, dim=-1)
+    return (att @ vv).permute(0, 2, 1, 3).reshape(B, L, H * d)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("case", ATT_CASES, ids=[f"B{c[0]}H{c[1]}L{c[2]}d{c[3]}" for c in ATT_CASES])
+def test_attention_simt(case, dtype):
+    from b200ldm import ops
+    B, H, L, d = case
+    qkv = q(rnd((B, L, 3 * H * d), 21), dtype)
+    o = ops.attention(qkv.to(DEV).to(dtype), H, d, d ** -0.5, engine=ops.ENGINE_SIMT)
+    e = relerr(o.float(), _att_ref(qkv, H, d))
+    assert e <= (2e-5 if dtype == torch.float32 else 6e-3), e
+
+
+@pytest.mark.parametrize("case", ATT_CASES[:5] + [(8, 4, 5544, 64), (1, 1, 4096, 256), (2, 16, 64, 64)],
+                         ids=lambda c: f"B{c[0]}H{c[1]}L{c[2]}d{c[3]}")
+def test_attention_tcgen05_bf16(case):
+    from b200ldm import ops
+    B, H, L, d = case
+    qkv = q(rnd((B, L, 3 * H * d), 22), torch.bfloat16)
+    dev_qkv = qkv.to(DEV).to(torch.bfloat16)
+    o = ops.attention(dev_qkv, H, d, d ** -0.5, engine=ops.ENGINE_TCGEN05)
+    if L <= 1024:
+        ref = _att_ref(qkv, H, d)
+    else:  # big cases: the SIMT engine (validated above against fp64 torch) is the checker
+        ref = ops.attention(dev_qkv, H, d, d ** -0.5, engine=ops.ENGINE_SIMT).float()
+    e = relerr(o.float(), ref)
+    assert e <= 1e-2, e
+
+
+def test_attention_tcgen05_peaked_softmax():
+    """large logits: exercises the lazy-rescale path (running max jumps by > 2^8 between KV tiles)"""
+    from b200ldm import ops
+    B, H, L, d = 1, 2, 700, 64
+    qkv = rnd((B, L, 3 * H * d), 23)
+    qkv[:, :, : 2 * H * d] *= 6.0
+    qkv[:, 400:, H * d: 2 * H * d] *= 3.0   # later keys dominate
+    qkv = q(qkv, torch.bfloat16)
+    o = ops.attention(qkv.to(DEV).to(torch.bfloat16), H, d, d ** -0.5, engine=ops.ENGINE_TCGEN05)
+    e = relerr(o.float(), _att_ref(qkv, H, d))
+    assert e <= 1e-2, e
+
+
+# ------------------------------------------------------------------------------------------
+# element-wise family
+# ------------------------------------------------------------------------------------------
+def test_layout_bridges_roundtrip_and_padding():
+    from b200ldm import ops
+    x = rnd((2, 5, 3, 4, 6), 31)
+    a = ops.to_ndhwc(x.to(DEV), 64, torch.float32)
+    assert a.shape == (2, 3, 4, 6, 64)
+    assert torch.equal(a[..., :5].cpu(), x.permute(0, 2, 3, 4, 1))
+    assert a[..., 5:].abs().max().item() == 0.0
+    assert torch.equal(ops.to_ncdhw(a, 5).cpu(), x)
+    ab = ops.to_ndhwc(x.to(DEV), 8, torch.bfloat16)
+    assert torch.equal(ops.to_ncdhw(ab, 5).cpu(), x.bfloat16().float())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_upsample_nearest2x(dtype):
+    from b200ldm import ops
+    x = q(rnd((2, 64, 3, 5, 4), 32), dtype)
+    y = ops.upsample_nearest2x(to_act(x, dtype))
+    assert torch.equal(from_act(y, 64), F.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+
+def test_timestep_embedding_and_silu():
+    from b200ldm import ops
+    from oracle.nets import get_timestep_embedding
+    ts = torch.tensor([0.0, 1.0, 37.0, 500.0, 999.0])
+    got = ops.timestep_embedding(ts.to(DEV), 256).cpu()
+    assert (got - get_timestep_embedding(ts, 256)).abs().max().item() <= 2e-4  # libm-level differences on args ~ 1e3
+    x = rnd((1000,), 33, 3.0)
+    assert torch.allclose(ops.silu_f32(x.to(DEV)).cpu(), F.silu(x), atol=1e-6, rtol=1e-5)
+
+
+def test_repack_weight_layout():
+    from b200ldm import ops
+    w = rnd((5, 6, 3, 3, 3), 34)
+    p = ops.repack_conv_weight(w.to(DEV), 16, 128, torch.float32, cin_split=4, cin_split_pad=64).cpu()
+    assert p.shape == (27, 16, 128)
+    want = torch.zeros(27, 16, 128)
+    wt = w.reshape(5, 6, 27).permute(2, 0, 1)
+    want[:, :5, :4] = wt[:, :, :4]
+    want[:, :5, 64:66] = wt[:, :, 4:]
+    assert torch.equal(p, want)
+
+
+@pytest.mark.parametrize("kind", ["ddpm", "ddim"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_scheduler_step_kernel_vs_oracle(kind, dtype):
+    import b200ldm
+    from b200ldm import ops
+    n = 10 if kind == "ddpm" else 50
+    ours, ref = gc.make_scheduler(b200ldm, kind, n), gc.make_scheduler(oracle, kind, n)
+    coef = ours.coef_table(DEV)
+    x, nz = rnd((2, 4, 3, 5, 4), 41), rnd((n, 2, 4, 3, 5, 4), 42)
+    eps = q(rnd((2, 4, 3, 5, 4), 43), dtype)
+    xa = ops.to_ndhwc(x.to(DEV), 4, torch.float32)
+    ea = ops.to_ndhwc(eps.to(DEV), 16, dtype)              # eps buffer wider than C, like the UNet output
+    xm = torch.zeros((2, 3, 5, 4, 64), dtype=dtype, device=DEV)
+    nza = ops.to_ndhwc(nz.reshape((n * 2, 4, 3, 5, 4)).to(DEV), 4, torch.float32)
+    counter = torch.zeros(1, dtype=torch.int32, device=DEV)
+    want = x
+    for i, t in enumerate(ref.timesteps):
+        x0 = torch.empty_like(xa)
+        ops.scheduler_step(ea, xa, coef, counter, 4, noise=nza, noise_step_stride=nza.numel() // n, x0_out=x0,
+                           x_model=xm)
+        ops.counter_add(counter, 1)
+        want, want0 = ref.step(eps, t, want, noise=nz[i])
+        assert relerr(ops.to_ncdhw(xa, 4), want) <= 2e-5, (i, relerr(ops.to_ncdhw(xa, 4), want))
+        assert relerr(ops.to_ncdhw(x0, 4), want0) <= 2e-5
+        assert torch.equal(xm[..., :4].float(), xa.to(dtype).float())
+        assert xm[..., 4:].abs().max().item() == 0
+    assert int(counter.item()) == n
+
+
+def test_scheduler_module_step_and_add_noise():
+    import b200ldm
+    ours, ref = gc.make_scheduler(b200ldm, "ddpm", 1000), gc.make_scheduler(oracle, "ddpm", 1000)
+    x, e, nz = rnd((2, 4, 4, 4, 4), 51), rnd((2, 4, 4, 4, 4), 52), rnd((2, 4, 4, 4, 4), 53)
+    for t in (999, 500, 0):
+        p, p0 = ours.step(e.to(DEV), t, x.to(DEV), noise=nz.to(DEV))
+        w, w0 = ref.step(e, t, x, noise=nz)
+        assert relerr(p, w) <= 2e-5 and relerr(p0, w0) <= 2e-5
+    tt = torch.tensor([3, 977])
+    assert relerr(ours.add_noise(x.to(DEV), nz.to(DEV), tt.to(DEV)), ref.add_noise(x, nz, tt)) <= 1e-6
+
+
+def test_philox_noise_is_standard_normal_and_matches_step_kernel():
+    import b200ldm
+    from b200ldm import ops
+    z = ops.philox_normal(1 << 20, 1234, 7, DEV)
+    assert abs(z.mean().item()) < 5e-3 and abs(z.std().item() - 1.0) < 5e-3
+    assert abs((z ** 4).mean().item() - 3.0) < 0.1
+    z2 = ops.philox_normal(1 << 20, 1234, 8, DEV)
+    assert abs((z * z2).mean().item()) < 5e-3          # streams of different steps are uncorrelated
+    # in-kernel noise == the standalone stream
+    s = gc.make_scheduler(b200ldm, "ddpm", 10)
+    coef = s.coef_table(DEV)
+    n_el = 2 * 3 * 5 * 4 * 4
+    counter = torch.full((1,), 3, dtype=torch.int32, device=DEV)
+    x = ops.to_ndhwc(rnd((2, 4, 3, 5, 4), 61).to(DEV), 4, torch.float32)
+    e = ops.to_ndhwc(rnd((2, 4, 3, 5, 4), 62).to(DEV), 4, torch.float32)
+    xa, xb = x.clone(), x.clone()
+    ops.scheduler_step(e, xa, coef, counter, 4, seed=99)
+    nz = ops.philox_normal(n_el, 99, 3, DEV).reshape(x.shape)
+    ops.scheduler_step(e, xb, coef, counter, 4, noise=nz)
+    assert torch.equal(xa, xb)
+
+
+def test_ae_sampling_and_mul_add():
+    from b200ldm import ops
+    mu, lv, nz = rnd((2, 3, 4, 5, 16), 71), rnd((2, 3, 4, 5, 16), 72, 20.0), rnd((2, 3, 4, 5, 16), 73)
+    z, sig = ops.ae_sampling(mu.to(DEV), lv.to(DEV), nz.to(DEV))
+    s_ref = torch.exp(lv.clamp(-30, 20) / 2)
+    assert relerr(sig, s_ref) <= 1e-5 and relerr(z, mu + s_ref * nz) <= 1e-5
+    assert relerr(ops.mul_add_f32(mu.to(DEV), lv.to(DEV), nz.to(DEV)), mu + lv * nz) <= 1e-6
