@@ -5,6 +5,7 @@ namespace b200ldm {
 
 static thread_local char t_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+void set_conv_trace(void* p);
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -45,6 +46,12 @@ int b200ldm_check_device(void) {
   if (major != 10)
     return b200ldm::fail(B200LDM_UNSUPPORTED_ARCH, "device %d is sm_%d%d; libb200ldm is sm_100a only", dev,
                          major, minor);
+  return B200LDM_OK;
+}
+
+/* debug only (not in the public header): 8 clock64 stamps per conv CTA are written to `buf` while it is set */
+int b200ldm_debug_set_conv_trace(void* buf) {
+  b200ldm::set_conv_trace(buf);
   return B200LDM_OK;
 }
 

@@ -56,6 +56,12 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   return d;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int D, int BN>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
@@ -172,25 +178,31 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       ptx::mbar_wait(s_full + 8 * (j & 1), (uint32_t)(j >> 1) & 1u, 20);
       ptx::tc_fence_after();
       const uint32_t tS = tmem + lane_off + Cfg::kSCol0 + (j & 1) * BN;
-      float sv[BN];
+      float sv[BN];  // RAW scores; the softmax scale is folded into the exp2 FFMA below
 #pragma unroll
       for (int c = 0; c < BN; c += 32) {
         uint32_t r[32];
         ptx::tmem_ld32(tS + c, r);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sv[c + i] = __uint_as_float(r[i]) * a.scale_log2;
+        for (int i = 0; i < 32; ++i) sv[c + i] = __uint_as_float(r[i]);
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(s_empty + 8 * (j & 1));  // S buffer may be overwritten by tile j+2
 
       const int kvalid = a.L - j * BN;  // keys in this tile that exist
-      float mx = -INFINITY;
+      if (kvalid < BN) {                // last tile only (warp-uniform)
 #pragma unroll
-      for (int i = 0; i < BN; ++i) {
-        if (i >= kvalid) sv[i] = -INFINITY;
-        mx = fmaxf(mx, sv[i]);
+        for (int i = 0; i < BN; ++i)
+          if (i >= kvalid) sv[i] = -INFINITY;
       }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 chains: no 128-deep dependency
+#pragma unroll
+      for (int i = 0; i < BN; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], sv[i + u]);
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * a.scale_log2;  // scale > 0
       // lazy rescale: keep the old reference unless the max grew by more than 2^8 (warp-uniform decision)
       const bool need = mx > m_used + 8.0f;
       const bool any_need = __any_sync(0xffffffffu, need);
@@ -217,25 +229,27 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
           ptx::tmem_st_wait();
         }
       }
-      // P = exp2(s - m_used) -> bf16, written in the SWIZZLE_128B K-major layout (16-byte chunk c of row r
-      // lives at r*128 + ((c ^ (r & 7)) << 4) inside each [128 x 64-key] sub-tile)
-      float psum = 0.f;
+      // P = exp2(s*scale - m_used) -> bf16, written in the SWIZZLE_128B K-major layout (16-byte chunk c of row r
+      // lives at r*128 + ((c ^ (r & 7)) << 4) inside each [128 x 64-key] sub-tile).  One FFMA + one MUFU.EX2 per
+      // element; the row sum is taken in fp32 over 4 independent chains.
+      const float neg_m = -m_used;
+      float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c8 = 0; c8 < BN / 8; ++c8) {
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float p0 = exp2f(sv[c8 * 8 + 2 * e] - m_used);
-          const float p1 = exp2f(sv[c8 * 8 + 2 * e + 1] - m_used);
+          const float p0 = ex2_approx(fmaf(sv[c8 * 8 + 2 * e], a.scale_log2, neg_m));
+          const float p1 = ex2_approx(fmaf(sv[c8 * 8 + 2 * e + 1], a.scale_log2, neg_m));
+          ps4[e] += p0 + p1;
           const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-          // the row sum uses the rounded values that the tensor core will actually multiply
-          psum += __low2float(hb) + __high2float(hb);
           pk[e] = *reinterpret_cast<const uint32_t*>(&hb);
         }
         const int sub = c8 >> 3, cc = c8 & 7;
         uint4* dst = reinterpret_cast<uint4*>(p_gen + sub * 16384 + row * 128 + ((cc ^ (row & 7)) << 4));
         *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
+      const float psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
       l_sum += psum;
       ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the UMMA (async proxy)
       ptx::tc_fence_before();     // orders the TMEM rescale stores before the MMA warp's next PV

@@ -17,6 +17,7 @@
 // warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -42,45 +43,46 @@ struct ConvTcArgs {
   const void* residual;
   void* y;
   double* gn_stats;
+  unsigned long long* trace;  // debug: per-CTA clock64 stamps (b200ldm_debug_set_conv_trace), else nullptr
 };
 
-constexpr int kConvThreads = 192;
-constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
+constexpr int kABytes = 128 * 128;  // one M sub-tile: 128 rows x 64 bf16
 
-template <int BN>
+// BN = Cout tile, MT = number of 128-row M sub-tiles per CTA that share one weight stage.
+// MT = 2 halves the L2->SMEM bytes per FLOP (the v1 kernel was L2-bandwidth bound: profiles/r01_ncu_conv3d_tc_first.md).
+// CL = CTAs per cluster sharing the weight stage: each loads BN/CL weight rows and multicasts them to all (CL = 2
+// takes the 256x256 tile from 64 to 48 B/clk/SM of L2->SMEM traffic).
+template <int BN, int MT>
 struct ConvTcCfg {
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kStageBytes = MT * kABytes + kBBytes;
+  static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+  static constexpr int kTmemCols = (MT * BN) < 32 ? 32 : (MT * BN);
+  static constexpr int kThreads = 64 + MT * 128;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(kStages >= 2, "pipeline needs at least two stages");
+  static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns must be a power of two <= 512");
 };
 
-template <int BN>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <int BN, int MT, int CL>
+__global__ void __launch_bounds__(ConvTcCfg<BN, MT>::kThreads, 1)
 conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
-  using Cfg = ConvTcCfg<BN>;
+  using Cfg = ConvTcCfg<BN, MT>;
+  uint32_t cta_rank = 0;
+  if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
-  // barriers: full[s] @ +8s, empty[s] @ +8(STAGES+s), tmem_full @ +16*STAGES, tmem slot after it
+  // barriers: full[s] @ +8s, empty[s] @ +8(STAGES+s), tmem_full[mt] @ +16*STAGES + 8mt, tmem slot after them
   const uint32_t tmem_full_bar = bar_base + 16 * STAGES;
-  const uint32_t tmem_slot = tmem_full_bar + 8;
+  const uint32_t tmem_slot = tmem_full_bar + 8 * MT;
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // ---- tile coordinates
-  int mt = blockIdx.x;
-  const int bw = mt % a.nb_w; mt /= a.nb_w;
-  const int bh = mt % a.nb_h; mt /= a.nb_h;
-  const int bd = mt % a.nb_d; mt /= a.nb_d;
-  const int n0 = mt * a.tn, d0 = bd * a.td, h0 = bh * a.th, w0 = bw * a.tw;
   const int co0 = blockIdx.y * BN;
-
   const int taps = a.ksize * a.ksize * a.ksize;
   const int nchunks = a.nchunk1 + a.nchunk2;
   const int iters = taps * nchunks;
@@ -90,21 +92,35 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
     ptx::prefetch_tmap(&maps.a[0]);
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(bar_base + 8 * s, 1);
-      ptx::mbar_init(bar_base + 8 * (STAGES + s), 1);
+      ptx::mbar_init(bar_base + 8 * (STAGES + s), CL);  // every CTA of the cluster must release the stage
     }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int mt = 0; mt < MT; ++mt) ptx::mbar_init(tmem_full_bar + 8 * mt, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync();  // peers' barriers exist before anyone multicasts into / arrives on them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  unsigned long long* trc = a.trace ? a.trace + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (trc && threadIdx.x == 0) trc[0] = clock64();
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)a.rows_box * 128u + (uint32_t)Cfg::kBBytes;
+      // box origins of the MT sub-tiles (a tile index past the end decodes to n0 >= N: every row is
+      // out of bounds, TMA zero-fills it and the epilogue masks it - no special case needed)
+      int n0[MT], d0[MT], h0[MT], w0[MT];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        int t = blockIdx.x * MT + mt;
+        w0[mt] = (t % a.nb_w) * a.tw; t /= a.nb_w;
+        h0[mt] = (t % a.nb_h) * a.th; t /= a.nb_h;
+        d0[mt] = (t % a.nb_d) * a.td; t /= a.nb_d;
+        n0[mt] = t * a.tn;
+      }
+      const uint32_t tx_bytes = (uint32_t)MT * (uint32_t)a.rows_box * 128u + (uint32_t)Cfg::kBBytes;
       for (int it = 0; it < iters; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -115,22 +131,35 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
         if (a.ksize == 3) { kd = tap / 9; kh = (tap / 3) % 3; kw = tap % 3; }
         const uint32_t full = bar_base + 8 * s;
         const uint32_t sa = smem_base + s * Cfg::kStageBytes;
-        const uint32_t sb = sa + kABytes;
+        const uint32_t sb = sa + MT * kABytes;
         ptx::mbar_expect_tx(full, tx_bytes);
         if (a.stride == 1) {
           const bool second = chunk >= a.nchunk1;
           const CUtensorMap* m = second ? &maps.a[1] : &maps.a[0];
           const int c0 = (second ? chunk - a.nchunk1 : chunk) * 64;
-          ptx::tma_load_5d(sa, m, full, c0, w0 + kw - a.pad_lo, h0 + kh - a.pad_lo, d0 + kd - a.pad_lo, n0);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            ptx::tma_load_5d(sa + mt * kABytes, m, full, c0, w0[mt] + kw - a.pad_lo, h0[mt] + kh - a.pad_lo,
+                             d0[mt] + kd - a.pad_lo, n0[mt]);
         } else {
           // input coord = 2*o + k - pad_lo  ->  parity grid (k-pad_lo)&1 at index o + floor((k-pad_lo)/2)
           const int od = kd - a.pad_lo, oh = kh - a.pad_lo, ow = kw - a.pad_lo;
           const int pd = od & 1, ph2 = oh & 1, pw = ow & 1;
           const CUtensorMap* m = &maps.a[pd * 4 + ph2 * 2 + pw];
-          ptx::tma_load_5d(sa, m, full, chunk * 64, w0 + ((ow - pw) >> 1), h0 + ((oh - ph2) >> 1),
-                           d0 + ((od - pd) >> 1), n0);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            ptx::tma_load_5d(sa + mt * kABytes, m, full, chunk * 64, w0[mt] + ((ow - pw) >> 1),
+                             h0[mt] + ((oh - ph2) >> 1), d0[mt] + ((od - pd) >> 1), n0[mt]);
         }
-        ptx::tma_load_3d(sb, &maps.w, full, chunk * 64, co0, tap);
+        if (CL == 1) {
+          ptx::tma_load_3d(sb, &maps.w, full, chunk * 64, co0, tap);
+        } else {
+          // this CTA fetches its 1/CL slice of the weight tile and multicasts it to the same offset in every
+          // CTA of the cluster; each CTA's full barrier collects all CL slices (tx_bytes counts the whole tile)
+          constexpr int kSliceRows = BN / CL;
+          ptx::tma_load_3d_mcast(sb + cta_rank * (kSliceRows * 128), &maps.w, full, chunk * 64,
+                                 co0 + (int)cta_rank * kSliceRows, tap, (uint16_t)((1u << CL) - 1));
+        }
       }
     }
   } else if (warp == 1) {
@@ -142,23 +171,36 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         ptx::mbar_wait(bar_base + 8 * s, ph, 1);
         ptx::tc_fence_after();
+        if (trc && it == 0) trc[1] = clock64();
         const uint32_t sa = smem_base + s * Cfg::kStageBytes;
-        const uint32_t sb = sa + kABytes;
+        const uint32_t sb = sa + MT * kABytes;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da = ptx::umma_desc_k_sw128(sa + k * 32);
-          const uint64_t db = ptx::umma_desc_k_sw128(sb + k * 32);
-          ptx::umma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = ptx::umma_desc_k_sw128(sa + mt * kABytes + k * 32);
+            const uint64_t db = ptx::umma_desc_k_sw128(sb + k * 32);
+            ptx::umma_bf16(tmem_base + mt * BN, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          if (it == iters - 1) ptx::umma_commit(tmem_full_bar + 8 * mt);  // this accumulator is complete
         }
-        ptx::umma_commit(bar_base + 8 * (STAGES + s));  // frees the smem stage when the MMAs retire
+        // frees the smem stage (in every CTA of the cluster) when the MMAs retire
+        if (CL == 1) ptx::umma_commit(bar_base + 8 * (STAGES + s));
+        else ptx::umma_commit_mcast(bar_base + 8 * (STAGES + s), (uint16_t)((1u << CL) - 1));
       }
-      ptx::umma_commit(tmem_full_bar);  // accumulator complete
+      if (trc) trc[2] = clock64();
     }
   } else {
-    // =========================== epilogue ===========================
+    // =========================== epilogue (4 warps per M sub-tile) ===========================
+    const int mt = (warp - 2) >> 2;    // which accumulator / sub-tile
     const int q = warp & 3;            // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane;     // accumulator row == voxel slot in the box
-    int t = row;
+    int t = blockIdx.x * MT + mt;
+    const int w0 = (t % a.nb_w) * a.tw; t /= a.nb_w;
+    const int h0 = (t % a.nb_h) * a.th; t /= a.nb_h;
+    const int d0 = (t % a.nb_d) * a.td; t /= a.nb_d;
+    const int n0 = t * a.tn;
+    t = row;
     const int rw = t % a.tw; t /= a.tw;
     const int rh = t % a.th; t /= a.th;
     const int rd = t % a.td; t /= a.td;
@@ -169,13 +211,15 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
     const size_t obase = vox * (size_t)a.Cout;
     const float* temb_row = a.temb ? a.temb + (size_t)(a.temb_stride ? n : 0) * a.temb_stride : nullptr;
     const int cpg = a.gn_stats ? a.Cout / a.gn_groups : 1;
+    const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * BN);
 
-    ptx::mbar_wait(tmem_full_bar, 0, 2);
+    ptx::mbar_wait(tmem_full_bar + 8 * mt, 0, 2);
     ptx::tc_fence_after();
+    if (trc && lane == 0 && q == 0) trc[3 + 2 * mt] = clock64();
 #pragma unroll 1
     for (int c = 0; c < BN; c += 16) {
       uint32_t r[16];
-      ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+      ptx::tmem_ld16(tacc + (uint32_t)c, r);
       ptx::tmem_ld_wait();
       const int co = co0 + c;
       if (co >= a.Cout) continue;  // warp-uniform
@@ -249,7 +293,7 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
             // rows of one warp belong to different samples only when tn > 1
             if (a.tn == 1) {
               const float t1 = warp_sum(s1), t2 = warp_sum(s2);
-              if (lane == 0) {
+              if (lane == 0 && n0 < a.N) {
                 atomicAdd(a.gn_stats + ((size_t)n0 * a.gn_groups + g) * 2, (double)t1);
                 atomicAdd(a.gn_stats + ((size_t)n0 * a.gn_groups + g) * 2 + 1, (double)t2);
               }
@@ -262,6 +306,7 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
         }
       }
     }
+    if (trc && lane == 0 && q == 0) trc[4 + 2 * mt] = clock64();
     ptx::tc_fence_before();
   }
   __syncthreads();
@@ -269,6 +314,8 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
+  if (trc && threadIdx.x == 0) trc[7] = clock64();
+  if (CL > 1) ptx::cluster_sync();  // do not exit while a peer can still arrive on our barriers
 }
 
 // ------------------------------------------------------------------------------------------
@@ -343,19 +390,45 @@ void choose_conv_tile(int N, int Do, int Ho, int Wo, int* tn, int* td, int* th, 
   *tn = b[0]; *td = b[1]; *th = b[2]; *tw = b[3];
 }
 
-template <int BN>
-static int launch_conv_tc(const ConvTcMaps& maps, const ConvTcArgs& args, dim3 grid, cudaStream_t st) {
-  using Cfg = ConvTcCfg<BN>;
+template <int BN, int MT, int CL>
+static int launch_conv_tc(const ConvTcMaps& maps, const ConvTcArgs& args, int m_tiles, int n_tiles, cudaStream_t st) {
+  using Cfg = ConvTcCfg<BN, MT>;
   static bool attr_done = false;
   if (!attr_done) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<BN, MT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
     attr_done = true;
   }
-  conv3d_tc_kernel<BN><<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(maps, args);
+  const unsigned gx = (unsigned)(ceil_div(ceil_div(m_tiles, MT), CL) * CL);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(gx, (unsigned)n_tiles, 1);
+  cfg.blockDim = dim3(Cfg::kThreads, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3d_tc_kernel<BN, MT, CL>, maps, args));
   B2_LAUNCH_CHECK();
   return B200LDM_OK;
 }
+
+static unsigned long long* g_conv_trace = nullptr;
+void set_conv_trace(void* p) { g_conv_trace = reinterpret_cast<unsigned long long*>(p); }
+
+// test / tuning hooks: B200LDM_CONV_MT=1|2 pins the M sub-tiles per CTA, B200LDM_CONV_CL=1|2 the cluster size
+static const int g_force_mt = [] {
+  const char* e = getenv("B200LDM_CONV_MT");
+  return e ? atoi(e) : 0;
+}();
+static const int g_force_cl = [] {
+  const char* e = getenv("B200LDM_CONV_CL");
+  return e ? atoi(e) : 0;
+}();
 
 int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
   B2_REQUIRE(p->dtype == B200LDM_BF16, B200LDM_BAD_ARG, "tcgen05 conv needs bf16 activations");
@@ -400,6 +473,7 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
   a.rows_box = a.tn * a.td * a.th * a.tw;
   a.temb_stride = p->temb_stride; a.out_f32 = p->out_f32; a.gn_groups = p->gn_groups;
   a.bias = p->bias; a.temb = p->temb; a.residual = p->residual; a.y = p->y; a.gn_stats = p->gn_stats;
+  a.trace = g_conv_trace;
 
   ConvTcMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -433,15 +507,28 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
   }
   // weight rows are padded by the packer to a multiple of 16 so small-Cout tiles stay in bounds
   const int cout_rows = (p->Cout + 15) / 16 * 16;
-  rc = make_weight_map(&maps.w, p->w, Cin, cout_rows, taps, bn);
+  const int m_tiles = nb_n * a.nb_d * a.nb_h * a.nb_w;
+  // two M sub-tiles per CTA (shared weight stage) once that still fills the machine
+  int mt = (ceil_div(m_tiles, 2) * n_tiles >= 148) ? 2 : 1;
+  if (g_force_mt == 1 || g_force_mt == 2) mt = g_force_mt;
+  // weight multicast over a 2-CTA cluster for the big launches (>= 2 full waves of 256-row CTAs)
+  int cl = (mt == 2 && bn >= 128 && ceil_div(m_tiles, 2) >= 2 * 148) ? 2 : 1;
+  if (g_force_cl == 1) cl = 1;
+  if (g_force_cl == 2 && mt == 2 && bn >= 128) cl = 2;
+  // the weight map box holds the rows ONE CTA fetches
+  rc = make_weight_map(&maps.w, p->w, Cin, cout_rows, taps, bn / cl);
   if (rc) return rc;
-
-  dim3 grid((unsigned)(nb_n * a.nb_d * a.nb_h * a.nb_w), (unsigned)n_tiles, 1);
   switch (bn) {
-    case 256: return launch_conv_tc<256>(maps, a, grid, st);
-    case 128: return launch_conv_tc<128>(maps, a, grid, st);
-    case 64: return launch_conv_tc<64>(maps, a, grid, st);
-    default: return launch_conv_tc<16>(maps, a, grid, st);
+    case 256: return mt == 2 ? (cl == 2 ? launch_conv_tc<256, 2, 2>(maps, a, m_tiles, n_tiles, st)
+                                        : launch_conv_tc<256, 2, 1>(maps, a, m_tiles, n_tiles, st))
+                             : launch_conv_tc<256, 1, 1>(maps, a, m_tiles, n_tiles, st);
+    case 128: return mt == 2 ? (cl == 2 ? launch_conv_tc<128, 2, 2>(maps, a, m_tiles, n_tiles, st)
+                                        : launch_conv_tc<128, 2, 1>(maps, a, m_tiles, n_tiles, st))
+                             : launch_conv_tc<128, 1, 1>(maps, a, m_tiles, n_tiles, st);
+    case 64: return mt == 2 ? launch_conv_tc<64, 2, 1>(maps, a, m_tiles, n_tiles, st)
+                            : launch_conv_tc<64, 1, 1>(maps, a, m_tiles, n_tiles, st);
+    default: return mt == 2 ? launch_conv_tc<16, 2, 1>(maps, a, m_tiles, n_tiles, st)
+                            : launch_conv_tc<16, 1, 1>(maps, a, m_tiles, n_tiles, st);
   }
 }
 

@@ -33,7 +33,18 @@ gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ x2, double* __res
     const bool second = cv * 8 >= C1;
     const int Cs = second ? C2 : C1;
     const T* base = (second ? x2 : x) + ((size_t)n * S) * Cs + (size_t)(second ? cv * 8 - C1 : cv * 8);
-    for (long long v = v0 + vslot; v < v1; v += vpp) {
+    // 4 independent 16-byte loads in flight per thread (memory-level parallelism), then the tail
+    long long v = v0 + vslot;
+    for (; v + 3LL * vpp < v1; v += 4LL * vpp) {
+      float f[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) Vec8<T>::load(base + (size_t)(v + (long long)u * vpp) * Cs, f[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s1[e] += f[u][e]; s2[e] += f[u][e] * f[u][e]; }
+    }
+    for (; v < v1; v += vpp) {
       float f[8];
       Vec8<T>::load(base + (size_t)v * Cs, f);
 #pragma unroll
@@ -65,7 +76,7 @@ template <typename T>
 __global__ void __launch_bounds__(kNormThreads)
 gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict__ y,
                 const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
-                long long S, int C1, int C2, int G, float eps, int silu, int vox_per_block) {
+                long long S, int C1, int C2, int G, float eps, int silu, int vox_per_block, double inv_cnt_arg) {
   const int n = blockIdx.y;
   const int C = C1 + C2;
   const int vecs = C >> 3;
@@ -75,18 +86,28 @@ gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict
   const int vslot = threadIdx.x / vecs;
   if (vslot >= vpp) return;
   float sc[8], sf[8];
-  const double cnt = (double)S * (double)cpg;
+  // mean / variance from the fp64 sums with two fp64 multiplies and one fp64 FMA (no fp64 divide / sqrt: the
+  // per-block prologue used to rival the streaming time); the cancellation-prone subtraction stays in fp64.
+  const double inv_cnt = inv_cnt_arg;
+  int g_prev = -1;
+  float mean_f = 0.f, rstd = 0.f;
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int c = cv * 8 + e;
     const int g = c / cpg;
-    const double m = stats[((size_t)n * G + g) * 2] / cnt;
-    double var = stats[((size_t)n * G + g) * 2 + 1] / cnt - m * m;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float ga = gamma[c], be = beta[c];
+    if (g != g_prev) {
+      const double m = stats[((size_t)n * G + g) * 2] * inv_cnt;
+      double var = fma(-m, m, stats[((size_t)n * G + g) * 2 + 1] * inv_cnt);
+      if (var < 0.0) var = 0.0;
+      mean_f = (float)m;
+      rstd = rsqrtf((float)var + eps);
+      // one Newton step brings rsqrtf (2 ulp) to fp32 round-off for the 1e-4 validation mode
+      rstd = rstd * (1.5f - 0.5f * ((float)var + eps) * rstd * rstd);
+      g_prev = g;
+    }
+    const float ga = __ldg(gamma + c), be = __ldg(beta + c);
     sc[e] = rstd * ga;
-    sf[e] = be - (float)m * rstd * ga;
+    sf[e] = be - mean_f * rstd * ga;
   }
   const long long v0 = (long long)blockIdx.x * vox_per_block;
   const long long v1 = min(v0 + vox_per_block, S);
@@ -94,12 +115,27 @@ gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict
   const bool second = cv * 8 >= C1;
   const int Cs = second ? C2 : C1;
   const T* src = (second ? x2 : x) + ((size_t)n * S) * Cs + (size_t)(second ? cv * 8 - C1 : cv * 8);
-  for (long long v = v0 + vslot; v < v1; v += vpp) {
+  long long v = v0 + vslot;
+  for (; v + 3LL * vpp < v1; v += 4LL * vpp) {
+    float f[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) Vec8<T>::load(src + (size_t)(v + (long long)u * vpp) * Cs, f[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float t = fmaf(f[u][e], sc[e], sf[e]);
+        f[u][e] = silu ? silu_f(t) : t;
+      }
+      Vec8<T>::store(y + off + (size_t)(v + (long long)u * vpp) * C, f[u]);
+    }
+  }
+  for (; v < v1; v += vpp) {
     float f[8];
     Vec8<T>::load(src + (size_t)v * Cs, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      float t = fmaf(f[e], sc[e], sf[e]);
+      const float t = fmaf(f[e], sc[e], sf[e]);
       f[e] = silu ? silu_f(t) : t;
     }
     Vec8<T>::store(y + off + (size_t)v * C, f);
@@ -111,10 +147,10 @@ static int norm_geometry(int N, long long S, int C, int G, int* vox_per_block, d
              8 * kNormThreads, C);
   B2_REQUIRE(G > 0 && C % G == 0 && G <= 1024, B200LDM_BAD_SHAPE, "bad group count %d for C=%d", G, C);
   const int vpp = kNormThreads / (C / 8);
-  // ~8 blocks per SM across the batch; each block at least 4 passes
-  long long want_blocks = (148LL * 8 + N - 1) / N;
+  // ~16 blocks per SM across the batch (8 resident x 2 waves); each block at least 8 passes
+  long long want_blocks = (148LL * 16 + N - 1) / N;
   long long vpb = (S + want_blocks - 1) / want_blocks;
-  if (vpb < 4LL * vpp) vpb = 4LL * vpp;
+  if (vpb < 8LL * vpp) vpb = 8LL * vpp;
   vpb = (vpb + vpp - 1) / vpp * vpp;
   *vox_per_block = (int)vpb;
   *grid = dim3((unsigned)((S + vpb - 1) / vpb), (unsigned)N, 1);
@@ -160,13 +196,14 @@ int b200ldm_groupnorm_apply(const void* x, const void* x2, void* y, const double
   int vpb; dim3 grid;
   int rc = norm_geometry(N, S, C1 + C2, G, &vpb, &grid);
   if (rc) return rc;
+  const double inv_cnt = 1.0 / ((double)S * (double)((C1 + C2) / G));
   if (dtype == B200LDM_BF16)
     gn_apply_kernel<__nv_bfloat16><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x, (const __nv_bfloat16*)x2, (__nv_bfloat16*)y, stats, gamma, beta, S, C1, C2, G, eps,
-        silu, vpb);
+        silu, vpb, inv_cnt);
   else if (dtype == B200LDM_F32)
     gn_apply_kernel<float><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(
-        (const float*)x, (const float*)x2, (float*)y, stats, gamma, beta, S, C1, C2, G, eps, silu, vpb);
+        (const float*)x, (const float*)x2, (float*)y, stats, gamma, beta, S, C1, C2, G, eps, silu, vpb, inv_cnt);
   else
     return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);
   B2_LAUNCH_CHECK();
