@@ -28,6 +28,8 @@ namespace b200ldm {
 struct ConvTcMaps {
   CUtensorMap a[8];  // stride 1: a[0] = x, a[1] = x2;  stride 2: a[pd*4+ph*2+pw]
   CUtensorMap w;     // [taps][Cout_pad][Cin_total]
+  CUtensorMap y;     // output, same voxel box as the A tiles (TMA-store epilogue)
+  CUtensorMap r;     // residual (same geometry as y) when fused
 };
 
 struct ConvTcArgs {
@@ -43,6 +45,7 @@ struct ConvTcArgs {
   const void* residual;
   void* y;
   double* gn_stats;
+  int tma_epilogue;           // 1: stage the tile in smem and TMA-store it (bf16, Cout % 64 == 0, no GN partials)
   unsigned long long* trace;  // debug: per-CTA clock64 stamps (b200ldm_debug_set_conv_trace), else nullptr
 };
 
@@ -77,8 +80,10 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
   // barriers: full[s] @ +8s, empty[s] @ +8(STAGES+s), tmem_full[mt] @ +16*STAGES + 8mt, tmem slot after them
   const uint32_t tmem_full_bar = bar_base + 16 * STAGES;
   const uint32_t tmem_slot = tmem_full_bar + 8 * MT;
+  const uint32_t res_bar = tmem_slot + 8;  // [MT] residual-tile arrival (TMA epilogue)
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));  // generic pointer to the aligned base
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -94,7 +99,10 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
       ptx::mbar_init(bar_base + 8 * s, 1);
       ptx::mbar_init(bar_base + 8 * (STAGES + s), CL);  // every CTA of the cluster must release the stage
     }
-    for (int mt = 0; mt < MT; ++mt) ptx::mbar_init(tmem_full_bar + 8 * mt, 1);
+    for (int mt = 0; mt < MT; ++mt) {
+      ptx::mbar_init(tmem_full_bar + 8 * mt, 1);
+      ptx::mbar_init(res_bar + 8 * mt, 1);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -216,6 +224,86 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
     ptx::mbar_wait(tmem_full_bar + 8 * mt, 0, 2);
     ptx::tc_fence_after();
     if (trc && lane == 0 && q == 0) trc[3 + 2 * mt] = clock64();
+    if (BN >= 64 && a.tma_epilogue) {
+      // ---- coalesced epilogue: the main-loop stages are dead now, so the tile is staged there in 64-channel
+      // SWIZZLE_128B groups ([group][128 rows][128 B], the layout of the y / residual tensor maps) and leaves
+      // through TMA stores, which also clip rows outside the tensor.  A fused residual arrives the same way
+      // (TMA load into the very slots the output will occupy; each thread only touches its own row).
+      constexpr int G = BN / 64;
+      // the LAST accumulator's MMAs still read the final stage: nobody may overwrite smem before they retire
+      if (mt != MT - 1) ptx::mbar_wait(tmem_full_bar + 8 * (MT - 1), 0, 4);
+      const uint32_t stg = smem_base + (uint32_t)mt * (G * 16384);
+      uint8_t* stg_gen = smem_gen + (size_t)mt * (G * 16384);
+      const bool issuer = (((warp - 2) & 3) == 0) && lane == 0;
+      const int gmax = min(G, (a.Cout - co0 + 63) / 64);  // groups that exist in this Cout tile (warp-uniform)
+      if (a.residual) {
+        if (issuer) {
+          ptx::mbar_expect_tx(res_bar + 8 * mt, (uint32_t)gmax * (uint32_t)a.rows_box * 128u);
+          for (int g = 0; g < gmax; ++g)
+            ptx::tma_load_5d(stg + g * 16384, &maps.r, res_bar + 8 * mt, co0 + g * 64, w0, h0, d0, n0);
+        }
+        ptx::mbar_wait(res_bar + 8 * mt, 0, 3);
+      }
+#pragma unroll 1
+      for (int g = 0; g < gmax; ++g) {
+        uint8_t* rowp = stg_gen + (size_t)g * 16384 + (size_t)row * 128;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t r[16];
+          ptx::tmem_ld16(tacc + (uint32_t)(g * 64 + cc * 16), r);
+          ptx::tmem_ld_wait();
+          const int co = co0 + g * 64 + cc * 16;
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          if (a.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + co + j));
+              v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+            }
+          }
+          if (temb_row && valid) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 tt = __ldg(reinterpret_cast<const float4*>(temb_row + co + j));
+              v[j] += tt.x; v[j + 1] += tt.y; v[j + 2] += tt.z; v[j + 3] += tt.w;
+            }
+          }
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            const int chunk = cc * 2 + hlf;  // 16-byte chunk inside the 128-byte row
+            uint4* slot = reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) << 4));
+            float f[8];
+            if (a.residual) {
+              const uint4 u = *slot;
+              const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t2 = __bfloat1622float2(hp[e]);
+                f[2 * e] = v[hlf * 8 + 2 * e] + t2.x;
+                f[2 * e + 1] = v[hlf * 8 + 2 * e + 1] + t2.y;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = v[hlf * 8 + e];
+            }
+            uint4 o;
+            __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+            *slot = o;
+          }
+        }
+        ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA store
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");  // the 4 warps of this accumulator
+        if (issuer) {
+          ptx::tma_store_5d(&maps.y, stg + g * 16384, co0 + g * 64, w0, h0, d0, n0);
+          ptx::tma_store_commit();
+        }
+      }
+      if (issuer) ptx::tma_store_wait_read0();  // smem must outlive the bulk reads
+    } else
 #pragma unroll 1
     for (int c = 0; c < BN; c += 16) {
       uint32_t r[16];
@@ -425,6 +513,10 @@ static const int g_force_mt = [] {
   const char* e = getenv("B200LDM_CONV_MT");
   return e ? atoi(e) : 0;
 }();
+static const int g_legacy_epilogue = [] {
+  const char* e = getenv("B200LDM_CONV_LEGACY_EPILOGUE");
+  return e ? atoi(e) : 0;
+}();
 static const int g_force_cl = [] {
   const char* e = getenv("B200LDM_CONV_CL");
   return e ? atoi(e) : 0;
@@ -507,6 +599,20 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
   }
   // weight rows are padded by the packer to a multiple of 16 so small-Cout tiles stay in bounds
   const int cout_rows = (p->Cout + 15) / 16 * 16;
+  // coalesced TMA-store epilogue whenever the output is bf16 in whole 64-channel groups
+  a.tma_epilogue = (!p->out_f32 && p->Cout % 64 == 0 && !p->gn_stats && bn >= 64 && g_legacy_epilogue == 0) ? 1 : 0;
+  if (a.tma_epilogue) {
+    const uint64_t Co = p->Cout, Wo = p->Wo, Ho = p->Ho, Do = p->Do;
+    rc = make_act_map(&maps.y, p->y, p->Cout, p->Wo, p->Ho, p->Do, p->N, Co, Wo * Co, Ho * Wo * Co, Do * Ho * Wo * Co,
+                      a.tw, a.th, a.td, a.tn);
+    if (rc) return rc;
+    if (p->residual) {
+      rc = make_act_map(&maps.r, p->residual, p->Cout, p->Wo, p->Ho, p->Do, p->N, Co, Wo * Co, Ho * Wo * Co,
+                        Do * Ho * Wo * Co, a.tw, a.th, a.td, a.tn);
+      if (rc) return rc;
+    }
+  }
+
   const int m_tiles = nb_n * a.nb_d * a.nb_h * a.nb_w;
   // two M sub-tiles per CTA (shared weight stage) once that still fills the machine
   int mt = (ceil_div(m_tiles, 2) * n_tiles >= 148) ? 2 : 1;
