@@ -97,6 +97,10 @@ def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo
         dtype=dtype_code(x.dtype), engine=engine, out_f32=int(out_f32))
     assert x.is_contiguous() and (x2 is None or x2.is_contiguous())
     assert residual is None or (residual.is_contiguous() and residual.shape == y.shape and residual.dtype == odt)
+    ws_bytes = lib.b200ldm_conv3d_workspace_bytes(C.byref(p))
+    if ws_bytes > 0:  # split-K partial sums (small-M convs): caller-owned scratch
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+        p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
     ev = PROFILER.start() if PROFILER is not None else None
     _lib.check(lib.b200ldm_conv3d(C.byref(p), _stream()), "conv3d")
     if ev is not None:

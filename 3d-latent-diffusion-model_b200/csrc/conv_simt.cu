@@ -167,8 +167,17 @@ int conv3d_simt(const b200ldm_conv3d_params* p, cudaStream_t st) {
 }
 
 int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st);
+long long conv3d_tcgen05_workspace_bytes(const b200ldm_conv3d_params* p);
 
 }  // namespace b200ldm
+
+extern "C" int64_t b200ldm_conv3d_workspace_bytes(const b200ldm_conv3d_params* p) {
+  if (!p) return 0;
+  int engine = p->engine;
+  if (engine == B200LDM_ENGINE_AUTO)
+    engine = (p->dtype == B200LDM_BF16) ? B200LDM_ENGINE_TCGEN05 : B200LDM_ENGINE_SIMT;
+  return engine == B200LDM_ENGINE_TCGEN05 ? (int64_t)b200ldm::conv3d_tcgen05_workspace_bytes(p) : 0;
+}
 
 extern "C" int b200ldm_conv3d(const b200ldm_conv3d_params* p, b200ldm_stream stream) {
   using namespace b200ldm;

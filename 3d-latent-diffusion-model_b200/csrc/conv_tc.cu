@@ -17,6 +17,7 @@
 // warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
 #include <cudaTypedefs.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 
@@ -45,6 +46,9 @@ struct ConvTcArgs {
   const void* residual;
   void* y;
   double* gn_stats;
+  int splits;                 // split-K: blockIdx.z handles k-iterations [z*I/S, (z+1)*I/S) and writes fp32 slab z
+  long long slab_elems;       // elements per fp32 slab (N*Do*Ho*Wo*Cout)
+  int ashift;                 // experiment: A sub-tile base shifted by ashift*128 bytes (swizzle-phase probe)
   int tma_epilogue;           // 1: stage the tile in smem and TMA-store it (bf16, Cout % 64 == 0, no GN partials)
   unsigned long long* trace;  // debug: per-CTA clock64 stamps (b200ldm_debug_set_conv_trace), else nullptr
 };
@@ -90,7 +94,9 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
   const int co0 = blockIdx.y * BN;
   const int taps = a.ksize * a.ksize * a.ksize;
   const int nchunks = a.nchunk1 + a.nchunk2;
-  const int iters = taps * nchunks;
+  const int iters_total = taps * nchunks;
+  const int it0 = (int)((long long)blockIdx.z * iters_total / a.splits);
+  const int it1 = (int)((long long)(blockIdx.z + 1) * iters_total / a.splits);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&maps.w);
@@ -129,9 +135,9 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
         n0[mt] = t * a.tn;
       }
       const uint32_t tx_bytes = (uint32_t)MT * (uint32_t)a.rows_box * 128u + (uint32_t)Cfg::kBBytes;
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      for (int it = it0; it < it1; ++it) {
+        const int s = (it - it0) % STAGES;
+        const uint32_t ph = (uint32_t)((it - it0) / STAGES) & 1u;
         ptx::mbar_wait(bar_base + 8 * (STAGES + s), ph ^ 1u, 0);
         const int tap = it / nchunks;
         const int chunk = it - tap * nchunks;
@@ -147,8 +153,8 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
           const int c0 = (second ? chunk - a.nchunk1 : chunk) * 64;
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
-            ptx::tma_load_5d(sa + mt * kABytes, m, full, c0, w0[mt] + kw - a.pad_lo, h0[mt] + kh - a.pad_lo,
-                             d0[mt] + kd - a.pad_lo, n0[mt]);
+            ptx::tma_load_5d(sa + mt * kABytes + a.ashift * 128, m, full, c0, w0[mt] + kw - a.pad_lo,
+                             h0[mt] + kh - a.pad_lo, d0[mt] + kd - a.pad_lo, n0[mt]);
         } else {
           // input coord = 2*o + k - pad_lo  ->  parity grid (k-pad_lo)&1 at index o + floor((k-pad_lo)/2)
           const int od = kd - a.pad_lo, oh = kh - a.pad_lo, ow = kw - a.pad_lo;
@@ -174,23 +180,23 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      for (int it = it0; it < it1; ++it) {
+        const int s = (it - it0) % STAGES;
+        const uint32_t ph = (uint32_t)((it - it0) / STAGES) & 1u;
         ptx::mbar_wait(bar_base + 8 * s, ph, 1);
         ptx::tc_fence_after();
-        if (trc && it == 0) trc[1] = clock64();
+        if (trc && it == it0) trc[1] = clock64();
         const uint32_t sa = smem_base + s * Cfg::kStageBytes;
         const uint32_t sb = sa + MT * kABytes;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t da = ptx::umma_desc_k_sw128(sa + mt * kABytes + k * 32);
+            const uint64_t da = ptx::umma_desc_k_sw128(sa + mt * kABytes + a.ashift * 128 + k * 32);
             const uint64_t db = ptx::umma_desc_k_sw128(sb + k * 32);
-            ptx::umma_bf16(tmem_base + mt * BN, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            ptx::umma_bf16(tmem_base + mt * BN, da, db, idesc, (it > it0 || k > 0) ? 1u : 0u);
           }
-          if (it == iters - 1) ptx::umma_commit(tmem_full_bar + 8 * mt);  // this accumulator is complete
+          if (it == it1 - 1) ptx::umma_commit(tmem_full_bar + 8 * mt);  // this accumulator is complete
         }
         // frees the smem stage (in every CTA of the cluster) when the MMAs retire
         if (CL == 1) ptx::umma_commit(bar_base + 8 * (STAGES + s));
@@ -216,7 +222,7 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
     const int n = n0 + rn, d = d0 + rd, h = h0 + rh, w = w0 + rw;
     const bool valid = row < a.rows_box && n < a.N && d < a.Do && h < a.Ho && w < a.Wo;
     const size_t vox = (((size_t)n * a.Do + d) * a.Ho + h) * a.Wo + w;
-    const size_t obase = vox * (size_t)a.Cout;
+    const size_t obase = vox * (size_t)a.Cout + (size_t)blockIdx.z * (size_t)a.slab_elems;  // split-K: fp32 slab z
     const float* temb_row = a.temb ? a.temb + (size_t)(a.temb_stride ? n : 0) * a.temb_stride : nullptr;
     const int cpg = a.gn_stats ? a.Cout / a.gn_groups : 1;
     const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * BN);
@@ -479,7 +485,8 @@ void choose_conv_tile(int N, int Do, int Ho, int Wo, int* tn, int* td, int* th, 
 }
 
 template <int BN, int MT, int CL>
-static int launch_conv_tc(const ConvTcMaps& maps, const ConvTcArgs& args, int m_tiles, int n_tiles, cudaStream_t st) {
+static int launch_conv_tc(const ConvTcMaps& maps, const ConvTcArgs& args, int m_tiles, int n_tiles, int splits,
+                          cudaStream_t st) {
   using Cfg = ConvTcCfg<BN, MT>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -489,7 +496,7 @@ static int launch_conv_tc(const ConvTcMaps& maps, const ConvTcArgs& args, int m_
   }
   const unsigned gx = (unsigned)(ceil_div(ceil_div(m_tiles, MT), CL) * CL);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(gx, (unsigned)n_tiles, 1);
+  cfg.gridDim = dim3(gx, (unsigned)n_tiles, (unsigned)splits);
   cfg.blockDim = dim3(Cfg::kThreads, 1, 1);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
@@ -503,6 +510,44 @@ static int launch_conv_tc(const ConvTcMaps& maps, const ConvTcArgs& args, int m_
   B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3d_tc_kernel<BN, MT, CL>, maps, args));
   B2_LAUNCH_CHECK();
   return B200LDM_OK;
+}
+
+// split-K finalize: y = bf16( sum_z ws[z] + bias + temb[n] + residual ), 8 channels per thread
+__global__ void splitk_finalize_kernel(const float* __restrict__ ws, int S, long long slab, long long M, int Cout,
+                                       long long vox_per_sample, const float* __restrict__ bias,
+                                       const float* __restrict__ temb, int temb_stride,
+                                       const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ y) {
+  const long long vecs = M * (Cout >> 3);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < vecs; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / (Cout >> 3);
+    const int c = (int)(i - m * (Cout >> 3)) * 8;
+    const size_t off = (size_t)m * Cout + c;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    for (int z = 0; z < S; ++z) {
+      float f[8];
+      Vec8<float>::load(ws + (size_t)z * slab + off, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += f[e];
+    }
+    if (bias) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += __ldg(bias + c + e);
+    }
+    if (temb) {
+      const long long n = temb_stride ? m / vox_per_sample : 0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += __ldg(temb + n * temb_stride + c + e);
+    }
+    if (residual) {
+      float f[8];
+      Vec8<__nv_bfloat16>::load(residual + off, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += f[e];
+    }
+    Vec8<__nv_bfloat16>::store(y + off, v);
+  }
 }
 
 static unsigned long long* g_conv_trace = nullptr;
@@ -521,6 +566,64 @@ static const int g_force_cl = [] {
   const char* e = getenv("B200LDM_CONV_CL");
   return e ? atoi(e) : 0;
 }();
+
+static const int g_force_splits = [] {
+  const char* e = getenv("B200LDM_CONV_SPLITS");
+  return e ? atoi(e) : 0;
+}();
+
+struct ConvPlan {
+  int bn, n_tiles, tn, td, th, tw, nb_n, nb_d, nb_h, nb_w, m_tiles, mt, cl, splits;
+};
+
+// Tile / cluster / split-K decisions (shared by the launch and by b200ldm_conv3d_workspace_bytes).
+static ConvPlan plan_conv(const b200ldm_conv3d_params* p) {
+  ConvPlan pl{};
+  if (p->Cout % 256 == 0) pl.bn = 256;
+  else if (p->Cout % 128 == 0) pl.bn = 128;
+  else if (p->Cout % 64 == 0) pl.bn = 64;
+  else if (p->Cout <= 16) pl.bn = 16;
+  else if (p->Cout <= 64) pl.bn = 64;
+  else if (p->Cout <= 128) pl.bn = 128;
+  else pl.bn = 256;
+  pl.n_tiles = ceil_div(p->Cout, pl.bn);
+  choose_conv_tile(p->N, p->Do, p->Ho, p->Wo, &pl.tn, &pl.td, &pl.th, &pl.tw);
+  pl.nb_n = ceil_div(p->N, pl.tn); pl.nb_d = ceil_div(p->Do, pl.td);
+  pl.nb_h = ceil_div(p->Ho, pl.th); pl.nb_w = ceil_div(p->Wo, pl.tw);
+  pl.m_tiles = pl.nb_n * pl.nb_d * pl.nb_h * pl.nb_w;
+  // two M sub-tiles per CTA (shared weight stage) once that still fills the machine
+  pl.mt = (ceil_div(pl.m_tiles, 2) * pl.n_tiles >= 148) ? 2 : 1;
+  if (g_force_mt == 1 || g_force_mt == 2) pl.mt = g_force_mt;
+  // weight multicast over a 2-CTA cluster for the big launches (>= 2 full waves of 256-row CTAs)
+  pl.cl = (pl.mt == 2 && pl.bn >= 128 && ceil_div(pl.m_tiles, 2) >= 2 * 148) ? 2 : 1;
+  if (g_force_cl == 1) pl.cl = 1;
+  if (g_force_cl == 2 && pl.mt == 2 && pl.bn >= 128) pl.cl = 2;
+  // split-K for launches that leave most SMs idle: minimise rounds x (main loop + fixed CTA overhead)
+  pl.splits = 1;
+  const int iters = p->ksize * p->ksize * p->ksize * ((p->C1 + p->C2) / 64);
+  const int ctas = ceil_div(pl.m_tiles, pl.mt) * pl.n_tiles;
+  if (pl.mt == 1 && !p->out_f32 && !p->gn_stats && p->Cout % 8 == 0 && ctas < 148) {
+    const double cyc_iter = 512.0 * pl.bn / 256.0 + 64.0, overhead = 14000.0;
+    double best = 1e30;
+    for (int s = 1; s <= 8 && iters / s >= 16; ++s) {
+      const double rounds = (double)ceil_div((long long)ctas * s, 148);
+      double t = rounds * (ceil_div(iters, s) * cyc_iter + overhead);
+      if (s > 1) t += 6000.0;  // finalize launch + slab traffic
+      if (t < best) { best = t; pl.splits = s; }
+    }
+  }
+  if (g_force_splits >= 1 && g_force_splits <= 8 && !p->out_f32 && !p->gn_stats && iters / g_force_splits >= 1)
+    pl.splits = g_force_splits;
+  if (pl.splits > 1) pl.cl = 1;
+  return pl;
+}
+
+long long conv3d_tcgen05_workspace_bytes(const b200ldm_conv3d_params* p) {
+  if (p->dtype != B200LDM_BF16 || p->C1 % 64 || p->C2 % 64 || p->Cout % 8) return 0;
+  const ConvPlan pl = plan_conv(p);
+  if (pl.splits <= 1) return 0;
+  return (long long)pl.splits * p->N * p->Do * p->Ho * p->Wo * p->Cout * 4;
+}
 
 int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
   B2_REQUIRE(p->dtype == B200LDM_BF16, B200LDM_BAD_ARG, "tcgen05 conv needs bf16 activations");
@@ -545,27 +648,33 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
 
   const int taps = p->ksize * p->ksize * p->ksize;
   const int Cin = p->C1 + p->C2;
-  int bn;
-  if (p->Cout % 256 == 0) bn = 256;
-  else if (p->Cout % 128 == 0) bn = 128;
-  else if (p->Cout % 64 == 0) bn = 64;
-  else if (p->Cout <= 16) bn = 16;
-  else if (p->Cout <= 64) bn = 64;
-  else if (p->Cout <= 128) bn = 128;
-  else bn = 256;
-  const int n_tiles = ceil_div(p->Cout, bn);
+  const ConvPlan pl = plan_conv(p);
+  const int bn = pl.bn, n_tiles = pl.n_tiles;
+  const long long M_total = (long long)p->N * p->Do * p->Ho * p->Wo;
+  if (pl.splits > 1)
+    B2_REQUIRE(p->workspace && p->workspace_bytes >= (long long)pl.splits * M_total * p->Cout * 4 &&
+                   aligned16(p->workspace),
+               B200LDM_BAD_ARG, "conv3d: split-K needs %lld workspace bytes (b200ldm_conv3d_workspace_bytes)",
+               (long long)pl.splits * M_total * p->Cout * 4);
 
   ConvTcArgs a{};
-  choose_conv_tile(p->N, p->Do, p->Ho, p->Wo, &a.tn, &a.td, &a.th, &a.tw);
-  a.nb_d = ceil_div(p->Do, a.td); a.nb_h = ceil_div(p->Ho, a.th); a.nb_w = ceil_div(p->Wo, a.tw);
-  const int nb_n = ceil_div(p->N, a.tn);
+  a.tn = pl.tn; a.td = pl.td; a.th = pl.th; a.tw = pl.tw;
+  a.nb_d = pl.nb_d; a.nb_h = pl.nb_h; a.nb_w = pl.nb_w;
   a.N = p->N; a.Do = p->Do; a.Ho = p->Ho; a.Wo = p->Wo; a.Cout = p->Cout;
+  a.splits = pl.splits; a.slab_elems = pl.splits > 1 ? M_total * p->Cout : 0;
   a.nchunk1 = p->C1 / 64; a.nchunk2 = p->C2 / 64;
   a.ksize = p->ksize; a.stride = p->stride; a.pad_lo = p->pad_lo;
   a.rows_box = a.tn * a.td * a.th * a.tw;
   a.temb_stride = p->temb_stride; a.out_f32 = p->out_f32; a.gn_groups = p->gn_groups;
   a.bias = p->bias; a.temb = p->temb; a.residual = p->residual; a.y = p->y; a.gn_stats = p->gn_stats;
+  if (pl.splits > 1) {  // partial sums go to fp32 slabs; bias / temb / residual are applied by the finalize kernel
+    a.out_f32 = 1; a.bias = nullptr; a.temb = nullptr; a.residual = nullptr; a.y = p->workspace;
+  }
   a.trace = g_conv_trace;
+  {
+    const char* e = getenv("B200LDM_CONV_ASHIFT");
+    a.ashift = (e && p->stride == 1 && a.rows_box + atoi(e) <= 128) ? atoi(e) : 0;
+  }
 
   ConvTcMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -600,7 +709,7 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
   // weight rows are padded by the packer to a multiple of 16 so small-Cout tiles stay in bounds
   const int cout_rows = (p->Cout + 15) / 16 * 16;
   // coalesced TMA-store epilogue whenever the output is bf16 in whole 64-channel groups
-  a.tma_epilogue = (!p->out_f32 && p->Cout % 64 == 0 && !p->gn_stats && bn >= 64 && g_legacy_epilogue == 0) ? 1 : 0;
+  a.tma_epilogue = (!a.out_f32 && p->Cout % 64 == 0 && !p->gn_stats && bn >= 64 && g_legacy_epilogue == 0) ? 1 : 0;
   if (a.tma_epilogue) {
     const uint64_t Co = p->Cout, Wo = p->Wo, Ho = p->Ho, Do = p->Do;
     rc = make_act_map(&maps.y, p->y, p->Cout, p->Wo, p->Ho, p->Do, p->N, Co, Wo * Co, Ho * Wo * Co, Do * Ho * Wo * Co,
@@ -613,29 +722,35 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
     }
   }
 
-  const int m_tiles = nb_n * a.nb_d * a.nb_h * a.nb_w;
-  // two M sub-tiles per CTA (shared weight stage) once that still fills the machine
-  int mt = (ceil_div(m_tiles, 2) * n_tiles >= 148) ? 2 : 1;
-  if (g_force_mt == 1 || g_force_mt == 2) mt = g_force_mt;
-  // weight multicast over a 2-CTA cluster for the big launches (>= 2 full waves of 256-row CTAs)
-  int cl = (mt == 2 && bn >= 128 && ceil_div(m_tiles, 2) >= 2 * 148) ? 2 : 1;
-  if (g_force_cl == 1) cl = 1;
-  if (g_force_cl == 2 && mt == 2 && bn >= 128) cl = 2;
+  const int m_tiles = pl.m_tiles, mt = pl.mt, cl = pl.cl;
   // the weight map box holds the rows ONE CTA fetches
   rc = make_weight_map(&maps.w, p->w, Cin, cout_rows, taps, bn / cl);
   if (rc) return rc;
+  const int sp = pl.splits;
   switch (bn) {
-    case 256: return mt == 2 ? (cl == 2 ? launch_conv_tc<256, 2, 2>(maps, a, m_tiles, n_tiles, st)
-                                        : launch_conv_tc<256, 2, 1>(maps, a, m_tiles, n_tiles, st))
-                             : launch_conv_tc<256, 1, 1>(maps, a, m_tiles, n_tiles, st);
-    case 128: return mt == 2 ? (cl == 2 ? launch_conv_tc<128, 2, 2>(maps, a, m_tiles, n_tiles, st)
-                                        : launch_conv_tc<128, 2, 1>(maps, a, m_tiles, n_tiles, st))
-                             : launch_conv_tc<128, 1, 1>(maps, a, m_tiles, n_tiles, st);
-    case 64: return mt == 2 ? launch_conv_tc<64, 2, 1>(maps, a, m_tiles, n_tiles, st)
-                            : launch_conv_tc<64, 1, 1>(maps, a, m_tiles, n_tiles, st);
-    default: return mt == 2 ? launch_conv_tc<16, 2, 1>(maps, a, m_tiles, n_tiles, st)
-                            : launch_conv_tc<16, 1, 1>(maps, a, m_tiles, n_tiles, st);
+    case 256: rc = mt == 2 ? (cl == 2 ? launch_conv_tc<256, 2, 2>(maps, a, m_tiles, n_tiles, sp, st)
+                                      : launch_conv_tc<256, 2, 1>(maps, a, m_tiles, n_tiles, sp, st))
+                           : launch_conv_tc<256, 1, 1>(maps, a, m_tiles, n_tiles, sp, st);
+      break;
+    case 128: rc = mt == 2 ? (cl == 2 ? launch_conv_tc<128, 2, 2>(maps, a, m_tiles, n_tiles, sp, st)
+                                      : launch_conv_tc<128, 2, 1>(maps, a, m_tiles, n_tiles, sp, st))
+                           : launch_conv_tc<128, 1, 1>(maps, a, m_tiles, n_tiles, sp, st);
+      break;
+    case 64: rc = mt == 2 ? launch_conv_tc<64, 2, 1>(maps, a, m_tiles, n_tiles, sp, st)
+                          : launch_conv_tc<64, 1, 1>(maps, a, m_tiles, n_tiles, sp, st);
+      break;
+    default: rc = mt == 2 ? launch_conv_tc<16, 2, 1>(maps, a, m_tiles, n_tiles, sp, st)
+                          : launch_conv_tc<16, 1, 1>(maps, a, m_tiles, n_tiles, sp, st);
   }
+  if (rc || sp == 1) return rc;
+  const long long vecs = M_total * (p->Cout / 8);
+  const unsigned blocks = (unsigned)std::min<long long>((vecs + 255) / 256, 148LL * 16);
+  splitk_finalize_kernel<<<blocks, 256, 0, st>>>(
+      reinterpret_cast<const float*>(p->workspace), sp, M_total * p->Cout, M_total, p->Cout,
+      (long long)p->Do * p->Ho * p->Wo, p->bias, p->temb, p->temb_stride,
+      reinterpret_cast<const __nv_bfloat16*>(p->residual), reinterpret_cast<__nv_bfloat16*>(p->y));
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
 }
 
 }  // namespace b200ldm

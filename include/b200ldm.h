@@ -90,9 +90,15 @@ typedef struct {
   int32_t dtype;         /* b200ldm_dtype of x, x2, w, residual, y */
   int32_t engine;        /* b200ldm_engine */
   int32_t out_f32;       /* 1: y (and residual) are fp32 even when dtype is bf16 */
+  int32_t reserved;
+  void* workspace;       /* caller-owned scratch for split-K partial sums (see b200ldm_conv3d_workspace_bytes) */
+  int64_t workspace_bytes;
 } b200ldm_conv3d_params;
 
 int b200ldm_conv3d(const b200ldm_conv3d_params* p, b200ldm_stream stream);
+/* bytes of `workspace` this exact problem needs (0 for most shapes; > 0 when the planner splits K over CTAs
+ * because the output has too few tiles to fill 148 SMs).  Pure host arithmetic, no CUDA call. */
+int64_t b200ldm_conv3d_workspace_bytes(const b200ldm_conv3d_params* p);
 
 /* src: fp32 [Cout][Cin][k][k][k] (PyTorch layout) -> dst: [k^3][Cout_pad][Cin_pad] in `dtype`,
  * zero padded; cin_offset lets a weight be split across padded concat sources:
