@@ -28,6 +28,9 @@ _PREC = {"bf16": torch.bfloat16, "fp32": torch.float32}
 FUSE_GN_STATS = os.environ.get("B200LDM_FUSE_GN_STATS", "0") != "0"
 
 
+FUSE_UPSAMPLE = os.environ.get("B200LDM_FUSE_UPSAMPLE", "1") != "0"
+
+
 def default_precision() -> str:
     return os.environ.get("B200LDM_PRECISION", "bf16")
 
@@ -91,6 +94,25 @@ class Conv(nn.Module):
         return ops.conv3d(x, w, b, self.cout_phys, self.ksize, self.stride, self.pad_lo, self.pad_hi, x2=x2, temb=temb,
                           temb_stride=temb_stride, residual=residual, gn_stats=gn_stats, gn_groups=gn_groups,
                           out_f32=out_f32)
+
+
+    def run_upsampled(self, x):
+        """conv(nearest_upsample_x2(x)) without materialising the upsampled tensor: on the tensor-core
+        path the 27 taps collapse to 8 per output phase (3.4x fewer MACs, weights pre-summed per phase)."""
+        cin_phys = x.shape[-1]
+        if x.dtype == torch.bfloat16 and FUSE_UPSAMPLE:
+            def build():
+                w = ops.repack_upconv_weight(self.weight, self.cout_phys, cin_phys, x.dtype)
+                b = torch.zeros(self.cout_phys, dtype=torch.float32, device=self.weight.device)
+                b[: self.cout] = self.bias.detach().float()
+                return w, b
+
+            w, b = self._cache.get(("up", x.dtype, cin_phys), (self.weight, self.bias), build)
+        else:
+            w, b = self.packed(x.dtype, cin_phys=cin_phys)
+            if not FUSE_UPSAMPLE:
+                return ops.conv3d(ops.upsample_nearest2x(x), w, b, self.cout_phys, 3, 1, 1, 1)
+        return ops.conv3d(x, w, b, self.cout_phys, 3, 1, 1, 1, upsample2x=True)
 
 
 class ConvOnly(nn.Module):
@@ -203,7 +225,7 @@ class NearestUp(nn.Module):
         self.postconv = ConvOnly(ch, ch, 3, 1, 1)
 
     def run(self, x):
-        return self.postconv.run(ops.upsample_nearest2x(x))
+        return self.postconv.conv.run_upsampled(x)
 
 
 # ------------------------------------------------------------------------------------------

@@ -79,22 +79,25 @@ def conv_out_extent(n: int, k: int, stride: int, pad_lo: int, pad_hi: int) -> in
 
 def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo: int = 1, pad_hi: int | None = None,
            x2=None, temb=None, temb_stride: int = 0, residual=None, gn_stats=None, gn_groups: int = 0,
-           out_f32: bool = False, engine: int = ENGINE_AUTO):
-    """y = conv3d(cat(x, x2)) + bias (+ temb) (+ residual); x: [N,D,H,W,C1] NDHWC."""
+           out_f32: bool = False, engine: int = ENGINE_AUTO, upsample2x: bool = False):
+    """y = conv3d(cat(x, x2)) + bias (+ temb) (+ residual); x: [N,D,H,W,C1] NDHWC.
+    upsample2x: the conv runs on the nearest-x2-upsampled x without materialising it (bf16: phase-decomposed
+    weights from repack_upconv_weight; fp32: ordinary weights)."""
     _need_cuda(x, x2, w_packed, bias, temb, residual)
     lib = _lib.load()
     N, D, H, W, C1 = x.shape
     C2 = 0 if x2 is None else x2.shape[-1]
     if pad_hi is None:
         pad_hi = pad_lo
-    Do, Ho, Wo = (conv_out_extent(v, ksize, stride, pad_lo, pad_hi) for v in (D, H, W))
+    up = 2 if upsample2x else 1
+    Do, Ho, Wo = (conv_out_extent(up * v, ksize, stride, pad_lo, pad_hi) for v in (D, H, W))
     odt = torch.float32 if out_f32 else x.dtype
     y = torch.empty((N, Do, Ho, Wo, cout), dtype=odt, device=x.device)
     p = _lib.ConvParams(
         x=_ptr(x), x2=_ptr(x2), w=_ptr(w_packed), bias=_ptr(bias), temb=_ptr(temb), residual=_ptr(residual),
         y=_ptr(y), gn_stats=_ptr(gn_stats), N=N, D=D, H=H, W=W, C1=C1, C2=C2, Cout=cout, Do=Do, Ho=Ho, Wo=Wo,
         ksize=ksize, stride=stride, pad_lo=pad_lo, temb_stride=temb_stride, gn_groups=gn_groups,
-        dtype=dtype_code(x.dtype), engine=engine, out_f32=int(out_f32))
+        dtype=dtype_code(x.dtype), engine=engine, out_f32=int(out_f32), upsample2x=int(upsample2x))
     assert x.is_contiguous() and (x2 is None or x2.is_contiguous())
     assert residual is None or (residual.is_contiguous() and residual.shape == y.shape and residual.dtype == odt)
     ws_bytes = lib.b200ldm_conv3d_workspace_bytes(C.byref(p))
@@ -105,8 +108,10 @@ def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo
     _lib.check(lib.b200ldm_conv3d(C.byref(p), _stream()), "conv3d")
     if ev is not None:
         # algorithmic FLOPs of the (padded) problem the kernel ran: 2*M*Cout*Cin*k^3
-        PROFILER.stop("conv3d", f"{C1 + C2}->{cout} k{ksize}s{stride} @{N}x{Do}x{Ho}x{Wo}",
-                      2.0 * N * Do * Ho * Wo * cout * (C1 + C2) * ksize ** 3, ev)
+        # (fused upsample on tensor cores: 8 of the 27 taps are executed per output voxel - EXECUTED flops)
+        taps = 8 if (upsample2x and x.dtype == torch.bfloat16) else ksize ** 3
+        PROFILER.stop("conv3d", f"{C1 + C2}->{cout} k{ksize}s{stride}{'up' if upsample2x else ''} @{N}x{Do}x{Ho}x{Wo}",
+                      2.0 * N * Do * Ho * Wo * cout * (C1 + C2) * taps, ev)
     return y
 
 
@@ -132,6 +137,17 @@ def repack_conv_weight(w: torch.Tensor, cout_pad: int, cin_pad: int, dtype: torc
     out = torch.empty((ksize ** 3, cout_pad, cin_pad), dtype=dtype, device=w.device)
     _lib.check(lib.b200ldm_repack_conv_weight(w.data_ptr(), out.data_ptr(), cout, cin, ksize, cout_pad, cin_pad,
                                               cin_split, cin_split_pad, dtype_code(dtype), _stream()), "repack")
+    return out
+
+
+def repack_upconv_weight(w: torch.Tensor, cout_pad: int, cin_pad: int, dtype: torch.dtype):
+    """fp32 [Cout,Cin,3,3,3] -> [64 = 8 phases x 8 taps][cout_pad][cin_pad] for the fused nearest-x2 upsample conv."""
+    _need_cuda(w)
+    w = w.detach().to(torch.float32).contiguous()
+    assert w.ndim == 5 and tuple(w.shape[2:]) == (3, 3, 3)
+    out = torch.empty((64, cout_pad, cin_pad), dtype=dtype, device=w.device)
+    _lib.check(_lib.load().b200ldm_repack_upconv_weight(w.data_ptr(), out.data_ptr(), w.shape[0], w.shape[1], cout_pad,
+                                                        cin_pad, dtype_code(dtype), _stream()), "repack_upconv")
     return out
 
 

@@ -13,7 +13,7 @@ struct ConvSimtArgs {
   double* gn_stats;
   int N, D, H, W, C1, C2, Cout, Cout_rows;
   int Do, Ho, Wo;
-  int ksize, stride, pad_lo, temb_stride, gn_groups, out_f32;
+  int ksize, stride, pad_lo, temb_stride, gn_groups, out_f32, up;
   long long M;  // N*Do*Ho*Wo
 };
 
@@ -56,6 +56,10 @@ conv3d_simt_kernel(const ConvSimtArgs a) {
         int iw = wo * a.stride + kw - a.pad_lo;
         int ih = ho * a.stride + kh - a.pad_lo;
         int id = dd * a.stride + kd - a.pad_lo;
+        if (a.up) {  // the conv runs on the (virtual) nearest-upsampled tensor: bounds in 2x space, then >> 1
+          const bool in = iw >= 0 && iw < 2 * a.W && ih >= 0 && ih < 2 * a.H && id >= 0 && id < 2 * a.D;
+          iw = in ? iw >> 1 : -1; ih >>= 1; id >>= 1;
+        }
         if (iw >= 0 && iw < a.W && ih >= 0 && ih < a.H && id >= 0 && id < a.D)
           off = (((long long)n * a.D + id) * a.H + ih) * a.W + iw;
       }
@@ -155,7 +159,7 @@ int conv3d_simt(const b200ldm_conv3d_params* p, cudaStream_t st) {
   a.Cout_rows = (p->Cout + 15) / 16 * 16;
   a.Do = p->Do; a.Ho = p->Ho; a.Wo = p->Wo;
   a.ksize = p->ksize; a.stride = p->stride; a.pad_lo = p->pad_lo; a.temb_stride = p->temb_stride;
-  a.gn_groups = p->gn_groups; a.out_f32 = p->out_f32;
+  a.gn_groups = p->gn_groups; a.out_f32 = p->out_f32; a.up = p->upsample2x ? 1 : 0;
   a.M = (long long)p->N * p->Do * p->Ho * p->Wo;
   dim3 grid((unsigned)ceil_div(a.M, SM_TM), (unsigned)ceil_div(p->Cout, SM_TN), 1);
   if (p->dtype == B200LDM_F32)
@@ -190,7 +194,7 @@ extern "C" int b200ldm_conv3d(const b200ldm_conv3d_params* p, b200ldm_stream str
   B2_REQUIRE(p->stride == 1 || p->stride == 2, B200LDM_BAD_SHAPE, "stride must be 1 or 2 (got %d)", p->stride);
   // output extents must agree with (k, stride, pad_lo) and a pad_hi in {0,1}
   for (int i = 0; i < 3; ++i) {
-    const int in = i == 0 ? p->D : (i == 1 ? p->H : p->W);
+    const int in = (i == 0 ? p->D : (i == 1 ? p->H : p->W)) * (p->upsample2x ? 2 : 1);
     const int out = i == 0 ? p->Do : (i == 1 ? p->Ho : p->Wo);
     const int last = (out - 1) * p->stride + (p->ksize - 1) - p->pad_lo;  // last input index touched
     B2_REQUIRE(last <= in && last >= in - 1 - (p->stride - 1), B200LDM_BAD_SHAPE,

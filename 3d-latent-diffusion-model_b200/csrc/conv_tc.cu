@@ -29,7 +29,7 @@ namespace b200ldm {
 struct ConvTcMaps {
   CUtensorMap a[8];  // stride 1: a[0] = x, a[1] = x2;  stride 2: a[pd*4+ph*2+pw]
   CUtensorMap w;     // [taps][Cout_pad][Cin_total]
-  CUtensorMap y;     // output, same voxel box as the A tiles (TMA-store epilogue)
+  CUtensorMap y[8];  // output, same voxel box as the A tiles (TMA-store epilogue); up mode: one strided map per phase
   CUtensorMap r;     // residual (same geometry as y) when fused
 };
 
@@ -46,6 +46,7 @@ struct ConvTcArgs {
   const void* residual;
   void* y;
   double* gn_stats;
+  int up;                     // 1: nearest-x2 upsample fused as 8 phase convs of 2x2x2 taps (blockIdx.z = phase)
   int splits;                 // split-K: blockIdx.z handles k-iterations [z*I/S, (z+1)*I/S) and writes fp32 slab z
   long long slab_elems;       // elements per fp32 slab (N*Do*Ho*Wo*Cout)
   int ashift;                 // experiment: A sub-tile base shifted by ashift*128 bytes (swizzle-phase probe)
@@ -92,11 +93,13 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int co0 = blockIdx.y * BN;
-  const int taps = a.ksize * a.ksize * a.ksize;
+  const int phase = a.up ? (int)blockIdx.z : 0;   // (a_d, a_h, a_w) = bits 2,1,0: output voxel (2d+a_d, 2h+a_h, 2w+a_w)
+  const int zsplit = a.up ? 0 : (int)blockIdx.z;
+  const int taps = a.up ? 8 : a.ksize * a.ksize * a.ksize;
   const int nchunks = a.nchunk1 + a.nchunk2;
   const int iters_total = taps * nchunks;
-  const int it0 = (int)((long long)blockIdx.z * iters_total / a.splits);
-  const int it1 = (int)((long long)(blockIdx.z + 1) * iters_total / a.splits);
+  const int it0 = (int)((long long)zsplit * iters_total / a.splits);
+  const int it1 = (int)((long long)(zsplit + 1) * iters_total / a.splits);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&maps.w);
@@ -142,7 +145,13 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
         const int tap = it / nchunks;
         const int chunk = it - tap * nchunks;
         int kd = 0, kh = 0, kw = 0;
-        if (a.ksize == 3) { kd = tap / 9; kh = (tap / 3) % 3; kw = tap % 3; }
+        int pad_d = a.pad_lo, pad_h = a.pad_lo, pad_w = a.pad_lo, wtap = tap;
+        if (a.up) {
+          // phase conv: low-res offset = a - 1 + i per dim (i in {0,1}); weights pre-summed per phase
+          kd = tap >> 2; kh = (tap >> 1) & 1; kw = tap & 1;
+          pad_d = 1 - (phase >> 2); pad_h = 1 - ((phase >> 1) & 1); pad_w = 1 - (phase & 1);
+          wtap = phase * 8 + tap;
+        } else if (a.ksize == 3) { kd = tap / 9; kh = (tap / 3) % 3; kw = tap % 3; }
         const uint32_t full = bar_base + 8 * s;
         const uint32_t sa = smem_base + s * Cfg::kStageBytes;
         const uint32_t sb = sa + MT * kABytes;
@@ -153,8 +162,8 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
           const int c0 = (second ? chunk - a.nchunk1 : chunk) * 64;
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
-            ptx::tma_load_5d(sa + mt * kABytes + a.ashift * 128, m, full, c0, w0[mt] + kw - a.pad_lo,
-                             h0[mt] + kh - a.pad_lo, d0[mt] + kd - a.pad_lo, n0[mt]);
+            ptx::tma_load_5d(sa + mt * kABytes + a.ashift * 128, m, full, c0, w0[mt] + kw - pad_w,
+                             h0[mt] + kh - pad_h, d0[mt] + kd - pad_d, n0[mt]);
         } else {
           // input coord = 2*o + k - pad_lo  ->  parity grid (k-pad_lo)&1 at index o + floor((k-pad_lo)/2)
           const int od = kd - a.pad_lo, oh = kh - a.pad_lo, ow = kw - a.pad_lo;
@@ -166,13 +175,13 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
                              h0[mt] + ((oh - ph2) >> 1), d0[mt] + ((od - pd) >> 1), n0[mt]);
         }
         if (CL == 1) {
-          ptx::tma_load_3d(sb, &maps.w, full, chunk * 64, co0, tap);
+          ptx::tma_load_3d(sb, &maps.w, full, chunk * 64, co0, wtap);
         } else {
           // this CTA fetches its 1/CL slice of the weight tile and multicasts it to the same offset in every
           // CTA of the cluster; each CTA's full barrier collects all CL slices (tx_bytes counts the whole tile)
           constexpr int kSliceRows = BN / CL;
           ptx::tma_load_3d_mcast(sb + cta_rank * (kSliceRows * 128), &maps.w, full, chunk * 64,
-                                 co0 + (int)cta_rank * kSliceRows, tap, (uint16_t)((1u << CL) - 1));
+                                 co0 + (int)cta_rank * kSliceRows, wtap, (uint16_t)((1u << CL) - 1));
         }
       }
     }
@@ -222,7 +231,7 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
     const int n = n0 + rn, d = d0 + rd, h = h0 + rh, w = w0 + rw;
     const bool valid = row < a.rows_box && n < a.N && d < a.Do && h < a.Ho && w < a.Wo;
     const size_t vox = (((size_t)n * a.Do + d) * a.Ho + h) * a.Wo + w;
-    const size_t obase = vox * (size_t)a.Cout + (size_t)blockIdx.z * (size_t)a.slab_elems;  // split-K: fp32 slab z
+    const size_t obase = vox * (size_t)a.Cout + (size_t)zsplit * (size_t)a.slab_elems;  // split-K: fp32 slab z
     const float* temb_row = a.temb ? a.temb + (size_t)(a.temb_stride ? n : 0) * a.temb_stride : nullptr;
     const int cpg = a.gn_stats ? a.Cout / a.gn_groups : 1;
     const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * BN);
@@ -304,7 +313,7 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
         ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA store
         asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");  // the 4 warps of this accumulator
         if (issuer) {
-          ptx::tma_store_5d(&maps.y, stg + g * 16384, co0 + g * 64, w0, h0, d0, n0);
+          ptx::tma_store_5d(&maps.y[phase], stg + g * 16384, co0 + g * 64, w0, h0, d0, n0);
           ptx::tma_store_commit();
         }
       }
@@ -587,9 +596,11 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p) {
   else if (p->Cout <= 128) pl.bn = 128;
   else pl.bn = 256;
   pl.n_tiles = ceil_div(p->Cout, pl.bn);
-  choose_conv_tile(p->N, p->Do, p->Ho, p->Wo, &pl.tn, &pl.td, &pl.th, &pl.tw);
-  pl.nb_n = ceil_div(p->N, pl.tn); pl.nb_d = ceil_div(p->Do, pl.td);
-  pl.nb_h = ceil_div(p->Ho, pl.th); pl.nb_w = ceil_div(p->Wo, pl.tw);
+  // M tiles enumerate output voxels; with the fused upsample they enumerate LOW-RES voxels (x 8 phases in grid.z)
+  const int eD = p->upsample2x ? p->D : p->Do, eH = p->upsample2x ? p->H : p->Ho, eW = p->upsample2x ? p->W : p->Wo;
+  choose_conv_tile(p->N, eD, eH, eW, &pl.tn, &pl.td, &pl.th, &pl.tw);
+  pl.nb_n = ceil_div(p->N, pl.tn); pl.nb_d = ceil_div(eD, pl.td);
+  pl.nb_h = ceil_div(eH, pl.th); pl.nb_w = ceil_div(eW, pl.tw);
   pl.m_tiles = pl.nb_n * pl.nb_d * pl.nb_h * pl.nb_w;
   // two M sub-tiles per CTA (shared weight stage) once that still fills the machine
   pl.mt = (ceil_div(pl.m_tiles, 2) * pl.n_tiles >= 148) ? 2 : 1;
@@ -602,7 +613,7 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p) {
   pl.splits = 1;
   const int iters = p->ksize * p->ksize * p->ksize * ((p->C1 + p->C2) / 64);
   const int ctas = ceil_div(pl.m_tiles, pl.mt) * pl.n_tiles;
-  if (pl.mt == 1 && !p->out_f32 && !p->gn_stats && p->Cout % 8 == 0 && ctas < 148) {
+  if (pl.mt == 1 && !p->out_f32 && !p->gn_stats && !p->upsample2x && p->Cout % 8 == 0 && ctas < 148) {
     const double cyc_iter = 512.0 * pl.bn / 256.0 + 64.0, overhead = 14000.0;
     double best = 1e30;
     for (int s = 1; s <= 8 && iters / s >= 16; ++s) {
@@ -612,7 +623,8 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p) {
       if (t < best) { best = t; pl.splits = s; }
     }
   }
-  if (g_force_splits >= 1 && g_force_splits <= 8 && !p->out_f32 && !p->gn_stats && iters / g_force_splits >= 1)
+  if (g_force_splits >= 1 && g_force_splits <= 8 && !p->out_f32 && !p->gn_stats && !p->upsample2x &&
+      iters / g_force_splits >= 1)
     pl.splits = g_force_splits;
   if (pl.splits > 1) pl.cl = 1;
   return pl;
@@ -646,7 +658,12 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
                "fused GroupNorm partials need channels/group a power of two >= 2 (got %d)", cpg);
   }
 
-  const int taps = p->ksize * p->ksize * p->ksize;
+  if (p->upsample2x)
+    B2_REQUIRE(p->ksize == 3 && p->stride == 1 && p->pad_lo == 1 && p->C2 == 0 && !p->out_f32 && !p->gn_stats &&
+                   !p->residual && !p->temb && p->Cout % 64 == 0 && p->Do == 2 * p->D && p->Ho == 2 * p->H &&
+                   p->Wo == 2 * p->W,
+               B200LDM_BAD_SHAPE, "fused upsample conv: needs k3 s1 p1, one source, bf16 out, Cout %% 64 == 0, out = 2x in");
+  const int taps = p->upsample2x ? 64 : p->ksize * p->ksize * p->ksize;  // rows of the packed weight tensor
   const int Cin = p->C1 + p->C2;
   const ConvPlan pl = plan_conv(p);
   const int bn = pl.bn, n_tiles = pl.n_tiles;
@@ -661,6 +678,8 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
   a.tn = pl.tn; a.td = pl.td; a.th = pl.th; a.tw = pl.tw;
   a.nb_d = pl.nb_d; a.nb_h = pl.nb_h; a.nb_w = pl.nb_w;
   a.N = p->N; a.Do = p->Do; a.Ho = p->Ho; a.Wo = p->Wo; a.Cout = p->Cout;
+  a.up = p->upsample2x ? 1 : 0;
+  if (a.up) { a.Do = p->D; a.Ho = p->H; a.Wo = p->W; }  // rows are low-res voxels
   a.splits = pl.splits; a.slab_elems = pl.splits > 1 ? M_total * p->Cout : 0;
   a.nchunk1 = p->C1 / 64; a.nchunk2 = p->C2 / 64;
   a.ksize = p->ksize; a.stride = p->stride; a.pad_lo = p->pad_lo;
@@ -710,11 +729,23 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
   const int cout_rows = (p->Cout + 15) / 16 * 16;
   // coalesced TMA-store epilogue whenever the output is bf16 in whole 64-channel groups
   a.tma_epilogue = (!a.out_f32 && p->Cout % 64 == 0 && !p->gn_stats && bn >= 64 && g_legacy_epilogue == 0) ? 1 : 0;
+  if (a.up) B2_REQUIRE(a.tma_epilogue, B200LDM_BAD_SHAPE, "fused upsample conv needs the TMA epilogue");
   if (a.tma_epilogue) {
     const uint64_t Co = p->Cout, Wo = p->Wo, Ho = p->Ho, Do = p->Do;
-    rc = make_act_map(&maps.y, p->y, p->Cout, p->Wo, p->Ho, p->Do, p->N, Co, Wo * Co, Ho * Wo * Co, Do * Ho * Wo * Co,
-                      a.tw, a.th, a.td, a.tn);
-    if (rc) return rc;
+    if (!a.up) {
+      rc = make_act_map(&maps.y[0], p->y, p->Cout, p->Wo, p->Ho, p->Do, p->N, Co, Wo * Co, Ho * Wo * Co,
+                        Do * Ho * Wo * Co, a.tw, a.th, a.td, a.tn);
+      if (rc) return rc;
+    } else {
+      // phase (a_d,a_h,a_w) writes output voxels (2d+a_d, 2h+a_h, 2w+a_w): a strided view per phase
+      for (int ph = 0; ph < 8; ++ph) {
+        const int ad = ph >> 2, ah = (ph >> 1) & 1, aw = ph & 1;
+        __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(p->y) + ((uint64_t)(ad * Ho + ah) * Wo + aw) * Co;
+        rc = make_act_map(&maps.y[ph], base, p->Cout, p->W, p->H, p->D, p->N, 2 * Co, 2 * Wo * Co, 2 * Ho * Wo * Co,
+                          Do * Ho * Wo * Co, a.tw, a.th, a.td, a.tn);
+        if (rc) return rc;
+      }
+    }
     if (p->residual) {
       rc = make_act_map(&maps.r, p->residual, p->Cout, p->Wo, p->Ho, p->Do, p->N, Co, Wo * Co, Ho * Wo * Co,
                         Do * Ho * Wo * Co, a.tw, a.th, a.td, a.tn);
@@ -726,7 +757,7 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
   // the weight map box holds the rows ONE CTA fetches
   rc = make_weight_map(&maps.w, p->w, Cin, cout_rows, taps, bn / cl);
   if (rc) return rc;
-  const int sp = pl.splits;
+  const int sp = a.up ? 8 : pl.splits;  // grid.z: split-K slabs, or the 8 upsample phases
   switch (bn) {
     case 256: rc = mt == 2 ? (cl == 2 ? launch_conv_tc<256, 2, 2>(maps, a, m_tiles, n_tiles, sp, st)
                                       : launch_conv_tc<256, 2, 1>(maps, a, m_tiles, n_tiles, sp, st))
@@ -742,11 +773,11 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
     default: rc = mt == 2 ? launch_conv_tc<16, 2, 1>(maps, a, m_tiles, n_tiles, sp, st)
                           : launch_conv_tc<16, 1, 1>(maps, a, m_tiles, n_tiles, sp, st);
   }
-  if (rc || sp == 1) return rc;
+  if (rc || pl.splits == 1) return rc;
   const long long vecs = M_total * (p->Cout / 8);
   const unsigned blocks = (unsigned)std::min<long long>((vecs + 255) / 256, 148LL * 16);
   splitk_finalize_kernel<<<blocks, 256, 0, st>>>(
-      reinterpret_cast<const float*>(p->workspace), sp, M_total * p->Cout, M_total, p->Cout,
+      reinterpret_cast<const float*>(p->workspace), pl.splits, M_total * p->Cout, M_total, p->Cout,
       (long long)p->Do * p->Ho * p->Wo, p->bias, p->temb, p->temb_stride,
       reinterpret_cast<const __nv_bfloat16*>(p->residual), reinterpret_cast<__nv_bfloat16*>(p->y));
   B2_LAUNCH_CHECK();

@@ -32,6 +32,37 @@ __global__ void repack_weight_kernel(const float* __restrict__ src, T* __restric
   }
 }
 
+// nearest-x2-upsample + conv3 == 8 phase convs of 2x2x2 taps on the low-res tensor; taps that read the same
+// low-res voxel are summed in fp32 before the single rounding to the storage dtype
+template <typename T>
+__global__ void repack_upconv_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, int Cout, int Cin,
+                                            int Cout_pad, int Cin_pad) {
+  const long long total = 64LL * Cout_pad * Cin_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin_pad);
+    long long t = i / Cin_pad;
+    const int co = (int)(t % Cout_pad);
+    const int pt = (int)(t / Cout_pad);  // phase*8 + tap
+    float v = 0.f;
+    if (co < Cout && ci < Cin) {
+      const int ph = pt >> 3, tp = pt & 7;
+      const int a[3] = {ph >> 2, (ph >> 1) & 1, ph & 1};
+      const int b[3] = {tp >> 2, (tp >> 1) & 1, tp & 1};
+      int lo[3], hi[3];
+      for (int d = 0; d < 3; ++d) {
+        if (a[d] == 0) { lo[d] = b[d] == 0 ? 0 : 1; hi[d] = b[d] == 0 ? 0 : 2; }
+        else           { lo[d] = b[d] == 0 ? 0 : 2; hi[d] = b[d] == 0 ? 1 : 2; }
+      }
+      const float* w = src + ((size_t)co * Cin + ci) * 27;
+      for (int kd = lo[0]; kd <= hi[0]; ++kd)
+        for (int kh = lo[1]; kh <= hi[1]; ++kh)
+          for (int kw = lo[2]; kw <= hi[2]; ++kw) v += w[(kd * 3 + kh) * 3 + kw];
+    }
+    dst[i] = from_f32<T>(v);
+  }
+}
+
 // ------------------------------------------------------------------ layout bridges
 template <typename T>
 __global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int C, long long S,
@@ -247,6 +278,23 @@ int b200ldm_repack_conv_weight(const float* src, void* dst, int32_t Cout, int32_
   else if (dtype == B200LDM_F32)
     repack_weight_kernel<float><<<ew_blocks(total), kEwThreads, 0, (cudaStream_t)stream>>>(
         src, (float*)dst, Cout, Cin, taps, Cout_pad, Cin_pad, cin_split, cin_split_pad);
+  else
+    return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+int b200ldm_repack_upconv_weight(const float* src, void* dst, int32_t Cout, int32_t Cin, int32_t Cout_pad,
+                                 int32_t Cin_pad, int32_t dtype, b200ldm_stream stream) {
+  B2_REQUIRE(src && dst && Cout > 0 && Cin > 0 && Cout_pad >= Cout && Cin_pad >= Cin, B200LDM_BAD_ARG,
+             "repack_upconv_weight: bad arguments");
+  const long long total = 64LL * Cout_pad * Cin_pad;
+  if (dtype == B200LDM_BF16)
+    repack_upconv_weight_kernel<__nv_bfloat16><<<ew_blocks(total), kEwThreads, 0, (cudaStream_t)stream>>>(
+        src, (__nv_bfloat16*)dst, Cout, Cin, Cout_pad, Cin_pad);
+  else if (dtype == B200LDM_F32)
+    repack_upconv_weight_kernel<float><<<ew_blocks(total), kEwThreads, 0, (cudaStream_t)stream>>>(
+        src, (float*)dst, Cout, Cin, Cout_pad, Cin_pad);
   else
     return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);
   B2_LAUNCH_CHECK();

@@ -90,7 +90,9 @@ typedef struct {
   int32_t dtype;         /* b200ldm_dtype of x, x2, w, residual, y */
   int32_t engine;        /* b200ldm_engine */
   int32_t out_f32;       /* 1: y (and residual) are fp32 even when dtype is bf16 */
-  int32_t reserved;
+  int32_t upsample2x;    /* 1: the input is nearest-upsampled x2 on the fly (Do = 2D ...): k3 s1 p1, one source.
+                            bf16/TCGEN05 expects weights from b200ldm_repack_upconv_weight (8 phases x 2^3 taps,
+                            27 -> 8 MACs per output); f32/SIMT takes the ordinary packed weights */
   void* workspace;       /* caller-owned scratch for split-K partial sums (see b200ldm_conv3d_workspace_bytes) */
   int64_t workspace_bytes;
 } b200ldm_conv3d_params;
@@ -106,6 +108,11 @@ int64_t b200ldm_conv3d_workspace_bytes(const b200ldm_conv3d_params* p);
 int b200ldm_repack_conv_weight(const float* src, void* dst, int32_t Cout, int32_t Cin, int32_t ksize,
                                int32_t Cout_pad, int32_t Cin_pad, int32_t cin_split, int32_t cin_split_pad,
                                int32_t dtype, b200ldm_stream stream);
+
+/* Phase-decomposed weights of "nearest x2 upsample -> conv 3x3x3 pad 1" (UNet / AE up-samplers):
+ * dst [64 = phase*8 + (i*4+j*2+k)][Cout_pad][Cin_pad]; per dimension phase 0 sums taps {0 | 1,2}, phase 1 {0,1 | 2}. */
+int b200ldm_repack_upconv_weight(const float* src, void* dst, int32_t Cout, int32_t Cin, int32_t Cout_pad,
+                                 int32_t Cin_pad, int32_t dtype, b200ldm_stream stream);
 
 /* ------------------------------------------------------------------------------------------
  * GroupNorm (+ optional SiLU), NDHWC; replaces F.group_norm + F.silu.

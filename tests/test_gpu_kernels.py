@@ -126,6 +126,35 @@ def test_conv3d_fused_groupnorm_partials(case, engine_dtype):
     assert relerr(stats, want) <= 1e-4, relerr(stats, want)
 
 
+UP_CASES = [(1, (4, 4, 4), 64, 64), (2, (5, 6, 3), 128, 256), (1, (9, 11, 7), 256, 256), (8, (2, 2, 2), 64, 128)]
+
+
+@pytest.mark.parametrize("case", UP_CASES, ids=[f"N{c[0]}_{'x'.join(map(str, c[1]))}_{c[2]}to{c[3]}" for c in UP_CASES])
+@pytest.mark.parametrize("mode", ["tc_bf16", "simt_f32"])
+def test_conv3d_fused_nearest_upsample(case, mode):
+    """conv3(nearest_x2(x)): 8-phase 2x2x2 decomposition on tcgen05 (pre-summed weights), virtual upsample on SIMT."""
+    from b200ldm import ops
+    N, sp, Cin, Cout = case
+    dtype = torch.bfloat16 if mode == "tc_bf16" else torch.float32
+    x = q(rnd((N, Cin) + sp, 81), dtype)
+    w = rnd((Cout, Cin, 3, 3, 3), 82, 1.0 / math.sqrt(Cin * 27))
+    b = rnd((Cout,), 83, 0.1)
+    if mode == "tc_bf16":
+        wp = ops.repack_upconv_weight(w.to(DEV), Cout, Cin, dtype)
+        # reference with the SAME pre-summed, bf16-rounded phase weights is not expressible as one conv3d; compare
+        # against the exact fp64 result of the un-rounded weights with a tolerance covering the weight rounding
+        tol = 1.5e-2
+    else:
+        wp = ops.repack_conv_weight(w.to(DEV), Cout, Cin, dtype)
+        tol = 1e-4
+    ref = F.conv3d(F.interpolate(x.double(), scale_factor=2.0, mode="nearest"), w.double(), b.double(), padding=1)
+    y = ops.conv3d(to_act(x, dtype), wp, b.to(DEV), Cout, 3, 1, 1, 1, upsample2x=True)
+    out = from_act(y, Cout)
+    assert out.shape == ref.shape
+    e = relerr(out, ref)
+    assert e <= tol, e
+
+
 def test_conv3d_rejects_bad_arguments():
     from b200ldm import ops
     x = torch.zeros((1, 4, 4, 4, 48), dtype=torch.bfloat16, device=DEV)
