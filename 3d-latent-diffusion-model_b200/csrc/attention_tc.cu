@@ -11,6 +11,7 @@
 // Warp roles (192 threads): warp0 TMA, warp1 MMA + TMEM owner, warps 2..5 softmax / correction / epilogue.
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -286,6 +287,258 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// v2: two 128-query tiles per CTA, one softmax warpgroup each ("ping-pong"): while warpgroup A runs the exp2 /
+// rescale / P-write of its tile, the tensor core works for warpgroup B (PV_B, S_B of the next KV tile) and vice
+// versa, so neither the MUFU pipe nor the MMA pipe waits on a single dependent chain; K/V tiles are fetched once
+// for both query tiles.  S is single-buffered per warpgroup (S_w(j+1) is issued right after PV_w(j), which already
+// requires P_w(j), i.e. that S_w(j) has been consumed).
+// Warp roles (320 threads): warp0 TMA, warp1 MMA + TMEM owner, warps 2..5 softmax A, warps 6..9 softmax B.
+template <int D, int BN>
+struct Attn2Cfg {
+  static constexpr int kStages = 3;
+  static constexpr int kQBytes = 2 * (D / 64) * 16384;       // two query tiles
+  static constexpr int kKVSub = BN * 128;
+  static constexpr int kKVBytes = (D / 64) * kKVSub;
+  static constexpr int kPBytes = (BN / 64) * 16384;           // per warpgroup
+  static constexpr int kSmem = kQBytes + kStages * 2 * kKVBytes + 2 * kPBytes + 1024 + 256;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kSCol = 0;             // S_w at w*BN
+  static constexpr int kOCol = 2 * BN;        // O_w at kOCol + w*D
+  static constexpr int kThreads = 320;
+  static_assert(2 * BN + 2 * D <= 512, "TMEM budget");
+  static_assert(kSmem <= 232448, "smem budget");
+};
+
+template <int D, int BN>
+__global__ void __launch_bounds__(Attn2Cfg<D, BN>::kThreads, 1)
+attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
+  using Cfg = Attn2Cfg<D, BN>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = smem_base;                                   // tile w at + w*(D/64)*16384
+  const uint32_t kv_smem = q_smem + Cfg::kQBytes;
+  const uint32_t p_smem = kv_smem + STAGES * 2 * Cfg::kKVBytes;        // P_w at + w*kPBytes
+  const uint32_t bar = p_smem + 2 * Cfg::kPBytes;
+  const uint32_t q_full = bar;
+  const uint32_t kv_full = bar + 8;                  // [STAGES]
+  const uint32_t kv_empty = kv_full + 8 * STAGES;    // [STAGES]
+  const uint32_t s_full = kv_empty + 8 * STAGES;     // [2]  (per warpgroup)
+  const uint32_t p_full = s_full + 16;               // [2]
+  const uint32_t pv_done = p_full + 16;              // [2]
+  const uint32_t tmem_slot = pv_done + 16;
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int ntiles = (a.L + BN - 1) / BN;
+  const int col0 = h * D;
+  const bool tileB_exists = q0 + 128 < a.L;   // CTA-uniform: the second query tile may be entirely past L
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&maps.q); ptx::prefetch_tmap(&maps.k); ptx::prefetch_tmap(&maps.v);
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(kv_full + 8 * s, 1); ptx::mbar_init(kv_empty + 8 * s, 1); }
+    for (int w = 0; w < 2; ++w) {
+      ptx::mbar_init(s_full + 8 * w, 1);
+      ptx::mbar_init(p_full + 8 * w, 128);
+      ptx::mbar_init(pv_done + 8 * w, 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const int nw = tileB_exists ? 2 : 1;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      ptx::mbar_expect_tx(q_full, Cfg::kQBytes);
+#pragma unroll
+      for (int w = 0; w < 2; ++w)
+#pragma unroll
+        for (int sub = 0; sub < D / 64; ++sub)
+          ptx::tma_load_3d(q_smem + (w * (D / 64) + sub) * 16384, &maps.q, q_full, col0 + sub * 64, q0 + w * 128, b);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % STAGES;
+        const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
+        ptx::mbar_wait(kv_empty + 8 * s, ph ^ 1u, 10);
+        const uint32_t ks = kv_smem + s * 2 * Cfg::kKVBytes, vs = ks + Cfg::kKVBytes;
+        ptx::mbar_expect_tx(kv_full + 8 * s, 2 * Cfg::kKVBytes);
+#pragma unroll
+        for (int sub = 0; sub < D / 64; ++sub) {
+          ptx::tma_load_3d(ks + sub * Cfg::kKVSub, &maps.k, kv_full + 8 * s, col0 + sub * 64, j * BN, b);
+          ptx::tma_load_3d(vs + sub * Cfg::kKVSub, &maps.v, kv_full + 8 * s, col0 + sub * 64, j * BN, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, BN);
+      constexpr uint32_t idesc_o = ptx::umma_idesc_bf16_bmn(128, D);
+      auto issue_s = [&](int w, int j) {   // S_w(j) = Q_w K_j^T (K_j must have landed)
+        const uint32_t ks = kv_smem + (j % STAGES) * 2 * Cfg::kKVBytes;
+        const uint32_t qs = q_smem + w * (D / 64) * 16384;
+        const uint32_t tS = tmem + Cfg::kSCol + w * BN;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint64_t da = ptx::umma_desc_k_sw128(qs + (kk >> 2) * 16384 + (kk & 3) * 32);
+          const uint64_t db = ptx::umma_desc_k_sw128(ks + (kk >> 2) * Cfg::kKVSub + (kk & 3) * 32);
+          ptx::umma_bf16(tS, da, db, idesc_s, kk > 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(s_full + 8 * w);
+      };
+      ptx::mbar_wait(q_full, 0, 13);
+      ptx::mbar_wait(kv_full, 0, 11);
+      ptx::tc_fence_after();
+      for (int w = 0; w < nw; ++w) issue_s(w, 0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % STAGES;
+        const uint32_t vs = kv_smem + s * 2 * Cfg::kKVBytes + Cfg::kKVBytes;
+        for (int w = 0; w < nw; ++w) {
+          ptx::mbar_wait(p_full + 8 * w, (uint32_t)j & 1u, 14);   // P_w(j) staged, S_w(j) consumed, O_w rescaled
+          ptx::tc_fence_after();
+          const uint32_t ps = p_smem + w * Cfg::kPBytes;
+          const uint32_t tO = tmem + Cfg::kOCol + w * D;
+#pragma unroll
+          for (int kk = 0; kk < BN / 16; ++kk) {
+            const uint64_t da = ptx::umma_desc_k_sw128(ps + (kk >> 2) * 16384 + (kk & 3) * 32);
+            const uint64_t db = umma_desc_mn_sw128(vs + kk * 2048, Cfg::kKVSub, 1024);
+            ptx::umma_bf16(tO, da, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(pv_done + 8 * w);
+          if (w == nw - 1) ptx::umma_commit(kv_empty + 8 * s);   // both PV(j) issued: K/V stage reusable when they retire
+          if (j + 1 < ntiles) {
+            if (w == 0) {
+              ptx::mbar_wait(kv_full + 8 * ((j + 1) % STAGES), (uint32_t)((j + 1) / STAGES) & 1u, 11);
+              ptx::tc_fence_after();
+            }
+            issue_s(w, j + 1);
+          }
+        }
+      }
+    }
+  } else {
+    // =========================== softmax warpgroups ===========================
+    const int w = (warp - 2) >> 2;          // 0 = A, 1 = B
+    if (w < nw) {
+      const int qd = warp & 3;
+      const int row = qd * 32 + lane;
+      const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+      float m_used = -INFINITY, l_sum = 0.f;
+      uint8_t* p_gen = smem_gen + (p_smem - smem_base) + (size_t)w * Cfg::kPBytes;
+      const uint32_t tS = tmem + lane_off + Cfg::kSCol + w * BN;
+      const uint32_t tO = tmem + lane_off + Cfg::kOCol + w * D;
+
+      for (int j = 0; j < ntiles; ++j) {
+        ptx::mbar_wait(s_full + 8 * w, (uint32_t)j & 1u, 20);
+        ptx::tc_fence_after();
+        float sv[BN];
+#pragma unroll
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld32(tS + c, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sv[c + i] = __uint_as_float(r[i]);
+        }
+        const int kvalid = a.L - j * BN;
+        if (kvalid < BN) {
+#pragma unroll
+          for (int i = 0; i < BN; ++i)
+            if (i >= kvalid) sv[i] = -INFINITY;
+        }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < BN; i += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], sv[i + u]);
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * a.scale_log2;
+        const bool need = mx > m_used + 8.0f;
+        const bool any_need = __any_sync(0xffffffffu, need);
+        float alpha = 1.0f;
+        if (j > 0) ptx::mbar_wait(pv_done + 8 * w, (uint32_t)(j - 1) & 1u, 21);  // PV_w(j-1) retired
+        if (any_need) {
+          if (need) {
+            alpha = exp2f(m_used - mx);
+            m_used = mx;
+            l_sum *= alpha;
+          }
+          if (j > 0) {
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < D; c += 16) {
+              uint32_t r[16];
+              ptx::tmem_ld16(tO + c, r);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+              ptx::tmem_st16(tO + c, r);
+            }
+            ptx::tmem_st_wait();
+          }
+        }
+        const float neg_m = -m_used;
+        float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c8 = 0; c8 < BN / 8; ++c8) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float p0 = ex2_approx(fmaf(sv[c8 * 8 + 2 * e], a.scale_log2, neg_m));
+            const float p1 = ex2_approx(fmaf(sv[c8 * 8 + 2 * e + 1], a.scale_log2, neg_m));
+            ps4[e] += p0 + p1;
+            const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+            pk[e] = *reinterpret_cast<const uint32_t*>(&hb);
+          }
+          const int sub = c8 >> 3, cc = c8 & 7;
+          uint4* dst = reinterpret_cast<uint4*>(p_gen + sub * 16384 + row * 128 + ((cc ^ (row & 7)) << 4));
+          *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+        ptx::fence_proxy_async();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(p_full + 8 * w);
+      }
+      // ---- epilogue
+      ptx::mbar_wait(pv_done + 8 * w, (uint32_t)(ntiles - 1) & 1u, 22);
+      ptx::tc_fence_after();
+      const int qi = q0 + w * 128 + row;
+      const float inv = 1.0f / l_sum;
+      __nv_bfloat16* orow = a.o + ((size_t)b * a.L + (qi < a.L ? qi : 0)) * ((size_t)a.H * D) + col0;
+#pragma unroll
+      for (int c = 0; c < D; c += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld16(tO + c, r);
+        ptx::tmem_ld_wait();
+        if (qi < a.L) {
+          float f[8];
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[hlf * 8 + e]) * inv;
+            Vec8<__nv_bfloat16>::store(orow + c + hlf * 8, f);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<Cfg::kTmemCols>(tmem);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host
 static PFN_cuTensorMapEncodeTiled_v12000 attn_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -338,6 +591,33 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
   return B200LDM_OK;
 }
 
+template <int D, int BN>
+static int launch_attention_tc2(const void* q, const void* k, const void* v, void* o, int B, int H, int L, long long ld,
+                                float scale, cudaStream_t st) {
+  using Cfg = Attn2Cfg<D, BN>;
+  AttnMaps maps;
+  int rc;
+  if ((rc = make_qkv_map(&maps.q, q, H * D, L, B, ld, 128))) return rc;
+  if ((rc = make_qkv_map(&maps.k, k, H * D, L, B, ld, BN))) return rc;
+  if ((rc = make_qkv_map(&maps.v, v, H * D, L, B, ld, BN))) return rc;
+  AttnArgs a{H, L, D, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o)};
+  static bool attr_done = false;
+  if (!attr_done) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<D, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmem));
+    attr_done = true;
+  }
+  dim3 grid((unsigned)ceil_div(L, 256), (unsigned)H, (unsigned)B);
+  attention_tc2_kernel<D, BN><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, a);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+static const int g_attn_v = [] {
+  const char* e = getenv("B200LDM_ATTN_VERSION");
+  return e ? atoi(e) : 2;
+}();
+
 bool attention_tcgen05_supported(int d) { return d == 64 || d == 128 || d == 256; }
 
 int attention_tcgen05(const void* q, const void* k, const void* v, void* o, int B, int H, int L, int d, long long ld,
@@ -346,6 +626,11 @@ int attention_tcgen05(const void* q, const void* k, const void* v, void* o, int 
              d);
   B2_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && ld % 8 == 0, B200LDM_BAD_ALIGN,
              "attention: pointers / row stride must be 16-byte aligned");
+  // v2 (two query tiles + two softmax warpgroups per CTA) once there are at least two query tiles
+  if (g_attn_v >= 2 && L > 128) {
+    if (d == 64) return launch_attention_tc2<64, 128>(q, k, v, o, B, H, L, ld, scale, st);
+    if (d == 128) return launch_attention_tc2<128, 64>(q, k, v, o, B, H, L, ld, scale, st);
+  }
   if (d == 64) return launch_attention_tc<64, 128>(q, k, v, o, B, H, L, ld, scale, st);
   if (d == 128) return launch_attention_tc<128, 128>(q, k, v, o, B, H, L, ld, scale, st);
   return launch_attention_tc<256, 64>(q, k, v, o, B, H, L, ld, scale, st);

@@ -4,6 +4,8 @@
 //   stats pass : 1 read;  apply pass : 1 read + 1 write  (algorithmic bytes)
 // Thread mapping: a thread owns one 8-channel vector position `cv` for its whole life, so its
 // group ids, gamma/beta and mean/rstd are loop invariant; it strides over voxels.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200ldm {
@@ -11,7 +13,7 @@ namespace b200ldm {
 constexpr int kNormThreads = 256;
 
 template <typename T>
-__global__ void __launch_bounds__(kNormThreads)
+__global__ void __launch_bounds__(kNormThreads, 4)
 gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ x2, double* __restrict__ stats, long long S,
                 int C1, int C2, int G, int vox_per_block) {
   extern __shared__ float sh[];  // [2*G]
@@ -72,8 +74,8 @@ gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ x2, double* __res
     atomicAdd(stats + (size_t)n * 2 * G + i, (double)sh[i]);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kNormThreads)
+template <typename T, int UNROLL, int MINB>
+__global__ void __launch_bounds__(kNormThreads, MINB)
 gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict__ y,
                 const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                 long long S, int C1, int C2, int G, float eps, int silu, int vox_per_block, double inv_cnt_arg) {
@@ -116,12 +118,12 @@ gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict
   const int Cs = second ? C2 : C1;
   const T* src = (second ? x2 : x) + ((size_t)n * S) * Cs + (size_t)(second ? cv * 8 - C1 : cv * 8);
   long long v = v0 + vslot;
-  for (; v + 3LL * vpp < v1; v += 4LL * vpp) {
-    float f[4][8];
+  for (; v + (long long)(UNROLL - 1) * vpp < v1; v += (long long)UNROLL * vpp) {
+    float f[UNROLL][8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) Vec8<T>::load(src + (size_t)(v + (long long)u * vpp) * Cs, f[u]);
+    for (int u = 0; u < UNROLL; ++u) Vec8<T>::load(src + (size_t)(v + (long long)u * vpp) * Cs, f[u]);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float t = fmaf(f[u][e], sc[e], sf[e]);
@@ -197,12 +199,23 @@ int b200ldm_groupnorm_apply(const void* x, const void* x2, void* y, const double
   int rc = norm_geometry(N, S, C1 + C2, G, &vpb, &grid);
   if (rc) return rc;
   const double inv_cnt = 1.0 / ((double)S * (double)((C1 + C2) / G));
-  if (dtype == B200LDM_BF16)
-    gn_apply_kernel<__nv_bfloat16><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)x2, (__nv_bfloat16*)y, stats, gamma, beta, S, C1, C2, G, eps,
-        silu, vpb, inv_cnt);
-  else if (dtype == B200LDM_F32)
-    gn_apply_kernel<float><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(
+  static const int variant = [] { const char* e = getenv("B200LDM_GN_VARIANT"); return e ? atoi(e) : 0; }();
+#define GN_APPLY_BF16(U, B)                                                                                      \
+  gn_apply_kernel<__nv_bfloat16, U, B><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(                         \
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)x2, (__nv_bfloat16*)y, stats, gamma, beta, S, C1, C2, G, eps, \
+      silu, vpb, inv_cnt)
+  if (dtype == B200LDM_BF16) {
+    switch (variant) {
+      case 1: GN_APPLY_BF16(1, 8); break;
+      case 2: GN_APPLY_BF16(2, 6); break;
+      case 3: GN_APPLY_BF16(2, 4); break;
+      case 4: GN_APPLY_BF16(4, 4); break;
+      case 5: GN_APPLY_BF16(8, 2); break;
+      case 6: GN_APPLY_BF16(4, 3); break;
+      default: GN_APPLY_BF16(4, 4); break;  // best of the on-GPU sweep (scripts/gn_bench.py): 5.1-5.8 TB/s
+    }
+  } else if (dtype == B200LDM_F32)
+    gn_apply_kernel<float, 4, 3><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(
         (const float*)x, (const float*)x2, (float*)y, stats, gamma, beta, S, C1, C2, G, eps, silu, vpb, inv_cnt);
   else
     return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);

@@ -8,7 +8,8 @@ from b200ldm import _lib, ops
 lib = _lib.load()
 lib.b200ldm_debug_set_conv_trace.argtypes = [ctypes.c_void_p]
 dev = "cuda"
-N, D, H, W, C, Cout = 8, 36, 44, 28, int(os.environ.get("CIN", 256)), 256
+D, H, W = (int(v) for v in os.environ.get("DHW", "36,44,28").split(","))
+N, C, Cout = 8, int(os.environ.get("CIN", 256)), int(os.environ.get("COUT", 256))
 x = torch.randn((N, D, H, W, C), device=dev).bfloat16()
 w = ops.repack_conv_weight(torch.randn((Cout, C, 3, 3, 3), device=dev) / math.sqrt(C * 27), Cout, C, torch.bfloat16)
 b = torch.zeros(Cout, device=dev)
@@ -30,4 +31,4 @@ vals = [t[:, 1] - t[:, 0], t[:, 2] - t[:, 1], t[:, 3] - t[:, 2], t[:, 4] - t[:, 
 for n, v in zip(names, vals):
     print(f"{n:36s} mean {v.mean():10.0f}  p10 {v.quantile(0.1):10.0f}  p90 {v.quantile(0.9):10.0f} cycles")
 iters = 27 * C // 64
-print("ideal MMA cycles per CTA:", iters * 8 * 128, " mainloop/ideal:", ((t[:, 2] - t[:, 1]).mean() / (iters * 8 * 128)).item())
+print("iters", iters, "ideal MMA cycles per CTA (MT=2,BN=256):", iters * 8 * 128, " mainloop/ideal:", ((t[:, 2] - t[:, 1]).mean() / (iters * 8 * 128)).item())

@@ -30,6 +30,12 @@ def report(title, fn, n=2):
         fn()
     torch.cuda.synchronize()
     kinds, tags = ops.PROFILER.summary()
+    dump = os.environ.get("TAGDUMP")
+    if dump:
+        for i, (kind, tag, work, e0, e1) in enumerate(ops.PROFILER.records):
+            if dump in tag:
+                prev = ops.PROFILER.records[i - 1]
+                print(f"   [{i}] {kind} {tag}: {e0.elapsed_time(e1):.3f} ms  (prev: {prev[0]} {prev[1]} {prev[3].elapsed_time(prev[4]):.3f} ms; gap {prev[4].elapsed_time(e0):.3f} ms)")
     ops.PROFILER = None
     tot = sum(v["ms"] for v in kinds.values()) / n
     print(f"== {title}: profiled kernels {tot:.3f} ms")
@@ -37,7 +43,7 @@ def report(title, fn, n=2):
         rate = v["work"] / (v["ms"] * 1e-3)
         unit = f"{rate / 1e12:7.1f} TF/s" if k in ("conv3d", "attention") else f"{rate / 1e9:7.0f} GB/s"
         print(f"   {k:10s} {v['ms'] / n:8.3f} ms  {v['launches'] // n:4d} launches  {unit}")
-    for (k, t), v in sorted(tags.items(), key=lambda kv: -kv[1]["ms"])[:14]:
+    for (k, t), v in sorted(tags.items(), key=lambda kv: -kv[1]["ms"])[:int(os.environ.get("TOPN", 14))]:
         rate = v["work"] / (v["ms"] * 1e-3)
         unit = f"{rate / 1e12:7.1f} TF/s" if k in ("conv3d", "attention") else f"{rate / 1e9:7.0f} GB/s"
         print(f"      {k:9s} {t:38s} {v['ms'] / n:7.3f} ms x{v['launches'] // n:3d} {unit}")
