@@ -25,7 +25,7 @@ class ConvParams(C.Structure):
         ("ksize", C.c_int32), ("stride", C.c_int32), ("pad_lo", C.c_int32),
         ("temb_stride", C.c_int32), ("gn_groups", C.c_int32), ("dtype", C.c_int32),
         ("engine", C.c_int32), ("out_f32", C.c_int32), ("upsample2x", C.c_int32),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("chunk_stats", C.c_void_p),
     ]
 
 
@@ -48,11 +48,14 @@ SIGNATURES = {
     "b200ldm_launch_count": (C.c_uint64, []),
     "b200ldm_conv3d": (C.c_int, [C.POINTER(ConvParams), _vp]),
     "b200ldm_conv3d_workspace_bytes": (C.c_int64, [C.POINTER(ConvParams)]),
+    "b200ldm_conv3d_emits_chunk_stats": (C.c_int, [C.POINTER(ConvParams)]),
     "b200ldm_repack_conv_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200ldm_repack_upconv_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200ldm_groupnorm_stats": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp]),
     "b200ldm_groupnorm_apply": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _f32, _i32,
                                           _i32, _vp]),
+    "b200ldm_groupnorm_apply_chunked": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _f32,
+                                                  _i32, _i32, _vp]),
     "b200ldm_fill_zero": (C.c_int, [_vp, _sz, _vp]),
     "b200ldm_attention": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _f32, _i32, _i32, _vp]),
     "b200ldm_upsample_nearest2x": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),

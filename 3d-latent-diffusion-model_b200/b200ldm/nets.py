@@ -25,7 +25,9 @@ _PREC = {"bf16": torch.bfloat16, "fp32": torch.float32}
 # GroupNorm partial sums accumulated in the producing conv's epilogue.  Measured (profiles/r01_ncu_conv3d_tc_first.md):
 # +0.35 ms per big conv vs 0.06 ms for the standalone stats kernel while the epilogue is not overlapped with the
 # MMA main loop, so it is opt-in for now.
-FUSE_GN_STATS = os.environ.get("B200LDM_FUSE_GN_STATS", "0") != "0"
+#   Superseded by the per-8-channel "chunk stats" of the TMA epilogue (ops.FUSE_GN_STATS, on by default); this flag
+#   only keeps the older per-group variant of the direct-store epilogue reachable for experiments.
+FUSE_GN_STATS = os.environ.get("B200LDM_FUSE_GN_GROUPSTATS", "0") != "0"
 
 
 FUSE_UPSAMPLE = os.environ.get("B200LDM_FUSE_UPSAMPLE", "1") != "0"
@@ -86,14 +88,14 @@ class Conv(nn.Module):
         return self._cache.get((dtype, c1, c1_phys, cin_phys), (self.weight, self.bias), build)
 
     def run(self, x, x2=None, c1: int | None = None, temb=None, temb_stride: int = 0, residual=None, gn_stats=None,
-            gn_groups: int = 0, out_f32: bool = False):
+            gn_groups: int = 0, out_f32: bool = False, want_stats: bool = False):
         if x2 is None:
             w, b = self.packed(x.dtype, cin_phys=x.shape[-1])
         else:
             w, b = self.packed(x.dtype, c1=c1, c1_phys=x.shape[-1], cin_phys=x.shape[-1] + x2.shape[-1])
         return ops.conv3d(x, w, b, self.cout_phys, self.ksize, self.stride, self.pad_lo, self.pad_hi, x2=x2, temb=temb,
                           temb_stride=temb_stride, residual=residual, gn_stats=gn_stats, gn_groups=gn_groups,
-                          out_f32=out_f32)
+                          out_f32=out_f32, want_stats=want_stats)
 
 
     def run_upsampled(self, x):
@@ -111,8 +113,8 @@ class Conv(nn.Module):
         else:
             w, b = self.packed(x.dtype, cin_phys=cin_phys)
             if not FUSE_UPSAMPLE:
-                return ops.conv3d(ops.upsample_nearest2x(x), w, b, self.cout_phys, 3, 1, 1, 1)
-        return ops.conv3d(x, w, b, self.cout_phys, 3, 1, 1, 1, upsample2x=True)
+                return ops.conv3d(ops.upsample_nearest2x(x), w, b, self.cout_phys, 3, 1, 1, 1, want_stats=True)
+        return ops.conv3d(x, w, b, self.cout_phys, 3, 1, 1, 1, upsample2x=True, want_stats=True)
 
 
 class ConvOnly(nn.Module):
@@ -201,8 +203,8 @@ class SABlock(nn.Module):
         qkv = ops.linear(xn.reshape(B * L, Cc), wqkv, bqkv, 3 * Cc)
         att = ops.attention(qkv.reshape(B, L, 3 * Cc), self.heads, self.head_dim, self.scale)
         wo, bo = self.out_proj.packed(xn.dtype)
-        y = ops.linear(att.reshape(B * L, Cc), wo, bo, Cc, residual=residual.reshape(B * L, Cc))
-        return y.reshape(shp)
+        # 1x1x1 conv on the 5-D view (keeps the per-sample axis so the epilogue can emit GroupNorm chunk stats)
+        return ops.conv3d(att.reshape(shp), wo, bo, Cc, ksize=1, stride=1, pad_lo=0, residual=residual, want_stats=True)
 
 
 class SpatialAttentionBlock(nn.Module):
@@ -249,13 +251,14 @@ class UNetResBlock(nn.Module):
         cpg = self.cout // self.groups
         if FUSE_GN_STATS and cpg >= 2 and (cpg & (cpg - 1)) == 0:
             stats = ops.zeros_f64(x.shape[0] * self.groups * 2, x.device)
-        h = self.conv1.run(h, temb=temb, temb_stride=temb_stride, gn_stats=stats, gn_groups=self.groups)
+        h = self.conv1.run(h, temb=temb, temb_stride=temb_stride, gn_stats=stats, gn_groups=self.groups,
+                           want_stats=stats is None)
         h = self.norm2.run(h, silu=True, stats=stats)
         if isinstance(self.skip_connection, nn.Identity):
             res = x
         else:
             res = self.skip_connection.run(x, x2=x2, c1=None if x2 is None else x.shape[-1])
-        return self.conv2.run(h, residual=res)
+        return self.conv2.run(h, residual=res, want_stats=True)
 
 
 class _DownOp(nn.Module):
@@ -428,7 +431,7 @@ class DiffusionModelUNet(nn.Module):
             i = next(it)
             return temb_all[:, offs[i]:]  # pointer offset only; the kernel strides rows by temb_stride
 
-        h = self.conv_in.run(x)
+        h = self.conv_in.run(x, want_stats=True)
         skips = [h]
         for blk in self.down_blocks:
             for j, r in enumerate(blk.resnets):
@@ -437,7 +440,7 @@ class DiffusionModelUNet(nn.Module):
                     h = blk.attentions[j].run(h)
                 skips.append(h)
             if blk.downsampler is not None:
-                h = blk.downsampler.op.run(h)
+                h = blk.downsampler.op.run(h, want_stats=True)
                 skips.append(h)
         mb = self.middle_block
         h = mb.resnet_1.run(h, temb_for(), temb_stride)
@@ -494,10 +497,10 @@ class AEResBlock(nn.Module):
         cpg = self.cout // self.groups
         if FUSE_GN_STATS and cpg >= 2 and (cpg & (cpg - 1)) == 0:
             stats = ops.zeros_f64(x.shape[0] * self.groups * 2, x.device)
-        h = self.conv1.run(h, gn_stats=stats, gn_groups=self.groups)
+        h = self.conv1.run(h, gn_stats=stats, gn_groups=self.groups, want_stats=stats is None)
         h = self.norm2.run(h, silu=True, stats=stats)
         res = x if isinstance(self.nin_shortcut, nn.Identity) else self.nin_shortcut.run(x)
-        return self.conv2.run(h, residual=res)
+        return self.conv2.run(h, residual=res, want_stats=True)
 
 
 class AEDownsample(nn.Module):
@@ -507,8 +510,8 @@ class AEDownsample(nn.Module):
         super().__init__()
         self.conv = ConvOnly(ch, ch, 3, 2, 0, 1)
 
-    def run(self, x):
-        return self.conv.run(x)
+    def run(self, x, want_stats=False):
+        return self.conv.run(x, want_stats=want_stats)
 
 
 class _AEStack(nn.Module):
@@ -516,6 +519,8 @@ class _AEStack(nn.Module):
         for b in self.blocks:
             if isinstance(b, GroupNorm):
                 x = b.run(x, silu=False)
+            elif isinstance(b, (ConvOnly, AEDownsample)):
+                x = b.run(x, want_stats=True)
             else:
                 x = b.run(x)
         return x

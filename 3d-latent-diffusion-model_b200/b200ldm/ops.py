@@ -45,6 +45,8 @@ class KernelProfiler:
 
 
 PROFILER: KernelProfiler | None = None
+# GroupNorm statistics fused into the producing conv's epilogue (per-8-channel chunk sums)
+FUSE_GN_STATS = __import__("os").environ.get("B200LDM_FUSE_GN_STATS", "1") != "0"
 
 
 def dtype_code(t: torch.dtype) -> int:
@@ -79,10 +81,12 @@ def conv_out_extent(n: int, k: int, stride: int, pad_lo: int, pad_hi: int) -> in
 
 def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo: int = 1, pad_hi: int | None = None,
            x2=None, temb=None, temb_stride: int = 0, residual=None, gn_stats=None, gn_groups: int = 0,
-           out_f32: bool = False, engine: int = ENGINE_AUTO, upsample2x: bool = False):
+           out_f32: bool = False, engine: int = ENGINE_AUTO, upsample2x: bool = False, want_stats: bool = False):
     """y = conv3d(cat(x, x2)) + bias (+ temb) (+ residual); x: [N,D,H,W,C1] NDHWC.
     upsample2x: the conv runs on the nearest-x2-upsampled x without materialising it (bf16: phase-decomposed
-    weights from repack_upconv_weight; fp32: ordinary weights)."""
+    weights from repack_upconv_weight; fp32: ordinary weights).
+    want_stats: when the tensor-core epilogue can, it also accumulates per-8-channel (sum, sumsq) of y; the result is
+    attached as `y.cstats` and lets the following GroupNorm skip its statistics pass."""
     _need_cuda(x, x2, w_packed, bias, temb, residual)
     lib = _lib.load()
     N, D, H, W, C1 = x.shape
@@ -104,8 +108,14 @@ def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo
     if ws_bytes > 0:  # split-K partial sums (small-M convs): caller-owned scratch
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
+    cstats = None
+    if want_stats and FUSE_GN_STATS and lib.b200ldm_conv3d_emits_chunk_stats(C.byref(p)):
+        cstats = zeros_f64(N * (cout // 8) * 2, x.device)
+        p.chunk_stats = cstats.data_ptr()
     ev = PROFILER.start() if PROFILER is not None else None
     _lib.check(lib.b200ldm_conv3d(C.byref(p), _stream()), "conv3d")
+    if cstats is not None:
+        y.cstats = cstats
     if ev is not None:
         # algorithmic FLOPs of the (padded) problem the kernel ran: 2*M*Cout*Cin*k^3
         # (fused upsample on tensor cores: 8 of the 27 taps are executed per output voxel - EXECUTED flops)
@@ -167,6 +177,17 @@ def groupnorm(x, gamma, beta, groups: int, eps: float, silu: bool, x2=None, stat
     S = x.numel() // (N * C1)
     dt = dtype_code(x.dtype)
     nbytes = float(N * S * (C1 + C2) * x.element_size())
+    cs1, cs2 = getattr(x, "cstats", None), (None if x2 is None else getattr(x2, "cstats", None))
+    if stats is None and cs1 is not None and (x2 is None or cs2 is not None) and ((C1 + C2) // groups) % 8 == 0:
+        # statistics already accumulated by the producing conv(s): one pass only
+        y = torch.empty(x.shape[:-1] + (C1 + C2,), dtype=x.dtype, device=x.device)
+        ev = PROFILER.start() if PROFILER is not None else None
+        _lib.check(lib.b200ldm_groupnorm_apply_chunked(_ptr(x), _ptr(x2), y.data_ptr(), cs1.data_ptr(), _ptr(cs2),
+                                                       gamma.data_ptr(), beta.data_ptr(), N, S, C1, C2, groups,
+                                                       float(eps), int(silu), dt, _stream()), "groupnorm_apply_chunked")
+        if ev is not None:
+            PROFILER.stop("gn_apply", f"C{C1 + C2} S{S}", 2.0 * nbytes, ev)
+        return y
     if stats is None:
         stats = zeros_f64(N * groups * 2, x.device)
         ev = PROFILER.start() if PROFILER is not None else None

@@ -172,8 +172,17 @@ int conv3d_simt(const b200ldm_conv3d_params* p, cudaStream_t st) {
 
 int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st);
 long long conv3d_tcgen05_workspace_bytes(const b200ldm_conv3d_params* p);
+int conv3d_tcgen05_emits_chunk_stats(const b200ldm_conv3d_params* p);
 
 }  // namespace b200ldm
+
+extern "C" int b200ldm_conv3d_emits_chunk_stats(const b200ldm_conv3d_params* p) {
+  if (!p) return 0;
+  int engine = p->engine;
+  if (engine == B200LDM_ENGINE_AUTO)
+    engine = (p->dtype == B200LDM_BF16) ? B200LDM_ENGINE_TCGEN05 : B200LDM_ENGINE_SIMT;
+  return engine == B200LDM_ENGINE_TCGEN05 ? b200ldm::conv3d_tcgen05_emits_chunk_stats(p) : 0;
+}
 
 extern "C" int64_t b200ldm_conv3d_workspace_bytes(const b200ldm_conv3d_params* p) {
   if (!p) return 0;
@@ -205,6 +214,9 @@ extern "C" int b200ldm_conv3d(const b200ldm_conv3d_params* p, b200ldm_stream str
   if (engine == B200LDM_ENGINE_AUTO)
     engine = (p->dtype == B200LDM_BF16) ? B200LDM_ENGINE_TCGEN05 : B200LDM_ENGINE_SIMT;
   if (engine == B200LDM_ENGINE_TCGEN05) return conv3d_tcgen05(p, (cudaStream_t)stream);
-  if (engine == B200LDM_ENGINE_SIMT) return conv3d_simt(p, (cudaStream_t)stream);
+  if (engine == B200LDM_ENGINE_SIMT) {
+    B2_REQUIRE(!p->chunk_stats, B200LDM_BAD_ARG, "chunk_stats is a tensor-core epilogue feature");
+    return conv3d_simt(p, (cudaStream_t)stream);
+  }
   return fail(B200LDM_BAD_ARG, "unknown engine %d", p->engine);
 }

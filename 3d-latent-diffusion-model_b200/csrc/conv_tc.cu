@@ -46,6 +46,7 @@ struct ConvTcArgs {
   const void* residual;
   void* y;
   double* gn_stats;
+  double* chunk_stats;        // [N][Cout/8][2] (sum, sumsq) per 8-channel chunk of y, accumulated by the TMA epilogue
   int up;                     // 1: nearest-x2 upsample fused as 8 phase convs of 2x2x2 taps (blockIdx.z = phase)
   int splits;                 // split-K: blockIdx.z handles k-iterations [z*I/S, (z+1)*I/S) and writes fp32 slab z
   long long slab_elems;       // elements per fp32 slab (N*Do*Ho*Wo*Cout)
@@ -67,7 +68,7 @@ struct ConvTcCfg {
   static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
   static constexpr int kTmemCols = (MT * BN) < 32 ? 32 : (MT * BN);
   static constexpr int kThreads = 64 + MT * 128;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*stats*/;
   static_assert(kStages >= 2, "pipeline needs at least two stages");
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns must be a power of two <= 512");
 };
@@ -251,6 +252,14 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
       uint8_t* stg_gen = smem_gen + (size_t)mt * (G * 16384);
       const bool issuer = (((warp - 2) & 3) == 0) && lane == 0;
       const int gmax = min(G, (a.Cout - co0 + 63) / 64);  // groups that exist in this Cout tile (warp-uniform)
+      // fused GroupNorm statistics: (sum, sumsq) per 8-channel chunk of the tile as stored (bf16), reduced in smem
+      uint8_t* vrow = smem_gen + (bar_base - smem_base) + 256 + mt * 512;   // [128] row-valid flags
+      float* csum = reinterpret_cast<float*>(vrow + 128);                   // [G*8][2]
+      const bool do_stats = a.chunk_stats != nullptr;
+      if (do_stats) {
+        vrow[row] = valid ? 1 : 0;
+        if (row < G * 16) csum[row] = 0.f;
+      }
       if (a.residual) {
         if (issuer) {
           ptx::mbar_expect_tx(res_bar + 8 * mt, (uint32_t)gmax * (uint32_t)a.rows_box * 128u);
@@ -315,6 +324,40 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
         if (issuer) {
           ptx::tma_store_5d(&maps.y[phase], stg + g * 16384, co0 + g * 64, w0, h0, d0, n0);
           ptx::tma_store_commit();
+        }
+        if (do_stats) {
+          // thread (slice = row>>3, chunk = row&7) sums 8 rows x 8 channels of the staged tile; lanes that share a
+          // chunk combine by shuffles, warps by shared-memory atomics
+          const int cch = row & 7, slice = row >> 3;
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = slice * 8 + i;
+            if (vrow[r]) {
+              const uint4 u = *reinterpret_cast<const uint4*>(stg_gen + (size_t)g * 16384 + (size_t)r * 128 +
+                                                              ((cch ^ (r & 7)) << 4));
+              const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t2 = __bfloat1622float2(hp[e]);
+                s1 += t2.x + t2.y;
+                s2 = fmaf(t2.x, t2.x, fmaf(t2.y, t2.y, s2));
+              }
+            }
+          }
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 8); s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 16); s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+          if (lane < 8) {
+            atomicAdd(&csum[(g * 8 + lane) * 2], s1);
+            atomicAdd(&csum[(g * 8 + lane) * 2 + 1], s2);
+          }
+        }
+      }
+      if (do_stats) {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
+        if (row < gmax * 16 && n0 < a.N) {
+          const int k = row >> 1, which = row & 1;   // chunk k of this Cout tile, 0 = sum / 1 = sumsq
+          atomicAdd(a.chunk_stats + ((size_t)n0 * (a.Cout >> 3) + (co0 >> 3) + k) * 2 + which, (double)csum[row]);
         }
       }
       if (issuer) ptx::tma_store_wait_read0();  // smem must outlive the bulk reads
@@ -630,6 +673,14 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p) {
   return pl;
 }
 
+// 1 when this exact problem runs the TMA epilogue with one sample per tile and no split-K, i.e. can emit chunk stats
+int conv3d_tcgen05_emits_chunk_stats(const b200ldm_conv3d_params* p) {
+  if (p->dtype != B200LDM_BF16 || p->C1 % 64 || p->C2 % 64 || p->Cout % 64 || p->out_f32 || p->gn_stats) return 0;
+  if (g_legacy_epilogue) return 0;
+  const ConvPlan pl = plan_conv(p);
+  return (pl.splits == 1 && pl.tn == 1 && pl.bn >= 64) ? 1 : 0;
+}
+
 long long conv3d_tcgen05_workspace_bytes(const b200ldm_conv3d_params* p) {
   if (p->dtype != B200LDM_BF16 || p->C1 % 64 || p->C2 % 64 || p->Cout % 8) return 0;
   const ConvPlan pl = plan_conv(p);
@@ -730,6 +781,10 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
   // coalesced TMA-store epilogue whenever the output is bf16 in whole 64-channel groups
   a.tma_epilogue = (!a.out_f32 && p->Cout % 64 == 0 && !p->gn_stats && bn >= 64 && g_legacy_epilogue == 0) ? 1 : 0;
   if (a.up) B2_REQUIRE(a.tma_epilogue, B200LDM_BAD_SHAPE, "fused upsample conv needs the TMA epilogue");
+  a.chunk_stats = p->chunk_stats;
+  if (p->chunk_stats)
+    B2_REQUIRE(a.tma_epilogue && pl.tn == 1 && pl.splits == 1, B200LDM_BAD_ARG,
+               "conv3d: chunk_stats not available for this problem (ask b200ldm_conv3d_emits_chunk_stats first)");
   if (a.tma_epilogue) {
     const uint64_t Co = p->Cout, Wo = p->Wo, Ho = p->Ho, Do = p->Do;
     if (!a.up) {

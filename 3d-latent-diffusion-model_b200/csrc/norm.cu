@@ -78,7 +78,8 @@ template <typename T, int UNROLL, int MINB>
 __global__ void __launch_bounds__(kNormThreads, MINB)
 gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict__ y,
                 const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
-                long long S, int C1, int C2, int G, float eps, int silu, int vox_per_block, double inv_cnt_arg) {
+                long long S, int C1, int C2, int G, float eps, int silu, int vox_per_block, double inv_cnt_arg,
+                const double* __restrict__ cst1, const double* __restrict__ cst2) {
   const int n = blockIdx.y;
   const int C = C1 + C2;
   const int vecs = C >> 3;
@@ -98,8 +99,21 @@ gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict
     const int c = cv * 8 + e;
     const int g = c / cpg;
     if (g != g_prev) {
-      const double m = stats[((size_t)n * G + g) * 2] * inv_cnt;
-      double var = fma(-m, m, stats[((size_t)n * G + g) * 2 + 1] * inv_cnt);
+      double sum1, sum2;
+      if (cst1) {
+        // assemble the group from per-8-channel chunk sums; chunks [0, C1/8) live in cst1, the rest in cst2
+        sum1 = 0.0; sum2 = 0.0;
+        const int k0 = (g * cpg) >> 3, k1 = ((g + 1) * cpg) >> 3, kc1 = C1 >> 3;
+        for (int k = k0; k < k1; ++k) {
+          const double* e2 = k < kc1 ? cst1 + ((size_t)n * kc1 + k) * 2 : cst2 + ((size_t)n * (C2 >> 3) + (k - kc1)) * 2;
+          sum1 += e2[0]; sum2 += e2[1];
+        }
+      } else {
+        sum1 = stats[((size_t)n * G + g) * 2];
+        sum2 = stats[((size_t)n * G + g) * 2 + 1];
+      }
+      const double m = sum1 * inv_cnt;
+      double var = fma(-m, m, sum2 * inv_cnt);
       if (var < 0.0) var = 0.0;
       mean_f = (float)m;
       rstd = rsqrtf((float)var + eps);
@@ -186,11 +200,15 @@ int b200ldm_groupnorm_stats(const void* x, const void* x2, double* stats, int32_
   return B200LDM_OK;
 }
 
-int b200ldm_groupnorm_apply(const void* x, const void* x2, void* y, const double* stats, const float* gamma,
-                            const float* beta, int32_t N, int64_t S, int32_t C1, int32_t C2, int32_t G, float eps,
-                            int32_t silu, int32_t dtype, b200ldm_stream stream) {
+static int gn_apply_impl(const void* x, const void* x2, void* y, const double* stats, const double* cst1,
+                         const double* cst2, const float* gamma, const float* beta, int32_t N, int64_t S, int32_t C1,
+                         int32_t C2, int32_t G, float eps, int32_t silu, int32_t dtype, b200ldm_stream stream) {
   using namespace b200ldm;
-  B2_REQUIRE(x && y && stats && gamma && beta && N > 0 && S > 0, B200LDM_BAD_ARG, "groupnorm_apply: bad arguments");
+  B2_REQUIRE(x && y && (stats || cst1) && gamma && beta && N > 0 && S > 0, B200LDM_BAD_ARG,
+             "groupnorm_apply: bad arguments");
+  if (cst1)
+    B2_REQUIRE(G > 0 && (C1 + C2) % G == 0 && ((C1 + C2) / G) % 8 == 0 && ((C2 > 0) == (cst2 != nullptr)),
+               B200LDM_BAD_SHAPE, "groupnorm_apply_chunked: channels/group must be a multiple of 8 and cstats2 match x2");
   B2_REQUIRE(aligned16(x) && aligned16(y) && aligned16(x2), B200LDM_BAD_ALIGN,
              "groupnorm_apply: x/y must be 16-byte aligned");
   B2_REQUIRE(C1 > 0 && C1 % 8 == 0 && C2 >= 0 && C2 % 8 == 0 && ((C2 > 0) == (x2 != nullptr)), B200LDM_BAD_SHAPE,
@@ -203,7 +221,7 @@ int b200ldm_groupnorm_apply(const void* x, const void* x2, void* y, const double
 #define GN_APPLY_BF16(U, B)                                                                                      \
   gn_apply_kernel<__nv_bfloat16, U, B><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(                         \
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)x2, (__nv_bfloat16*)y, stats, gamma, beta, S, C1, C2, G, eps, \
-      silu, vpb, inv_cnt)
+      silu, vpb, inv_cnt, cst1, cst2)
   if (dtype == B200LDM_BF16) {
     switch (variant) {
       case 1: GN_APPLY_BF16(1, 8); break;
@@ -216,11 +234,27 @@ int b200ldm_groupnorm_apply(const void* x, const void* x2, void* y, const double
     }
   } else if (dtype == B200LDM_F32)
     gn_apply_kernel<float, 4, 3><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(
-        (const float*)x, (const float*)x2, (float*)y, stats, gamma, beta, S, C1, C2, G, eps, silu, vpb, inv_cnt);
+        (const float*)x, (const float*)x2, (float*)y, stats, gamma, beta, S, C1, C2, G, eps, silu, vpb, inv_cnt, cst1,
+        cst2);
   else
     return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);
   B2_LAUNCH_CHECK();
   return B200LDM_OK;
+}
+
+int b200ldm_groupnorm_apply(const void* x, const void* x2, void* y, const double* stats, const float* gamma,
+                            const float* beta, int32_t N, int64_t S, int32_t C1, int32_t C2, int32_t G, float eps,
+                            int32_t silu, int32_t dtype, b200ldm_stream stream) {
+  B2_REQUIRE(stats, B200LDM_BAD_ARG, "groupnorm_apply: null stats");
+  return gn_apply_impl(x, x2, y, stats, nullptr, nullptr, gamma, beta, N, S, C1, C2, G, eps, silu, dtype, stream);
+}
+
+int b200ldm_groupnorm_apply_chunked(const void* x, const void* x2, void* y, const double* cstats1,
+                                    const double* cstats2, const float* gamma, const float* beta, int32_t N, int64_t S,
+                                    int32_t C1, int32_t C2, int32_t G, float eps, int32_t silu, int32_t dtype,
+                                    b200ldm_stream stream) {
+  B2_REQUIRE(cstats1, B200LDM_BAD_ARG, "groupnorm_apply_chunked: null cstats1");
+  return gn_apply_impl(x, x2, y, nullptr, cstats1, cstats2, gamma, beta, N, S, C1, C2, G, eps, silu, dtype, stream);
 }
 
 }  // extern "C"

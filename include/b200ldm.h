@@ -95,12 +95,18 @@ typedef struct {
                             27 -> 8 MACs per output); f32/SIMT takes the ordinary packed weights */
   void* workspace;       /* caller-owned scratch for split-K partial sums (see b200ldm_conv3d_workspace_bytes) */
   int64_t workspace_bytes;
+  double* chunk_stats;   /* optional [N][Cout/8][2]: (sum, sumsq) of y per 8-channel chunk, ACCUMULATED (caller zeroes)
+                            by the conv epilogue so the following GroupNorm needs no statistics pass; only when
+                            b200ldm_conv3d_emits_chunk_stats(p) == 1 */
 } b200ldm_conv3d_params;
 
 int b200ldm_conv3d(const b200ldm_conv3d_params* p, b200ldm_stream stream);
 /* bytes of `workspace` this exact problem needs (0 for most shapes; > 0 when the planner splits K over CTAs
  * because the output has too few tiles to fill 148 SMs).  Pure host arithmetic, no CUDA call. */
 int64_t b200ldm_conv3d_workspace_bytes(const b200ldm_conv3d_params* p);
+/* 1 if this exact problem can accumulate `chunk_stats` in its epilogue (bf16 tensor-core path, Cout % 64 == 0,
+ * one sample per tile, no split-K), else 0.  Pure host arithmetic. */
+int b200ldm_conv3d_emits_chunk_stats(const b200ldm_conv3d_params* p);
 
 /* src: fp32 [Cout][Cin][k][k][k] (PyTorch layout) -> dst: [k^3][Cout_pad][Cin_pad] in `dtype`,
  * zero padded; cin_offset lets a weight be split across padded concat sources:
@@ -128,6 +134,13 @@ int b200ldm_groupnorm_stats(const void* x, const void* x2, double* stats, int32_
 int b200ldm_groupnorm_apply(const void* x, const void* x2, void* y, const double* stats, const float* gamma,
                             const float* beta, int32_t N, int64_t S, int32_t C1, int32_t C2, int32_t G, float eps,
                             int32_t silu, int32_t dtype, b200ldm_stream stream);
+/* same, with the statistics given per 8-channel chunk of each source (cstats1: [N][C1/8][2], cstats2: [N][C2/8][2],
+ * as accumulated by b200ldm_conv3d); needs (C1+C2)/G % 8 == 0.  Group sums are assembled from the chunks, so a group
+ * may straddle the two sources of a channel concat. */
+int b200ldm_groupnorm_apply_chunked(const void* x, const void* x2, void* y, const double* cstats1,
+                                    const double* cstats2, const float* gamma, const float* beta, int32_t N, int64_t S,
+                                    int32_t C1, int32_t C2, int32_t G, float eps, int32_t silu, int32_t dtype,
+                                    b200ldm_stream stream);
 int b200ldm_fill_zero(void* p, size_t bytes, b200ldm_stream stream);
 
 /* ------------------------------------------------------------------------------------------

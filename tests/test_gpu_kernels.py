@@ -155,6 +155,45 @@ def test_conv3d_fused_nearest_upsample(case, mode):
     assert e <= tol, e
 
 
+STATS_CASES = [CONV_CASES[13], CONV_CASES[3],
+               ("s_64_256", 2, (16, 16, 16), 64, 0, 256, 3, 1, 1, 1, False, False),
+               ("s_two_src", 2, (9, 11, 7), 64, 64, 192, 3, 1, 1, 1, False, False),
+               ("s_stride2", 2, (16, 12, 10), 64, 0, 128, 3, 2, 1, 1, False, False)]
+
+
+@pytest.mark.parametrize("case", STATS_CASES, ids=[c[0] for c in STATS_CASES])
+def test_conv3d_chunk_stats_feed_groupnorm(case):
+    """conv epilogue chunk stats == sums over the stored bf16 output; GroupNorm applied from them == two-pass GroupNorm,
+    including a group that straddles two concatenated sources."""
+    from b200ldm import ops
+    name, N, (D, H, W), C1, C2, Cout, k, s, pl, phi, use_temb, use_res = case
+    Cin = C1 + C2
+    dtype = torch.bfloat16
+    x = q(rnd((N, Cin, D, H, W), 1), dtype)
+    w = q(rnd((Cout, Cin, k, k, k), 2, 1.0 / math.sqrt(Cin * k ** 3)), dtype)
+    wp = ops.repack_conv_weight(w.to(DEV), ops.round_up(Cout, 16), Cin, dtype)
+    b = rnd((Cout,), 3, 0.1).to(DEV)
+    xa = to_act(x[:, :C1], dtype)
+    x2a = to_act(x[:, C1:], dtype) if C2 else None
+    y = ops.conv3d(xa, wp, b, Cout, k, s, pl, phi, x2=x2a, want_stats=True)
+    if not hasattr(y, "cstats"):
+        pytest.skip("planner chose split-K / batch-in-tile for this shape: statistics fall back to the stats kernel")
+    out = from_act(y, Cout).double()                                   # values as stored
+    yy = out.reshape(N, Cout // 8, 8, -1)
+    want = torch.stack([yy.sum((2, 3)), (yy * yy).sum((2, 3))], dim=-1).reshape(-1)
+    assert relerr(y.cstats, want) <= 1e-5, relerr(y.cstats, want)
+    # GroupNorm over cat(y, y2) with 32 groups: group size (Cout + 64)/32 need not divide Cout
+    y2 = ops.conv3d(xa, ops.repack_conv_weight(w[:64].contiguous().to(DEV), 64, Cin, dtype), b[:64].contiguous(), 64, k, s,
+                    pl, phi, x2=x2a, want_stats=True)
+    Ct = Cout + 64
+    if (Ct // 32) % 8 == 0 and Ct % 32 == 0 and hasattr(y2, "cstats"):
+        gamma, beta = (1.0 + 0.1 * rnd((Ct,), 5)).to(DEV), (0.1 * rnd((Ct,), 6)).to(DEV)
+        got = ops.groupnorm(y, gamma, beta, 32, 1e-6, True, x2=y2)
+        cat = torch.cat([out, from_act(y2, 64).double()], dim=1)
+        ref = F.silu(F.group_norm(cat, 32, gamma.double().cpu(), beta.double().cpu(), eps=1e-6))
+        assert relerr(from_act(got, Ct), ref) <= 6e-3
+
+
 def test_conv3d_rejects_bad_arguments():
     from b200ldm import ops
     x = torch.zeros((1, 4, 4, 4, 48), dtype=torch.bfloat16, device=DEV)
