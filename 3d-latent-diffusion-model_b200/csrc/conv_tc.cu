@@ -271,15 +271,17 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
 #pragma unroll 1
       for (int g = 0; g < gmax; ++g) {
         uint8_t* rowp = stg_gen + (size_t)g * 16384 + (size_t)row * 128;
+        // all 64 columns of the group in flight before the single wait (the TMEM round trip is ~230 cycles)
+        uint32_t rr[4][16];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) ptx::tmem_ld16(tacc + (uint32_t)(g * 64 + cc * 16), rr[cc]);
+        ptx::tmem_ld_wait();
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-          uint32_t r[16];
-          ptx::tmem_ld16(tacc + (uint32_t)(g * 64 + cc * 16), r);
-          ptx::tmem_ld_wait();
           const int co = co0 + g * 64 + cc * 16;
           float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[cc][j]);
           if (a.bias) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
@@ -645,25 +647,32 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p) {
   pl.nb_n = ceil_div(p->N, pl.tn); pl.nb_d = ceil_div(eD, pl.td);
   pl.nb_h = ceil_div(eH, pl.th); pl.nb_w = ceil_div(eW, pl.tw);
   pl.m_tiles = pl.nb_n * pl.nb_d * pl.nb_h * pl.nb_w;
-  // two M sub-tiles per CTA (shared weight stage) once that still fills the machine
-  pl.mt = (ceil_div(pl.m_tiles, 2) * pl.n_tiles >= 148) ? 2 : 1;
-  if (g_force_mt == 1 || g_force_mt == 2) pl.mt = g_force_mt;
-  // weight multicast over a 2-CTA cluster for the big launches (>= 2 full waves of 256-row CTAs)
-  pl.cl = (pl.mt == 2 && pl.bn >= 128 && ceil_div(pl.m_tiles, 2) >= 2 * 148) ? 2 : 1;
-  if (g_force_cl == 1) pl.cl = 1;
-  if (g_force_cl == 2 && pl.mt == 2 && pl.bn >= 128) pl.cl = 2;
-  // split-K for launches that leave most SMs idle: minimise rounds x (main loop + fixed CTA overhead)
-  pl.splits = 1;
-  const int iters = p->ksize * p->ksize * p->ksize * ((p->C1 + p->C2) / 64);
-  const int ctas = ceil_div(pl.m_tiles, pl.mt) * pl.n_tiles;
-  if (pl.mt == 1 && !p->out_f32 && !p->gn_stats && !p->upsample2x && p->Cout % 8 == 0 && ctas < 148) {
-    const double cyc_iter = 512.0 * pl.bn / 256.0 + 64.0, overhead = 14000.0;
-    double best = 1e30;
-    for (int s = 1; s <= 8 && iters / s >= 16; ++s) {
-      const double rounds = (double)ceil_div((long long)ctas * s, 148);
-      double t = rounds * (ceil_div(iters, s) * cyc_iter + overhead);
-      if (s > 1) t += 6000.0;  // finalize launch + slab traffic
-      if (t < best) { best = t; pl.splits = s; }
+  // (mt, cl, splits) by a small cost model calibrated on the clock64 traces (scripts/conv_trace.py):
+  //   time = rounds(ctas / 148) x (k-iterations x cycles/iteration + fixed CTA overhead)
+  //   cycles/iteration = max(MMA issue time, bytes staged per iteration / ~55 B/clk/SM of L2->SMEM bandwidth)
+  const int taps_eff = p->upsample2x ? 8 : p->ksize * p->ksize * p->ksize;
+  const int iters = taps_eff * ((p->C1 + p->C2) / 64);
+  const int zmul = p->upsample2x ? 8 : 1;
+  const bool split_ok = !p->out_f32 && !p->gn_stats && !p->upsample2x && p->Cout % 8 == 0;
+  double best = 1e30;
+  pl.mt = 1; pl.cl = 1; pl.splits = 1;
+  for (int mt = 1; mt <= 2; ++mt) {
+    if ((g_force_mt == 1 || g_force_mt == 2) && mt != g_force_mt) continue;
+    for (int cl = 1; cl <= 2; ++cl) {
+      if (cl == 2 && pl.bn < 128) continue;
+      if ((g_force_cl == 1 || g_force_cl == 2) && cl != g_force_cl && !(cl == 1 && pl.bn < 128)) continue;
+      const double mma = mt * 4.0 * (128.0 * pl.bn / 256.0);
+      const double load = (mt * 16384.0 + pl.bn * 128.0 / cl) / 55.0;
+      const double cyc_iter = (mma > load ? mma : load) + 8.0;
+      const double overhead = 4000.0 + 5000.0 * mt;   // prologue + epilogue (10K cycles for two accumulators)
+      const long long ctas = (long long)ceil_div(ceil_div(pl.m_tiles, mt), cl) * cl * pl.n_tiles * zmul;
+      for (int sp = 1; sp <= 8; ++sp) {
+        if (sp > 1 && (!split_ok || mt != 1 || cl != 1 || iters / sp < 16 || ctas >= 148)) break;
+        const double rounds = (double)ceil_div(ctas * sp, 148);
+        double t = rounds * (ceil_div(iters, sp) * cyc_iter + overhead);
+        if (sp > 1) t += 6000.0;  // finalize launch + slab traffic
+        if (t < best * 0.98) { best = t; pl.mt = mt; pl.cl = cl; pl.splits = sp; }
+      }
     }
   }
   if (g_force_splits >= 1 && g_force_splits <= 8 && !p->out_f32 && !p->gn_stats && !p->upsample2x &&
@@ -816,11 +825,13 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
   switch (bn) {
     case 256: rc = mt == 2 ? (cl == 2 ? launch_conv_tc<256, 2, 2>(maps, a, m_tiles, n_tiles, sp, st)
                                       : launch_conv_tc<256, 2, 1>(maps, a, m_tiles, n_tiles, sp, st))
-                           : launch_conv_tc<256, 1, 1>(maps, a, m_tiles, n_tiles, sp, st);
+                           : (cl == 2 ? launch_conv_tc<256, 1, 2>(maps, a, m_tiles, n_tiles, sp, st)
+                                      : launch_conv_tc<256, 1, 1>(maps, a, m_tiles, n_tiles, sp, st));
       break;
     case 128: rc = mt == 2 ? (cl == 2 ? launch_conv_tc<128, 2, 2>(maps, a, m_tiles, n_tiles, sp, st)
                                       : launch_conv_tc<128, 2, 1>(maps, a, m_tiles, n_tiles, sp, st))
-                           : launch_conv_tc<128, 1, 1>(maps, a, m_tiles, n_tiles, sp, st);
+                           : (cl == 2 ? launch_conv_tc<128, 1, 2>(maps, a, m_tiles, n_tiles, sp, st)
+                                      : launch_conv_tc<128, 1, 1>(maps, a, m_tiles, n_tiles, sp, st));
       break;
     case 64: rc = mt == 2 ? launch_conv_tc<64, 2, 1>(maps, a, m_tiles, n_tiles, sp, st)
                           : launch_conv_tc<64, 1, 1>(maps, a, m_tiles, n_tiles, sp, st);
