@@ -63,6 +63,19 @@ __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { retu
 // fast path: ex2.approx + rcp.approx (2 ulp) instead of the ~10-instruction IEEE division
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
+// bf16 outputs: x*sigmoid(x) = h + h*tanh(h), h = x/2: ONE MUFU op (tanh.approx, rel. err 2^-11 < bf16 ulp) instead of
+// ex2 + rcp - the GroupNorm+SiLU pass was XU-pipe limited (ncu: 66 % XU at 53 % DRAM, profiles/r01_ncu_full_final.md)
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+template <typename T>
+__device__ __forceinline__ float silu_for(float x) { return silu_f(x); }
+template <>
+__device__ __forceinline__ float silu_for<__nv_bfloat16>(float x) { return silu_tanh(x); }
+
 // 8 consecutive elements <-> 8 floats, 16-byte (bf16) / 2x16-byte (fp32) vector access
 template <typename T>
 struct Vec8;

@@ -141,7 +141,7 @@ gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float t = fmaf(f[u][e], sc[e], sf[e]);
-        f[u][e] = silu ? silu_f(t) : t;
+        f[u][e] = silu ? silu_for<T>(t) : t;
       }
       Vec8<T>::store(y + off + (size_t)(v + (long long)u * vpp) * C, f[u]);
     }
@@ -152,7 +152,7 @@ gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float t = fmaf(f[e], sc[e], sf[e]);
-      f[e] = silu ? silu_f(t) : t;
+      f[e] = silu ? silu_for<T>(t) : t;
     }
     Vec8<T>::store(y + off + (size_t)v * C, f);
   }
