@@ -26,6 +26,8 @@ class ConvParams(C.Structure):
         ("temb_stride", C.c_int32), ("gn_groups", C.c_int32), ("dtype", C.c_int32),
         ("engine", C.c_int32), ("out_f32", C.c_int32), ("upsample2x", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("chunk_stats", C.c_void_p),
+        ("skip_x", C.c_void_p), ("skip_x2", C.c_void_p), ("skip_w", C.c_void_p),
+        ("skip_C1", C.c_int32), ("skip_C2", C.c_int32),
     ]
 
 

@@ -31,6 +31,8 @@ FUSE_GN_STATS = os.environ.get("B200LDM_FUSE_GN_GROUPSTATS", "0") != "0"
 
 
 FUSE_UPSAMPLE = os.environ.get("B200LDM_FUSE_UPSAMPLE", "1") != "0"
+# ResNet 1x1x1 skip_connection / nin_shortcut accumulated inside conv2 (extra K iterations) on the tensor-core path
+FUSE_SKIP = os.environ.get("B200LDM_FUSE_SKIP", "1") != "0"
 
 
 def default_precision() -> str:
@@ -97,6 +99,23 @@ class Conv(nn.Module):
                           temb_stride=temb_stride, residual=residual, gn_stats=gn_stats, gn_groups=gn_groups,
                           out_f32=out_f32, want_stats=want_stats)
 
+
+    def run_with_skip(self, x, skip_conv: "Conv", sx, sx2=None, want_stats: bool = False):
+        """self(x) + skip_conv(cat(sx, sx2)) in ONE kernel: the 1x1x1 skip conv is a few more K iterations into the same
+        TMEM accumulator (no second launch, no residual round trip)."""
+        w, _ = self.packed(x.dtype, cin_phys=x.shape[-1])
+        c1 = None if sx2 is None else sx.shape[-1]
+        cs = sx.shape[-1] + (0 if sx2 is None else sx2.shape[-1])
+        sw, _ = skip_conv.packed(x.dtype, c1=c1, c1_phys=c1, cin_phys=cs)
+
+        def build():
+            b = torch.zeros(self.cout_phys, dtype=torch.float32, device=self.weight.device)
+            b[: self.cout] = self.bias.detach().float() + skip_conv.bias.detach().float()
+            return b
+
+        b = self._cache.get(("bias+skip",), (self.bias, skip_conv.bias), build)
+        return ops.conv3d(x, w, b, self.cout_phys, self.ksize, self.stride, self.pad_lo, self.pad_hi,
+                          skip=(sx, sx2, sw), want_stats=want_stats)
 
     def run_upsampled(self, x):
         """conv(nearest_upsample_x2(x)) without materialising the upsampled tensor: on the tensor-core
@@ -255,9 +274,10 @@ class UNetResBlock(nn.Module):
                            want_stats=stats is None)
         h = self.norm2.run(h, silu=True, stats=stats)
         if isinstance(self.skip_connection, nn.Identity):
-            res = x
-        else:
-            res = self.skip_connection.run(x, x2=x2, c1=None if x2 is None else x.shape[-1])
+            return self.conv2.run(h, residual=x, want_stats=True)
+        if FUSE_SKIP and h.dtype == torch.bfloat16:
+            return self.conv2.conv.run_with_skip(h, self.skip_connection.conv, x, x2, want_stats=True)
+        res = self.skip_connection.run(x, x2=x2, c1=None if x2 is None else x.shape[-1])
         return self.conv2.run(h, residual=res, want_stats=True)
 
 
@@ -499,8 +519,11 @@ class AEResBlock(nn.Module):
             stats = ops.zeros_f64(x.shape[0] * self.groups * 2, x.device)
         h = self.conv1.run(h, gn_stats=stats, gn_groups=self.groups, want_stats=stats is None)
         h = self.norm2.run(h, silu=True, stats=stats)
-        res = x if isinstance(self.nin_shortcut, nn.Identity) else self.nin_shortcut.run(x)
-        return self.conv2.run(h, residual=res, want_stats=True)
+        if isinstance(self.nin_shortcut, nn.Identity):
+            return self.conv2.run(h, residual=x, want_stats=True)
+        if FUSE_SKIP and h.dtype == torch.bfloat16:
+            return self.conv2.conv.run_with_skip(h, self.nin_shortcut.conv, x, want_stats=True)
+        return self.conv2.run(h, residual=self.nin_shortcut.run(x), want_stats=True)
 
 
 class AEDownsample(nn.Module):

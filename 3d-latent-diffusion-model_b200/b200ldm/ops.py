@@ -81,10 +81,13 @@ def conv_out_extent(n: int, k: int, stride: int, pad_lo: int, pad_hi: int) -> in
 
 def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo: int = 1, pad_hi: int | None = None,
            x2=None, temb=None, temb_stride: int = 0, residual=None, gn_stats=None, gn_groups: int = 0,
-           out_f32: bool = False, engine: int = ENGINE_AUTO, upsample2x: bool = False, want_stats: bool = False):
+           out_f32: bool = False, engine: int = ENGINE_AUTO, upsample2x: bool = False, want_stats: bool = False,
+           skip=None):
     """y = conv3d(cat(x, x2)) + bias (+ temb) (+ residual); x: [N,D,H,W,C1] NDHWC.
     upsample2x: the conv runs on the nearest-x2-upsampled x without materialising it (bf16: phase-decomposed
     weights from repack_upconv_weight; fp32: ordinary weights).
+    skip: (sx, sx2 | None, sw_packed): a 1x1x1 conv of cat(sx, sx2) accumulated into the same output (ResNet
+    skip_connection fused as extra K iterations; `bias` must already include its bias).  bf16 only.
     want_stats: when the tensor-core epilogue can, it also accumulates per-8-channel (sum, sumsq) of y; the result is
     attached as `y.cstats` and lets the following GroupNorm skip its statistics pass."""
     _need_cuda(x, x2, w_packed, bias, temb, residual)
@@ -102,6 +105,12 @@ def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo
         y=_ptr(y), gn_stats=_ptr(gn_stats), N=N, D=D, H=H, W=W, C1=C1, C2=C2, Cout=cout, Do=Do, Ho=Ho, Wo=Wo,
         ksize=ksize, stride=stride, pad_lo=pad_lo, temb_stride=temb_stride, gn_groups=gn_groups,
         dtype=dtype_code(x.dtype), engine=engine, out_f32=int(out_f32), upsample2x=int(upsample2x))
+    if skip is not None:
+        sx, sx2, sw = skip
+        _need_cuda(sx, sx2, sw)
+        assert sx.is_contiguous() and tuple(sx.shape[:-1]) == (N, Do, Ho, Wo) and (sx2 is None or sx2.is_contiguous())
+        p.skip_x, p.skip_x2, p.skip_w = _ptr(sx), _ptr(sx2), _ptr(sw)
+        p.skip_C1, p.skip_C2 = sx.shape[-1], 0 if sx2 is None else sx2.shape[-1]
     assert x.is_contiguous() and (x2 is None or x2.is_contiguous())
     assert residual is None or (residual.is_contiguous() and residual.shape == y.shape and residual.dtype == odt)
     ws_bytes = lib.b200ldm_conv3d_workspace_bytes(C.byref(p))
@@ -120,8 +129,10 @@ def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo
         # algorithmic FLOPs of the (padded) problem the kernel ran: 2*M*Cout*Cin*k^3
         # (fused upsample on tensor cores: 8 of the 27 taps are executed per output voxel - EXECUTED flops)
         taps = 8 if (upsample2x and x.dtype == torch.bfloat16) else ksize ** 3
-        PROFILER.stop("conv3d", f"{C1 + C2}->{cout} k{ksize}s{stride}{'up' if upsample2x else ''} @{N}x{Do}x{Ho}x{Wo}",
-                      2.0 * N * Do * Ho * Wo * cout * (C1 + C2) * taps, ev)
+        kk = (C1 + C2) * taps + (0 if skip is None else p.skip_C1 + p.skip_C2)
+        PROFILER.stop("conv3d", f"{C1 + C2}->{cout} k{ksize}s{stride}{'up' if upsample2x else ''}"
+                                f"{'+skip' if skip is not None else ''} @{N}x{Do}x{Ho}x{Wo}",
+                      2.0 * N * Do * Ho * Wo * cout * kk, ev)
     return y
 
 

@@ -215,7 +215,8 @@ extern "C" int b200ldm_conv3d(const b200ldm_conv3d_params* p, b200ldm_stream str
     engine = (p->dtype == B200LDM_BF16) ? B200LDM_ENGINE_TCGEN05 : B200LDM_ENGINE_SIMT;
   if (engine == B200LDM_ENGINE_TCGEN05) return conv3d_tcgen05(p, (cudaStream_t)stream);
   if (engine == B200LDM_ENGINE_SIMT) {
-    B2_REQUIRE(!p->chunk_stats, B200LDM_BAD_ARG, "chunk_stats is a tensor-core epilogue feature");
+    B2_REQUIRE(!p->chunk_stats && !p->skip_x, B200LDM_BAD_ARG,
+               "chunk_stats / fused skip conv are tensor-core path features");
     return conv3d_simt(p, (cudaStream_t)stream);
   }
   return fail(B200LDM_BAD_ARG, "unknown engine %d", p->engine);

@@ -31,6 +31,8 @@ struct ConvTcMaps {
   CUtensorMap w;     // [taps][Cout_pad][Cin_total]
   CUtensorMap y[8];  // output, same voxel box as the A tiles (TMA-store epilogue); up mode: one strided map per phase
   CUtensorMap r;     // residual (same geometry as y) when fused
+  CUtensorMap s[2];  // fused 1x1x1 skip conv: its one or two (concat) sources, output geometry
+  CUtensorMap sw;    // skip weights [1][Cout_pad][Cs1+Cs2]
 };
 
 struct ConvTcArgs {
@@ -38,6 +40,7 @@ struct ConvTcArgs {
   int nb_d, nb_h, nb_w;    // tiles per spatial dim (tiles over N = gridDim.x / (nb_d*nb_h*nb_w))
   int N, Do, Ho, Wo, Cout;
   int nchunk1, nchunk2;    // 64-channel chunks in x / x2
+  int nsk1, nsk2;          // 64-channel chunks of the fused 1x1x1 skip conv's sources (extra K iterations, centre tap)
   int ksize, stride, pad_lo;
   int rows_box;            // tn*td*th*tw
   int temb_stride, out_f32, gn_groups;
@@ -98,7 +101,8 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
   const int zsplit = a.up ? 0 : (int)blockIdx.z;
   const int taps = a.up ? 8 : a.ksize * a.ksize * a.ksize;
   const int nchunks = a.nchunk1 + a.nchunk2;
-  const int iters_total = taps * nchunks;
+  const int iters_main = taps * nchunks;
+  const int iters_total = iters_main + a.nsk1 + a.nsk2;   // + the ResBlock's 1x1x1 skip conv accumulated in place
   const int it0 = (int)((long long)zsplit * iters_total / a.splits);
   const int it1 = (int)((long long)(zsplit + 1) * iters_total / a.splits);
 
@@ -143,6 +147,22 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
         const int s = (it - it0) % STAGES;
         const uint32_t ph = (uint32_t)((it - it0) / STAGES) & 1u;
         ptx::mbar_wait(bar_base + 8 * (STAGES + s), ph ^ 1u, 0);
+        const uint32_t full = bar_base + 8 * s;
+        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+        const uint32_t sb = sa + MT * kABytes;
+        ptx::mbar_expect_tx(full, tx_bytes);
+        if (it >= iters_main) {
+          // fused skip conv: same output box, no tap shift, its own sources and weights
+          const int sc = it - iters_main;
+          const bool second = sc >= a.nsk1;
+          const CUtensorMap* m = second ? &maps.s[1] : &maps.s[0];
+          const int c0 = (second ? sc - a.nsk1 : sc) * 64;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            ptx::tma_load_5d(sa + mt * kABytes, m, full, c0, w0[mt], h0[mt], d0[mt], n0[mt]);
+          ptx::tma_load_3d(sb, &maps.sw, full, sc * 64, co0, 0);
+          continue;
+        }
         const int tap = it / nchunks;
         const int chunk = it - tap * nchunks;
         int kd = 0, kh = 0, kw = 0;
@@ -153,10 +173,6 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
           pad_d = 1 - (phase >> 2); pad_h = 1 - ((phase >> 1) & 1); pad_w = 1 - (phase & 1);
           wtap = phase * 8 + tap;
         } else if (a.ksize == 3) { kd = tap / 9; kh = (tap / 3) % 3; kw = tap % 3; }
-        const uint32_t full = bar_base + 8 * s;
-        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
-        const uint32_t sb = sa + MT * kABytes;
-        ptx::mbar_expect_tx(full, tx_bytes);
         if (a.stride == 1) {
           const bool second = chunk >= a.nchunk1;
           const CUtensorMap* m = second ? &maps.a[1] : &maps.a[0];
@@ -237,7 +253,7 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
     const int cpg = a.gn_stats ? a.Cout / a.gn_groups : 1;
     const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * BN);
 
-    ptx::mbar_wait(tmem_full_bar + 8 * mt, 0, 2);
+    ptx::mbar_wait_long(tmem_full_bar + 8 * mt, 0, 2);
     ptx::tc_fence_after();
     if (trc && lane == 0 && q == 0) trc[3 + 2 * mt] = clock64();
     if (BN >= 64 && a.tma_epilogue) {
@@ -651,7 +667,7 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p) {
   //   time = rounds(ctas / 148) x (k-iterations x cycles/iteration + fixed CTA overhead)
   //   cycles/iteration = max(MMA issue time, bytes staged per iteration / ~55 B/clk/SM of L2->SMEM bandwidth)
   const int taps_eff = p->upsample2x ? 8 : p->ksize * p->ksize * p->ksize;
-  const int iters = taps_eff * ((p->C1 + p->C2) / 64);
+  const int iters = taps_eff * ((p->C1 + p->C2) / 64) + (p->skip_x ? (p->skip_C1 + p->skip_C2) / 64 : 0);
   const int zmul = p->upsample2x ? 8 : 1;
   const bool split_ok = !p->out_f32 && !p->gn_stats && !p->upsample2x && p->Cout % 8 == 0;
   double best = 1e30;
@@ -659,7 +675,7 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p) {
   for (int mt = 1; mt <= 2; ++mt) {
     if ((g_force_mt == 1 || g_force_mt == 2) && mt != g_force_mt) continue;
     for (int cl = 1; cl <= 2; ++cl) {
-      if (cl == 2 && pl.bn < 128) continue;
+      if (cl == 2 && (pl.bn < 128 || p->skip_x)) continue;
       if ((g_force_cl == 1 || g_force_cl == 2) && cl != g_force_cl && !(cl == 1 && pl.bn < 128)) continue;
       const double mma = mt * 4.0 * (128.0 * pl.bn / 256.0);
       const double load = (mt * 16384.0 + pl.bn * 128.0 / cl) / 55.0;
@@ -742,6 +758,7 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
   if (a.up) { a.Do = p->D; a.Ho = p->H; a.Wo = p->W; }  // rows are low-res voxels
   a.splits = pl.splits; a.slab_elems = pl.splits > 1 ? M_total * p->Cout : 0;
   a.nchunk1 = p->C1 / 64; a.nchunk2 = p->C2 / 64;
+  a.nsk1 = p->skip_x ? p->skip_C1 / 64 : 0; a.nsk2 = p->skip_x ? p->skip_C2 / 64 : 0;
   a.ksize = p->ksize; a.stride = p->stride; a.pad_lo = p->pad_lo;
   a.rows_box = a.tn * a.td * a.th * a.tw;
   a.temb_stride = p->temb_stride; a.out_f32 = p->out_f32; a.gn_groups = p->gn_groups;
@@ -784,6 +801,24 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
                             a.td, a.tn);
           if (rc) return rc;
         }
+  }
+  if (p->skip_x) {
+    B2_REQUIRE(p->stride == 1 && !p->upsample2x && p->skip_w && p->skip_C1 > 0 && p->skip_C1 % 64 == 0 &&
+                   p->skip_C2 >= 0 && p->skip_C2 % 64 == 0 && ((p->skip_C2 > 0) == (p->skip_x2 != nullptr)) &&
+                   pl.cl == 1 && aligned16(p->skip_x) && aligned16(p->skip_w) && (!p->skip_x2 || aligned16(p->skip_x2)),
+               B200LDM_BAD_SHAPE, "fused skip conv: stride-1 conv, 64-multiple skip channels, aligned pointers");
+    const uint64_t Wo = p->Wo, Ho = p->Ho, Do = p->Do, S1 = p->skip_C1, S2 = p->skip_C2;
+    rc = make_act_map(&maps.s[0], p->skip_x, p->skip_C1, p->Wo, p->Ho, p->Do, p->N, S1, Wo * S1, Ho * Wo * S1,
+                      Do * Ho * Wo * S1, a.tw, a.th, a.td, a.tn);
+    if (rc) return rc;
+    maps.s[1] = maps.s[0];
+    if (p->skip_C2 > 0) {
+      rc = make_act_map(&maps.s[1], p->skip_x2, p->skip_C2, p->Wo, p->Ho, p->Do, p->N, S2, Wo * S2, Ho * Wo * S2,
+                        Do * Ho * Wo * S2, a.tw, a.th, a.td, a.tn);
+      if (rc) return rc;
+    }
+    rc = make_weight_map(&maps.sw, p->skip_w, p->skip_C1 + p->skip_C2, (p->Cout + 15) / 16 * 16, 1, bn);
+    if (rc) return rc;
   }
   // weight rows are padded by the packer to a multiple of 16 so small-Cout tiles stay in bounds
   const int cout_rows = (p->Cout + 15) / 16 * 16;

@@ -98,6 +98,14 @@ typedef struct {
   double* chunk_stats;   /* optional [N][Cout/8][2]: (sum, sumsq) of y per 8-channel chunk, ACCUMULATED (caller zeroes)
                             by the conv epilogue so the following GroupNorm needs no statistics pass; only when
                             b200ldm_conv3d_emits_chunk_stats(p) == 1 */
+  /* optional fused 1x1x1 conv of a second input set, accumulated into the same output (the ResNet blocks'
+   * `skip_connection(x) + conv2(h)`): y += skip_w[co][ci] * cat(skip_x, skip_x2)[voxel][ci].  Sources have the
+   * OUTPUT's spatial extents; skip_w is packed [1][Cout_pad][skip_C1+skip_C2]; `bias` must already hold both
+   * biases.  bf16/TCGEN05 only, stride 1, channels multiples of 64. */
+  const void* skip_x;
+  const void* skip_x2;
+  const void* skip_w;
+  int32_t skip_C1, skip_C2;
 } b200ldm_conv3d_params;
 
 int b200ldm_conv3d(const b200ldm_conv3d_params* p, b200ldm_stream stream);

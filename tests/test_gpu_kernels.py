@@ -194,6 +194,28 @@ def test_conv3d_chunk_stats_feed_groupnorm(case):
         assert relerr(from_act(got, Ct), ref) <= 6e-3
 
 
+@pytest.mark.parametrize("shape", [(2, (6, 8, 4), 128, 256, 192, 64), (1, (9, 11, 7), 64, 128, 64, 0),
+                                   (8, (4, 4, 4), 256, 256, 512, 256), (2, (16, 16, 16), 64, 64, 128, 0)],
+                         ids=["two_src_skip", "odd", "batch_tile", "big"])
+def test_conv3d_fused_skip_conv(shape):
+    """y = conv3(h) + conv1(cat(sx, sx2)) in one launch == the two convs of a ResNet block with a channel change"""
+    from b200ldm import ops
+    N, sp, C, Cout, S1, S2 = shape
+    dtype = torch.bfloat16
+    h = q(rnd((N, C) + sp, 91), dtype)
+    sx = q(rnd((N, S1 + S2) + sp, 92), dtype)
+    w = q(rnd((Cout, C, 3, 3, 3), 93, 1.0 / math.sqrt(C * 27)), dtype)
+    ws = q(rnd((Cout, S1 + S2, 1, 1, 1), 94, 1.0 / math.sqrt(S1 + S2)), dtype)
+    b = rnd((Cout,), 95, 0.1)
+    ref = F.conv3d(h.double(), w.double(), b.double(), padding=1) + F.conv3d(sx.double(), ws.double())
+    wp = ops.repack_conv_weight(w.to(DEV), Cout, C, dtype)
+    wsp = ops.repack_conv_weight(ws.to(DEV), Cout, S1 + S2, dtype)
+    y = ops.conv3d(to_act(h, dtype), wp, b.to(DEV), Cout, 3, 1, 1, 1,
+                   skip=(to_act(sx[:, :S1], dtype), to_act(sx[:, S1:], dtype) if S2 else None, wsp), want_stats=True)
+    e = relerr(from_act(y, Cout), ref)
+    assert e <= 1e-2, e
+
+
 def test_conv3d_rejects_bad_arguments():
     from b200ldm import ops
     x = torch.zeros((1, 4, 4, 4, 48), dtype=torch.bfloat16, device=DEV)
