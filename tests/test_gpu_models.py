@@ -167,3 +167,69 @@ def test_unet_32g_step_vs_oracle(precision):
     e = relerr(got, want)
     print(f"unet32g/{precision}: eps relerr {e:.3e}")
     assert e <= EPS_TOL[precision], e
+
+
+def test_inference_cli_dropin(tmp_path):
+    """The reference CLI flow (3d_ldm/inference.py:31-102) through b200ldm: JSON config with MONAI `_target_`s ->
+    define_instance -> DDPMScheduler -> LatentDiffusionInferer.sample -> NIfTI on disk."""
+    import json
+    import subprocess
+    import sys
+    from b200ldm.nifti import load_nifti
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = {
+        "spatial_dims": 3, "image_channels": 1, "latent_channels": 4,
+        "autoencoder_def": {"_target_": "monai.networks.nets.AutoencoderKL", "spatial_dims": "@spatial_dims",
+                            "in_channels": "$@image_channels", "out_channels": "@image_channels",
+                            "latent_channels": "@latent_channels", "channels": [64, 128, 128], "num_res_blocks": 1,
+                            "norm_num_groups": 32, "norm_eps": 1e-06, "attention_levels": [False, False, True],
+                            "with_encoder_nonlocal_attn": False, "with_decoder_nonlocal_attn": False},
+        "diffusion_def": {"_target_": "monai.networks.nets.DiffusionModelUNet", "spatial_dims": "@spatial_dims",
+                          "in_channels": 8, "out_channels": "@latent_channels", "channels": [64, 128],
+                          "attention_levels": [False, True], "num_head_channels": [0, 64], "num_res_blocks": 1},
+        "diffusion_train": {"patch_size": [32, 48, 16]},
+        "NoiseScheduler": {"num_train_timesteps": 1000, "beta_start": 0.0015, "beta_end": 0.0195},
+    }
+    env = {"model_dir": str(tmp_path), "output_dir": str(tmp_path / "out")}
+    (tmp_path / "cfg.json").write_text(json.dumps(cfg))
+    (tmp_path / "env.json").write_text(json.dumps(env))
+    cli = os.path.join(root, "3d-latent-diffusion-model_b200", "inference.py")
+    r = subprocess.run([sys.executable, cli, "-e", str(tmp_path / "env.json"), "-c", str(tmp_path / "cfg.json"), "-n", "2",
+                        "--steps", "4", "--random-init"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    outs = sorted(os.listdir(tmp_path / "out"))
+    assert len(outs) == 2 and all(o.endswith(".nii") for o in outs)
+    vol, aff = load_nifti(str(tmp_path / "out" / outs[0]))
+    assert vol.shape == (32, 48, 16, 1) and bool((vol == vol).all())
+
+
+def test_cfg1_default_config_sampling_psnr():
+    """BASELINE.json configs[0]: the reference's default config_train_32g UNet + AutoencoderKL, 1 x 16^3 latent -> 64^3
+    volume, 10 DDPM steps (inference.py flow with concat conditioning), bf16 tensor-core path vs the fp32 CPU oracle on
+    identical weights / x_T / per-step noise: decoded volume PSNR >= 40 dB."""
+    import b200ldm
+    ukw = dict(spatial_dims=3, in_channels=32, out_channels=16, channels=[256, 512, 1024],
+               attention_levels=[False, True, True], num_head_channels=[0, 64, 64], num_res_blocks=2)
+    akw = dict(spatial_dims=3, in_channels=1, out_channels=1, latent_channels=16, channels=[64, 128, 256],
+               num_res_blocks=2, norm_num_groups=32, norm_eps=1e-6, attention_levels=[False, False, True],
+               with_encoder_nonlocal_attn=False, with_decoder_nonlocal_attn=False)
+    r_unet = oracle.randomize_parameters(oracle.DiffusionModelUNet(**ukw), 1234).eval()
+    r_ae = oracle.randomize_parameters(oracle.AutoencoderKL(**akw), 4321).eval()
+    unet = port(r_unet, b200ldm.DiffusionModelUNet, ukw, "bf16")
+    ae = port(r_ae, b200ldm.AutoencoderKL, akw, "bf16")
+    n = 10
+    g = gc.gen(42)
+    x_T = torch.randn((1, 16, 16, 16, 16), generator=g)
+    cond = torch.randn((1, 16, 16, 16, 16), generator=g)
+    step_noise = torch.randn((n, 1, 16, 16, 16, 16), generator=g)
+    s_ours, s_ref = gc.make_scheduler(b200ldm, "ddpm", n), gc.make_scheduler(oracle, "ddpm", n)
+    img = b200ldm.LatentDiffusionInferer(s_ours, 1.0).sample(
+        input_noise=x_T.to(DEV), autoencoder_model=ae, diffusion_model=unet, scheduler=s_ours,
+        conditioning=cond.to(DEV), mode="concat", verbose=False, step_noise=step_noise.to(DEV))
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    want = oracle.LatentDiffusionInferer(s_ref, 1.0).sample(x_T, r_ae, r_unet, s_ref, conditioning=cond, mode="concat",
+                                                            verbose=False, step_noise=step_noise)
+    assert img.shape == (1, 1, 64, 64, 64)
+    p = psnr(img, want)
+    print(f"cfg1 (32g, 16^3 -> 64^3, DDPM-10, bf16): decoded volume PSNR {p:.1f} dB")
+    assert p >= 40.0, p

@@ -180,3 +180,19 @@ def test_gather_world2_gloo(total):
     for _, vals, seeds in res:
         assert vals == [float(i) for i in range(total)]
         assert seeds == want_seeds
+
+
+def test_nifti_roundtrip(tmp_path):
+    """NIfTI-1 egress of the inference CLI (3d_ldm/inference.py:100-102 writes volume[..., None] with an identity affine)."""
+    import numpy as np
+    from b200ldm.nifti import load_nifti, save_nifti
+    vol = np.random.default_rng(0).random((5, 6, 7, 1)).astype(np.float32)
+    path = save_nifti(vol, str(tmp_path / "synimg_test"))
+    assert path.endswith(".nii") and os.path.getsize(path) == 352 + vol.size * 4
+    raw = open(path, "rb").read()
+    assert raw[344:348] == b"n+1\x00" and int.from_bytes(raw[0:4], "little") == 348
+    back, aff = load_nifti(path)
+    assert np.array_equal(back, vol) and np.array_equal(aff, np.eye(4))
+    # first index fastest on disk (what nibabel writes for a C-ordered array of this shape)
+    first = np.frombuffer(raw, dtype="<f4", count=5, offset=352)
+    assert np.array_equal(first, vol[:, 0, 0, 0])
