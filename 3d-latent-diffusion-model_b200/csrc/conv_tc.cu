@@ -677,21 +677,25 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p) {
     for (int cl = 1; cl <= 2; ++cl) {
       if (cl == 2 && (pl.bn < 128 || p->skip_x)) continue;
       if ((g_force_cl == 1 || g_force_cl == 2) && cl != g_force_cl && !(cl == 1 && pl.bn < 128)) continue;
+      // An SM ingests at most ~64-72 B/clk from L2 (measured: 128x256 tiles run at 680 instead of 512 cycles per
+      // k-iteration even with 96 CTAs on the chip; 256x256 tiles need exactly 64 B/clk and run at the MMA rate).
+      // Multicast does not lower the bytes that enter each SM, so it does not change this bound.
       const double mma = mt * 4.0 * (128.0 * pl.bn / 256.0);
-      const double load = (mt * 16384.0 + pl.bn * 128.0 / cl) / 55.0;
+      const double load = (mt * 16384.0 + pl.bn * 128.0) / 72.0;
       const double cyc_iter = (mma > load ? mma : load) + 8.0;
       const double overhead = 4000.0 + 5000.0 * mt;   // prologue + epilogue (10K cycles for two accumulators)
       const long long ctas = (long long)ceil_div(ceil_div(pl.m_tiles, mt), cl) * cl * pl.n_tiles * zmul;
-      for (int sp = 1; sp <= 8; ++sp) {
-        if (sp > 1 && (!split_ok || mt != 1 || cl != 1 || iters / sp < 16 || ctas >= 148)) break;
+      for (int sp = 1; sp <= 12; ++sp) {
+        if (sp > 1 && (!split_ok || cl != 1 || iters / sp < 16 || ctas >= 148)) break;
         const double rounds = (double)ceil_div(ctas * sp, 148);
         double t = rounds * (ceil_div(iters, sp) * cyc_iter + overhead);
         if (sp > 1) t += 6000.0;  // finalize launch + slab traffic
+        if (cl == 2) t *= 0.99;   // multicast: slightly less L2 traffic chip-wide
         if (t < best * 0.98) { best = t; pl.mt = mt; pl.cl = cl; pl.splits = sp; }
       }
     }
   }
-  if (g_force_splits >= 1 && g_force_splits <= 8 && !p->out_f32 && !p->gn_stats && !p->upsample2x &&
+  if (g_force_splits >= 1 && g_force_splits <= 12 && !p->out_f32 && !p->gn_stats && !p->upsample2x &&
       iters / g_force_splits >= 1)
     pl.splits = g_force_splits;
   if (pl.splits > 1) pl.cl = 1;
