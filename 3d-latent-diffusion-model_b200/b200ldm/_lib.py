@@ -48,6 +48,7 @@ SIGNATURES = {
     "b200ldm_last_error": (C.c_int, [C.c_char_p, _sz]),
     "b200ldm_check_device": (C.c_int, []),
     "b200ldm_launch_count": (C.c_uint64, []),
+    "b200ldm_sizeof_params": (_sz, [_i32]),
     "b200ldm_conv3d": (C.c_int, [C.POINTER(ConvParams), _vp]),
     "b200ldm_conv3d_workspace_bytes": (C.c_int64, [C.POINTER(ConvParams)]),
     "b200ldm_conv3d_emits_chunk_stats": (C.c_int, [C.POINTER(ConvParams)]),
@@ -90,6 +91,10 @@ def load() -> C.CDLL:
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the export is missing
         fn.restype, fn.argtypes = res, args
+    for which, st in ((0, ConvParams), (1, SchedParams)):
+        if lib.b200ldm_sizeof_params(which) != C.sizeof(st):
+            raise RuntimeError(f"{st.__name__}: ctypes layout ({C.sizeof(st)} B) != compiled struct "
+                               f"({lib.b200ldm_sizeof_params(which)} B); rebuild libb200ldm.so")
     _lib = lib
     return lib
 

@@ -37,6 +37,10 @@ int b200ldm_last_error(char* buf, size_t n) {
 
 uint64_t b200ldm_launch_count(void) { return b200ldm::g_launches.load(); }
 
+size_t b200ldm_sizeof_params(int32_t which) {
+  return which == 0 ? sizeof(b200ldm_conv3d_params) : which == 1 ? sizeof(b200ldm_sched_params) : 0;
+}
+
 int b200ldm_check_device(void) {
   int dev = 0;
   B2_CHECK_CUDA(cudaGetDevice(&dev));

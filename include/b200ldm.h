@@ -59,6 +59,9 @@ int b200ldm_last_error(char* buf, size_t n);
 int b200ldm_check_device(void);
 /* number of kernels this library has launched from the calling process (bench.py gpu_launches) */
 uint64_t b200ldm_launch_count(void);
+/* sizeof() of the parameter structs as compiled (0: b200ldm_conv3d_params, 1: b200ldm_sched_params) so a foreign
+ * binding can verify its own struct declaration before the first call */
+size_t b200ldm_sizeof_params(int32_t which);
 
 /* ------------------------------------------------------------------------------------------
  * Conv3d, NDHWC, k in {1,3}, stride in {1,2}; replaces F.conv3d reached from
