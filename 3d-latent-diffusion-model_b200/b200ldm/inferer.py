@@ -18,54 +18,76 @@ import os
 import torch
 
 from . import ops
-from .nets import AutoencoderKL, DiffusionModelUNet, _PREC, _pad64
+from .nets import AutoencoderKL, DiffusionModelUNet, _PREC, _pad64, param_signature
 
 USE_GRAPH = os.environ.get("B200LDM_CUDA_GRAPH", "1") != "0"
 
 
 class SamplingLoop:
-    """Device-resident state + (optionally graph-captured) body of one denoising step."""
+    """Device-resident state + (optionally graph-captured) body of one denoising step.
+
+    All state lives in buffers allocated once per (model, shapes, timesteps); `reset` refills them in place, so the
+    captured graph (whose kernels hold these pointers) serves every later batch of the same shape - including a new
+    seed, which the scheduler kernel reads from device memory."""
 
     def __init__(self, unet: DiffusionModelUNet, scheduler, input_noise: torch.Tensor, conditioning, mode: str,
                  step_noise=None, seed: int = 0, use_graph: bool = True):
         dev = input_noise.device
-        self.unet, self.scheduler = unet, scheduler
+        self.unet = unet
         self.dtype = _PREC[unet.precision]
         N, self.c_lat = input_noise.shape[:2]
+        self.shape = tuple(input_noise.shape)
         self.spatial = tuple(input_noise.shape[2:])
-        c_in = self.c_lat + (conditioning.shape[1] if mode == "concat" else 0)
-        if c_in != unet.in_channels:
-            raise ValueError(f"UNet expects {unet.in_channels} input channels, sampling provides {c_in}")
+        self.mode = mode
+        self.c_in = self.c_lat + (conditioning.shape[1] if mode == "concat" else 0)
+        if self.c_in != unet.in_channels:
+            raise ValueError(f"UNet expects {unet.in_channels} input channels, sampling provides {self.c_in}")
         if self.c_lat % 4:
             raise ValueError("latent channel count must be a multiple of 4")
         self.n_steps = len(scheduler.timesteps)
         # state
         self.x_t = ops.to_ndhwc(input_noise, self.c_lat, torch.float32)            # fp32 master [N,D,H,W,C]
-        self.x_model = ops.to_ndhwc(input_noise, _pad64(c_in), self.dtype)          # UNet input buffer
-        if mode == "concat":
-            ops.to_ndhwc(conditioning, _pad64(c_in), self.dtype, out=self.x_model, c_offset=self.c_lat)
+        self.x_model = ops.to_ndhwc(input_noise, _pad64(self.c_in), self.dtype)     # UNet input buffer (padding = 0)
         ts = torch.as_tensor([float(t) for t in scheduler.timesteps], dtype=torch.float32, device=dev)
         self.temb_table = unet.time_embedding_table(ts)                            # [n_steps, total]
         self.temb_cur = torch.empty((1, self.temb_table.shape[1]), dtype=torch.float32, device=dev)
-        self.coef = scheduler.coef_table(dev)
+        self.coef = scheduler.coef_table(dev).clone()
         self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.seed = seed
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.noise, self.noise_stride = None, 0
         if step_noise is not None:
-            if step_noise.shape[0] != self.n_steps or tuple(step_noise.shape[1:]) != tuple(input_noise.shape):
-                raise ValueError("step_noise must be [n_steps, *input_noise.shape]")
-            sn = step_noise.to(dev).reshape((self.n_steps * N,) + tuple(input_noise.shape[1:]))
-            self.noise = ops.to_ndhwc(sn, self.c_lat, torch.float32)
+            self.noise = torch.empty((self.n_steps * N,) + self.spatial + (self.c_lat,), dtype=torch.float32, device=dev)
             self.noise_stride = self.noise.numel() // self.n_steps
         self.graph = None
         self.launches_per_step = 0
         self.use_graph = use_graph and USE_GRAPH
+        self.reset(input_noise, conditioning, step_noise, seed, scheduler, _fresh=True)
+
+    def reset(self, input_noise, conditioning, step_noise, seed: int, scheduler, _fresh: bool = False):
+        """Start a new trajectory in the existing buffers (same shapes / timesteps as at construction)."""
+        if tuple(input_noise.shape) != self.shape or len(scheduler.timesteps) != self.n_steps:
+            raise ValueError("SamplingLoop.reset: shapes / number of steps differ from the captured loop")
+        if (step_noise is not None) != (self.noise is not None):
+            raise ValueError("SamplingLoop.reset: step_noise presence differs from the captured loop")
+        if not _fresh:
+            ops.to_ndhwc(input_noise, self.c_lat, torch.float32, out=self.x_t)
+            ops.to_ndhwc(input_noise, _pad64(self.c_in), self.dtype, out=self.x_model)
+            self.coef.copy_(scheduler.coef_table(self.coef.device))
+        if self.mode == "concat":
+            ops.to_ndhwc(conditioning, _pad64(self.c_in), self.dtype, out=self.x_model, c_offset=self.c_lat)
+        if step_noise is not None:
+            if step_noise.shape[0] != self.n_steps or tuple(step_noise.shape[1:]) != self.shape:
+                raise ValueError("step_noise must be [n_steps, *input_noise.shape]")
+            sn = step_noise.to(self.x_t.device).reshape((self.n_steps * self.shape[0],) + self.shape[1:])
+            ops.to_ndhwc(sn, self.c_lat, torch.float32, out=self.noise)
+        self.seed_dev.fill_(int(seed) & (2 ** 63 - 1))
+        self.counter.zero_()
 
     def _body(self):
         ops.select_row(self.temb_table, self.counter, self.temb_cur)
         eps = self.unet.forward_ndhwc(self.x_model, self.temb_cur, 0)
         ops.scheduler_step(eps, self.x_t, self.coef, self.counter, self.c_lat, noise=self.noise,
-                           noise_step_stride=self.noise_stride, x_model=self.x_model, seed=self.seed)
+                           noise_step_stride=self.noise_stride, x_model=self.x_model, seed=self.seed_dev)
         ops.counter_add(self.counter, 1)
 
     def _capture(self):
@@ -90,7 +112,7 @@ class SamplingLoop:
         self.graph = g
 
     def step(self):
-        if self.use_graph:
+        if self.use_graph and USE_GRAPH:
             if self.graph is None:
                 self._capture()
             self.graph.replay()
@@ -102,8 +124,28 @@ class SamplingLoop:
 
 
 class DiffusionInferer:
+    MAX_CACHED_LOOPS = 2   # each holds a CUDA graph + its private activation pool
+
     def __init__(self, scheduler):
         self.scheduler = scheduler
+        self._loops = {}
+
+    def _loop_for(self, unet, scheduler, input_noise, conditioning, mode, step_noise, seed):
+        """Cached SamplingLoop (buffers + captured graph) for this model / shape / schedule; a repeated `sample` call
+        then costs T graph replays and nothing else (capture and its allocator traffic were 0.2-1.1 s per call)."""
+        key = (id(unet), param_signature(unet), unet.precision, tuple(input_noise.shape), str(input_noise.device),
+               None if conditioning is None else tuple(conditioning.shape), mode,
+               tuple(int(t) for t in scheduler.timesteps), step_noise is not None)
+        loop = self._loops.get(key)
+        if loop is None:
+            while len(self._loops) >= self.MAX_CACHED_LOOPS:
+                self._loops.pop(next(iter(self._loops)))
+            loop = SamplingLoop(unet, scheduler, input_noise, conditioning, mode, step_noise=step_noise, seed=seed,
+                                use_graph=len(scheduler.timesteps) > 2)
+            self._loops[key] = loop
+        else:
+            loop.reset(input_noise, conditioning, step_noise, seed, scheduler)
+        return loop
 
     @torch.no_grad()
     def sample(self, input_noise, diffusion_model, scheduler=None, save_intermediates=False, intermediate_steps=100,
@@ -122,8 +164,7 @@ class DiffusionInferer:
             raise RuntimeError("b200ldm sampling needs CUDA tensors (there is no CPU fallback)")
         if seed is None:
             seed = int(torch.initial_seed()) & (2 ** 63 - 1)
-        loop = SamplingLoop(diffusion_model, scheduler, input_noise, conditioning, mode, step_noise=step_noise,
-                            seed=seed, use_graph=len(scheduler.timesteps) > 2)
+        loop = self._loop_for(diffusion_model, scheduler, input_noise, conditioning, mode, step_noise, seed)
         intermediates = []
         for t in scheduler.timesteps:
             loop.step()
@@ -180,7 +221,7 @@ class LatentDiffusionInferer(DiffusionInferer):
             inv = torch.full((lat.shape[0],), 1.0 / float(self.scale_factor), dtype=torch.float32, device=lat.device)
             zero = torch.zeros_like(inv)
             lat = ops.add_noise(lat, lat, inv, zero)  # lat * (1/scale) on our own kernel
-        return ae.decode_stage_2_outputs(lat)
+        return ae.decode_graphed(lat) if USE_GRAPH else ae.decode_stage_2_outputs(lat)
 
     @torch.no_grad()
     def __call__(self, inputs, autoencoder_model, diffusion_model, noise, timesteps, condition=None, mode="crossattn",

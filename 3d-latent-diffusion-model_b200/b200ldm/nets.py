@@ -59,6 +59,12 @@ class PackedCache:
         return val
 
 
+def param_signature(module: nn.Module) -> int:
+    """Changes whenever any parameter is rewritten in place (load_state_dict, optimizer step) or moved: captured
+    CUDA graphs bake in the packed-weight pointers, so they are keyed by this."""
+    return hash(tuple((p.data_ptr(), p._version) for p in module.parameters()))
+
+
 class Conv(nn.Module):
     """Leaf that owns `weight` [Cout,Cin,k,k,k] + `bias` like nn.Conv3d and runs the conv3d kernel."""
 
@@ -638,6 +644,7 @@ class AutoencoderKL(nn.Module):
         self.precision = precision or default_precision()
         self.encoder = Encoder(in_channels, channels, latent_channels, nres, norm_num_groups, norm_eps,
                                attention_levels, with_encoder_nonlocal_attn)
+        self._decode_graphs = {}
         self.decoder = Decoder(channels, latent_channels, out_channels, nres, norm_num_groups, norm_eps,
                                attention_levels, with_decoder_nonlocal_attn)
         self.quant_conv_mu = ConvOnly(latent_channels, latent_channels, 1, 1, 0, terminal=True)
@@ -689,4 +696,28 @@ class AutoencoderKL(nn.Module):
 
     def decode_stage_2_outputs(self, z):
         return self.decode(z)
+
+    @torch.no_grad()
+    def decode_graphed(self, z):
+        """decode(z) through a CUDA graph cached per (shape, weights): the sampling hot path's decode.  Replays reuse the
+        graph's private activation pool, so there is no allocator traffic after the first call."""
+        key = (tuple(z.shape), str(z.device), self.precision, param_signature(self))
+        hit = self._decode_graphs.get(key)
+        if hit is None:
+            self._decode_graphs.clear()
+            static_in = z.detach().to(torch.float32).clone()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self.decode(static_in)      # warm-up: weight repack, cudaFuncSetAttribute
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = self.decode(static_in)
+            hit = (g, static_in, static_out)
+            self._decode_graphs[key] = hit
+        g, static_in, static_out = hit
+        static_in.copy_(z)
+        g.replay()
+        return static_out.clone()
 

@@ -299,14 +299,21 @@ def counter_add(counter, delta: int = 1):
 
 
 def scheduler_step(eps, x_t, coef, counter, c: int, noise=None, noise_step_stride: int = 0, x0_out=None, x_model=None,
-                   seed: int = 0):
-    """In-place x_t <- step(eps, x_t); eps [.., C_eps] NDHWC, x_t fp32 [.., C] NDHWC."""
+                   seed=0):
+    """In-place x_t <- step(eps, x_t); eps [.., C_eps] NDHWC, x_t fp32 [.., C] NDHWC.
+    seed: int, or a device int64[1] tensor read by the kernel (a captured graph then serves any seed)."""
     _need_cuda(eps, x_t, coef, noise, x_model)
+    seed_dev = None
+    if torch.is_tensor(seed):
+        _need_cuda(seed)
+        assert seed.dtype == torch.int64 and seed.numel() == 1
+        seed_dev, seed = seed, 0
     n_vox = x_t.numel() // c
     p = _lib.SchedParams(
         eps=_ptr(eps), x_t=_ptr(x_t), noise=_ptr(noise), x0_out=_ptr(x0_out), x_model=_ptr(x_model), coef=_ptr(coef),
         counter=_ptr(counter), n_vox=n_vox, noise_step_stride=noise_step_stride, C=c, C_eps=eps.shape[-1],
-        C_model=0 if x_model is None else x_model.shape[-1], dtype=dtype_code(eps.dtype), seed=seed)
+        C_model=0 if x_model is None else x_model.shape[-1], dtype=dtype_code(eps.dtype), seed=seed,
+        seed_dev=_ptr(seed_dev))
     _lib.check(_lib.load().b200ldm_scheduler_step(C.byref(p), _stream()), "scheduler_step")
 
 

@@ -22,43 +22,10 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "conv_tc.cuh"
 #include "tc_ptx.cuh"
 
 namespace b200ldm {
-
-struct ConvTcMaps {
-  CUtensorMap a[8];  // stride 1: a[0] = x, a[1] = x2;  stride 2: a[pd*4+ph*2+pw]
-  CUtensorMap w;     // [taps][Cout_pad][Cin_total]
-  CUtensorMap y[8];  // output, same voxel box as the A tiles (TMA-store epilogue); up mode: one strided map per phase
-  CUtensorMap r;     // residual (same geometry as y) when fused
-  CUtensorMap s[2];  // fused 1x1x1 skip conv: its one or two (concat) sources, output geometry
-  CUtensorMap sw;    // skip weights [1][Cout_pad][Cs1+Cs2]
-};
-
-struct ConvTcArgs {
-  int tn, td, th, tw;      // voxel box of one M tile
-  int nb_d, nb_h, nb_w;    // tiles per spatial dim (tiles over N = gridDim.x / (nb_d*nb_h*nb_w))
-  int N, Do, Ho, Wo, Cout;
-  int nchunk1, nchunk2;    // 64-channel chunks in x / x2
-  int nsk1, nsk2;          // 64-channel chunks of the fused 1x1x1 skip conv's sources (extra K iterations, centre tap)
-  int ksize, stride, pad_lo;
-  int rows_box;            // tn*td*th*tw
-  int temb_stride, out_f32, gn_groups;
-  const float* bias;
-  const float* temb;
-  const void* residual;
-  void* y;
-  double* gn_stats;
-  double* chunk_stats;        // [N][Cout/8][2] (sum, sumsq) per 8-channel chunk of y, accumulated by the TMA epilogue
-  int up;                     // 1: nearest-x2 upsample fused as 8 phase convs of 2x2x2 taps (blockIdx.z = phase)
-  int splits;                 // split-K: blockIdx.z handles k-iterations [z*I/S, (z+1)*I/S) and writes fp32 slab z
-  long long slab_elems;       // elements per fp32 slab (N*Do*Ho*Wo*Cout)
-  int ashift;                 // experiment: A sub-tile base shifted by ashift*128 bytes (swizzle-phase probe)
-  int tma_epilogue;           // 1: stage the tile in smem and TMA-store it (bf16, Cout % 64 == 0, no GN partials)
-  unsigned long long* trace;  // debug: per-CTA clock64 stamps (b200ldm_debug_set_conv_trace), else nullptr
-};
-
-constexpr int kABytes = 128 * 128;  // one M sub-tile: 128 rows x 64 bf16
 
 // BN = Cout tile, MT = number of 128-row M sub-tiles per CTA that share one weight stage.
 // MT = 2 halves the L2->SMEM bytes per FLOP (the v1 kernel was L2-bandwidth bound: profiles/r01_ncu_conv3d_tc_first.md).

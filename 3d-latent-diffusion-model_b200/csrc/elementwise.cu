@@ -189,6 +189,7 @@ __global__ void philox_normal_kernel(float* __restrict__ out, long long n, uint6
 template <typename T>
 __global__ void scheduler_step_kernel(const b200ldm_sched_params p) {
   const int step = p.counter ? p.counter[0] : 0;
+  const uint64_t seed = p.seed_dev ? *p.seed_dev : p.seed;
   const float* cf = p.coef + (size_t)step * 8;
   const float inv_sqrt_acp = cf[0], sqrt_1m = cf[1], c_x0 = cf[2], c_xt = cf[3], c_eps = cf[4], sigma = cf[5],
               lo = cf[6], hi = cf[7];
@@ -210,7 +211,7 @@ __global__ void scheduler_step_kernel(const b200ldm_sched_params p) {
         const float4 nz = *reinterpret_cast<const float4*>(p.noise + (size_t)step * p.noise_step_stride + xi);
         z[0] = nz.x; z[1] = nz.y; z[2] = nz.z; z[3] = nz.w;
       } else {
-        philox_normal4(p.seed, (uint32_t)step, (uint64_t)q, z);
+        philox_normal4(seed, (uint32_t)step, (uint64_t)q, z);
       }
     }
 #pragma unroll

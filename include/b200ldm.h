@@ -209,6 +209,8 @@ typedef struct {
   int32_t C, C_eps, C_model;
   int32_t dtype;
   uint64_t seed;
+  const uint64_t* seed_dev; /* optional device-side seed; when non-NULL it replaces `seed`, so one captured CUDA
+                               graph of the denoising step can be replayed for a new batch with a new seed */
 } b200ldm_sched_params;
 int b200ldm_scheduler_step(const b200ldm_sched_params* p, b200ldm_stream stream);
 /* standalone Philox normal stream identical to the one scheduler_step draws (parity tests) */

@@ -127,6 +127,38 @@ def test_sampling_graph_equals_eager_and_intermediates(precision):
     assert relerr(c1, c2) <= tol and relerr(c1, c3) > 5e-2
 
 
+def test_cached_sampling_loop_tracks_inputs_and_weights():
+    """sample() keeps one captured loop per (model, shape, schedule): a second call must see the NEW noise /
+    conditioning / seed, and rewritten weights must invalidate the captured graphs (UNet step and decode)."""
+    import b200ldm
+    unet = port(gc.tiny_unet(), b200ldm.DiffusionModelUNet, gc.UNET_KW, "bf16")
+    ae = port(gc.tiny_ae(), b200ldm.AutoencoderKL, gc.AE_KW, "bf16")
+    sched = gc.make_scheduler(b200ldm, "ddpm", 5)
+    x_T, cond, step_noise = gc.sampling_inputs(5)
+    g = torch.Generator().manual_seed(99)
+    x2, c2 = torch.randn(x_T.shape, generator=g), torch.randn(cond.shape, generator=g)
+    inf = b200ldm.LatentDiffusionInferer(sched)
+
+    def run(i, x, c):
+        return i.sample(input_noise=x.to(DEV), autoencoder_model=ae, diffusion_model=unet, scheduler=sched,
+                        conditioning=c.to(DEV), mode="concat", verbose=False, step_noise=step_noise.to(DEV))
+
+    a1 = run(inf, x_T, cond)
+    b1 = run(inf, x2, c2)                                   # cached loop, new inputs
+    assert len(inf._loops) == 1
+    b_fresh = run(b200ldm.LatentDiffusionInferer(sched), x2, c2)
+    assert relerr(b1, b_fresh) <= 2e-2 and relerr(b1, a1) > 5e-2
+    a2 = run(inf, x_T, cond)
+    assert relerr(a2, a1) <= 2e-2
+    # new weights: both cached graphs hold stale packed-weight pointers and must be rebuilt
+    sd = {k: v * 1.25 for k, v in unet.state_dict().items()}
+    unet.load_state_dict(sd)
+    ae.load_state_dict({k: v * 0.9 for k, v in ae.state_dict().items()})
+    a3 = run(inf, x_T, cond)
+    a3_fresh = run(b200ldm.LatentDiffusionInferer(sched), x_T, cond)
+    assert relerr(a3, a3_fresh) <= 2e-2 and relerr(a3, a1) > 5e-2
+
+
 def test_inferer_call_matches_oracle():
     """LatentDiffusionInferer.__call__ (3d_ldm/train_diffusion.py:197-205): encode -> add_noise -> concat -> UNet."""
     import b200ldm
