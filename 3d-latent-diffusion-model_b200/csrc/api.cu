@@ -6,6 +6,7 @@ namespace b200ldm {
 static thread_local char t_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 void set_conv_trace(void* p);
+void set_conv_trace2(void* p);
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -56,6 +57,7 @@ int b200ldm_check_device(void) {
 /* debug only (not in the public header): 8 clock64 stamps per conv CTA are written to `buf` while it is set */
 int b200ldm_debug_set_conv_trace(void* buf) {
   b200ldm::set_conv_trace(buf);
+  b200ldm::set_conv_trace2(buf);
   return B200LDM_OK;
 }
 

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <map>
 #include <mutex>
 
 #include "common.cuh"
@@ -604,6 +605,13 @@ static const int g_force_cl = [] {
   return e ? atoi(e) : 0;
 }();
 
+// B200LDM_CONV_TC2=0: never use the persistent CTA-pair kernel (conv_tc2.cu); 1: whenever it supports the problem;
+// unset: the planner decides
+static const int g_tc2 = [] {
+  const char* e = getenv("B200LDM_CONV_TC2");
+  return e ? atoi(e) : -1;
+}();
+
 static const int g_force_splits = [] {
   const char* e = getenv("B200LDM_CONV_SPLITS");
   return e ? atoi(e) : 0;
@@ -611,10 +619,33 @@ static const int g_force_splits = [] {
 
 struct ConvPlan {
   int bn, n_tiles, tn, td, th, tw, nb_n, nb_d, nb_h, nb_w, m_tiles, mt, cl, splits;
+  int tc2;   // 1: persistent CTA-pair kernel (conv_tc2.cu)
+  int tc2_ok;  // the problem is eligible for it
 };
 
+// Which of the two tensor-core kernels runs a problem is MEASURED once per problem signature (first un-captured call:
+// both candidates are timed on the caller's own buffers with CUDA events) and remembered here; until then - and
+// always with B200LDM_CONV_AUTOTUNE=0 or while the stream is being captured - the cost model below decides.
+struct ConvKey {
+  int v[20];
+  bool operator<(const ConvKey& o) const { return memcmp(v, o.v, sizeof(v)) < 0; }
+};
+static ConvKey conv_key(const b200ldm_conv3d_params* p) {
+  ConvKey k{{p->N, p->D, p->H, p->W, p->C1, p->C2, p->Cout, p->Do, p->Ho, p->Wo, p->ksize, p->stride, p->pad_lo,
+             p->upsample2x, p->out_f32, p->gn_stats != nullptr, p->residual != nullptr, p->temb != nullptr,
+             p->skip_x ? p->skip_C1 : 0, p->skip_x ? p->skip_C2 : 0}};
+  return k;
+}
+static std::mutex g_choice_mu;
+static std::map<ConvKey, int> g_choice;   // 0: one CTA per tile (conv3d_tc_kernel), 1: persistent CTA pairs (tc2)
+static const int g_autotune = [] {
+  const char* e = getenv("B200LDM_CONV_AUTOTUNE");
+  return e ? atoi(e) : 1;
+}();
+
 // Tile / cluster / split-K decisions (shared by the launch and by b200ldm_conv3d_workspace_bytes).
-static ConvPlan plan_conv(const b200ldm_conv3d_params* p) {
+// force_tc2: -1 = remembered measurement, else cost model; 0 / 1 = that kernel (tuning runs).
+static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
   ConvPlan pl{};
   if (p->Cout % 256 == 0) pl.bn = 256;
   else if (p->Cout % 128 == 0) pl.bn = 128;
@@ -662,8 +693,32 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p) {
       }
     }
   }
-  if (g_force_splits >= 1 && g_force_splits <= 12 && !p->out_f32 && !p->gn_stats && !p->upsample2x &&
-      iters / g_force_splits >= 1)
+  {
+    // persistent CTA-pair kernel (conv_tc2.cu): rounds of 74 pair-tiles, per-tile cost = max(main loop, epilogue) since
+    // the two overlap.  Measured (scripts/conv_trace2.py): a cta_group::2 k-iteration takes ~600 cycles against 512
+    // for two single-CTA ones, ~745 with the loads (44 B/clk/SM), and the 4-warp epilogue ~2450 cycles per 64 channels.
+    const bool tma_epi = !p->out_f32 && p->Cout % 64 == 0 && !p->gn_stats && pl.bn >= 64 && g_legacy_epilogue == 0;
+    pl.tc2_ok = tma_epi ? 1 : 0;
+    pl.tc2 = 0;
+    if (tma_epi && g_tc2 != 0) {
+      const double mma = 4.0 * (pl.bn / 2 + 23.0);
+      const double load = (16384.0 + pl.bn * 64.0) / 44.0;
+      const double main_loop = iters * ((mma > load ? mma : load) + 8.0);
+      const double epi = 2450.0 * (pl.bn / 64);
+      const long long work = (long long)ceil_div(pl.m_tiles, 2) * pl.n_tiles * zmul;
+      const double t2 = ceil_div(work, 74) * (main_loop > epi ? main_loop : epi) + 3000.0 + epi;
+      int choice = (g_tc2 == 1 || t2 < best) ? 1 : 0;
+      if (force_tc2 >= 0) choice = force_tc2;
+      else if (g_tc2 < 0) {
+        std::lock_guard<std::mutex> lk(g_choice_mu);
+        auto it = g_choice.find(conv_key(p));
+        if (it != g_choice.end()) choice = it->second;
+      }
+      pl.tc2 = choice;
+    }
+    if (pl.tc2) { pl.mt = 1; pl.cl = 1; pl.splits = 1; }
+  }
+  if (!pl.tc2 && g_force_splits >= 1 && g_force_splits <= 12 && split_ok && iters / g_force_splits >= 1)
     pl.splits = g_force_splits;
   if (pl.splits > 1) pl.cl = 1;
   return pl;
@@ -674,7 +729,7 @@ int conv3d_tcgen05_emits_chunk_stats(const b200ldm_conv3d_params* p) {
   if (p->dtype != B200LDM_BF16 || p->C1 % 64 || p->C2 % 64 || p->Cout % 64 || p->out_f32 || p->gn_stats) return 0;
   if (g_legacy_epilogue) return 0;
   const ConvPlan pl = plan_conv(p);
-  return (pl.splits == 1 && pl.tn == 1 && pl.bn >= 64) ? 1 : 0;
+  return (pl.splits == 1 && pl.tn == 1 && pl.bn >= 64) ? 1 : 0;   // holds for both tensor-core kernels
 }
 
 long long conv3d_tcgen05_workspace_bytes(const b200ldm_conv3d_params* p) {
@@ -683,6 +738,8 @@ long long conv3d_tcgen05_workspace_bytes(const b200ldm_conv3d_params* p) {
   if (pl.splits <= 1) return 0;
   return (long long)pl.splits * p->N * p->Do * p->Ho * p->Wo * p->Cout * 4;
 }
+
+static int conv3d_run_plan(const b200ldm_conv3d_params* p, const ConvPlan& pl, cudaStream_t st);
 
 int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
   B2_REQUIRE(p->dtype == B200LDM_BF16, B200LDM_BAD_ARG, "tcgen05 conv needs bf16 activations");
@@ -710,9 +767,66 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
                    !p->residual && !p->temb && p->Cout % 64 == 0 && p->Do == 2 * p->D && p->Ho == 2 * p->H &&
                    p->Wo == 2 * p->W,
                B200LDM_BAD_SHAPE, "fused upsample conv: needs k3 s1 p1, one source, bf16 out, Cout %% 64 == 0, out = 2x in");
+  const ConvPlan pl = plan_conv(p);
+  if (g_autotune && g_tc2 < 0 && pl.tc2_ok) {
+    const ConvKey key = conv_key(p);
+    bool known;
+    {
+      std::lock_guard<std::mutex> lk(g_choice_mu);
+      known = g_choice.count(key) != 0;
+    }
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (!known && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+      // time both kernels on the caller's buffers (the result is the same tensor either way); the one-CTA-per-tile
+      // candidate may need split-K scratch the caller sized for the cost model's plan - skip it if there is none
+      ConvPlan cand[2] = {plan_conv(p, 0), plan_conv(p, 1)};
+      const long long M_total = (long long)p->N * p->Do * p->Ho * p->Wo;
+      float ms[2] = {1e30f, 1e30f};
+      cudaEvent_t e0, e1;
+      B2_CHECK_CUDA(cudaEventCreate(&e0));
+      B2_CHECK_CUDA(cudaEventCreate(&e1));
+      int rc = B200LDM_OK;
+      for (int c = 0; c < 2 && rc == B200LDM_OK; ++c) {
+        if (cand[c].splits > 1 && (!p->workspace || p->workspace_bytes < (long long)cand[c].splits * M_total * p->Cout * 4))
+          continue;
+        b200ldm_conv3d_params q = *p;
+        // statistics are accumulated by atomics: tuning launches must not add to the caller's buffer
+        if (cand[c].splits > 1 || cand[c].tn != 1) q.chunk_stats = nullptr;
+        for (int rep = 0; rep < 3 && rc == B200LDM_OK; ++rep) {
+          if (rep == 1) cudaEventRecord(e0, st);
+          rc = conv3d_run_plan(&q, cand[c], st);
+        }
+        cudaEventRecord(e1, st);
+        if (rc == B200LDM_OK && cudaEventSynchronize(e1) == cudaSuccess) cudaEventElapsedTime(&ms[c], e0, e1);
+      }
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      if (rc != B200LDM_OK) return rc;
+      if (p->chunk_stats)   // undo what the tuning launches accumulated
+        B2_CHECK_CUDA(cudaMemsetAsync(p->chunk_stats, 0, (size_t)p->N * (p->Cout / 8) * 2 * sizeof(double), st));
+      const int best = ms[1] < ms[0] ? 1 : 0;
+      {
+        std::lock_guard<std::mutex> lk(g_choice_mu);
+        g_choice[key] = best;
+      }
+      if (getenv("B200LDM_CONV_AUTOTUNE_LOG"))
+        fprintf(stderr, "b200ldm autotune: %d+%d->%d k%d s%d%s @%dx%dx%dx%d: tile-per-CTA %.3f ms, CTA pairs %.3f ms\n",
+                p->C1, p->C2, p->Cout, p->ksize, p->stride, p->upsample2x ? " up" : "", p->N, p->Do, p->Ho, p->Wo,
+                ms[0] / 2, ms[1] / 2);
+      // the caller asked workspace_bytes / emits_chunk_stats under the cost-model plan: honour that contract for this
+      // call (no stats where it was told there would be none), later calls see the remembered choice
+      ConvPlan run = cand[best];
+      if (p->chunk_stats && (run.splits > 1 || run.tn != 1)) run = pl;
+      if (run.splits > 1 && (!p->workspace || p->workspace_bytes < (long long)run.splits * M_total * p->Cout * 4)) run = pl;
+      return conv3d_run_plan(p, run, st);
+    }
+  }
+  return conv3d_run_plan(p, pl, st);
+}
+
+static int conv3d_run_plan(const b200ldm_conv3d_params* p, const ConvPlan& pl, cudaStream_t st) {
   const int taps = p->upsample2x ? 64 : p->ksize * p->ksize * p->ksize;  // rows of the packed weight tensor
   const int Cin = p->C1 + p->C2;
-  const ConvPlan pl = plan_conv(p);
   const int bn = pl.bn, n_tiles = pl.n_tiles;
   const long long M_total = (long long)p->N * p->Do * p->Ho * p->Wo;
   if (pl.splits > 1)
@@ -824,6 +938,16 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
   }
 
   const int m_tiles = pl.m_tiles, mt = pl.mt, cl = pl.cl;
+  if (pl.tc2 && conv_tc2_supported(bn, a)) {
+    // each CTA of a pair stages half of the weight tile
+    rc = make_weight_map(&maps.w, p->w, Cin, cout_rows, taps, bn / 2);
+    if (rc) return rc;
+    if (p->skip_x) {
+      rc = make_weight_map(&maps.sw, p->skip_w, p->skip_C1 + p->skip_C2, cout_rows, 1, bn / 2);
+      if (rc) return rc;
+    }
+    return launch_conv_tc2(maps, a, bn, m_tiles, n_tiles, a.up ? 8 : 1, st);
+  }
   // the weight map box holds the rows ONE CTA fetches
   rc = make_weight_map(&maps.w, p->w, Cin, cout_rows, taps, bn / cl);
   if (rc) return rc;

@@ -37,6 +37,7 @@ struct ConvTcArgs {
   int ashift;                 // experiment: A sub-tile base shifted by ashift*128 bytes (swizzle-phase probe)
   int tma_epilogue;           // 1: stage the tile in smem and TMA-store it (bf16, Cout % 64 == 0, no GN partials)
   unsigned long long* trace;  // debug: per-CTA clock64 stamps (b200ldm_debug_set_conv_trace), else nullptr
+  int work_x, work_y, work_z; // conv_tc2: M pair-tiles, Cout tiles, upsample phases of the persistent work list
 };
 
 constexpr int kABytes = 128 * 128;  // one M sub-tile: 128 rows x 64 bf16

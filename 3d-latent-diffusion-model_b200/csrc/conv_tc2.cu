@@ -77,7 +77,8 @@ conv3d_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
   const uint32_t bar_base = out_base + Cfg::kOutBytes;
   const uint32_t full_bar = bar_base;                       // [STAGES]  (leader's copy is the live one)
   const uint32_t empty_bar = bar_base + 8 * STAGES;         // [STAGES]
-  const uint32_t tfull_bar = bar_base + 16 * STAGES;        // [2] accumulator complete (multicast to both CTAs)
+  const uint32_t pfull_bar = bar_base + 16 * STAGES;        // [STAGES] relay mode: the peer's stage is full (leader's copy)
+  const uint32_t tfull_bar = bar_base + 24 * STAGES;        // [2] accumulator complete (multicast to both CTAs)
   const uint32_t tempty_bar = tfull_bar + 16;               // [2] accumulator drained (leader's copy, 8 warp arrivals)
   const uint32_t res_bar = tempty_bar + 16;                 // [2] residual tile landed in staging buffer b
   const uint32_t tmem_slot = res_bar + 16;
@@ -93,6 +94,9 @@ conv3d_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
   const int nchunks = a.nchunk1 + a.nchunk2;
   const int iters_main = taps * nchunks;
   const int iters_total = iters_main + a.nsk1 + a.nsk2;
+  // experiment switches (B200LDM_CONV_TC2_MODE): bit0 = dry run (no loads: barrier handshake + MMA rate only),
+  // bit1 = relay (each CTA's loads credit its OWN full barrier; the peer's idle MMA warp forwards one arrive per stage)
+  const bool dry = (a.ashift & 1) != 0, relay = (a.ashift & 2) != 0;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&maps.w);
@@ -101,6 +105,7 @@ conv3d_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(full_bar + 8 * s, 1);
       ptx::mbar_init(empty_bar + 8 * s, 1);
+      ptx::mbar_init(pfull_bar + 8 * s, 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(tfull_bar + 8 * i, 1);
@@ -115,29 +120,46 @@ conv3d_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
   ptx::cluster_sync();   // the peer's barriers exist before anyone credits / arrives on them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // debug timeline (b200ldm_debug_set_conv_trace): [0] start, [1] MMA waits on full, [2] MMA waits on tmem_empty,
+  // [3] producer waits on empty, [4] epilogue waits on tmem_full, [5] epilogue busy, [6] tiles, [7] end
+  unsigned long long* trc = a.trace ? a.trace + (size_t)blockIdx.x * 8 : nullptr;
+  if (trc && threadIdx.x == 0) trc[0] = clock64();
 
   if (warp == 0) {
     // =========================== TMA producer (both CTAs) ===========================
     if (lane == 0) {
       const uint32_t tx_pair = 2u * ((uint32_t)a.rows_box * 128u + (uint32_t)Cfg::kBBytes);
       uint32_t itg = 0;
+      long long w_empty = 0;
       for (int wk = pair; wk < total; wk += pairs) {
         const TileCoord c = decode_tile(a, wk, (int)rank, BN);
         const int brow0 = c.co0 + (int)rank * Cfg::kBHalf;
         for (int it = 0; it < iters_total; ++it, ++itg) {
           const int s = (int)(itg % STAGES);
           const uint32_t ph = (itg / STAGES) & 1u;
+          const long long tw0 = trc ? clock64() : 0;
           ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1u, 0);
+          if (trc) w_empty += clock64() - tw0;
           const uint32_t full = full_bar + 8 * s;
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
           const uint32_t sb = sa + kABytes;
-          if (rank == 0) ptx::mbar_expect_tx(full, tx_pair);
+          if (dry) {
+            if (rank == 0) ptx::mbar_arrive(full);
+            continue;
+          }
+          if (relay) ptx::mbar_expect_tx(full, tx_pair >> 1);
+          else if (rank == 0) ptx::mbar_expect_tx(full, tx_pair);
           if (it >= iters_main) {
             const int sc = it - iters_main;
             const bool second = sc >= a.nsk1;
             const CUtensorMap* m = second ? &maps.s[1] : &maps.s[0];
-            ptx::tma_load_5d_2sm(sa, m, full, (second ? sc - a.nsk1 : sc) * 64, c.w0, c.h0, c.d0, c.n0);
-            ptx::tma_load_3d_2sm(sb, &maps.sw, full, sc * 64, brow0, 0);
+            if (relay) {
+              ptx::tma_load_5d(sa, m, full, (second ? sc - a.nsk1 : sc) * 64, c.w0, c.h0, c.d0, c.n0);
+              ptx::tma_load_3d(sb, &maps.sw, full, sc * 64, brow0, 0);
+            } else {
+              ptx::tma_load_5d_2sm(sa, m, full, (second ? sc - a.nsk1 : sc) * 64, c.w0, c.h0, c.d0, c.n0);
+              ptx::tma_load_3d_2sm(sb, &maps.sw, full, sc * 64, brow0, 0);
+            }
             continue;
           }
           const int tap = it / nchunks;
@@ -152,32 +174,48 @@ conv3d_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
           if (a.stride == 1) {
             const bool second = chunk >= a.nchunk1;
             const CUtensorMap* m = second ? &maps.a[1] : &maps.a[0];
-            ptx::tma_load_5d_2sm(sa, m, full, (second ? chunk - a.nchunk1 : chunk) * 64, c.w0 + kw - pad_w,
-                                 c.h0 + kh - pad_h, c.d0 + kd - pad_d, c.n0);
+            const int c0 = (second ? chunk - a.nchunk1 : chunk) * 64;
+            if (relay)
+              ptx::tma_load_5d(sa, m, full, c0, c.w0 + kw - pad_w, c.h0 + kh - pad_h, c.d0 + kd - pad_d, c.n0);
+            else
+              ptx::tma_load_5d_2sm(sa, m, full, c0, c.w0 + kw - pad_w, c.h0 + kh - pad_h, c.d0 + kd - pad_d, c.n0);
           } else {
             const int od = kd - a.pad_lo, oh = kh - a.pad_lo, ow = kw - a.pad_lo;
             const int pd = od & 1, ph2 = oh & 1, pw = ow & 1;
-            ptx::tma_load_5d_2sm(sa, &maps.a[pd * 4 + ph2 * 2 + pw], full, chunk * 64, c.w0 + ((ow - pw) >> 1),
-                                 c.h0 + ((oh - ph2) >> 1), c.d0 + ((od - pd) >> 1), c.n0);
+            const CUtensorMap* m = &maps.a[pd * 4 + ph2 * 2 + pw];
+            if (relay)
+              ptx::tma_load_5d(sa, m, full, chunk * 64, c.w0 + ((ow - pw) >> 1), c.h0 + ((oh - ph2) >> 1),
+                               c.d0 + ((od - pd) >> 1), c.n0);
+            else
+              ptx::tma_load_5d_2sm(sa, m, full, chunk * 64, c.w0 + ((ow - pw) >> 1), c.h0 + ((oh - ph2) >> 1),
+                                   c.d0 + ((od - pd) >> 1), c.n0);
           }
-          ptx::tma_load_3d_2sm(sb, &maps.w, full, chunk * 64, brow0, wtap);
+          if (relay) ptx::tma_load_3d(sb, &maps.w, full, chunk * 64, brow0, wtap);
+          else ptx::tma_load_3d_2sm(sb, &maps.w, full, chunk * 64, brow0, wtap);
         }
       }
+      if (trc) trc[3] = (unsigned long long)w_empty;
     }
   } else if (warp == 1) {
     // =========================== MMA issuer (leader CTA only) ===========================
     if (rank == 0 && lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, BN);
       uint32_t itg = 0, tile = 0;
+      long long w_full = 0, w_tempty = 0;
       for (int wk = pair; wk < total; wk += pairs, ++tile) {
         const uint32_t acc = tile & 1u, use = tile >> 1;
+        long long tw0 = trc ? clock64() : 0;
         ptx::mbar_wait_cluster(tempty_bar + 8 * acc, (use & 1u) ^ 1u, 5);   // both CTAs drained this accumulator
+        if (trc) w_tempty += clock64() - tw0;
         ptx::tc_fence_after();
         const uint32_t td = tmem_base + acc * BN;
         for (int it = 0; it < iters_total; ++it, ++itg) {
           const int s = (int)(itg % STAGES);
           const uint32_t ph = (itg / STAGES) & 1u;
+          tw0 = trc ? clock64() : 0;
           ptx::mbar_wait(full_bar + 8 * s, ph, 1);
+          if (relay) ptx::mbar_wait_cluster(pfull_bar + 8 * s, ph, 6);   // the peer's half of the stage has landed too
+          if (trc) w_full += clock64() - tw0;
           ptx::tc_fence_after();
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
           const uint32_t sb = sa + kABytes;
@@ -189,6 +227,17 @@ conv3d_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
         }
         ptx::umma_commit_2sm(tfull_bar + 8 * acc, 3);   // accumulator complete: wake both epilogues
       }
+      if (trc) { trc[1] = (unsigned long long)w_full; trc[2] = (unsigned long long)w_tempty; trc[6] = tile; }
+    } else if (rank == 1 && lane == 0 && relay && !dry) {
+      // relay: one remote arrive per stage tells the leader that this CTA's operands are in place
+      const uint32_t pfull_leader = ptx::mapa(pfull_bar, 0);
+      uint32_t itg = 0;
+      for (int wk = pair; wk < total; wk += pairs)
+        for (int it = 0; it < iters_total; ++it, ++itg) {
+          const int s = (int)(itg % STAGES);
+          ptx::mbar_wait(full_bar + 8 * s, (itg / STAGES) & 1u, 7);
+          ptx::mbar_arrive_cluster(pfull_leader + 8 * s);
+        }
     }
   } else {
     // =========================== epilogue (4 warps, both CTAs) ===========================
@@ -218,8 +267,16 @@ conv3d_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
         vrow[row] = valid ? 1 : 0;
         if (row < G * 16) csum[row] = 0.f;
       }
+      const long long te0 = (trc && issuer) ? clock64() : 0;
       ptx::mbar_wait_long(tfull_bar + 8 * acc, use & 1u, 2);
       ptx::tc_fence_after();
+      const long long te1 = (trc && issuer) ? clock64() : 0;
+      if (a.ashift & 4) {   // experiment: no epilogue work at all, only the accumulator hand-back
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader + 8 * acc);
+        continue;
+      }
 #pragma unroll 1
       for (int g = 0; g < gmax; ++g, ++gcount) {
         const uint32_t b = gcount & 1u;
@@ -333,11 +390,13 @@ conv3d_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
           atomicAdd(a.chunk_stats + ((size_t)c.n0 * (a.Cout >> 3) + (c.co0 >> 3) + k) * 2 + which, (double)csum[row]);
         }
       }
+      if (trc && issuer) { trc[4] += (unsigned long long)(te1 - te0); trc[5] += (unsigned long long)(clock64() - te1); }
     }
     if (issuer) ptx::tma_store_wait_all();   // smem must outlive the bulk reads; writes complete before exit
     ptx::tc_fence_before();
   }
   __syncthreads();
+  if (trc && threadIdx.x == 0) trc[7] = clock64();
   ptx::cluster_sync();   // nobody leaves (or frees TMEM) while the peer can still touch this CTA's smem / barriers
   if (warp == 1) {
     ptx::tc_fence_after();
@@ -346,8 +405,11 @@ conv3d_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------ host
+static unsigned long long* g_conv_trace2 = nullptr;
+void set_conv_trace2(void* p) { g_conv_trace2 = reinterpret_cast<unsigned long long*>(p); }
+
 bool conv_tc2_supported(int bn, const ConvTcArgs& a) {
-  return (bn == 256 || bn == 128 || bn == 64) && a.tma_epilogue && a.splits == 1 && a.ashift == 0 && !a.out_f32 &&
+  return (bn == 256 || bn == 128 || bn == 64) && a.tma_epilogue && a.splits == 1 && !a.out_f32 &&
          !a.gn_stats;
 }
 
@@ -382,6 +444,11 @@ static int launch_tc2(const ConvTcMaps& maps, ConvTcArgs a, int m_tiles, int n_t
   });
   B2_CHECK_CUDA(init_err);
   a.work_x = ceil_div(m_tiles, 2); a.work_y = n_tiles; a.work_z = zdim;
+  a.trace = g_conv_trace2;
+  {
+    static const int mode = [] { const char* e = getenv("B200LDM_CONV_TC2_MODE"); return e ? atoi(e) : 0; }();
+    a.ashift = mode;
+  }
   const long long total = (long long)a.work_x * a.work_y * a.work_z;
   const int pairs = (int)(total < max_pairs ? total : max_pairs);
   cudaLaunchConfig_t cfg{};
@@ -408,7 +475,5 @@ int launch_conv_tc2(const ConvTcMaps& maps, const ConvTcArgs& a, int bn, int m_t
   }
   return fail(B200LDM_BAD_SHAPE, "conv_tc2: unsupported Cout tile %d", bn);
 }
-
-int conv_tc2_max_pairs() { return 74; }
 
 }  // namespace b200ldm
