@@ -605,10 +605,10 @@ static const int g_force_cl = [] {
   return e ? atoi(e) : 0;
 }();
 
-// B200LDM_CONV_TC2=0: never use the persistent CTA-pair kernel (conv_tc2.cu); 1: whenever it supports the problem;
-// unset: the planner decides
+// B200LDM_CONV_KERNEL pins the kernel wherever it supports the problem: 0 = one CTA per tile (conv3d_tc_kernel),
+// 1 = persistent CTA pairs (conv_tc2.cu), 2 = persistent single CTAs (conv_tcp.cu); unset: measured / cost model
 static const int g_tc2 = [] {
-  const char* e = getenv("B200LDM_CONV_TC2");
+  const char* e = getenv("B200LDM_CONV_KERNEL");
   return e ? atoi(e) : -1;
 }();
 
@@ -619,8 +619,8 @@ static const int g_force_splits = [] {
 
 struct ConvPlan {
   int bn, n_tiles, tn, td, th, tw, nb_n, nb_d, nb_h, nb_w, m_tiles, mt, cl, splits;
-  int tc2;   // 1: persistent CTA-pair kernel (conv_tc2.cu)
-  int tc2_ok;  // the problem is eligible for it
+  int tc2;     // kernel: 0 one CTA per tile, 1 persistent CTA pairs (conv_tc2.cu), 2 persistent single CTAs (conv_tcp.cu)
+  int tc2_ok;  // the problem is eligible for the persistent kernels
 };
 
 // Which of the two tensor-core kernels runs a problem is MEASURED once per problem signature (first un-captured call:
@@ -701,13 +701,16 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
     pl.tc2_ok = tma_epi ? 1 : 0;
     pl.tc2 = 0;
     if (tma_epi && g_tc2 != 0) {
-      const double mma = 4.0 * (pl.bn / 2 + 23.0);
-      const double load = (16384.0 + pl.bn * 64.0) / 44.0;
+      // cost-model fallback (no measurement yet / tuning disabled): persistent single-CTA kernel, per-tile cost =
+      // max(main loop, epilogue) since they overlap
+      const int pmt = conv_tcp_mt(pl.bn);
+      const double mma = pmt * 4.0 * (128.0 * pl.bn / 256.0);
+      const double load = (pmt * 16384.0 + pl.bn * 128.0) / 72.0;
       const double main_loop = iters * ((mma > load ? mma : load) + 8.0);
-      const double epi = 2450.0 * (pl.bn / 64);
-      const long long work = (long long)ceil_div(pl.m_tiles, 2) * pl.n_tiles * zmul;
-      const double t2 = ceil_div(work, 74) * (main_loop > epi ? main_loop : epi) + 3000.0 + epi;
-      int choice = (g_tc2 == 1 || t2 < best) ? 1 : 0;
+      const double epi = 2000.0 * (pl.bn / 64);
+      const long long work = (long long)ceil_div(pl.m_tiles, pmt) * pl.n_tiles * zmul;
+      const double t2 = ceil_div(work, 148) * (main_loop > epi ? main_loop : epi) + 3000.0 + epi;
+      int choice = (g_tc2 > 0) ? g_tc2 : (t2 < best ? 2 : 0);
       if (force_tc2 >= 0) choice = force_tc2;
       else if (g_tc2 < 0) {
         std::lock_guard<std::mutex> lk(g_choice_mu);
@@ -779,14 +782,16 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
     if (!known && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
       // time both kernels on the caller's buffers (the result is the same tensor either way); the one-CTA-per-tile
       // candidate may need split-K scratch the caller sized for the cost model's plan - skip it if there is none
-      ConvPlan cand[2] = {plan_conv(p, 0), plan_conv(p, 1)};
+      constexpr int NC = 3;
+      ConvPlan cand[NC] = {plan_conv(p, 0), plan_conv(p, 1), plan_conv(p, 2)};
       const long long M_total = (long long)p->N * p->Do * p->Ho * p->Wo;
-      float ms[2] = {1e30f, 1e30f};
+      float ms[NC] = {1e30f, 1e30f, 1e30f};
       cudaEvent_t e0, e1;
       B2_CHECK_CUDA(cudaEventCreate(&e0));
       B2_CHECK_CUDA(cudaEventCreate(&e1));
       int rc = B200LDM_OK;
-      for (int c = 0; c < 2 && rc == B200LDM_OK; ++c) {
+      for (int c = 0; c < NC && rc == B200LDM_OK; ++c) {
+        if (c == 1 && !getenv("B200LDM_CONV_TUNE_PAIRS")) continue;   // CTA pairs: measured slower almost everywhere
         if (cand[c].splits > 1 && (!p->workspace || p->workspace_bytes < (long long)cand[c].splits * M_total * p->Cout * 4))
           continue;
         b200ldm_conv3d_params q = *p;
@@ -804,15 +809,18 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
       if (rc != B200LDM_OK) return rc;
       if (p->chunk_stats)   // undo what the tuning launches accumulated
         B2_CHECK_CUDA(cudaMemsetAsync(p->chunk_stats, 0, (size_t)p->N * (p->Cout / 8) * 2 * sizeof(double), st));
-      const int best = ms[1] < ms[0] ? 1 : 0;
+      int best = 0;
+      for (int c = 1; c < NC; ++c)
+        if (ms[c] < ms[best]) best = c;
       {
         std::lock_guard<std::mutex> lk(g_choice_mu);
         g_choice[key] = best;
       }
       if (getenv("B200LDM_CONV_AUTOTUNE_LOG"))
-        fprintf(stderr, "b200ldm autotune: %d+%d->%d k%d s%d%s @%dx%dx%dx%d: tile-per-CTA %.3f ms, CTA pairs %.3f ms\n",
-                p->C1, p->C2, p->Cout, p->ksize, p->stride, p->upsample2x ? " up" : "", p->N, p->Do, p->Ho, p->Wo,
-                ms[0] / 2, ms[1] / 2);
+        fprintf(stderr, "b200ldm autotune: %d+%d->%d k%d s%d%s%s%s @%dx%dx%dx%d: tile-per-CTA %.3f ms, CTA pairs %.3f ms, "
+                        "persistent %.3f ms -> %d\n",
+                p->C1, p->C2, p->Cout, p->ksize, p->stride, p->upsample2x ? " up" : "", p->residual ? " +res" : "",
+                p->skip_x ? " +skip" : "", p->N, p->Do, p->Ho, p->Wo, ms[0] / 2, ms[1] / 2, ms[2] / 2, best);
       // the caller asked workspace_bytes / emits_chunk_stats under the cost-model plan: honour that contract for this
       // call (no stats where it was told there would be none), later calls see the remembered choice
       ConvPlan run = cand[best];
@@ -938,7 +946,12 @@ static int conv3d_run_plan(const b200ldm_conv3d_params* p, const ConvPlan& pl, c
   }
 
   const int m_tiles = pl.m_tiles, mt = pl.mt, cl = pl.cl;
-  if (pl.tc2 && conv_tc2_supported(bn, a)) {
+  if (pl.tc2 == 2 && conv_tcp_supported(bn, a)) {
+    rc = make_weight_map(&maps.w, p->w, Cin, cout_rows, taps, bn);
+    if (rc) return rc;
+    return launch_conv_tcp(maps, a, bn, m_tiles, n_tiles, a.up ? 8 : 1, st);
+  }
+  if (pl.tc2 == 1 && conv_tc2_supported(bn, a)) {
     // each CTA of a pair stages half of the weight tile
     rc = make_weight_map(&maps.w, p->w, Cin, cout_rows, taps, bn / 2);
     if (rc) return rc;

@@ -47,4 +47,12 @@ bool conv_tc2_supported(int bn, const ConvTcArgs& a);
 int launch_conv_tc2(const ConvTcMaps& maps, const ConvTcArgs& a, int bn, int m_tiles, int n_tiles, int zdim,
                     cudaStream_t st);
 
+
+// conv_tcp.cu: persistent single-CTA kernel with two accumulator sets (epilogue of tile i overlaps the main loop of
+// tile i+1); MT sub-tiles per CTA = conv_tcp_mt(bn)
+bool conv_tcp_supported(int bn, const ConvTcArgs& a);
+int conv_tcp_mt(int bn);
+int launch_conv_tcp(const ConvTcMaps& maps, const ConvTcArgs& a, int bn, int m_tiles, int n_tiles, int zdim,
+                    cudaStream_t st);
+
 }  // namespace b200ldm
