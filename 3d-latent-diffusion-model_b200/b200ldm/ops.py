@@ -234,6 +234,20 @@ def attention(qkv, heads: int, head_dim: int, scale: float, engine: int = ENGINE
     return o
 
 
+def tap_gather(z, bias, cp: int, cy: int):
+    """y[v][co] = bias[co] + sum_tap z[v + shift(tap)][tap*cp + co]: second half of a narrow-output 3x3x3 conv."""
+    _need_cuda(z, bias)
+    N, D, H, W, ldz = z.shape
+    assert z.is_contiguous()
+    y = torch.empty((N, D, H, W, cy), dtype=z.dtype, device=z.device)
+    ev = PROFILER.start() if PROFILER is not None else None
+    _lib.check(_lib.load().b200ldm_tap_gather(z.data_ptr(), _ptr(bias), y.data_ptr(), N, D, H, W, ldz, cp, cy,
+                                              dtype_code(z.dtype), _stream()), "tap_gather")
+    if ev is not None:
+        PROFILER.stop("tap_gather", f"cp{cp} S{D * H * W}", float(N * D * H * W) * (27 * cp + cy) * z.element_size(), ev)
+    return y
+
+
 def upsample_nearest2x(x):
     _need_cuda(x)
     N, D, H, W, Cc = x.shape

@@ -228,6 +228,70 @@ __global__ void scheduler_step_kernel(const b200ldm_sched_params p) {
   }
 }
 
+// ------------------------------------------------------------------ narrow-output 3x3x3 conv, second half
+// A 3x3x3 conv with very few output channels (UNet `out.2`: 256 -> 8|16, decoder `conv_out`: 64 -> 1) is bound by
+// re-reading its input 27 times, not by math.  It runs as a 1x1x1 GEMM Z[v][tap*cp + co] = sum_ci W[tap][co][ci] x[v][ci]
+// on the tensor cores (input read ONCE) followed by this gather:  y[v][co] = bias[co] + sum_tap Z[v + shift(tap)][tap*cp + co]
+// (taps that fall outside the volume contribute zero = the conv's zero padding).  One thread per voxel; every
+// 16*cp-byte slice of Z is read exactly once.
+template <typename T, int CP>
+__global__ void tap_gather_kernel(const T* __restrict__ z, const float* __restrict__ bias, T* __restrict__ y, int N, int D,
+                                  int H, int W, int ldz, int cy) {
+  const long long vox = (long long)N * D * H * W;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < vox; v += (long long)gridDim.x * blockDim.x) {
+    long long t = v;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H); t /= H;
+    const int d = (int)(t % D);
+    float acc[CP];
+#pragma unroll
+    for (int j = 0; j < CP; ++j) acc[j] = bias ? __ldg(bias + j) : 0.f;
+#pragma unroll 1
+    for (int kd = 0; kd < 3; ++kd) {
+      const int dd = d + kd - 1;
+      if (dd < 0 || dd >= D) continue;
+#pragma unroll 1
+      for (int kh = 0; kh < 3; ++kh) {
+        const int hh = h + kh - 1;
+        if (hh < 0 || hh >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int ww = w + kw - 1;
+          if (ww < 0 || ww >= W) continue;
+          const long long src = v + ((long long)(kd - 1) * H + (kh - 1)) * W + (kw - 1);
+          const T* zr = z + src * ldz + ((kd * 3 + kh) * 3 + kw) * CP;
+          if (CP % 8 == 0) {
+#pragma unroll
+            for (int j = 0; j < CP; j += 8) {
+              float f[8];
+              Vec8<T>::load(zr + j, f);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[j + e] += f[e];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CP; ++j) acc[j] += to_f32<T>(zr[j]);
+          }
+        }
+      }
+    }
+    T* yr = y + v * cy;
+#pragma unroll
+    for (int j0 = 0; j0 < 16; j0 += 8) {   // compile-time indices keep acc[] in registers
+      if (j0 < cy) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = (j0 + e < CP) ? acc[(j0 + e < CP) ? j0 + e : 0] : 0.f;
+        Vec8<T>::store(yr + j0, f);
+      }
+    }
+    for (int j0 = 16; j0 < cy; j0 += 8) {
+      const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      Vec8<T>::store(yr + j0, zero);
+    }
+  }
+}
+
 template <typename T>
 __global__ void ae_sampling_kernel(const T* __restrict__ mu, const T* __restrict__ logvar,
                                    const float* __restrict__ noise, float* __restrict__ z, float* __restrict__ sig,
@@ -349,6 +413,33 @@ int b200ldm_upsample_nearest2x(const void* x, void* y, int32_t N, int32_t D, int
                                                                                         D, H, W, C);
   else
     return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+int b200ldm_tap_gather(const void* z, const float* bias, void* y, int32_t N, int32_t D, int32_t H, int32_t W, int32_t ldz,
+                       int32_t cp, int32_t cy, int32_t dtype, b200ldm_stream stream) {
+  B2_REQUIRE(z && y && N > 0 && D > 0 && H > 0 && W > 0, B200LDM_BAD_ARG, "tap_gather: bad arguments");
+  B2_REQUIRE((cp == 1 || cp == 2 || cp == 4 || cp == 8 || cp == 16) && cy >= cp && cy % 8 == 0 && ldz >= 27 * cp &&
+                 ldz % 8 == 0,
+             B200LDM_BAD_SHAPE, "tap_gather: channels per tap must be 1/2/4/8/16, cy a multiple of 8 >= cp, ldz >= 27*cp");
+  B2_REQUIRE(aligned16(z) && aligned16(y), B200LDM_BAD_ALIGN, "tap_gather: pointers must be 16-byte aligned");
+  B2_REQUIRE(dtype == B200LDM_BF16 || dtype == B200LDM_F32, B200LDM_BAD_ARG, "bad dtype %d", dtype);
+  const long long vox = (long long)N * D * H * W;
+  const cudaStream_t st = (cudaStream_t)stream;
+#define B2_TG(T, CP)                                                                                                  \
+  tap_gather_kernel<T, CP><<<ew_blocks(vox), kEwThreads, 0, st>>>((const T*)z, bias, (T*)y, N, D, H, W, ldz, cy)
+#define B2_TG_T(T)                    \
+  switch (cp) {                       \
+    case 1: B2_TG(T, 1); break;       \
+    case 2: B2_TG(T, 2); break;       \
+    case 4: B2_TG(T, 4); break;       \
+    case 8: B2_TG(T, 8); break;       \
+    default: B2_TG(T, 16); break;     \
+  }
+  if (dtype == B200LDM_BF16) { B2_TG_T(__nv_bfloat16) } else { B2_TG_T(float) }
+#undef B2_TG_T
+#undef B2_TG
   B2_LAUNCH_CHECK();
   return B200LDM_OK;
 }

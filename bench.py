@@ -10,8 +10,10 @@ Default workload (N = 1 .. 8, weak scaling, one replica + one batch per GPU):
   value = volume-steps/s (batch * steps / device time, max over ranks) with everything resident in HBM;
   e2e   = the same metric through the public module API (unet(x, t); scheduler.step) with pinned HOST buffers,
           the H2D copy of x_t and the D2H read of x_{t-1} inside the timed region.
-`--workload sample_32g`: full LatentDiffusionInferer.sample (DDPM, --T steps, config_train_32g, latent 20^3 ->
-  80^3 volume, batch 8 per GPU, final gather over NCCL): metric = generated volumes/s.
+  The same JSON line also carries "sampling": generated volumes/s of BASELINE.json configs[2] per GPU (full 1000-step
+  DDPM sampling with the config_train_32g UNet at a 20^3 latent + AutoencoderKL decode to 80^3, batch 8 per GPU, final
+  gather over NCCL) - the other half of BASELINE.json's metric (--no-sampling skips it, --sampling-T shortens it).
+`--workload sample_32g`: that sampling workload alone as the headline line (--T steps, --latent edge).
 `--impl reference`: the CPU oracle (pure-PyTorch restatement of the MONAI path; the reference itself is not
   installable here - DESIGN.md) timed on the host cores of the box on a bounded sample of the same workload.
 """
@@ -265,6 +267,14 @@ def bench_unet_step(args, rank, world, local):
     roof["top_shapes"] = [{"shape": k[1], "ms": by_tag[k]["ms"] / n_prof,
                            "TFLOPs": by_tag[k]["work"] / (by_tag[k]["ms"] * 1e-3) / 1e12} for _, k in top]
 
+    # ---- second half of BASELINE.json's metric: generated volumes/s (full sampling + decode), one warm-up batch
+    sampling = None
+    if not args.no_sampling:
+        del loop
+        torch.cuda.empty_cache()
+        ms_batch, _, _ = run_sampling(rank, world, local, args.sampling_T, 20, 1, 1)
+        sampling = sampling_summary(ms_batch, world, args.sampling_T, 20)
+
     if rank != 0:
         return
     cpu = None
@@ -282,41 +292,69 @@ def bench_unet_step(args, rank, world, local):
             "e2e": {"value": e2e_value, "unit": "volume-steps/s", "h2d_bytes_per_step": nbytes,
                     "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
             "gpu_launches": per_graph * args.steps, "launches_per_step": per_graph,
-            "roofline": roof, "kernel_breakdown": breakdown, "cpu_baseline": cpu, "clocks": clk.summary()}
+            "roofline": roof, "kernel_breakdown": breakdown, "sampling": sampling, "cpu_baseline": cpu,
+            "clocks": clk.summary()}
     print(json.dumps(line))
 
 
-def bench_sample(args, rank, world, local):
+FLOP_UNET_32G = {16: 465.6e9, 20: 914.5e9, 40: 7910.7e9}     # per volume per step
+FLOP_DEC_32G = {16: 888.7e9, 20: 1799.7e9, 40: 21738e9}      # per volume
+
+
+def run_sampling(rank, world, local, T, latent, reps, warm):
+    """BASELINE.json configs[2] per GPU: full DDPM latent sampling (config_train_32g UNet, concat conditioning) +
+    AutoencoderKL decode, batch 8 volumes per GPU, final NCCL gather of volumes and seeds.  Returns (ms per batch
+    [max over ranks], launches, clocks)."""
     import b200ldm
     from b200ldm import dist as bd, ops
     dev = torch.device("cuda", local)
     unet = seeded_init(b200ldm.DiffusionModelUNet(**UNET_32G, precision="bf16"), 1234).to(dev).eval()
     ae = seeded_init(b200ldm.AutoencoderKL(**AE_32G, precision="bf16"), 4321).to(dev).eval()
     sched = b200ldm.DDPMScheduler(**SCHED)
-    sched.set_timesteps(args.T)
+    sched.set_timesteps(T)
     inf = b200ldm.LatentDiffusionInferer(sched, scale_factor=1.0)
-    lat = (16, args.latent, args.latent, args.latent)
+    lat = (16, latent, latent, latent)
     total = BATCH * world
     cond = torch.randn((total, 16) + lat[1:], generator=torch.Generator().manual_seed(7))
+    seed = [42]
 
     def one():
-        return bd.sample_sharded(inf, ae, unet, sched, total, lat, base_seed=42, conditioning=cond, mode="concat",
+        seed[0] += 1   # a new batch of volumes every call (new x_T, new in-kernel noise stream)
+        return bd.sample_sharded(inf, ae, unet, sched, total, lat, base_seed=seed[0], conditioning=cond, mode="concat",
                                  device=dev)
 
-    l0 = ops.launch_count()
-    for _ in range(max(1, args.warmup)):
+    for _ in range(warm):
         one()
+    l0 = ops.launch_count()
     with ClockSampler(local) as clk:
-        ms = timed_region(one, args.steps, world)
+        ms = timed_region(one, reps, world)
+    return ms / reps, (ops.launch_count() - l0) // reps, clk.summary()
+
+
+def sampling_summary(ms_batch, world, T, latent):
+    pk = peaks()
+    vps = world * BATCH / (ms_batch * 1e-3)
+    out = {"metric": "generated_volumes_per_sec", "value": vps, "unit": "volumes/s", "ms_per_batch": ms_batch,
+           "workload": f"sample_32g: DDPM {T}-step latent sampling + AutoencoderKL decode, latent {latent}^3 -> "
+                       f"{4 * latent}^3, concat conditioning, batch {BATCH}/GPU, final gather of volumes + seeds"}
+    if latent in FLOP_UNET_32G:
+        flop = BATCH * (T * FLOP_UNET_32G[latent] + FLOP_DEC_32G[latent])
+        out["tflops_algorithmic"] = flop / (ms_batch * 1e-3) / 1e12
+        out["frac_of_sustained_peak"] = out["tflops_algorithmic"] / pk["bf16_sustained"]
+    return out
+
+
+def bench_sample(args, rank, world, local):
+    ms_batch, launches, clocks = run_sampling(rank, world, local, args.T, args.latent, args.steps, max(1, args.warmup))
     if rank != 0:
         return
-    line = {"metric": "generated_volumes_per_sec", "value": total * args.steps / (ms * 1e-3), "unit": "volumes/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"sample_32g: DDPM {args.T}-step latent sampling + AutoencoderKL decode, latent "
-                                   f"{args.latent}^3 -> {4 * args.latent}^3, concat conditioning, final NCCL gather",
-                       "batch_per_gpu": BATCH, "parallelism": f"batch-sharded x{world}"},
-            "gpu_launches": ops.launch_count() - l0, "clocks": clk.summary()}
+    sm = sampling_summary(ms_batch, world, args.T, args.latent)
+    line = {"metric": sm["metric"], "value": sm["value"], "unit": sm["unit"], "n_gpus": world, "steps": args.steps,
+            "warmup": max(1, args.warmup), "ms_per_step": ms_batch, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": sm["workload"], "batch_per_gpu": BATCH, "parallelism": f"batch-sharded x{world}"},
+            "tflops_algorithmic": sm.get("tflops_algorithmic"), "frac_of_sustained_peak": sm.get("frac_of_sustained_peak"),
+            "gpu_launches": launches * args.steps, "clocks": clocks}
     print(json.dumps(line))
 
 
@@ -330,6 +368,8 @@ def main():
     ap.add_argument("--T", type=int, default=50, help="sample_32g: number of DDPM steps")
     ap.add_argument("--latent", type=int, default=20, help="sample_32g: latent edge")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sampling", action="store_true", help="skip the volumes/s leg of the default workload")
+    ap.add_argument("--sampling-T", type=int, default=1000, help="DDPM steps of the volumes/s leg (reference: 1000)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

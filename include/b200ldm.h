@@ -164,6 +164,14 @@ int b200ldm_attention(const void* q, const void* k, const void* v, void* o, int3
                       int32_t L, int32_t d, int64_t ld, float scale, int32_t dtype, int32_t engine,
                       b200ldm_stream stream);
 
+/* Second half of a narrow-output 3x3x3 conv (SURVEY.md 8a a2 `out.2`, a4 decoder `conv_out`; replaces F.conv3d there):
+ * the conv is run as a 1x1x1 GEMM z[v][tap*cp + co] = sum_ci w[tap][co][ci] x[v][ci] (b200ldm_conv3d, ksize 1, weights
+ * stacked [27*cp][Cin]) so the input is read once instead of 27 times, then
+ *   y[n,d,h,w,co] = bias[co] + sum_{tap=(kd,kh,kw)} z[n, d+kd-1, h+kh-1, w+kw-1, tap*cp + co]   (zero outside the volume)
+ * z: [N][D][H][W][ldz], y: [N][D][H][W][cy] (channels >= cp are written as zero), cp in {1,2,4,8,16}. */
+int b200ldm_tap_gather(const void* z, const float* bias, void* y, int32_t N, int32_t D, int32_t H, int32_t W,
+                       int32_t ldz, int32_t cp, int32_t cy, int32_t dtype, b200ldm_stream stream);
+
 /* nearest x2 up-sampling, NDHWC: [N][D][H][W][C] -> [N][2D][2H][2W][C] */
 int b200ldm_upsample_nearest2x(const void* x, void* y, int32_t N, int32_t D, int32_t H, int32_t W,
                                int32_t C, int32_t dtype, b200ldm_stream stream);

@@ -216,6 +216,52 @@ def test_conv3d_fused_skip_conv(shape):
     assert e <= 1e-2, e
 
 
+@pytest.mark.parametrize("case", [(2, (5, 6, 7), 64, 1), (1, (9, 11, 7), 128, 8), (2, (8, 8, 8), 256, 16), (1, (4, 5, 3), 64, 3)],
+                         ids=lambda c: f"N{c[0]}_{'x'.join(map(str, c[1]))}_C{c[2]}->{c[3]}")
+def test_narrow_conv_tap_expanded_matches_direct_and_torch(case):
+    """terminal 3x3x3 convs with <= 16 outputs (UNet out.2, decoder conv_out): 1x1x1 GEMM over stacked taps + tap_gather
+    must equal F.conv3d (borders = zero padding) and the direct tensor-core conv"""
+    from b200ldm import nets
+    N, sp, cin, cout = case
+    conv = nets.Conv(cin, cout, terminal=True).to(DEV)
+    with torch.no_grad():
+        conv.weight.copy_(q(rnd(conv.weight.shape, 41) * (cin * 27) ** -0.5, torch.bfloat16))
+        conv.bias.copy_(0.1 * rnd(conv.bias.shape, 42))
+    x = q(rnd((N, cin) + sp, 43), torch.bfloat16)
+    ref = F.conv3d(x.double(), conv.weight.detach().cpu().double(), conv.bias.detach().cpu().double(), padding=1)
+    xa = to_act(x, torch.bfloat16)
+    assert nets.TAP_EXPAND
+    y = conv.run(xa)
+    nets.TAP_EXPAND = False
+    try:
+        y_direct = conv.run(xa)
+    finally:
+        nets.TAP_EXPAND = True
+    assert y.shape == y_direct.shape == (N,) + sp + (16,)
+    assert relerr(from_act(y, cout), ref) <= 1e-2
+    assert relerr(from_act(y_direct, cout), ref) <= 1e-2
+    if cout < 16:
+        assert y[..., cout:].abs().max().item() == 0.0      # padded output channels stay exactly zero
+
+
+def test_tap_gather_fp32_exact():
+    """the gather alone, fp32: y = bias + sum over in-bounds taps, checked against an index-by-index torch restatement"""
+    from b200ldm import ops
+    N, D, H, W, cp = 2, 3, 4, 5, 2
+    z = rnd((N, D, H, W, 64), 44)
+    b = rnd((16,), 45)
+    y = ops.tap_gather(z.to(DEV), b.to(DEV), cp, 16).cpu()
+    zp = F.pad(z.permute(0, 4, 1, 2, 3), (1, 1, 1, 1, 1, 1))          # [N, 64, D+2, H+2, W+2]
+    want = torch.zeros(N, D, H, W, 16)
+    want[..., :cp] = b[:cp]
+    for kd in range(3):
+        for kh in range(3):
+            for kw in range(3):
+                t = (kd * 3 + kh) * 3 + kw
+                want[..., :cp] += zp[:, t * cp:(t + 1) * cp, kd:kd + D, kh:kh + H, kw:kw + W].permute(0, 2, 3, 4, 1)
+    assert torch.allclose(y, want, atol=1e-5, rtol=1e-5)
+
+
 def test_conv3d_rejects_bad_arguments():
     from b200ldm import ops
     x = torch.zeros((1, 4, 4, 4, 48), dtype=torch.bfloat16, device=DEV)
