@@ -621,6 +621,7 @@ struct ConvPlan {
   int bn, n_tiles, tn, td, th, tw, nb_n, nb_d, nb_h, nb_w, m_tiles, mt, cl, splits;
   int tc2;     // kernel: 0 one CTA per tile, 1 persistent CTA pairs (conv_tc2.cu), 2 persistent single CTAs (conv_tcp.cu)
   int tc2_ok;  // the problem is eligible for the persistent kernels
+  int split_ok, ctas1, iters;   // split-K allowed; CTAs of the one-CTA-per-tile kernel at splits = 1 (mt = 1); k-iterations
 };
 
 // Which of the two tensor-core kernels runs a problem is MEASURED once per problem signature (first un-captured call:
@@ -644,7 +645,8 @@ static const int g_autotune = [] {
 }();
 
 // Tile / cluster / split-K decisions (shared by the launch and by b200ldm_conv3d_workspace_bytes).
-// force_tc2: -1 = remembered measurement, else cost model; 0 / 1 = that kernel (tuning runs).
+// A choice is kernel | splits << 4 | mt << 12 (splits / mt only for kernel 0; 0 = the cost model's value).
+// force_tc2: -1 = remembered measurement, else cost model; >= 0 = that choice (tuning runs).
 static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
   ConvPlan pl{};
   if (p->Cout % 256 == 0) pl.bn = 256;
@@ -699,7 +701,11 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
     // for two single-CTA ones, ~745 with the loads (44 B/clk/SM), and the 4-warp epilogue ~2450 cycles per 64 channels.
     const bool tma_epi = !p->out_f32 && p->Cout % 64 == 0 && !p->gn_stats && pl.bn >= 64 && g_legacy_epilogue == 0;
     pl.tc2_ok = tma_epi ? 1 : 0;
+    pl.split_ok = split_ok ? 1 : 0;
+    pl.ctas1 = pl.m_tiles * pl.n_tiles * zmul;
+    pl.iters = iters;
     pl.tc2 = 0;
+    int choice = 0;
     if (tma_epi && g_tc2 != 0) {
       // cost-model fallback (no measurement yet / tuning disabled): persistent single-CTA kernel, per-tile cost =
       // max(main loop, epilogue) since they overlap
@@ -710,16 +716,21 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
       const double epi = 2000.0 * (pl.bn / 64);
       const long long work = (long long)ceil_div(pl.m_tiles, pmt) * pl.n_tiles * zmul;
       const double t2 = ceil_div(work, 148) * (main_loop > epi ? main_loop : epi) + 3000.0 + epi;
-      int choice = (g_tc2 > 0) ? g_tc2 : (t2 < best ? 2 : 0);
-      if (force_tc2 >= 0) choice = force_tc2;
-      else if (g_tc2 < 0) {
-        std::lock_guard<std::mutex> lk(g_choice_mu);
-        auto it = g_choice.find(conv_key(p));
-        if (it != g_choice.end()) choice = it->second;
-      }
-      pl.tc2 = choice;
+      choice = (g_tc2 > 0) ? g_tc2 : (t2 < best ? 2 : 0);
     }
+    if (force_tc2 >= 0) choice = force_tc2;
+    else if (g_tc2 < 0) {
+      std::lock_guard<std::mutex> lk(g_choice_mu);
+      auto it = g_choice.find(conv_key(p));
+      if (it != g_choice.end()) choice = it->second;
+    }
+    pl.tc2 = tma_epi ? (choice & 15) : 0;
     if (pl.tc2) { pl.mt = 1; pl.cl = 1; pl.splits = 1; }
+    else {
+      const int sp = (choice >> 4) & 255, mt = choice >> 12;
+      if (mt == 1 || mt == 2) pl.mt = mt;
+      if (sp >= 1 && (sp == 1 || split_ok)) { pl.splits = sp; pl.cl = sp > 1 ? 1 : pl.cl; }
+    }
   }
   if (!pl.tc2 && g_force_splits >= 1 && g_force_splits <= 12 && split_ok && iters / g_force_splits >= 1)
     pl.splits = g_force_splits;
@@ -738,8 +749,20 @@ int conv3d_tcgen05_emits_chunk_stats(const b200ldm_conv3d_params* p) {
 long long conv3d_tcgen05_workspace_bytes(const b200ldm_conv3d_params* p) {
   if (p->dtype != B200LDM_BF16 || p->C1 % 64 || p->C2 % 64 || p->Cout % 8) return 0;
   const ConvPlan pl = plan_conv(p);
-  if (pl.splits <= 1) return 0;
-  return (long long)pl.splits * p->N * p->Do * p->Ho * p->Wo * p->Cout * 4;
+  int splits = pl.splits;
+  if (g_autotune && g_tc2 < 0 && pl.split_ok && pl.ctas1 < 148 && pl.iters >= 16) {
+    bool known;
+    {
+      std::lock_guard<std::mutex> lk(g_choice_mu);
+      known = g_choice.count(conv_key(p)) != 0;
+    }
+    if (!known) {   // the first call measures split factors up to 16 (those that keep >= 8 k-iterations per CTA)
+      for (int sp = 16; sp > splits; --sp)
+        if (pl.iters / sp >= 8 && (long long)pl.m_tiles * pl.n_tiles * sp <= 2 * 148) { splits = sp; break; }
+    }
+  }
+  if (splits <= 1) return 0;
+  return (long long)splits * p->N * p->Do * p->Ho * p->Wo * p->Cout * 4;
 }
 
 static int conv3d_run_plan(const b200ldm_conv3d_params* p, const ConvPlan& pl, cudaStream_t st);
@@ -771,7 +794,8 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
                    p->Wo == 2 * p->W,
                B200LDM_BAD_SHAPE, "fused upsample conv: needs k3 s1 p1, one source, bf16 out, Cout %% 64 == 0, out = 2x in");
   const ConvPlan pl = plan_conv(p);
-  if (g_autotune && g_tc2 < 0 && pl.tc2_ok) {
+  const bool splittable = pl.split_ok && pl.ctas1 < 148 && pl.iters >= 16;
+  if (g_autotune && g_tc2 < 0 && (pl.tc2_ok || splittable)) {
     const ConvKey key = conv_key(p);
     bool known;
     {
@@ -780,50 +804,64 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
     }
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (!known && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
-      // time both kernels on the caller's buffers (the result is the same tensor either way); the one-CTA-per-tile
-      // candidate may need split-K scratch the caller sized for the cost model's plan - skip it if there is none
-      constexpr int NC = 3;
-      ConvPlan cand[NC] = {plan_conv(p, 0), plan_conv(p, 1), plan_conv(p, 2)};
+      // time the candidates on the caller's own buffers (the result is the same tensor every time): the cost model's
+      // plan, the persistent kernel, and - for launches that cannot fill the chip - other split-K factors / tile
+      // heights of the one-CTA-per-tile kernel
+      int choices[24], nc = 0;
+      choices[nc++] = 0;
+      if (pl.tc2_ok) choices[nc++] = 2;
+      if (pl.tc2_ok && getenv("B200LDM_CONV_TUNE_PAIRS")) choices[nc++] = 1;   // CTA pairs: measured slower almost everywhere
+      if (splittable) {
+        static const int sps[] = {1, 2, 3, 4, 6, 8, 12, 16};
+        for (int mt = 1; mt <= 2; ++mt)
+          for (int sp : sps) {
+            const long long ctas = (long long)ceil_div(pl.m_tiles, mt) * pl.n_tiles * sp;
+            if (pl.iters / sp < 8 || ctas > 2 * 148 || (sp > 1 && ctas < 32)) continue;
+            choices[nc++] = (sp << 4) | (mt << 12);
+          }
+      }
       const long long M_total = (long long)p->N * p->Do * p->Ho * p->Wo;
-      float ms[NC] = {1e30f, 1e30f, 1e30f};
+      float ms_best = 1e30f, ms0 = 0.f, ms_tcp = 0.f;
+      int best = 0;
       cudaEvent_t e0, e1;
       B2_CHECK_CUDA(cudaEventCreate(&e0));
       B2_CHECK_CUDA(cudaEventCreate(&e1));
       int rc = B200LDM_OK;
-      for (int c = 0; c < NC && rc == B200LDM_OK; ++c) {
-        if (c == 1 && !getenv("B200LDM_CONV_TUNE_PAIRS")) continue;   // CTA pairs: measured slower almost everywhere
-        if (cand[c].splits > 1 && (!p->workspace || p->workspace_bytes < (long long)cand[c].splits * M_total * p->Cout * 4))
-          continue;
+      for (int c = 0; c < nc && rc == B200LDM_OK; ++c) {
+        const ConvPlan cp = plan_conv(p, choices[c]);
+        if (cp.splits > 1 && (!p->workspace || p->workspace_bytes < (long long)cp.splits * M_total * p->Cout * 4)) continue;
         b200ldm_conv3d_params q = *p;
         // statistics are accumulated by atomics: tuning launches must not add to the caller's buffer
-        if (cand[c].splits > 1 || cand[c].tn != 1) q.chunk_stats = nullptr;
+        if (cp.splits > 1 || cp.tn != 1) q.chunk_stats = nullptr;
         for (int rep = 0; rep < 3 && rc == B200LDM_OK; ++rep) {
           if (rep == 1) cudaEventRecord(e0, st);
-          rc = conv3d_run_plan(&q, cand[c], st);
+          rc = conv3d_run_plan(&q, cp, st);
         }
         cudaEventRecord(e1, st);
-        if (rc == B200LDM_OK && cudaEventSynchronize(e1) == cudaSuccess) cudaEventElapsedTime(&ms[c], e0, e1);
+        float ms = 1e30f;
+        if (rc == B200LDM_OK && cudaEventSynchronize(e1) == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+        if (choices[c] == 0) ms0 = ms;
+        if (choices[c] == 2) ms_tcp = ms;
+        if (ms < ms_best * 0.98f) { ms_best = ms; best = choices[c]; }   // a later candidate must win by 2 %
       }
       cudaEventDestroy(e0);
       cudaEventDestroy(e1);
       if (rc != B200LDM_OK) return rc;
       if (p->chunk_stats)   // undo what the tuning launches accumulated
         B2_CHECK_CUDA(cudaMemsetAsync(p->chunk_stats, 0, (size_t)p->N * (p->Cout / 8) * 2 * sizeof(double), st));
-      int best = 0;
-      for (int c = 1; c < NC; ++c)
-        if (ms[c] < ms[best]) best = c;
       {
         std::lock_guard<std::mutex> lk(g_choice_mu);
         g_choice[key] = best;
       }
       if (getenv("B200LDM_CONV_AUTOTUNE_LOG"))
-        fprintf(stderr, "b200ldm autotune: %d+%d->%d k%d s%d%s%s%s @%dx%dx%dx%d: tile-per-CTA %.3f ms, CTA pairs %.3f ms, "
-                        "persistent %.3f ms -> %d\n",
+        fprintf(stderr, "b200ldm autotune: %d+%d->%d k%d s%d%s%s%s @%dx%dx%dx%d: model plan %.3f ms, persistent %.3f ms, "
+                        "best %.3f ms = kernel %d splits %d mt %d (%d candidates)\n",
                 p->C1, p->C2, p->Cout, p->ksize, p->stride, p->upsample2x ? " up" : "", p->residual ? " +res" : "",
-                p->skip_x ? " +skip" : "", p->N, p->Do, p->Ho, p->Wo, ms[0] / 2, ms[1] / 2, ms[2] / 2, best);
-      // the caller asked workspace_bytes / emits_chunk_stats under the cost-model plan: honour that contract for this
-      // call (no stats where it was told there would be none), later calls see the remembered choice
-      ConvPlan run = cand[best];
+                p->skip_x ? " +skip" : "", p->N, p->Do, p->Ho, p->Wo, ms0 / 2, ms_tcp / 2, ms_best / 2, best & 15,
+                (best >> 4) & 255, best >> 12, nc);
+      // the caller asked workspace_bytes / emits_chunk_stats before this call: honour that contract now (no stats
+      // where it was told there would be none), later calls see the remembered choice
+      ConvPlan run = plan_conv(p, best);
       if (p->chunk_stats && (run.splits > 1 || run.tn != 1)) run = pl;
       if (run.splits > 1 && (!p->workspace || p->workspace_bytes < (long long)run.splits * M_total * p->Cout * 4)) run = pl;
       return conv3d_run_plan(p, run, st);

@@ -158,6 +158,59 @@ gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict
   }
 }
 
+// Small tensors (the 4^3 ... 10^3 levels: one (sample, group) slab is a few KB): statistics and normalisation in ONE
+// launch, one CTA per (group, sample).  The slab is read twice (the second read hits L1/L2); the two-kernel path with
+// its fp64 atomics and memset costs three launches of ~5 us each for ~1 us of traffic.
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+gn_small_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict__ y, const float* __restrict__ gamma,
+                const float* __restrict__ beta, int S, int C1, int C2, int G, float eps, int silu) {
+  __shared__ double red[2][kNormThreads / 32];
+  __shared__ float s_mean, s_rstd;
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int C = C1 + C2, cpg = C / G, vpg = cpg >> 3;   // 8-channel vectors per group
+  const int items = S * vpg;
+  float a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int v = i / vpg, c = g * cpg + (i - v * vpg) * 8;
+    const T* src = c < C1 ? x + ((size_t)n * S + v) * C1 + c : x2 + ((size_t)n * S + v) * C2 + (c - C1);
+    float f[8];
+    Vec8<T>::load(src, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { a += f[e]; b = fmaf(f[e], f[e], b); }
+  }
+  double da = (double)warp_sum(a), db = (double)warp_sum(b);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = da; red[1][threadIdx.x >> 5] = db; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int w = 0; w < kNormThreads / 32; ++w) { s1 += red[0][w]; s2 += red[1][w]; }
+    const double inv = 1.0 / ((double)S * cpg);
+    const double m = s1 * inv;
+    double var = fma(-m, m, s2 * inv);
+    if (var < 0.0) var = 0.0;
+    float r = rsqrtf((float)var + eps);
+    r = r * (1.5f - 0.5f * ((float)var + eps) * r * r);
+    s_mean = (float)m;
+    s_rstd = r;
+  }
+  __syncthreads();
+  const float mean = s_mean, rstd = s_rstd;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int v = i / vpg, c = g * cpg + (i - v * vpg) * 8;
+    const T* src = c < C1 ? x + ((size_t)n * S + v) * C1 + c : x2 + ((size_t)n * S + v) * C2 + (c - C1);
+    float f[8];
+    Vec8<T>::load(src, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float ga = __ldg(gamma + c + e) * rstd;
+      const float t = fmaf(f[e] - mean, ga, __ldg(beta + c + e));
+      f[e] = silu ? silu_for<T>(t) : t;
+    }
+    Vec8<T>::store(y + ((size_t)n * S + v) * C + c, f);
+  }
+}
+
 static int norm_geometry(int N, long long S, int C, int G, int* vox_per_block, dim3* grid) {
   B2_REQUIRE(C % 8 == 0 && C / 8 <= kNormThreads, B200LDM_BAD_SHAPE, "GroupNorm needs C %% 8 == 0 and C <= %d (got %d)",
              8 * kNormThreads, C);
@@ -255,6 +308,29 @@ int b200ldm_groupnorm_apply_chunked(const void* x, const void* x2, void* y, cons
                                     b200ldm_stream stream) {
   B2_REQUIRE(cstats1, B200LDM_BAD_ARG, "groupnorm_apply_chunked: null cstats1");
   return gn_apply_impl(x, x2, y, nullptr, cstats1, cstats2, gamma, beta, N, S, C1, C2, G, eps, silu, dtype, stream);
+}
+
+int b200ldm_groupnorm_small(const void* x, const void* x2, void* y, const float* gamma, const float* beta, int32_t N,
+                            int64_t S, int32_t C1, int32_t C2, int32_t G, float eps, int32_t silu, int32_t dtype,
+                            b200ldm_stream stream) {
+  using namespace b200ldm;
+  B2_REQUIRE(x && y && gamma && beta && N > 0 && S > 0 && S <= 4096, B200LDM_BAD_ARG,
+             "groupnorm_small: bad arguments (S must be <= 4096)");
+  B2_REQUIRE(C1 > 0 && C1 % 8 == 0 && C2 >= 0 && C2 % 8 == 0 && ((C2 > 0) == (x2 != nullptr)) && G > 0 &&
+                 (C1 + C2) % G == 0 && ((C1 + C2) / G) % 8 == 0,
+             B200LDM_BAD_SHAPE, "groupnorm_small: C1/C2 multiples of 8 matching x2, channels/group a multiple of 8");
+  B2_REQUIRE(aligned16(x) && aligned16(y) && aligned16(x2), B200LDM_BAD_ALIGN, "groupnorm_small: 16-byte alignment");
+  const dim3 grid((unsigned)G, (unsigned)N, 1);
+  if (dtype == B200LDM_BF16)
+    gn_small_kernel<__nv_bfloat16><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)x2, (__nv_bfloat16*)y, gamma, beta, (int)S, C1, C2, G, eps, silu);
+  else if (dtype == B200LDM_F32)
+    gn_small_kernel<float><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)x2, (float*)y,
+                                                                            gamma, beta, (int)S, C1, C2, G, eps, silu);
+  else
+    return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
 }
 
 }  // extern "C"

@@ -282,10 +282,12 @@ GN_CASES = [(2, (4, 6, 5), 64, 0), (1, (8, 8, 8), 256, 0), (2, (3, 5, 7), 512, 2
             (3, (2, 3, 5), 1024, 512), (1, (16, 16, 16), 128, 0)]
 
 
+@pytest.mark.parametrize("path", ["auto", "two_pass"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 @pytest.mark.parametrize("silu", [True, False])
 @pytest.mark.parametrize("case", GN_CASES, ids=[f"N{c[0]}_C{c[2]}+{c[3]}" for c in GN_CASES])
-def test_groupnorm(case, silu, dtype):
+def test_groupnorm(case, silu, dtype, path):
+    """auto: small tensors take the single-launch kernel (one CTA per (group, sample)); two_pass: stats + apply"""
     from b200ldm import ops
     N, sp, C1, C2 = case
     C = C1 + C2
@@ -296,7 +298,12 @@ def test_groupnorm(case, silu, dtype):
         ref = F.silu(ref)
     xa = to_act(x[:, :C1], dtype)
     x2a = to_act(x[:, C1:], dtype) if C2 else None
-    y = ops.groupnorm(xa, gamma.to(DEV), beta.to(DEV), 32, 1e-6, silu, x2=x2a)
+    keep = ops.GN_SMALL_MAX_S
+    ops.GN_SMALL_MAX_S = keep if path == "auto" else 0
+    try:
+        y = ops.groupnorm(xa, gamma.to(DEV), beta.to(DEV), 32, 1e-6, silu, x2=x2a)
+    finally:
+        ops.GN_SMALL_MAX_S = keep
     e = relerr(from_act(y, C), ref)
     assert e <= (1e-5 if dtype == torch.float32 else 6e-3), e
 
