@@ -10,5 +10,6 @@ from .config import ConfigParser, define_instance  # noqa: F401
 from .inferer import DiffusionInferer, LatentDiffusionInferer  # noqa: F401
 from .nets import AutoencoderKL, DiffusionModelUNet  # noqa: F401
 from .schedulers import DDIMScheduler, DDPMScheduler  # noqa: F401
+from .serving import LatentDiffusionGenerator  # noqa: F401
 
 __version__ = "0.1.0"

@@ -643,6 +643,36 @@ static const int g_autotune = [] {
   const char* e = getenv("B200LDM_CONV_AUTOTUNE");
   return e ? atoi(e) : 1;
 }();
+// B200LDM_CONV_TUNE_FILE=<path>: measured choices are appended to / preloaded from this text file (21 integers per
+// line), so a later process - a profiler run, a serving replica - starts with them and never times anything.
+static const char* g_tune_file = [] {
+  const char* path = getenv("B200LDM_CONV_TUNE_FILE");
+  if (path && *path) {
+    if (FILE* f = fopen(path, "r")) {
+      ConvKey k;
+      int choice;
+      for (;;) {
+        bool ok = true;
+        for (int i = 0; i < 20 && ok; ++i) ok = fscanf(f, "%d", &k.v[i]) == 1;
+        if (!ok || fscanf(f, "%d", &choice) != 1) break;
+        g_choice[k] = choice;
+      }
+      fclose(f);
+    }
+  }
+  return (path && *path) ? path : nullptr;
+}();
+static void remember_choice(const ConvKey& key, int choice) {
+  std::lock_guard<std::mutex> lk(g_choice_mu);
+  g_choice[key] = choice;
+  if (g_tune_file) {
+    if (FILE* f = fopen(g_tune_file, "a")) {
+      for (int i = 0; i < 20; ++i) fprintf(f, "%d ", key.v[i]);
+      fprintf(f, "%d\n", choice);
+      fclose(f);
+    }
+  }
+}
 
 // Tile / cluster / split-K decisions (shared by the launch and by b200ldm_conv3d_workspace_bytes).
 // A choice is kernel | splits << 4 | mt << 12 (splits / mt only for kernel 0; 0 = the cost model's value).
@@ -849,10 +879,7 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
       if (rc != B200LDM_OK) return rc;
       if (p->chunk_stats)   // undo what the tuning launches accumulated
         B2_CHECK_CUDA(cudaMemsetAsync(p->chunk_stats, 0, (size_t)p->N * (p->Cout / 8) * 2 * sizeof(double), st));
-      {
-        std::lock_guard<std::mutex> lk(g_choice_mu);
-        g_choice[key] = best;
-      }
+      remember_choice(key, best);
       if (getenv("B200LDM_CONV_AUTOTUNE_LOG"))
         fprintf(stderr, "b200ldm autotune: %d+%d->%d k%d s%d%s%s%s @%dx%dx%dx%d: model plan %.3f ms, persistent %.3f ms, "
                         "best %.3f ms = kernel %d splits %d mt %d (%d candidates)\n",

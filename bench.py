@@ -254,7 +254,10 @@ def bench_unet_step(args, rank, world, local):
     step_ms_prof = sum(v["ms"] for v in kinds.values()) / n_prof
     roof = {"bound": "tensor", "kernel": "conv3d_tc_kernel (tcgen05 implicit GEMM, all conv launches of one step)",
             "achieved": conv_tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": conv_tf / pk["bf16_sustained"],
-            "peak_source": f"{pk['src']} (sustained: kernels timed inside a full step)", "traffic": None,
+            "peak_source": f"{pk['src']} (sustained: kernels timed inside a full step)",
+            # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (256->256 k3 @8x36x44x28, 844 us,
+            # tensor pipe 83.5 %) from the committed ncu --set full capture; algorithmic in + out = 363 MB
+            "traffic": 330.2e6, "traffic_source": "profiles/r01b_ncu_full.md (per launch of conv3d_tc_kernel<256,2,1>)",
             "launches_per_step": conv["launches"] // n_prof, "share_of_step": conv["ms"] / n_prof / step_ms_prof}
     breakdown = {k: {"ms_per_step": v["ms"] / n_prof, "launches_per_step": v["launches"] // n_prof} for k, v in kinds.items()}
     for k in ("gn_stats", "gn_apply"):

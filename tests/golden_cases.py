@@ -46,10 +46,10 @@ def sampling_inputs(n_steps, batch=2):
     return x_T, cond, step_noise
 
 
-def make_scheduler(mod, kind, n_steps):
+def make_scheduler(mod, kind, n_steps, **extra):
     """mod: `oracle` or `b200ldm` - same constructor surface (3d_ldm/inference.py:79-84)."""
     cls = mod.DDPMScheduler if kind == "ddpm" else mod.DDIMScheduler
-    s = cls(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0195)
+    s = cls(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0195, **extra)
     s.set_timesteps(n_steps)
     return s
 

@@ -435,6 +435,21 @@ def test_scheduler_step_kernel_vs_oracle(kind, dtype):
     assert int(counter.item()) == n
 
 
+@pytest.mark.parametrize("pred", ["sample", "v_prediction"])
+@pytest.mark.parametrize("kind", ["ddpm", "ddim"])
+def test_scheduler_step_prediction_types(kind, pred):
+    """sample / v_prediction heads and DDIM eta > 0 through the same fused kernel (only the coefficient row changes)"""
+    import b200ldm
+    ours = gc.make_scheduler(b200ldm, kind, 50, prediction_type=pred)
+    ref = gc.make_scheduler(oracle, kind, 50, prediction_type=pred)
+    x, m, nz = rnd((2, 4, 4, 4, 4), 54), rnd((2, 4, 4, 4, 4), 55) * 0.5, rnd((2, 4, 4, 4, 4), 56)
+    kw = {} if kind == "ddpm" else {"eta": 0.5}
+    for t in (int(ref.timesteps[0]), int(ref.timesteps[20]), int(ref.timesteps[-1])):
+        p, p0 = ours.step(m.to(DEV), t, x.to(DEV), noise=nz.to(DEV), **kw)
+        w, w0 = ref.step(m, t, x, noise=nz, **kw)
+        assert relerr(p, w) <= 3e-5 and relerr(p0, w0) <= 3e-5, (t, relerr(p, w), relerr(p0, w0))
+
+
 def test_scheduler_module_step_and_add_noise():
     import b200ldm
     ours, ref = gc.make_scheduler(b200ldm, "ddpm", 1000), gc.make_scheduler(oracle, "ddpm", 1000)

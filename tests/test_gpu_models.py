@@ -159,6 +159,26 @@ def test_cached_sampling_loop_tracks_inputs_and_weights():
     assert relerr(a3, a3_fresh) <= 2e-2 and relerr(a3, a1) > 5e-2
 
 
+def test_serving_generator_batches_requests():
+    """LatentDiffusionGenerator.generate == the reference request loop's `model.generate(noise, ...)`, batched: results
+    are seed-deterministic, shaped like the request, finite, and padded batches reuse one captured loop."""
+    import b200ldm
+    unet = port(gc.tiny_unet(), b200ldm.DiffusionModelUNet, gc.UNET_KW, "bf16")
+    ae = port(gc.tiny_ae(), b200ldm.AutoencoderKL, gc.AE_KW, "bf16")
+    gen = b200ldm.LatentDiffusionGenerator(ae, unet, dict(num_train_timesteps=1000, schedule="scaled_linear_beta",
+                                                          beta_start=0.0015, beta_end=0.0195), sampler="ddpm", max_batch=2,
+                                           downsample=2)       # the tiny AE has one down-sampling level
+    patch = tuple(2 * v for v in gc.LATENT)
+    a = gen.generate_many(3, patch, DEV, num_inference_steps=4, seed=11)
+    b = gen.generate_many(3, patch, DEV, num_inference_steps=4, seed=11)
+    c = gen.generate_many(3, patch, DEV, num_inference_steps=4, seed=12)
+    assert a.shape == (3, 1) + patch and bool(torch.isfinite(a).all())
+    assert relerr(a, b) <= 2e-2 and relerr(a, c) > 5e-2
+    assert len(gen.inferer._loops) == 1                      # 2 + 1(padded to 2): one shape, one captured graph
+    out = gen(torch.empty((1, 1) + patch, device=DEV))       # `model(noise)` branch
+    assert out.shape == (1, 1) + patch
+
+
 def test_inferer_call_matches_oracle():
     """LatentDiffusionInferer.__call__ (3d_ldm/train_diffusion.py:197-205): encode -> add_noise -> concat -> UNet."""
     import b200ldm

@@ -110,21 +110,53 @@ def test_constructor_errors_match_reference_surface():
         u(torch.zeros((1, 8) + gc.LATENT), torch.tensor([1.0]), context=torch.zeros(1, 1, 4))
 
 
+@pytest.mark.parametrize("pred", ["epsilon", "sample", "v_prediction"])
 @pytest.mark.parametrize("kind,n", [("ddpm", 10), ("ddpm", 1000), ("ddim", 50)])
-def test_coef_table_reproduces_oracle_step(kind, n):
-    """x' = c_x0*clamp((x - s1m*eps)*isa) + c_xt*x + c_eps*eps + sigma*z with our host-side table == oracle.step."""
+def test_coef_table_reproduces_oracle_step(kind, n, pred):
+    """x0 = clamp(a_x*x + a_e*m); x' = c_x0*x0 + c_xt*x + c_e*m + sigma*z with our host-side table == oracle.step,
+    for every prediction type and (DDIM) eta in {0, 0.7}."""
     import b200ldm
-    ours, ref = gc.make_scheduler(b200ldm, kind, n), gc.make_scheduler(oracle, kind, n)
+    ours, ref = gc.make_scheduler(b200ldm, kind, n, prediction_type=pred), gc.make_scheduler(oracle, kind, n, prediction_type=pred)
     assert ours.timesteps.tolist() == ref.timesteps.tolist()
     g = torch.Generator().manual_seed(3)
     x, e, z = (torch.randn(1, 4, 3, 3, 3, generator=g) for _ in range(3))
-    for t in [int(ref.timesteps[0]), int(ref.timesteps[len(ref.timesteps) // 2]), int(ref.timesteps[-1])]:
-        isa, s1m, c0, ct, ce, sg, lo, hi = ours.coef_row(t)
-        x0 = ((x - s1m * e) * isa).clamp(lo, hi)
-        mine = c0 * x0 + ct * x + ce * e + sg * z
-        want, want0 = ref.step(e, t, x, noise=z)
-        assert torch.allclose(mine, want, atol=3e-5, rtol=1e-5), (kind, t)
-        assert torch.allclose(x0, want0, atol=3e-5, rtol=1e-5)
+    for eta in ((0.0, 0.7) if kind == "ddim" else (None,)):
+        for t in [int(ref.timesteps[0]), int(ref.timesteps[len(ref.timesteps) // 2]), int(ref.timesteps[-1])]:
+            a_x, a_e, c0, ct, ce, sg, lo, hi = ours.coef_row(t) if eta is None else ours.coef_row(t, eta)
+            x0 = (a_x * x + a_e * e).clamp(lo, hi)
+            mine = c0 * x0 + ct * x + ce * e + sg * z
+            want, want0 = ref.step(e, t, x, noise=z) if eta is None else ref.step(e, t, x, eta=eta, noise=z)
+            assert torch.allclose(mine, want, atol=5e-5, rtol=2e-5), (kind, t, pred, eta)
+            assert torch.allclose(x0, want0, atol=5e-5, rtol=2e-5)
+
+
+def test_scheduler_constructor_errors():
+    import b200ldm
+    with pytest.raises(ValueError):
+        b200ldm.DDPMScheduler(prediction_type="nonsense")
+    with pytest.raises(ValueError):
+        b200ldm.DDIMScheduler(prediction_type="nonsense")
+    with pytest.raises(NotImplementedError):
+        b200ldm.DDPMScheduler(variance_type="learned_range")   # needs a 2C-channel UNet head: not in any reference config
+
+
+def test_serving_batch_plan_and_surface():
+    """request batching of the serving shim (reference loop: api_server.py:163-176, one sample at a time)"""
+    import b200ldm
+    from b200ldm.serving import plan_batches
+    assert plan_batches(0, 8) == []
+    assert plan_batches(3, 8) == [(0, 3)]
+    assert plan_batches(19, 8) == [(0, 8), (8, 8), (16, 3)]
+    with pytest.raises(ValueError):
+        plan_batches(4, 0)
+    gen = b200ldm.LatentDiffusionGenerator(b200ldm.AutoencoderKL(**gc.AE_KW), b200ldm.DiffusionModelUNet(**gc.UNET_KW),
+                                           dict(num_train_timesteps=1000, schedule="scaled_linear_beta",
+                                                beta_start=0.0015, beta_end=0.0195), sampler="ddim", max_batch=2)
+    assert gen.cond_channels == gc.UNET_KW["in_channels"] - gc.AE_KW["latent_channels"]
+    with pytest.raises(RuntimeError):          # no CPU fallback
+        gen.generate(torch.zeros(1, 1, 16, 16, 16), num_inference_steps=2)
+    with pytest.raises(ValueError):
+        gen._latent_spatial((10, 16, 16))
 
 
 def test_shard_range_partitions_exactly():
