@@ -45,13 +45,13 @@ class Scheduler:
     _PRED = ("epsilon", "sample", "v_prediction")
 
     def _x0_coefs(self, a_t):
-        """(a_x, a_e): x0 = a_x * x_t + a_e * model_output for this scheduler's prediction type."""
+        """(a_x, r): x0 = a_x * (x_t + r * model_output), or r * model_output when a_x == 0 (include/b200ldm.h)."""
         b_t = 1 - a_t
         if self.prediction_type == "epsilon":
-            return 1.0 / a_t ** 0.5, -(b_t ** 0.5) / a_t ** 0.5
+            return 1.0 / a_t ** 0.5, -(b_t ** 0.5)
         if self.prediction_type == "sample":
             return torch.tensor(0.0), torch.tensor(1.0)
-        return a_t ** 0.5, -(b_t ** 0.5)
+        return a_t ** 0.5, -(b_t ** 0.5) / a_t ** 0.5
 
     def add_noise(self, original_samples: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
         t = timesteps.to("cpu").long().reshape(-1)
@@ -115,7 +115,7 @@ class DDPMScheduler(Scheduler):
         return torch.clamp(var, min=1e-20) if self.variance_type == "fixed_small" else self.betas[t]
 
     def coef_row(self, t: int) -> list[float]:
-        """{a_x, a_e, c_x0, c_xt, c_e, sigma, clip_lo, clip_hi} (include/b200ldm.h) in fp32 torch arithmetic that mirrors
+        """{a_x, r, c_x0, c_xt, c_e, sigma, clip_lo, clip_hi} (include/b200ldm.h) in fp32 torch arithmetic that mirrors
         upstream's operation order (alphas_cumprod[t-1] even after set_timesteps(n<T))."""
         a_t = self.alphas_cumprod[t]
         a_prev = self.alphas_cumprod[t - 1] if t > 0 else self.one

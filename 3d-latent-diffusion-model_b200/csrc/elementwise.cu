@@ -191,7 +191,7 @@ __global__ void scheduler_step_kernel(const b200ldm_sched_params p) {
   const int step = p.counter ? p.counter[0] : 0;
   const uint64_t seed = p.seed_dev ? *p.seed_dev : p.seed;
   const float* cf = p.coef + (size_t)step * 8;
-  const float a_x = cf[0], a_e = cf[1], c_x0 = cf[2], c_xt = cf[3], c_eps = cf[4], sigma = cf[5], lo = cf[6], hi = cf[7];
+  const float a_x = cf[0], r_e = cf[1], c_x0 = cf[2], c_xt = cf[3], c_eps = cf[4], sigma = cf[5], lo = cf[6], hi = cf[7];
   const int qpv = p.C >> 2;  // 4-channel groups per voxel
   const long long quads = p.n_vox * qpv;
   const T* eps = reinterpret_cast<const T*>(p.eps);
@@ -215,7 +215,8 @@ __global__ void scheduler_step_kernel(const b200ldm_sched_params p) {
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      x0[j] = fminf(fmaxf(fmaf(a_x, x[j], a_e * e[j]), lo), hi);
+      const float u = r_e * e[j];
+      x0[j] = fminf(fmaxf(a_x != 0.f ? (x[j] + u) * a_x : u, lo), hi);
       o[j] = c_x0 * x0[j] + c_xt * x[j] + c_eps * e[j] + sigma * z[j];
     }
     *reinterpret_cast<float4*>(p.x_t + xi) = make_float4(o[0], o[1], o[2], o[3]);

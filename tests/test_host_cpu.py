@@ -113,7 +113,7 @@ def test_constructor_errors_match_reference_surface():
 @pytest.mark.parametrize("pred", ["epsilon", "sample", "v_prediction"])
 @pytest.mark.parametrize("kind,n", [("ddpm", 10), ("ddpm", 1000), ("ddim", 50)])
 def test_coef_table_reproduces_oracle_step(kind, n, pred):
-    """x0 = clamp(a_x*x + a_e*m); x' = c_x0*x0 + c_xt*x + c_e*m + sigma*z with our host-side table == oracle.step,
+    """x0 = clamp(a_x*(x + r*m) | r*m); x' = c_x0*x0 + c_xt*x + c_e*m + sigma*z with our host-side table == oracle.step,
     for every prediction type and (DDIM) eta in {0, 0.7}."""
     import b200ldm
     ours, ref = gc.make_scheduler(b200ldm, kind, n, prediction_type=pred), gc.make_scheduler(oracle, kind, n, prediction_type=pred)
@@ -122,8 +122,8 @@ def test_coef_table_reproduces_oracle_step(kind, n, pred):
     x, e, z = (torch.randn(1, 4, 3, 3, 3, generator=g) for _ in range(3))
     for eta in ((0.0, 0.7) if kind == "ddim" else (None,)):
         for t in [int(ref.timesteps[0]), int(ref.timesteps[len(ref.timesteps) // 2]), int(ref.timesteps[-1])]:
-            a_x, a_e, c0, ct, ce, sg, lo, hi = ours.coef_row(t) if eta is None else ours.coef_row(t, eta)
-            x0 = (a_x * x + a_e * e).clamp(lo, hi)
+            a_x, r, c0, ct, ce, sg, lo, hi = ours.coef_row(t) if eta is None else ours.coef_row(t, eta)
+            x0 = ((x + r * e) * a_x if a_x != 0 else r * e).clamp(lo, hi)
             mine = c0 * x0 + ct * x + ce * e + sg * z
             want, want0 = ref.step(e, t, x, noise=z) if eta is None else ref.step(e, t, x, eta=eta, noise=z)
             assert torch.allclose(mine, want, atol=5e-5, rtol=2e-5), (kind, t, pred, eta)
