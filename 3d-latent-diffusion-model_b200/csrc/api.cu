@@ -7,6 +7,7 @@ static thread_local char t_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 void set_conv_trace(void* p);
 void set_conv_trace2(void* p);
+void set_attn_trace(void* p);
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -58,6 +59,7 @@ int b200ldm_check_device(void) {
 int b200ldm_debug_set_conv_trace(void* buf) {
   b200ldm::set_conv_trace(buf);
   b200ldm::set_conv_trace2(buf);
+  b200ldm::set_attn_trace(buf);
   return B200LDM_OK;
 }
 

@@ -27,6 +27,8 @@ struct AttnArgs {
   int H, L, d;
   float scale_log2;  // softmax scale * log2(e)
   __nv_bfloat16* o;  // [B][L][H*d]
+  unsigned long long* trace;  // debug (b200ldm_debug_set_conv_trace): per-CTA cycle counters of the softmax warps
+  int dbg;                    // debug: bit0 = exp2 replaced by a multiply (is the MUFU pipe the limiter?)
 };
 
 constexpr int kAttnThreads = 192;
@@ -294,6 +296,9 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
 // for both query tiles.  S is single-buffered per warpgroup (S_w(j+1) is issued right after PV_w(j), which already
 // requires P_w(j), i.e. that S_w(j) has been consumed).
 // Warp roles (320 threads): warp0 TMA, warp1 MMA + TMEM owner, warps 2..5 softmax A, warps 6..9 softmax B.
+static unsigned long long* g_attn_trace = nullptr;
+void set_attn_trace(void* p) { g_attn_trace = reinterpret_cast<unsigned long long*>(p); }
+
 template <int D, int BN>
 struct Attn2Cfg {
   static constexpr int kStages = 3;
@@ -327,7 +332,8 @@ attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   const uint32_t s_full = kv_empty + 8 * STAGES;     // [2]  (per warpgroup)
   const uint32_t p_full = s_full + 16;               // [2]
   const uint32_t pv_done = p_full + 16;              // [2]
-  const uint32_t tmem_slot = pv_done + 16;
+  const uint32_t s_free = pv_done + 16;              // [2]  S_w is in the softmax warps' registers (4 warp arrivals)
+  const uint32_t tmem_slot = s_free + 16;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -346,6 +352,7 @@ attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       ptx::mbar_init(s_full + 8 * w, 1);
       ptx::mbar_init(p_full + 8 * w, 128);
       ptx::mbar_init(pv_done + 8 * w, 1);
+      ptx::mbar_init(s_free + 8 * w, 4);
     }
     ptx::fence_barrier_init();
   }
@@ -402,8 +409,19 @@ attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       for (int j = 0; j < ntiles; ++j) {
         const int s = j % STAGES;
         const uint32_t vs = kv_smem + s * 2 * Cfg::kKVBytes + Cfg::kKVBytes;
+        // S_w(j+1) goes out as soon as the softmax warps hold S_w(j) in registers - a whole exp phase before P_w(j)
+        // exists - so the next tile's scores are waiting when the warpgroup comes back for them (the chain
+        // softmax -> PV -> S -> softmax used to cost ~600 tensor-pipe cycles of idle MUFU per tile)
+        if (j + 1 < ntiles) {
+          ptx::mbar_wait(kv_full + 8 * ((j + 1) % STAGES), (uint32_t)((j + 1) / STAGES) & 1u, 11);
+          for (int w = 0; w < nw; ++w) {
+            ptx::mbar_wait(s_free + 8 * w, (uint32_t)j & 1u, 15);
+            ptx::tc_fence_after();
+            issue_s(w, j + 1);
+          }
+        }
         for (int w = 0; w < nw; ++w) {
-          ptx::mbar_wait(p_full + 8 * w, (uint32_t)j & 1u, 14);   // P_w(j) staged, S_w(j) consumed, O_w rescaled
+          ptx::mbar_wait(p_full + 8 * w, (uint32_t)j & 1u, 14);   // P_w(j) staged, O_w rescaled
           ptx::tc_fence_after();
           const uint32_t ps = p_smem + w * Cfg::kPBytes;
           const uint32_t tO = tmem + Cfg::kOCol + w * D;
@@ -415,13 +433,6 @@ attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
           }
           ptx::umma_commit(pv_done + 8 * w);
           if (w == nw - 1) ptx::umma_commit(kv_empty + 8 * s);   // both PV(j) issued: K/V stage reusable when they retire
-          if (j + 1 < ntiles) {
-            if (w == 0) {
-              ptx::mbar_wait(kv_full + 8 * ((j + 1) % STAGES), (uint32_t)((j + 1) / STAGES) & 1u, 11);
-              ptx::tc_fence_after();
-            }
-            issue_s(w, j + 1);
-          }
         }
       }
     }
@@ -437,18 +448,36 @@ attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       const uint32_t tS = tmem + lane_off + Cfg::kSCol + w * BN;
       const uint32_t tO = tmem + lane_off + Cfg::kOCol + w * D;
 
+      // trace slots (per CTA, per warpgroup): [0] wait s_full, [1] TMEM load, [2] max, [3] wait pv_done, [4] rescale,
+      // [5] exp + P store, [6] tiles, [7] total
+#ifdef B200LDM_ATTN_TRACE
+      const bool tr = a.trace != nullptr && lane == 0 && qd == 0;
+#else
+      constexpr bool tr = false;   // the clock64 bookkeeping costs registers (spills): compiled in only for tracing
+#endif
+      long long tc[6] = {0, 0, 0, 0, 0, 0};
+      const long long t_begin = tr ? clock64() : 0;
       for (int j = 0; j < ntiles; ++j) {
+        long long t0 = tr ? clock64() : 0, t1;
         ptx::mbar_wait(s_full + 8 * w, (uint32_t)j & 1u, 20);
         ptx::tc_fence_after();
+        if (tr) { t1 = clock64(); tc[0] += t1 - t0; t0 = t1; }
         float sv[BN];
+        {
+          // all of S_w(j) in flight before the single wait (four serialised ~230-cycle TMEM round trips before)
+          uint32_t r[BN / 32][32];
 #pragma unroll
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld32(tS + c, r);
+          for (int c = 0; c < BN / 32; ++c) ptx::tmem_ld32(tS + c * 32, r[c]);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sv[c + i] = __uint_as_float(r[i]);
+          for (int c = 0; c < BN / 32; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sv[c * 32 + i] = __uint_as_float(r[c][i]);
         }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(s_free + 8 * w);   // the tensor core may overwrite S_w with the next tile's scores
+        if (tr) { t1 = clock64(); tc[1] += t1 - t0; t0 = t1; }
         const int kvalid = a.L - j * BN;
         if (kvalid < BN) {
 #pragma unroll
@@ -465,7 +494,9 @@ attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         const bool need = mx > m_used + 8.0f;
         const bool any_need = __any_sync(0xffffffffu, need);
         float alpha = 1.0f;
+        if (tr) { t1 = clock64(); tc[2] += t1 - t0; t0 = t1; }
         if (j > 0) ptx::mbar_wait(pv_done + 8 * w, (uint32_t)(j - 1) & 1u, 21);  // PV_w(j-1) retired
+        if (tr) { t1 = clock64(); tc[3] += t1 - t0; t0 = t1; }
         if (any_need) {
           if (need) {
             alpha = exp2f(m_used - mx);
@@ -486,15 +517,23 @@ attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
             ptx::tmem_st_wait();
           }
         }
+        if (tr) { t1 = clock64(); tc[4] += t1 - t0; t0 = t1; }
         const float neg_m = -m_used;
+#ifdef B200LDM_ATTN_TRACE
+        const bool no_mufu = (a.dbg & 1) != 0;
+#else
+        constexpr bool no_mufu = false;
+#endif
         float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c8 = 0; c8 < BN / 8; ++c8) {
           uint32_t pk[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float p0 = ex2_approx(fmaf(sv[c8 * 8 + 2 * e], a.scale_log2, neg_m));
-            const float p1 = ex2_approx(fmaf(sv[c8 * 8 + 2 * e + 1], a.scale_log2, neg_m));
+            const float x0 = fmaf(sv[c8 * 8 + 2 * e], a.scale_log2, neg_m);
+            const float x1 = fmaf(sv[c8 * 8 + 2 * e + 1], a.scale_log2, neg_m);
+            const float p0 = no_mufu ? x0 * 0.001f : ex2_approx(x0);
+            const float p1 = no_mufu ? x1 * 0.001f : ex2_approx(x1);
             ps4[e] += p0 + p1;
             const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
             pk[e] = *reinterpret_cast<const uint32_t*>(&hb);
@@ -507,6 +546,16 @@ attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         ptx::fence_proxy_async();
         ptx::tc_fence_before();
         ptx::mbar_arrive(p_full + 8 * w);
+        if (tr) { t1 = clock64(); tc[5] += t1 - t0; }
+      }
+      if (tr) {
+        const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        if (cta < 1024) {
+          unsigned long long* o = a.trace + (cta * 2 + w) * 8;
+          for (int i = 0; i < 6; ++i) o[i] = (unsigned long long)tc[i];
+          o[6] = (unsigned long long)ntiles;
+          o[7] = (unsigned long long)(clock64() - t_begin);
+        }
       }
       // ---- epilogue
       ptx::mbar_wait(pv_done + 8 * w, (uint32_t)(ntiles - 1) & 1u, 22);
@@ -578,7 +627,8 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
   if ((rc = make_qkv_map(&maps.q, q, H * D, L, B, ld, 128))) return rc;
   if ((rc = make_qkv_map(&maps.k, k, H * D, L, B, ld, BN))) return rc;
   if ((rc = make_qkv_map(&maps.v, v, H * D, L, B, ld, BN))) return rc;
-  AttnArgs a{H, L, D, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o)};
+  static const int dbg = [] { const char* e = getenv("B200LDM_ATTN_DBG"); return e ? atoi(e) : 0; }();
+  AttnArgs a{H, L, D, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o), g_attn_trace, dbg};
   static bool attr_done = false;
   if (!attr_done) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -600,7 +650,8 @@ static int launch_attention_tc2(const void* q, const void* k, const void* v, voi
   if ((rc = make_qkv_map(&maps.q, q, H * D, L, B, ld, 128))) return rc;
   if ((rc = make_qkv_map(&maps.k, k, H * D, L, B, ld, BN))) return rc;
   if ((rc = make_qkv_map(&maps.v, v, H * D, L, B, ld, BN))) return rc;
-  AttnArgs a{H, L, D, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o)};
+  static const int dbg = [] { const char* e = getenv("B200LDM_ATTN_DBG"); return e ? atoi(e) : 0; }();
+  AttnArgs a{H, L, D, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o), g_attn_trace, dbg};
   static bool attr_done = false;
   if (!attr_done) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<D, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,

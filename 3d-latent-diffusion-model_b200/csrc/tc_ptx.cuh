@@ -74,6 +74,7 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
 }
 __device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity, int who) {
   if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait_hint(bar, parity, 1000000u)) return;   // the usual case: one suspended wait, no spin-loop code
   const long long t0 = clock64();
   while (!mbar_try_wait_hint(bar, parity, 1000000u)) {
     if (clock64() - t0 > 4000000000LL) {
