@@ -8,6 +8,7 @@ std::atomic<uint64_t> g_launches{0};
 void set_conv_trace(void* p);
 void set_conv_trace2(void* p);
 void set_attn_trace(void* p);
+void set_conv_kernel(int k);
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -60,6 +61,12 @@ int b200ldm_debug_set_conv_trace(void* buf) {
   b200ldm::set_conv_trace(buf);
   b200ldm::set_conv_trace2(buf);
   b200ldm::set_attn_trace(buf);
+  return B200LDM_OK;
+}
+
+/* debug only (not in the public header): pin the conv kernel like B200LDM_CONV_KERNEL does (-1 = measured / model) */
+int b200ldm_debug_set_conv_kernel(int k) {
+  b200ldm::set_conv_kernel(k);
   return B200LDM_OK;
 }
 

@@ -607,10 +607,11 @@ static const int g_force_cl = [] {
 
 // B200LDM_CONV_KERNEL pins the kernel wherever it supports the problem: 0 = one CTA per tile (conv3d_tc_kernel),
 // 1 = persistent CTA pairs (conv_tc2.cu), 2 = persistent single CTAs (conv_tcp.cu); unset: measured / cost model
-static const int g_tc2 = [] {
+static int g_tc2 = [] {
   const char* e = getenv("B200LDM_CONV_KERNEL");
   return e ? atoi(e) : -1;
 }();
+void set_conv_kernel(int k) { g_tc2 = k; }   // tests: exercise every kernel in one process (b200ldm_debug_set_conv_kernel)
 
 static const int g_force_splits = [] {
   const char* e = getenv("B200LDM_CONV_SPLITS");

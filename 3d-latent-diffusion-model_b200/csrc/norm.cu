@@ -17,7 +17,9 @@ __global__ void __launch_bounds__(kNormThreads, 4)
 gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ x2, double* __restrict__ stats, long long S,
                 int C1, int C2, int G, int vox_per_block) {
   extern __shared__ float sh[];  // [2*G]
-  const int n = blockIdx.y;
+  // blocks walk the tensor BACKWARDS: the producing conv wrote it front to back, so its tail is what still sits in the
+  // 126 MB L2 (an activation at the top level is 181-363 MB); reading that first turns part of the pass into L2 hits
+  const int n = gridDim.y - 1 - blockIdx.y;
   const int C = C1 + C2;
   const int vecs = C >> 3;
   const int cpg = C / G;
@@ -30,7 +32,7 @@ gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ x2, double* __res
 #pragma unroll
   for (int e = 0; e < 8; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
   if (vslot < vpp) {
-    const long long v0 = (long long)blockIdx.x * vox_per_block;
+    const long long v0 = (long long)(gridDim.x - 1 - blockIdx.x) * vox_per_block;
     const long long v1 = min(v0 + vox_per_block, S);
     const bool second = cv * 8 >= C1;
     const int Cs = second ? C2 : C1;
@@ -80,7 +82,7 @@ gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict
                 const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                 long long S, int C1, int C2, int G, float eps, int silu, int vox_per_block, double inv_cnt_arg,
                 const double* __restrict__ cst1, const double* __restrict__ cst2) {
-  const int n = blockIdx.y;
+  const int n = gridDim.y - 1 - blockIdx.y;   // back to front, see gn_stats_kernel
   const int C = C1 + C2;
   const int vecs = C >> 3;
   const int cpg = C / G;
@@ -125,7 +127,7 @@ gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict
     sc[e] = rstd * ga;
     sf[e] = be - mean_f * rstd * ga;
   }
-  const long long v0 = (long long)blockIdx.x * vox_per_block;
+  const long long v0 = (long long)(gridDim.x - 1 - blockIdx.x) * vox_per_block;
   const long long v1 = min(v0 + vox_per_block, S);
   const size_t off = ((size_t)n * S) * C + (size_t)cv * 8;
   const bool second = cv * 8 >= C1;

@@ -262,6 +262,44 @@ def test_tap_gather_fp32_exact():
     assert torch.allclose(y, want, atol=1e-5, rtol=1e-5)
 
 
+@pytest.mark.parametrize("kernel", [0, 1, 2], ids=["tile_per_cta", "cta_pairs", "persistent"])
+@pytest.mark.parametrize("case", [(2, (9, 11, 7), 128, 0, 256, 3, 1), (1, (8, 8, 8), 64, 64, 64, 3, 1), (2, (6, 10, 6), 64, 0, 128, 3, 2),
+                                  (3, (5, 5, 5), 256, 0, 512, 1, 1), (1, (18, 22, 14), 64, 0, 64, 3, 1)],
+                         ids=lambda c: f"N{c[0]}_{'x'.join(map(str, c[1]))}_C{c[2]}+{c[3]}->{c[4]}_k{c[5]}s{c[6]}")
+def test_conv3d_every_tensor_core_kernel(case, kernel):
+    """the three tcgen05 conv kernels (one CTA per tile, persistent CTA pairs, persistent single CTAs) pinned one by one:
+    same tensor, residual + time-embedding + GroupNorm chunk statistics included"""
+    import ctypes
+    from b200ldm import _lib, ops
+    lib = _lib.load()
+    lib.b200ldm_debug_set_conv_kernel.argtypes = [ctypes.c_int]
+    N, sp, C1, C2, Cout, k, stride = case
+    C = C1 + C2
+    x = q(rnd((N, C) + sp, 81), torch.bfloat16)
+    w = q(rnd((Cout, C, k, k, k), 82) * (C * k ** 3) ** -0.5, torch.bfloat16)
+    b, temb = 0.1 * rnd((Cout,), 83), 0.1 * rnd((N, Cout), 84)
+    pad = k // 2
+    ref = F.conv3d(x.double(), w.double(), b.double(), stride=stride, padding=pad) + temb.double()[:, :, None, None, None]
+    res = q(rnd(tuple(ref.shape), 85), torch.bfloat16) if stride == 1 else None
+    if res is not None:
+        ref = ref + res.double()
+    xa = to_act(x[:, :C1], torch.bfloat16)
+    x2a = to_act(x[:, C1:], torch.bfloat16) if C2 else None
+    wp = ops.repack_conv_weight(w.to(DEV), Cout, C, torch.bfloat16, C1 if C2 else None, C1 if C2 else None)
+    lib.b200ldm_debug_set_conv_kernel(kernel)
+    try:
+        y = ops.conv3d(xa, wp, b.to(DEV), Cout, ksize=k, stride=stride, pad_lo=pad, x2=x2a, temb=temb.to(DEV),
+                       temb_stride=Cout, residual=None if res is None else to_act(res, torch.bfloat16), want_stats=True)
+    finally:
+        lib.b200ldm_debug_set_conv_kernel(-1)
+    assert relerr(from_act(y, Cout), ref) <= 1e-2
+    cs = getattr(y, "cstats", None)
+    if cs is not None:      # (sum, sumsq) per 8-channel chunk of the tensor as stored
+        yf = from_act(y, Cout).double()
+        want = torch.stack([yf.reshape(N, Cout // 8, 8, -1).sum(dim=(2, 3)), (yf ** 2).reshape(N, Cout // 8, 8, -1).sum(dim=(2, 3))], dim=-1)
+        assert relerr(cs.reshape(N, Cout // 8, 2).cpu(), want) <= 1e-4
+
+
 def test_conv3d_rejects_bad_arguments():
     from b200ldm import ops
     x = torch.zeros((1, 4, 4, 4, 48), dtype=torch.bfloat16, device=DEV)
