@@ -299,26 +299,28 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
 static unsigned long long* g_attn_trace = nullptr;
 void set_attn_trace(void* p) { g_attn_trace = reinterpret_cast<unsigned long long*>(p); }
 
-template <int D, int BN>
+// OCC = CTAs per SM: 2 (only D = 64, BN = 64: 256 TMEM columns, ~99 KB smem, <= 102 registers) puts FOUR softmax warps
+// on every SM sub-partition - the exp loop is latency / issue bound with two (profiles/r01_attention_experiments.md).
+template <int D, int BN, int OCC = 1>
 struct Attn2Cfg {
-  static constexpr int kStages = 3;
+  static constexpr int kStages = OCC == 2 ? 2 : 3;
   static constexpr int kQBytes = 2 * (D / 64) * 16384;       // two query tiles
   static constexpr int kKVSub = BN * 128;
   static constexpr int kKVBytes = (D / 64) * kKVSub;
   static constexpr int kPBytes = (BN / 64) * 16384;           // per warpgroup
   static constexpr int kSmem = kQBytes + kStages * 2 * kKVBytes + 2 * kPBytes + 1024 + 256;
-  static constexpr int kTmemCols = 512;
+  static constexpr int kTmemCols = OCC == 2 ? 256 : 512;
   static constexpr int kSCol = 0;             // S_w at w*BN
   static constexpr int kOCol = 2 * BN;        // O_w at kOCol + w*D
   static constexpr int kThreads = 320;
-  static_assert(2 * BN + 2 * D <= 512, "TMEM budget");
-  static_assert(kSmem <= 232448, "smem budget");
+  static_assert(2 * BN + 2 * D <= kTmemCols, "TMEM budget");
+  static_assert(kSmem <= (OCC == 2 ? 115712 : 232448), "smem budget");
 };
 
-template <int D, int BN>
-__global__ void __launch_bounds__(Attn2Cfg<D, BN>::kThreads, 1)
+template <int D, int BN, int OCC>
+__global__ void __launch_bounds__(Attn2Cfg<D, BN, OCC>::kThreads, OCC)
 attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
-  using Cfg = Attn2Cfg<D, BN>;
+  using Cfg = Attn2Cfg<D, BN, OCC>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -641,10 +643,10 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
   return B200LDM_OK;
 }
 
-template <int D, int BN>
+template <int D, int BN, int OCC>
 static int launch_attention_tc2(const void* q, const void* k, const void* v, void* o, int B, int H, int L, long long ld,
                                 float scale, cudaStream_t st) {
-  using Cfg = Attn2Cfg<D, BN>;
+  using Cfg = Attn2Cfg<D, BN, OCC>;
   AttnMaps maps;
   int rc;
   if ((rc = make_qkv_map(&maps.q, q, H * D, L, B, ld, 128))) return rc;
@@ -654,12 +656,12 @@ static int launch_attention_tc2(const void* q, const void* k, const void* v, voi
   AttnArgs a{H, L, D, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o), g_attn_trace, dbg};
   static bool attr_done = false;
   if (!attr_done) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<D, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B2_CHECK_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<D, BN, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmem));
     attr_done = true;
   }
   dim3 grid((unsigned)ceil_div(L, 256), (unsigned)H, (unsigned)B);
-  attention_tc2_kernel<D, BN><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, a);
+  attention_tc2_kernel<D, BN, OCC><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, a);
   B2_LAUNCH_CHECK();
   return B200LDM_OK;
 }
@@ -679,8 +681,11 @@ int attention_tcgen05(const void* q, const void* k, const void* v, void* o, int 
              "attention: pointers / row stride must be 16-byte aligned");
   // v2 (two query tiles + two softmax warpgroups per CTA) once there are at least two query tiles
   if (g_attn_v >= 2 && L > 128) {
-    if (d == 64) return launch_attention_tc2<64, 128>(q, k, v, o, B, H, L, ld, scale, st);
-    if (d == 128) return launch_attention_tc2<128, 64>(q, k, v, o, B, H, L, ld, scale, st);
+    // d = 64: B200LDM_ATTN_OCC=2 runs 64-key tiles with two CTAs per SM (four softmax warps per sub-partition)
+    static const int occ = [] { const char* e = getenv("B200LDM_ATTN_OCC"); return e ? atoi(e) : 1; }();
+    if (d == 64 && occ == 2) return launch_attention_tc2<64, 64, 2>(q, k, v, o, B, H, L, ld, scale, st);
+    if (d == 64) return launch_attention_tc2<64, 128, 1>(q, k, v, o, B, H, L, ld, scale, st);
+    if (d == 128) return launch_attention_tc2<128, 64, 1>(q, k, v, o, B, H, L, ld, scale, st);
   }
   if (d == 64) return launch_attention_tc<64, 128>(q, k, v, o, B, H, L, ld, scale, st);
   if (d == 128) return launch_attention_tc<128, 128>(q, k, v, o, B, H, L, ld, scale, st);
