@@ -676,7 +676,8 @@ static void remember_choice(const ConvKey& key, int choice) {
 }
 
 // Tile / cluster / split-K decisions (shared by the launch and by b200ldm_conv3d_workspace_bytes).
-// A choice is kernel | splits << 4 | mt << 12 (splits / mt only for kernel 0; 0 = the cost model's value).
+// A choice is kernel | splits << 4 | mt << 12 | cl << 16 (splits / mt / cluster size only for kernel 0; 0 = the cost
+// model's value).
 // force_tc2: -1 = remembered measurement, else cost model; >= 0 = that choice (tuning runs).
 static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
   ConvPlan pl{};
@@ -758,9 +759,10 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
     pl.tc2 = tma_epi ? (choice & 15) : 0;
     if (pl.tc2) { pl.mt = 1; pl.cl = 1; pl.splits = 1; }
     else {
-      const int sp = (choice >> 4) & 255, mt = choice >> 12;
+      const int sp = (choice >> 4) & 255, mt = (choice >> 12) & 15, cl = choice >> 16;
       if (mt == 1 || mt == 2) pl.mt = mt;
       if (sp >= 1 && (sp == 1 || split_ok)) { pl.splits = sp; pl.cl = sp > 1 ? 1 : pl.cl; }
+      if ((cl == 1 || cl == 2) && pl.splits == 1 && (cl == 1 || (pl.bn >= 128 && !p->skip_x))) pl.cl = cl;
     }
   }
   if (!pl.tc2 && g_force_splits >= 1 && g_force_splits <= 12 && split_ok && iters / g_force_splits >= 1)
@@ -842,6 +844,8 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
       choices[nc++] = 0;
       if (pl.tc2_ok) choices[nc++] = 2;
       if (pl.tc2_ok && getenv("B200LDM_CONV_TUNE_PAIRS")) choices[nc++] = 1;   // CTA pairs: measured slower almost everywhere
+      if (!splittable && pl.bn >= 128 && !p->skip_x && pl.ctas1 >= 2 * 148)   // big launches: 2-CTA weight multicast
+        for (int mt = 1; mt <= 2; ++mt) choices[nc++] = (1 << 4) | (mt << 12) | (2 << 16);
       if (splittable) {
         static const int sps[] = {1, 2, 3, 4, 6, 8, 12, 16};
         for (int mt = 1; mt <= 2; ++mt)
@@ -883,10 +887,10 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
       remember_choice(key, best);
       if (getenv("B200LDM_CONV_AUTOTUNE_LOG"))
         fprintf(stderr, "b200ldm autotune: %d+%d->%d k%d s%d%s%s%s @%dx%dx%dx%d: model plan %.3f ms, persistent %.3f ms, "
-                        "best %.3f ms = kernel %d splits %d mt %d (%d candidates)\n",
+                        "best %.3f ms = kernel %d splits %d mt %d cl %d (%d candidates)\n",
                 p->C1, p->C2, p->Cout, p->ksize, p->stride, p->upsample2x ? " up" : "", p->residual ? " +res" : "",
                 p->skip_x ? " +skip" : "", p->N, p->Do, p->Ho, p->Wo, ms0 / 2, ms_tcp / 2, ms_best / 2, best & 15,
-                (best >> 4) & 255, best >> 12, nc);
+                (best >> 4) & 255, (best >> 12) & 15, best >> 16, nc);
       // the caller asked workspace_bytes / emits_chunk_stats before this call: honour that contract now (no stats
       // where it was told there would be none), later calls see the remembered choice
       ConvPlan run = plan_conv(p, best);
