@@ -119,7 +119,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       for (int j = 0; j < ntiles; ++j) {
         const int s = j % STAGES;
         const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
-        ptx::mbar_wait(kv_empty + 8 * s, ph ^ 1u, 10);
+        ptx::mbar_wait_long(kv_empty + 8 * s, ph ^ 1u, 10);   // suspended wait: the producer has stages of slack and must not steal issue slots
         const uint32_t ks = kv_smem + s * 2 * Cfg::kKVBytes, vs = ks + Cfg::kKVBytes;
         ptx::mbar_expect_tx(kv_full + 8 * s, 2 * Cfg::kKVBytes);
 #pragma unroll
@@ -377,7 +377,7 @@ attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       for (int j = 0; j < ntiles; ++j) {
         const int s = j % STAGES;
         const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
-        ptx::mbar_wait(kv_empty + 8 * s, ph ^ 1u, 10);
+        ptx::mbar_wait_long(kv_empty + 8 * s, ph ^ 1u, 10);   // suspended wait: the producer has stages of slack and must not steal issue slots
         const uint32_t ks = kv_smem + s * 2 * Cfg::kKVBytes, vs = ks + Cfg::kKVBytes;
         ptx::mbar_expect_tx(kv_full + 8 * s, 2 * Cfg::kKVBytes);
 #pragma unroll
