@@ -21,6 +21,7 @@ from . import ops
 from .nets import AutoencoderKL, DiffusionModelUNet, _PREC, _pad64, param_signature
 
 USE_GRAPH = os.environ.get("B200LDM_CUDA_GRAPH", "1") != "0"
+FUSE_SCHED = os.environ.get("B200LDM_FUSE_SCHED", "1") != "0"
 
 
 class SamplingLoop:
@@ -59,6 +60,7 @@ class SamplingLoop:
             self.noise = torch.empty((self.n_steps * N,) + self.spatial + (self.c_lat,), dtype=torch.float32, device=dev)
             self.noise_stride = self.noise.numel() // self.n_steps
         self.graph = None
+        self._sched = None
         self.launches_per_step = 0
         self.use_graph = use_graph and USE_GRAPH
         self.reset(input_noise, conditioning, step_noise, seed, scheduler, _fresh=True)
@@ -85,9 +87,17 @@ class SamplingLoop:
 
     def _body(self):
         ops.select_row(self.temb_table, self.counter, self.temb_cur)
-        eps = self.unet.forward_ndhwc(self.x_model, self.temb_cur, 0)
-        ops.scheduler_step(eps, self.x_t, self.coef, self.counter, self.c_lat, noise=self.noise,
-                           noise_step_stride=self.noise_stride, x_model=self.x_model, seed=self.seed_dev)
+        if FUSE_SCHED and self.unet.out[2].conv.tap_expanded(self.x_model):
+            # the scheduler update runs inside the UNet's last kernel (the output conv's tap gather) on the fp32 sums
+            if self._sched is None:
+                self._sched = ops.make_sched_params(self.x_t, self.coef, self.counter, self.c_lat, self.dtype,
+                                                    noise=self.noise, noise_step_stride=self.noise_stride,
+                                                    x_model=self.x_model, seed=self.seed_dev)
+            self.unet.forward_ndhwc(self.x_model, self.temb_cur, 0, sched=self._sched)
+        else:
+            eps = self.unet.forward_ndhwc(self.x_model, self.temb_cur, 0)
+            ops.scheduler_step(eps, self.x_t, self.coef, self.counter, self.c_lat, noise=self.noise,
+                               noise_step_stride=self.noise_stride, x_model=self.x_model, seed=self.seed_dev)
         ops.counter_add(self.counter, 1)
 
     def _capture(self):

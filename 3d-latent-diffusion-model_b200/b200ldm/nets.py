@@ -100,11 +100,11 @@ class Conv(nn.Module):
         return self._cache.get((dtype, c1, c1_phys, cin_phys), (self.weight, self.bias), build)
 
     def run(self, x, x2=None, c1: int | None = None, temb=None, temb_stride: int = 0, residual=None, gn_stats=None,
-            gn_groups: int = 0, out_f32: bool = False, want_stats: bool = False):
-        if (TAP_EXPAND and self.terminal and self.cout <= 16 and self.ksize == 3 and self.stride == 1 and self.pad_lo == 1
-                and self.pad_hi == 1 and x.dtype == torch.bfloat16 and x2 is None and temb is None and residual is None
-                and gn_stats is None and not out_f32):
-            return self._run_tap_expanded(x)
+            gn_groups: int = 0, out_f32: bool = False, want_stats: bool = False, sched=None):
+        if self.tap_expanded(x) and x2 is None and temb is None and residual is None and gn_stats is None and not out_f32:
+            return self._run_tap_expanded(x, sched)
+        if sched is not None:
+            raise RuntimeError("the fused scheduler update needs the stacked-tap output conv (Conv.tap_expanded)")
         if x2 is None:
             w, b = self.packed(x.dtype, cin_phys=x.shape[-1])
         else:
@@ -114,8 +114,14 @@ class Conv(nn.Module):
                           out_f32=out_f32, want_stats=want_stats)
 
 
-    def _run_tap_expanded(self, x):
-        """3x3x3 conv with <= 16 output channels = 1x1x1 GEMM to 27*cp stacked tap outputs + gather (ops.tap_gather)."""
+    def tap_expanded(self, x) -> bool:
+        """True when this conv runs as a 1x1x1 GEMM over stacked taps + ops.tap_gather for activations like `x`."""
+        return (TAP_EXPAND and self.terminal and self.cout <= 16 and self.ksize == 3 and self.stride == 1
+                and self.pad_lo == 1 and self.pad_hi == 1 and x.dtype == torch.bfloat16)
+
+    def _run_tap_expanded(self, x, sched=None):
+        """3x3x3 conv with <= 16 output channels = 1x1x1 GEMM to 27*cp stacked tap outputs + gather (ops.tap_gather);
+        sched: the scheduler update is applied by the gather kernel and the conv output is not materialised."""
         cin_phys = x.shape[-1]
         cp = 1
         while cp < self.cout:
@@ -133,7 +139,7 @@ class Conv(nn.Module):
 
         wz, b = self._cache.get(("tapexp", x.dtype, cin_phys), (self.weight, self.bias), build)
         z = ops.conv3d(x, wz, None, nz, ksize=1, stride=1, pad_lo=0)
-        return ops.tap_gather(z, b, cp, self.cout_phys)
+        return ops.tap_gather(z, b, cp, self.cout_phys, sched=sched, want_y=sched is None)
 
     def run_with_skip(self, x, skip_conv: "Conv", sx, sx2=None, want_stats: bool = False):
         """self(x) + skip_conv(cat(sx, sx2)) in ONE kernel: the 1x1x1 skip conv is a few more K iterations into the same
@@ -476,7 +482,7 @@ class DiffusionModelUNet(nn.Module):
         return ops.linear(ops.silu_f32(h), wall, ball, total)
 
     # ---- NDHWC core
-    def forward_ndhwc(self, x, temb_all, temb_stride: int):
+    def forward_ndhwc(self, x, temb_all, temb_stride: int, sched=None):
         """x: [N,D,H,W,pad64(in_channels)] (bf16|fp32); temb_all: fp32 [n_t, total] rows (n_t = 1 -> stride 0).
         Returns eps [N,D,H,W,round16(out_channels)]."""
         offs, _ = self._temb_layout()
@@ -509,7 +515,7 @@ class DiffusionModelUNet(nn.Module):
             if blk.upsampler is not None:
                 h = blk.upsampler.upsample.run(h)
         h = self.out[0].run(h, silu=True)
-        return self.out[2].run(h)
+        return self.out[2].run(h, sched=sched)   # sched: the scheduler update rides in the output conv's last kernel
 
     def forward(self, x, timesteps, context=None, class_labels=None, down_block_additional_residuals=None,
                 mid_block_additional_residual=None):

@@ -244,17 +244,21 @@ def attention(qkv, heads: int, head_dim: int, scale: float, engine: int = ENGINE
     return o
 
 
-def tap_gather(z, bias, cp: int, cy: int):
-    """y[v][co] = bias[co] + sum_tap z[v + shift(tap)][tap*cp + co]: second half of a narrow-output 3x3x3 conv."""
+def tap_gather(z, bias, cp: int, cy: int, sched=None, want_y: bool = True):
+    """y[v][co] = bias[co] + sum_tap z[v + shift(tap)][tap*cp + co]: second half of a narrow-output 3x3x3 conv.
+    sched: a SchedParams (make_sched_params) -> the gathered tensor is the noise prediction and the scheduler update is
+    applied in the same kernel; with want_y=False the prediction itself is never written (returns None)."""
     _need_cuda(z, bias)
     N, D, H, W, ldz = z.shape
     assert z.is_contiguous()
-    y = torch.empty((N, D, H, W, cy), dtype=z.dtype, device=z.device)
+    y = torch.empty((N, D, H, W, cy), dtype=z.dtype, device=z.device) if (want_y or sched is None) else None
     ev = PROFILER.start() if PROFILER is not None else None
-    _lib.check(_lib.load().b200ldm_tap_gather(z.data_ptr(), _ptr(bias), y.data_ptr(), N, D, H, W, ldz, cp, cy,
-                                              dtype_code(z.dtype), _stream()), "tap_gather")
+    _lib.check(_lib.load().b200ldm_tap_gather(z.data_ptr(), _ptr(bias), _ptr(y), N, D, H, W, ldz, cp, cy,
+                                              dtype_code(z.dtype), None if sched is None else C.byref(sched), _stream()),
+               "tap_gather")
     if ev is not None:
-        PROFILER.stop("tap_gather", f"cp{cp} S{D * H * W}", float(N * D * H * W) * (27 * cp + cy) * z.element_size(), ev)
+        PROFILER.stop("tap_gather", f"cp{cp} S{D * H * W}{'+sched' if sched is not None else ''}",
+                      float(N * D * H * W) * (27 * cp + cy) * z.element_size(), ev)
     return y
 
 
@@ -322,22 +326,31 @@ def counter_add(counter, delta: int = 1):
     _lib.check(_lib.load().b200ldm_counter_add(counter.data_ptr(), delta, _stream()), "counter_add")
 
 
-def scheduler_step(eps, x_t, coef, counter, c: int, noise=None, noise_step_stride: int = 0, x0_out=None, x_model=None,
-                   seed=0):
-    """In-place x_t <- step(eps, x_t); eps [.., C_eps] NDHWC, x_t fp32 [.., C] NDHWC.
-    seed: int, or a device int64[1] tensor read by the kernel (a captured graph then serves any seed)."""
+def make_sched_params(x_t, coef, counter, c: int, dtype: torch.dtype, eps=None, noise=None, noise_step_stride: int = 0,
+                      x0_out=None, x_model=None, seed=0):
+    """b200ldm_sched_params for `scheduler_step` or for the fused update inside `tap_gather`.  The returned struct holds
+    raw pointers: keep the tensors alive (the sampling loop owns them for its whole life)."""
     _need_cuda(eps, x_t, coef, noise, x_model)
     seed_dev = None
     if torch.is_tensor(seed):
         _need_cuda(seed)
         assert seed.dtype == torch.int64 and seed.numel() == 1
         seed_dev, seed = seed, 0
-    n_vox = x_t.numel() // c
     p = _lib.SchedParams(
         eps=_ptr(eps), x_t=_ptr(x_t), noise=_ptr(noise), x0_out=_ptr(x0_out), x_model=_ptr(x_model), coef=_ptr(coef),
-        counter=_ptr(counter), n_vox=n_vox, noise_step_stride=noise_step_stride, C=c, C_eps=eps.shape[-1],
-        C_model=0 if x_model is None else x_model.shape[-1], dtype=dtype_code(eps.dtype), seed=seed,
-        seed_dev=_ptr(seed_dev))
+        counter=_ptr(counter), n_vox=x_t.numel() // c, noise_step_stride=noise_step_stride, C=c,
+        C_eps=c if eps is None else eps.shape[-1], C_model=0 if x_model is None else x_model.shape[-1],
+        dtype=dtype_code(dtype), seed=seed, seed_dev=_ptr(seed_dev))
+    p._keep = (eps, x_t, noise, x0_out, x_model, coef, counter, seed_dev)
+    return p
+
+
+def scheduler_step(eps, x_t, coef, counter, c: int, noise=None, noise_step_stride: int = 0, x0_out=None, x_model=None,
+                   seed=0):
+    """In-place x_t <- step(eps, x_t); eps [.., C_eps] NDHWC, x_t fp32 [.., C] NDHWC.
+    seed: int, or a device int64[1] tensor read by the kernel (a captured graph then serves any seed)."""
+    p = make_sched_params(x_t, coef, counter, c, eps.dtype, eps=eps, noise=noise, noise_step_stride=noise_step_stride,
+                          x0_out=x0_out, x_model=x_model, seed=seed)
     _lib.check(_lib.load().b200ldm_scheduler_step(C.byref(p), _stream()), "scheduler_step")
 
 

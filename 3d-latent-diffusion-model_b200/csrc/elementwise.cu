@@ -234,10 +234,22 @@ __global__ void scheduler_step_kernel(const b200ldm_sched_params p) {
 // on the tensor cores (input read ONCE) followed by this gather:  y[v][co] = bias[co] + sum_tap Z[v + shift(tap)][tap*cp + co]
 // (taps that fall outside the volume contribute zero = the conv's zero padding).  One thread per voxel; every
 // 16*cp-byte slice of Z is read exactly once.
-template <typename T, int CP>
+// SCHED: the gathered tensor is the UNet's noise prediction and the scheduler update (b200ldm_scheduler_step, same
+// coefficient row / noise stream / element indexing) is applied right here, on the fp32 sums, before anything is
+// stored: "the scheduler update fused into the last UNet epilogue".  y may then be NULL (eps is not materialised).
+template <typename T, int CP, bool SCHED>
 __global__ void tap_gather_kernel(const T* __restrict__ z, const float* __restrict__ bias, T* __restrict__ y, int N, int D,
-                                  int H, int W, int ldz, int cy) {
+                                  int H, int W, int ldz, int cy, const b200ldm_sched_params sp) {
   const long long vox = (long long)N * D * H * W;
+  int step = 0;
+  uint64_t seed = 0;
+  float cf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (SCHED) {
+    step = sp.counter ? sp.counter[0] : 0;
+    seed = sp.seed_dev ? *sp.seed_dev : sp.seed;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cf[i] = sp.coef[(size_t)step * 8 + i];
+  }
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < vox; v += (long long)gridDim.x * blockDim.x) {
     long long t = v;
     const int w = (int)(t % W); t /= W;
@@ -274,6 +286,43 @@ __global__ void tap_gather_kernel(const T* __restrict__ z, const float* __restri
           }
         }
       }
+    }
+    if (SCHED) {
+      // identical arithmetic to scheduler_step_kernel: quad q = voxel * (C / 4) + quad-in-voxel
+      const float a_x = cf[0], r_e = cf[1], c_x0 = cf[2], c_xt = cf[3], c_eps = cf[4], sigma = cf[5], lo = cf[6], hi = cf[7];
+      const int qpv = sp.C >> 2;
+      T* xm = reinterpret_cast<T*>(sp.x_model);
+#pragma unroll
+      for (int qi = 0; qi < CP / 4; ++qi) {
+        if (qi < qpv) {
+          const size_t xi = (size_t)v * sp.C + qi * 4;
+          const float4 xt = *reinterpret_cast<const float4*>(sp.x_t + xi);
+          const float x[4] = {xt.x, xt.y, xt.z, xt.w};
+          float zz[4] = {0.f, 0.f, 0.f, 0.f}, o[4], x0[4];
+          if (sigma != 0.f) {
+            if (sp.noise) {
+              const float4 nz = *reinterpret_cast<const float4*>(sp.noise + (size_t)step * sp.noise_step_stride + xi);
+              zz[0] = nz.x; zz[1] = nz.y; zz[2] = nz.z; zz[3] = nz.w;
+            } else {
+              philox_normal4(seed, (uint32_t)step, (uint64_t)(v * qpv + qi), zz);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float e = acc[qi * 4 + j];
+            const float u = r_e * e;
+            x0[j] = fminf(fmaxf(a_x != 0.f ? (x[j] + u) * a_x : u, lo), hi);
+            o[j] = c_x0 * x0[j] + c_xt * x[j] + c_eps * e + sigma * zz[j];
+          }
+          *reinterpret_cast<float4*>(sp.x_t + xi) = make_float4(o[0], o[1], o[2], o[3]);
+          if (sp.x0_out) *reinterpret_cast<float4*>(sp.x0_out + xi) = make_float4(x0[0], x0[1], x0[2], x0[3]);
+          if (xm) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xm[(size_t)v * sp.C_model + qi * 4 + j] = from_f32<T>(o[j]);
+          }
+        }
+      }
+      if (y == nullptr) continue;
     }
     T* yr = y + v * cy;
 #pragma unroll
@@ -418,24 +467,43 @@ int b200ldm_upsample_nearest2x(const void* x, void* y, int32_t N, int32_t D, int
 }
 
 int b200ldm_tap_gather(const void* z, const float* bias, void* y, int32_t N, int32_t D, int32_t H, int32_t W, int32_t ldz,
-                       int32_t cp, int32_t cy, int32_t dtype, b200ldm_stream stream) {
-  B2_REQUIRE(z && y && N > 0 && D > 0 && H > 0 && W > 0, B200LDM_BAD_ARG, "tap_gather: bad arguments");
+                       int32_t cp, int32_t cy, int32_t dtype, const b200ldm_sched_params* sched, b200ldm_stream stream) {
+  B2_REQUIRE(z && (y || sched) && N > 0 && D > 0 && H > 0 && W > 0, B200LDM_BAD_ARG, "tap_gather: bad arguments");
   B2_REQUIRE((cp == 1 || cp == 2 || cp == 4 || cp == 8 || cp == 16) && cy >= cp && cy % 8 == 0 && ldz >= 27 * cp &&
                  ldz % 8 == 0,
              B200LDM_BAD_SHAPE, "tap_gather: channels per tap must be 1/2/4/8/16, cy a multiple of 8 >= cp, ldz >= 27*cp");
   B2_REQUIRE(aligned16(z) && aligned16(y), B200LDM_BAD_ALIGN, "tap_gather: pointers must be 16-byte aligned");
   B2_REQUIRE(dtype == B200LDM_BF16 || dtype == B200LDM_F32, B200LDM_BAD_ARG, "bad dtype %d", dtype);
+  b200ldm_sched_params sp;
+  memset(&sp, 0, sizeof(sp));
+  if (sched) {
+    sp = *sched;
+    B2_REQUIRE(sp.x_t && sp.coef && sp.C > 0 && sp.C % 4 == 0 && sp.C <= cp && sp.n_vox == (int64_t)N * D * H * W &&
+                   (!sp.x_model || sp.C_model >= sp.C) && sp.dtype == dtype,
+               B200LDM_BAD_ARG, "tap_gather: fused scheduler update needs x_t, coef, C %% 4 == 0, C <= cp, n_vox = N*D*H*W");
+    B2_REQUIRE(aligned16(sp.x_t) && aligned16(sp.noise) && aligned16(sp.x0_out) && sp.noise_step_stride % 4 == 0,
+               B200LDM_BAD_ALIGN, "tap_gather: fp32 scheduler buffers must be 16-byte aligned");
+  }
   const long long vox = (long long)N * D * H * W;
   const cudaStream_t st = (cudaStream_t)stream;
-#define B2_TG(T, CP)                                                                                                  \
-  tap_gather_kernel<T, CP><<<ew_blocks(vox), kEwThreads, 0, st>>>((const T*)z, bias, (T*)y, N, D, H, W, ldz, cy)
-#define B2_TG_T(T)                    \
-  switch (cp) {                       \
-    case 1: B2_TG(T, 1); break;       \
-    case 2: B2_TG(T, 2); break;       \
-    case 4: B2_TG(T, 4); break;       \
-    case 8: B2_TG(T, 8); break;       \
-    default: B2_TG(T, 16); break;     \
+#define B2_TG(T, CP, S)                                                                                              \
+  tap_gather_kernel<T, CP, S><<<ew_blocks(vox), kEwThreads, 0, st>>>((const T*)z, bias, (T*)y, N, D, H, W, ldz, cy, sp)
+#define B2_TG_T(T)                                                       \
+  if (sched) {                                                           \
+    switch (cp) {                                                        \
+      case 4: B2_TG(T, 4, true); break;                                  \
+      case 8: B2_TG(T, 8, true); break;                                  \
+      case 16: B2_TG(T, 16, true); break;                                \
+      default: return fail(B200LDM_BAD_SHAPE, "tap_gather: fused scheduler update needs cp >= 4"); \
+    }                                                                    \
+  } else {                                                               \
+    switch (cp) {                                                        \
+      case 1: B2_TG(T, 1, false); break;                                 \
+      case 2: B2_TG(T, 2, false); break;                                 \
+      case 4: B2_TG(T, 4, false); break;                                 \
+      case 8: B2_TG(T, 8, false); break;                                 \
+      default: B2_TG(T, 16, false); break;                               \
+    }                                                                    \
   }
   if (dtype == B200LDM_BF16) { B2_TG_T(__nv_bfloat16) } else { B2_TG_T(float) }
 #undef B2_TG_T

@@ -173,9 +173,14 @@ int b200ldm_attention(const void* q, const void* k, const void* v, void* o, int3
  * the conv is run as a 1x1x1 GEMM z[v][tap*cp + co] = sum_ci w[tap][co][ci] x[v][ci] (b200ldm_conv3d, ksize 1, weights
  * stacked [27*cp][Cin]) so the input is read once instead of 27 times, then
  *   y[n,d,h,w,co] = bias[co] + sum_{tap=(kd,kh,kw)} z[n, d+kd-1, h+kh-1, w+kw-1, tap*cp + co]   (zero outside the volume)
- * z: [N][D][H][W][ldz], y: [N][D][H][W][cy] (channels >= cp are written as zero), cp in {1,2,4,8,16}. */
+ * z: [N][D][H][W][ldz], y: [N][D][H][W][cy] (channels >= cp are written as zero), cp in {1,2,4,8,16}.
+ * sched != NULL: y is the UNet's noise prediction and the scheduler update of b200ldm_scheduler_step (same struct, its
+ * `eps` field is ignored) is applied to the fp32 sums right here - the scheduler step fused into the last UNet epilogue
+ * (SURVEY.md 8a a3); y may then be NULL so the prediction is never written.  Needs cp >= 4 and sched->C <= cp. */
+struct b200ldm_sched_params_s;
 int b200ldm_tap_gather(const void* z, const float* bias, void* y, int32_t N, int32_t D, int32_t H, int32_t W,
-                       int32_t ldz, int32_t cp, int32_t cy, int32_t dtype, b200ldm_stream stream);
+                       int32_t ldz, int32_t cp, int32_t cy, int32_t dtype, const struct b200ldm_sched_params_s* sched,
+                       b200ldm_stream stream);
 
 /* nearest x2 up-sampling, NDHWC: [N][D][H][W][C] -> [N][2D][2H][2W][C] */
 int b200ldm_upsample_nearest2x(const void* x, void* y, int32_t N, int32_t D, int32_t H, int32_t W,
@@ -212,7 +217,7 @@ int b200ldm_counter_add(int32_t* counter, int32_t delta, b200ldm_stream stream);
  * pre-generated stack) or NULL -> Philox4x32-10 + Box-Muller keyed by (seed, counter[0], element).  x_model (optional): the UNet input buffer
  * [N][S][C_model] `dtype`, channels [0,C) are refreshed with x'.  x0_out optional fp32.
  * ------------------------------------------------------------------------------------------ */
-typedef struct {
+typedef struct b200ldm_sched_params_s {
   const void* eps;
   float* x_t;
   const float* noise;

@@ -244,6 +244,38 @@ def test_narrow_conv_tap_expanded_matches_direct_and_torch(case):
         assert y[..., cout:].abs().max().item() == 0.0      # padded output channels stay exactly zero
 
 
+@pytest.mark.parametrize("use_noise", [True, False], ids=["noise_stack", "philox"])
+def test_tap_gather_fused_scheduler_update_equals_two_kernels(use_noise):
+    """scheduler update inside the gather kernel == gather, then b200ldm_scheduler_step (same coefficient row, same
+    noise stream and element indexing); fp32 buffers so the only difference is the order of two roundings"""
+    import b200ldm
+    from b200ldm import ops
+    N, D, H, W, cp, Cl = 2, 3, 4, 5, 4, 4
+    z = rnd((N, D, H, W, 27 * cp + 20), 91).to(DEV)            # ldz = 128 > 27*cp
+    bias = rnd((16,), 92).to(DEV)
+    sched = gc.make_scheduler(b200ldm, "ddpm", 10)
+    coef = sched.coef_table(DEV)
+    counter = torch.full((1,), 3, dtype=torch.int32, device=DEV)
+    x0 = rnd((N, D, H, W, Cl), 93).to(DEV)
+    nz = rnd((10 * N, D, H, W, Cl), 94).to(DEV) if use_noise else None
+    stride = 0 if nz is None else nz.numel() // 10
+    xm_a = torch.zeros((N, D, H, W, 64), device=DEV)
+    xm_b = torch.zeros_like(xm_a)
+    # two kernels
+    xa = x0.clone()
+    eps = ops.tap_gather(z, bias, cp, 16)
+    ops.scheduler_step(eps, xa, coef, counter, Cl, noise=nz, noise_step_stride=stride, x_model=xm_a, seed=77)
+    # one kernel
+    xb = x0.clone()
+    sp = ops.make_sched_params(xb, coef, counter, Cl, torch.float32, noise=nz, noise_step_stride=stride, x_model=xm_b,
+                               seed=77)
+    assert ops.tap_gather(z, bias, cp, 16, sched=sp, want_y=False) is None
+    assert torch.allclose(xa, xb, atol=1e-5, rtol=1e-5) and torch.allclose(xm_a, xm_b, atol=1e-5, rtol=1e-5)
+    assert not torch.equal(xb, x0)
+    eps2 = ops.tap_gather(z, bias, cp, 16, sched=ops.make_sched_params(xb.clone(), coef, counter, Cl, torch.float32, seed=1))
+    assert torch.equal(eps2, eps)                               # the prediction is still available when asked for
+
+
 def test_tap_gather_fp32_exact():
     """the gather alone, fp32: y = bias + sum over in-bounds taps, checked against an index-by-index torch restatement"""
     from b200ldm import ops

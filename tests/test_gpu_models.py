@@ -179,6 +179,29 @@ def test_serving_generator_batches_requests():
     assert out.shape == (1, 1) + patch
 
 
+def test_sampling_fused_scheduler_equals_separate_kernel():
+    """north_star (4): the scheduler update rides in the UNet's last kernel.  Same trajectory as with the separate
+    scheduler kernel (which reads a bf16-rounded prediction instead of the fp32 sums)."""
+    import b200ldm
+    from b200ldm import inferer as inf_mod
+    unet = port(gc.tiny_unet(), b200ldm.DiffusionModelUNet, gc.UNET_KW, "bf16")
+    ae = port(gc.tiny_ae(), b200ldm.AutoencoderKL, gc.AE_KW, "bf16")
+    sched = gc.make_scheduler(b200ldm, "ddpm", 5)
+    x_T, cond, step_noise = gc.sampling_inputs(5)
+    kw = dict(input_noise=x_T.to(DEV), autoencoder_model=ae, diffusion_model=unet, scheduler=sched,
+              conditioning=cond.to(DEV), mode="concat", verbose=False, step_noise=step_noise.to(DEV), return_latent=True)
+    assert inf_mod.FUSE_SCHED and unet.out[2].conv.tap_expanded(torch.empty(0, dtype=torch.bfloat16))
+    inf = b200ldm.LatentDiffusionInferer(sched)
+    img_f, lat_f = inf.sample(**kw)
+    assert inf._loops and next(iter(inf._loops.values()))._sched is not None      # the fused path really ran
+    inf_mod.FUSE_SCHED = False
+    try:
+        img_s, lat_s = b200ldm.LatentDiffusionInferer(sched).sample(**kw)
+    finally:
+        inf_mod.FUSE_SCHED = True
+    assert relerr(lat_f, lat_s) <= 1e-2 and relerr(img_f, img_s) <= 2e-2
+
+
 def test_inferer_call_matches_oracle():
     """LatentDiffusionInferer.__call__ (3d_ldm/train_diffusion.py:197-205): encode -> add_noise -> concat -> UNet."""
     import b200ldm
