@@ -39,12 +39,13 @@ struct AttnCfg {
   static constexpr int kQBytes = (D / 64) * 16384;
   static constexpr int kKVSub = BN * 128;             // one 64-column sub-tile of K or V
   static constexpr int kKVBytes = (D / 64) * kKVSub;  // K (or V) tile
-  static constexpr int kPBytes = (BN / 64) * 16384;
-  static constexpr int kSmem = kQBytes + kStages * 2 * kKVBytes + kPBytes + 1024 + 256;
+  static constexpr int kPBytes = (BN / 64) * 16384;   // one P tile; there are TWO (tile parity) so exp(j+1) never waits for PV(j)
+  static constexpr int kSmem = kQBytes + kStages * 2 * kKVBytes + 2 * kPBytes + 1024 + 256;
   static constexpr int kTmemCols = 512;
   static constexpr int kSCol0 = 0;        // S buffers at columns [0, 2*BN)
   static constexpr int kOCol = 2 * BN;    // O at [2*BN, 2*BN + D)
   static_assert(2 * BN + D <= 512, "TMEM budget");
+  static_assert(kSmem <= 232448, "smem budget");
 };
 
 // MN-major SWIZZLE_128B operand (V as landed by TMA: rows = keys (K dim), 64 head-dim columns per 128-byte row).
@@ -73,18 +74,24 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t q_smem = smem_base;
-  const uint32_t kv_smem = q_smem + Cfg::kQBytes;                  // stage s: K at +s*2*kKVBytes, V after K
-  const uint32_t p_smem = kv_smem + STAGES * 2 * Cfg::kKVBytes;
-  const uint32_t bar = p_smem + Cfg::kPBytes;
+  // K and V are staged and released SEPARATELY: K_j is free as soon as S_j retires, a whole tile before PV_j frees
+  // V_j, so the load of K_{j+STAGES} starts that much earlier (with a shared stage the d = 256 kernel waited ~1400
+  // cycles per tile for the next S: the TMA round trip sat between PV_j and S_{j+2}, gpurun_out/attn_trace_d256.log)
+  const uint32_t k_smem = q_smem + Cfg::kQBytes;                   // K stage s at + s*kKVBytes
+  const uint32_t v_smem = k_smem + STAGES * Cfg::kKVBytes;         // V stage s at + s*kKVBytes
+  const uint32_t p_smem = v_smem + STAGES * Cfg::kKVBytes;
+  const uint32_t bar = p_smem + 2 * Cfg::kPBytes;
   // barrier map (8 bytes each)
   const uint32_t q_full = bar;
-  const uint32_t kv_full = bar + 8;                  // [STAGES]
-  const uint32_t kv_empty = kv_full + 8 * STAGES;    // [STAGES]
-  const uint32_t s_full = kv_empty + 8 * STAGES;     // [2]
+  const uint32_t k_full = bar + 8;                   // [STAGES]
+  const uint32_t k_empty = k_full + 8 * STAGES;      // [STAGES]
+  const uint32_t v_full = k_empty + 8 * STAGES;      // [STAGES]
+  const uint32_t v_empty = v_full + 8 * STAGES;      // [STAGES]
+  const uint32_t s_full = v_empty + 8 * STAGES;      // [2]
   const uint32_t s_empty = s_full + 16;              // [2]
   const uint32_t p_full = s_empty + 16;
-  const uint32_t pv_done = p_full + 8;
-  const uint32_t tmem_slot = pv_done + 8;
+  const uint32_t pv_done = p_full + 8;               // [2]: PV of even / odd tiles (one per P buffer)
+  const uint32_t tmem_slot = pv_done + 16;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -97,10 +104,14 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&maps.q); ptx::prefetch_tmap(&maps.k); ptx::prefetch_tmap(&maps.v);
     ptx::mbar_init(q_full, 1);
-    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(kv_full + 8 * s, 1); ptx::mbar_init(kv_empty + 8 * s, 1); }
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(k_full + 8 * s, 1); ptx::mbar_init(k_empty + 8 * s, 1);
+      ptx::mbar_init(v_full + 8 * s, 1); ptx::mbar_init(v_empty + 8 * s, 1);
+    }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(s_full + 8 * s, 1); ptx::mbar_init(s_empty + 8 * s, 128); }
     ptx::mbar_init(p_full, 128);
     ptx::mbar_init(pv_done, 1);
+    ptx::mbar_init(pv_done + 8, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -116,17 +127,26 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
 #pragma unroll
       for (int sub = 0; sub < D / 64; ++sub)
         ptx::tma_load_3d(q_smem + sub * 16384, &maps.q, q_full, col0 + sub * 64, q0, b);
-      for (int j = 0; j < ntiles; ++j) {
+      auto load_k = [&](int j) {
         const int s = j % STAGES;
-        const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
-        ptx::mbar_wait_long(kv_empty + 8 * s, ph ^ 1u, 10);   // suspended wait: the producer has stages of slack and must not steal issue slots
-        const uint32_t ks = kv_smem + s * 2 * Cfg::kKVBytes, vs = ks + Cfg::kKVBytes;
-        ptx::mbar_expect_tx(kv_full + 8 * s, 2 * Cfg::kKVBytes);
+        ptx::mbar_wait_long(k_empty + 8 * s, ((uint32_t)(j / STAGES) & 1u) ^ 1u, 10);
+        ptx::mbar_expect_tx(k_full + 8 * s, Cfg::kKVBytes);
 #pragma unroll
-        for (int sub = 0; sub < D / 64; ++sub) {
-          ptx::tma_load_3d(ks + sub * Cfg::kKVSub, &maps.k, kv_full + 8 * s, col0 + sub * 64, j * BN, b);
-          ptx::tma_load_3d(vs + sub * Cfg::kKVSub, &maps.v, kv_full + 8 * s, col0 + sub * 64, j * BN, b);
-        }
+        for (int sub = 0; sub < D / 64; ++sub)
+          ptx::tma_load_3d(k_smem + s * Cfg::kKVBytes + sub * Cfg::kKVSub, &maps.k, k_full + 8 * s, col0 + sub * 64, j * BN, b);
+      };
+      auto load_v = [&](int j) {
+        const int s = j % STAGES;
+        ptx::mbar_wait_long(v_empty + 8 * s, ((uint32_t)(j / STAGES) & 1u) ^ 1u, 10);
+        ptx::mbar_expect_tx(v_full + 8 * s, Cfg::kKVBytes);
+#pragma unroll
+        for (int sub = 0; sub < D / 64; ++sub)
+          ptx::tma_load_3d(v_smem + s * Cfg::kKVBytes + sub * Cfg::kKVSub, &maps.v, v_full + 8 * s, col0 + sub * 64, j * BN, b);
+      };
+      load_k(0);   // K runs one tile ahead of V: its stage frees first and S needs it first
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) load_k(j + 1);
+        load_v(j);
       }
     }
   } else if (warp == 1) {
@@ -136,10 +156,10 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       constexpr uint32_t idesc_o = ptx::umma_idesc_bf16_bmn(128, D);
       auto issue_s = [&](int j) {
         const int s = j % STAGES;
-        ptx::mbar_wait(kv_full + 8 * s, (uint32_t)(j / STAGES) & 1u, 11);
+        ptx::mbar_wait(k_full + 8 * s, (uint32_t)(j / STAGES) & 1u, 11);
         if (j >= 2) ptx::mbar_wait(s_empty + 8 * (j & 1), (uint32_t)((j >> 1) - 1) & 1u, 12);
         ptx::tc_fence_after();
-        const uint32_t ks = kv_smem + s * 2 * Cfg::kKVBytes;
+        const uint32_t ks = k_smem + s * Cfg::kKVBytes;
         const uint32_t tS = tmem + Cfg::kSCol0 + (j & 1) * BN;
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
@@ -148,24 +168,26 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
           ptx::umma_bf16(tS, da, db, idesc_s, kk > 0 ? 1u : 0u);
         }
         ptx::umma_commit(s_full + 8 * (j & 1));
+        ptx::umma_commit(k_empty + 8 * s);   // K_j is free once S_j retires
       };
       ptx::mbar_wait(q_full, 0, 13);
       issue_s(0);
       for (int j = 0; j < ntiles; ++j) {
         if (j + 1 < ntiles) issue_s(j + 1);
         const int s = j % STAGES;
+        ptx::mbar_wait(v_full + 8 * s, (uint32_t)(j / STAGES) & 1u, 16);
         ptx::mbar_wait(p_full, (uint32_t)j & 1u, 14);
         ptx::tc_fence_after();
-        const uint32_t vs = kv_smem + s * 2 * Cfg::kKVBytes + Cfg::kKVBytes;
+        const uint32_t vs = v_smem + s * Cfg::kKVBytes;
         const uint32_t tO = tmem + Cfg::kOCol;
 #pragma unroll
         for (int kk = 0; kk < BN / 16; ++kk) {
-          const uint64_t da = ptx::umma_desc_k_sw128(p_smem + (kk >> 2) * 16384 + (kk & 3) * 32);
+          const uint64_t da = ptx::umma_desc_k_sw128(p_smem + (j & 1) * Cfg::kPBytes + (kk >> 2) * 16384 + (kk & 3) * 32);
           const uint64_t db = umma_desc_mn_sw128(vs + kk * 2048, Cfg::kKVSub, 1024);
           ptx::umma_bf16(tO, da, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
         }
-        ptx::umma_commit(kv_empty + 8 * s);  // K/V stage reusable once S_j and PV_j retired
-        ptx::umma_commit(pv_done);
+        ptx::umma_commit(v_empty + 8 * s);   // V_j is free once PV_j retires
+        ptx::umma_commit(pv_done + 8 * (j & 1));
       }
     }
   } else {
@@ -175,23 +197,36 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
     float m_used = -INFINITY;  // reference max (log2 domain) the running sums are expressed against
     float l_sum = 0.f;
-    uint8_t* p_gen = smem_gen + (p_smem - smem_base);
+    uint8_t* p_base = smem_gen + (p_smem - smem_base);
 
+#ifdef B200LDM_ATTN_TRACE
+    const bool tr = a.trace != nullptr && lane == 0 && qd == 0;
+#else
+    constexpr bool tr = false;
+#endif
+    long long tc[6] = {0, 0, 0, 0, 0, 0};
+    const long long t_begin = tr ? clock64() : 0;
     for (int j = 0; j < ntiles; ++j) {
+      long long t0 = tr ? clock64() : 0, t1;
+      uint8_t* p_gen = p_base + (size_t)(j & 1) * Cfg::kPBytes;
       ptx::mbar_wait(s_full + 8 * (j & 1), (uint32_t)(j >> 1) & 1u, 20);
       ptx::tc_fence_after();
+      if (tr) { t1 = clock64(); tc[0] += t1 - t0; t0 = t1; }
       const uint32_t tS = tmem + lane_off + Cfg::kSCol0 + (j & 1) * BN;
       float sv[BN];  // RAW scores; the softmax scale is folded into the exp2 FFMA below
+      {
+        uint32_t r[BN / 32][32];   // every load in flight before the single wait
 #pragma unroll
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld32(tS + c, r);
+        for (int c = 0; c < BN / 32; ++c) ptx::tmem_ld32(tS + c * 32, r[c]);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sv[c + i] = __uint_as_float(r[i]);
+        for (int c = 0; c < BN / 32; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sv[c * 32 + i] = __uint_as_float(r[c][i]);
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(s_empty + 8 * (j & 1));  // S buffer may be overwritten by tile j+2
+      if (tr) { t1 = clock64(); tc[1] += t1 - t0; t0 = t1; }
 
       const int kvalid = a.L - j * BN;  // keys in this tile that exist
       if (kvalid < BN) {                // last tile only (warp-uniform)
@@ -210,7 +245,12 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       const bool need = mx > m_used + 8.0f;
       const bool any_need = __any_sync(0xffffffffu, need);
       float alpha = 1.0f;
-      if (j > 0) ptx::mbar_wait(pv_done, (uint32_t)(j - 1) & 1u, 21);  // PV_{j-1} retired: O and P buffer are ours
+      if (tr) { t1 = clock64(); tc[2] += t1 - t0; t0 = t1; }
+      // P is double-buffered by tile parity: writing P(j) only needs PV(j-2) (same buffer) to have retired, so this
+      // tile's exp phase overlaps PV(j-1) - with a single buffer the chain softmax -> PV -> softmax serialised a
+      // ~900-cycle MMA round trip behind every tile.  O itself is only touched when the lazy rescale fires.
+      if (j >= 2) ptx::mbar_wait(pv_done + 8 * (j & 1), (uint32_t)((j >> 1) - 1) & 1u, 21);
+      if (tr) { t1 = clock64(); tc[3] += t1 - t0; t0 = t1; }
       if (any_need) {
         if (need) {
           alpha = exp2f(m_used - mx);  // 0 on the first tile (m_used = -inf)
@@ -218,6 +258,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
           l_sum *= alpha;
         }
         if (j > 0) {
+          ptx::mbar_wait(pv_done + 8 * ((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u, 23);  // PV_{j-1} retired: O is ours
           ptx::tc_fence_after();
           const uint32_t tO = tmem + lane_off + Cfg::kOCol;
 #pragma unroll
@@ -232,6 +273,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
           ptx::tmem_st_wait();
         }
       }
+      if (tr) { t1 = clock64(); tc[4] += t1 - t0; t0 = t1; }
       // P = exp2(s*scale - m_used) -> bf16, written in the SWIZZLE_128B K-major layout (16-byte chunk c of row r
       // lives at r*128 + ((c ^ (r & 7)) << 4) inside each [128 x 64-key] sub-tile).  One FFMA + one MUFU.EX2 per
       // element; the row sum is taken in fp32 over 4 independent chains.
@@ -257,9 +299,19 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the UMMA (async proxy)
       ptx::tc_fence_before();     // orders the TMEM rescale stores before the MMA warp's next PV
       ptx::mbar_arrive(p_full);
+      if (tr) { t1 = clock64(); tc[5] += t1 - t0; }
+    }
+    if (tr) {
+      const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      if (cta < 1024) {
+        unsigned long long* o = a.trace + cta * 2 * 8;
+        for (int i = 0; i < 6; ++i) o[i] = (unsigned long long)tc[i];
+        o[6] = (unsigned long long)ntiles;
+        o[7] = (unsigned long long)(clock64() - t_begin);
+      }
     }
     // ---- epilogue: O / l -> bf16 -> global
-    ptx::mbar_wait(pv_done, (uint32_t)(ntiles - 1) & 1u, 22);
+    ptx::mbar_wait(pv_done + 8 * ((ntiles - 1) & 1), (uint32_t)((ntiles - 1) >> 1) & 1u, 22);
     ptx::tc_fence_after();
     const int qi = q0 + row;
     const float inv = 1.0f / l_sum;

@@ -8,7 +8,7 @@ from b200ldm import _lib, ops
 lib = _lib.load()
 lib.b200ldm_debug_set_conv_trace.argtypes = [ctypes.c_void_p]
 dev = "cuda"
-B, H, L, d = 8, 4, 5544, 64
+B, H, L, d = (int(v) for v in os.environ.get("SHAPE", "8,4,5544,64").split(","))
 qkv = torch.randn((B, L, 3 * H * d), device=dev).to(torch.bfloat16)
 for _ in range(3):
     ops.attention(qkv, H, d, d ** -0.5)
