@@ -48,12 +48,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Bounded wait: a protocol bug traps (with a code) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who) {
   if (mbar_try_wait(bar, parity)) return;
-  // The bound is a poll COUNT (each failed try_wait already sleeps a hardware-defined while, so 2^24 polls are
+  // The bound is a poll COUNT (each failed try_wait already sleeps a hardware-defined while, so 2^26 polls are
   // seconds): reading clock64 and doing 64-bit compares on every poll made a spinning TMA / MMA-issuer thread execute
   // more instructions than the softmax warps it shares a sub-partition with (ncu source page of the attention kernel).
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++polls == (1u << 24)) {
+    if (++polls == (1u << 26)) {
       printf("b200ldm: mbarrier timeout who=%d block=(%d,%d) thread=%d parity=%u\n", who, blockIdx.x,
              blockIdx.y, threadIdx.x, parity);
       __trap();
