@@ -41,7 +41,10 @@ struct AttnCfg {
   static constexpr int kKVBytes = (D / 64) * kKVSub;  // K (or V) tile
   static constexpr int kPBytes = (BN / 64) * 16384;   // one P tile; there are TWO (tile parity) so exp(j+1) never waits for PV(j)
   static constexpr int kSmem = kQBytes + kStages * 2 * kKVBytes + 2 * kPBytes + 1024 + 256;
-  static constexpr int kTmemCols = 512;
+  // 2*BN + D <= 256 columns and <= ~113 KB of smem (head dim 64 with 64-key tiles): TWO CTAs per SM, i.e. two
+  // independent softmax warps per sub-partition that are never in lock-step
+  static constexpr int kOcc = (2 * BN + D <= 256 && kSmem <= 115712) ? 2 : 1;
+  static constexpr int kTmemCols = kOcc == 2 ? 256 : 512;
   static constexpr int kSCol0 = 0;        // S buffers at columns [0, 2*BN)
   static constexpr int kOCol = 2 * BN;    // O at [2*BN, 2*BN + D)
   static_assert(2 * BN + D <= 512, "TMEM budget");
@@ -67,7 +70,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 template <int D, int BN>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, AttnCfg<D, BN>::kOcc)
 attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   using Cfg = AttnCfg<D, BN>;
   constexpr int STAGES = Cfg::kStages;
@@ -764,9 +767,11 @@ static int launch_attention_tc2(const void* q, const void* k, const void* v, voi
   return B200LDM_OK;
 }
 
+// B200LDM_ATTN_VERSION: 0 (default) = measured best per head dim; 1 = one-query-tile kernels everywhere; 2 = the
+// two-query-tile ping-pong kernel wherever it exists (d = 64 / 128, L > 128)
 static const int g_attn_v = [] {
   const char* e = getenv("B200LDM_ATTN_VERSION");
-  return e ? atoi(e) : 2;
+  return e ? atoi(e) : 0;
 }();
 
 bool attention_tcgen05_supported(int d) { return d == 64 || d == 128 || d == 256; }
@@ -777,14 +782,18 @@ int attention_tcgen05(const void* q, const void* k, const void* v, void* o, int 
              d);
   B2_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && ld % 8 == 0, B200LDM_BAD_ALIGN,
              "attention: pointers / row stride must be 16-byte aligned");
-  // v2 (two query tiles + two softmax warpgroups per CTA) once there are at least two query tiles
-  if (g_attn_v >= 2 && L > 128) {
+  // head dim 64: the one-query-tile kernel with 64-key tiles runs TWO CTAs per SM (96 KB smem, 256 TMEM columns each)
+  // and beats the two-tile ping-pong kernel by 7-19 % (0.406 vs 0.436 ms at B8 H4 L5544): its two softmax warps per
+  // sub-partition belong to independent CTAs and never fall into lock-step.  Head dim 128 keeps the ping-pong kernel.
+  const bool pingpong = L > 128 && ((d == 128 && g_attn_v != 1) || (d == 64 && g_attn_v == 2));
+  if (pingpong) {
     // d = 64: B200LDM_ATTN_OCC=2 runs 64-key tiles with two CTAs per SM (four softmax warps per sub-partition)
     static const int occ = [] { const char* e = getenv("B200LDM_ATTN_OCC"); return e ? atoi(e) : 1; }();
     if (d == 64 && occ == 2) return launch_attention_tc2<64, 64, 2>(q, k, v, o, B, H, L, ld, scale, st);
     if (d == 64) return launch_attention_tc2<64, 128, 1>(q, k, v, o, B, H, L, ld, scale, st);
-    if (d == 128) return launch_attention_tc2<128, 64, 1>(q, k, v, o, B, H, L, ld, scale, st);
+    return launch_attention_tc2<128, 64, 1>(q, k, v, o, B, H, L, ld, scale, st);
   }
+  if (d == 64 && L > 128) return launch_attention_tc<64, 64>(q, k, v, o, B, H, L, ld, scale, st);
   if (d == 64) return launch_attention_tc<64, 128>(q, k, v, o, B, H, L, ld, scale, st);
   if (d == 128) return launch_attention_tc<128, 128>(q, k, v, o, B, H, L, ld, scale, st);
   return launch_attention_tc<256, 64>(q, k, v, o, B, H, L, ld, scale, st);
