@@ -59,6 +59,7 @@ SIGNATURES = {
                                           _i32, _vp]),
     "b200ldm_groupnorm_apply_chunked": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _f32,
                                                   _i32, _i32, _vp]),
+    "b200ldm_groupnorm_small_fits": (C.c_int, [_i64, _i32, _i32, _i32]),
     "b200ldm_groupnorm_small": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _f32, _i32, _i32, _vp]),
     "b200ldm_fill_zero": (C.c_int, [_vp, _sz, _vp]),
     "b200ldm_attention": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _f32, _i32, _i32, _vp]),

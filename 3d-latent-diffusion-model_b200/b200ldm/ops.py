@@ -47,7 +47,7 @@ class KernelProfiler:
 PROFILER: KernelProfiler | None = None
 # GroupNorm statistics fused into the producing conv's epilogue (per-8-channel chunk sums)
 FUSE_GN_STATS = __import__("os").environ.get("B200LDM_FUSE_GN_STATS", "1") != "0"
-GN_SMALL_MAX_S = int(__import__("os").environ.get("B200LDM_GN_SMALL_MAX_S", "2048"))
+GN_SMALL_MAX_S = int(__import__("os").environ.get("B200LDM_GN_SMALL_MAX_S", "256"))
 
 
 def dtype_code(t: torch.dtype) -> int:
@@ -200,7 +200,7 @@ def groupnorm(x, gamma, beta, groups: int, eps: float, silu: bool, x2=None, stat
         if ev is not None:
             PROFILER.stop("gn_apply", f"C{C1 + C2} S{S}", 2.0 * nbytes, ev)
         return y
-    if stats is None and S <= GN_SMALL_MAX_S and ((C1 + C2) // groups) % 8 == 0:
+    if stats is None and S <= GN_SMALL_MAX_S and lib.b200ldm_groupnorm_small_fits(S, C1 + C2, groups, dt):
         # small levels: one launch instead of memset + stats + apply
         y = torch.empty(x.shape[:-1] + (C1 + C2,), dtype=x.dtype, device=x.device)
         ev = PROFILER.start() if PROFILER is not None else None

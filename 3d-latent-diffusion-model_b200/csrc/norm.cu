@@ -160,9 +160,12 @@ gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict
   }
 }
 
-// Small tensors (the 4^3 ... 10^3 levels: one (sample, group) slab is a few KB): statistics and normalisation in ONE
-// launch, one CTA per (group, sample).  The slab is read twice (the second read hits L1/L2); the two-kernel path with
-// its fp64 atomics and memset costs three launches of ~5 us each for ~1 us of traffic.
+// Tiny tensors (the 4^3 / 5^3 levels: one (sample, group) slab is a few KB): statistics and normalisation in ONE launch,
+// one CTA per (group, sample); the slab is read twice (the second read hits L1/L2).  ncu, 8 x 125 voxels x 1024
+// channels: 7.0 us against 5.7 + 7.1 us (+ memset) for the stats + apply pair.  From ~700 voxels on the pair wins
+// (12.4 us against 11.7 / 16.8 us at 693 / 1000 voxels) because a slab is a 32-byte sliver of every row; a
+// sample-in-shared-memory cluster kernel (8 CTAs per sample, DSMEM reduction) was tried and was slower still
+// (34 us at 693 voxels: too few threads in flight) - so this path is only taken up to 256 voxels.
 template <typename T>
 __global__ void __launch_bounds__(kNormThreads)
 gn_small_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict__ y, const float* __restrict__ gamma,
@@ -310,6 +313,11 @@ int b200ldm_groupnorm_apply_chunked(const void* x, const void* x2, void* y, cons
                                     b200ldm_stream stream) {
   B2_REQUIRE(cstats1, B200LDM_BAD_ARG, "groupnorm_apply_chunked: null cstats1");
   return gn_apply_impl(x, x2, y, nullptr, cstats1, cstats2, gamma, beta, N, S, C1, C2, G, eps, silu, dtype, stream);
+}
+
+int b200ldm_groupnorm_small_fits(int64_t S, int32_t C, int32_t G, int32_t dtype) {
+  (void)dtype;
+  return (S > 0 && S <= 4096 && C > 0 && C % 8 == 0 && G > 0 && C % G == 0 && (C / G) % 8 == 0) ? 1 : 0;
 }
 
 int b200ldm_groupnorm_small(const void* x, const void* x2, void* y, const float* gamma, const float* beta, int32_t N,

@@ -152,8 +152,10 @@ int b200ldm_groupnorm_apply_chunked(const void* x, const void* x2, void* y, cons
                                     const double* cstats2, const float* gamma, const float* beta, int32_t N, int64_t S,
                                     int32_t C1, int32_t C2, int32_t G, float eps, int32_t silu, int32_t dtype,
                                     b200ldm_stream stream);
-/* statistics + normalisation (+SiLU) in ONE launch for small tensors (S <= 4096 voxels per sample, channels/group a
- * multiple of 8): one CTA per (group, sample).  Same math as stats + apply. */
+/* statistics + normalisation (+SiLU) in ONE launch for tiny tensors (S <= 4096 voxels per sample, channels/group a
+ * multiple of 8): one CTA per (group, sample).  Same math as stats + apply.  b200ldm_groupnorm_small_fits(S, C1 + C2, G,
+ * dtype) == 1 says whether a tensor qualifies; the host side uses it up to 256 voxels, where it beats the pair. */
+int b200ldm_groupnorm_small_fits(int64_t S, int32_t C, int32_t G, int32_t dtype);
 int b200ldm_groupnorm_small(const void* x, const void* x2, void* y, const float* gamma, const float* beta, int32_t N,
                             int64_t S, int32_t C1, int32_t C2, int32_t G, float eps, int32_t silu, int32_t dtype,
                             b200ldm_stream stream);
