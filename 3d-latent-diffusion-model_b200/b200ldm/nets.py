@@ -34,6 +34,8 @@ FUSE_UPSAMPLE = os.environ.get("B200LDM_FUSE_UPSAMPLE", "1") != "0"
 # narrow-output 3x3x3 convs (Cout <= 16) as a 1x1x1 tensor-core GEMM over stacked taps + a gather (ops.tap_gather):
 # the direct kernel re-reads its input 27 times for 16 output columns (0.58 ms for the UNet's out conv, 135 TFLOP/s)
 TAP_EXPAND = os.environ.get("B200LDM_TAP_EXPAND", "1") != "0"
+# DiffusionModelUNet.forward (the public module call) replays a cached CUDA graph from the second call of a signature on
+FORWARD_GRAPH = os.environ.get("B200LDM_FORWARD_GRAPH", "1") != "0"
 # ResNet 1x1x1 skip_connection / nin_shortcut accumulated inside conv2 (extra K iterations) on the tensor-core path
 FUSE_SKIP = os.environ.get("B200LDM_FUSE_SKIP", "1") != "0"
 
@@ -417,6 +419,7 @@ class DiffusionModelUNet(nn.Module):
             raise ValueError("`num_res_blocks` should be a single integer or a tuple of integers with the same length "
                              "as `channels`.")
         self.in_channels, self.out_channels = in_channels, out_channels
+        self._fwd_graphs = {}
         self.block_out_channels = list(channels)
         self.with_conditioning = with_conditioning
         self.precision = precision or default_precision()
@@ -531,12 +534,43 @@ class DiffusionModelUNet(nn.Module):
         if timesteps.numel() not in (1, x.shape[0]):
             raise ValueError("timesteps must have 1 or batch elements")
         with torch.no_grad():
-            dt = _PREC[self.precision]
-            xa = ops.to_ndhwc(x, _pad64(self.in_channels), dt)
-            temb_all = self.time_embedding_table(timesteps.to(x.device))
-            stride = 0 if timesteps.numel() == 1 else temb_all.shape[1]
-            eps = self.forward_ndhwc(xa, temb_all, stride)
-            return ops.to_ncdhw(eps, self.out_channels)
+            if FORWARD_GRAPH and x.is_cuda and not torch.cuda.is_current_stream_capturing():
+                return self._forward_graphed(x, timesteps)
+            return self._forward_eager(x, timesteps)
+
+    def _forward_eager(self, x, timesteps):
+        dt = _PREC[self.precision]
+        xa = ops.to_ndhwc(x, _pad64(self.in_channels), dt)
+        temb_all = self.time_embedding_table(timesteps.to(device=x.device, dtype=torch.float32))
+        stride = 0 if timesteps.numel() == 1 else temb_all.shape[1]
+        eps = self.forward_ndhwc(xa, temb_all, stride)
+        return ops.to_ncdhw(eps, self.out_channels)
+
+    def _forward_graphed(self, x, timesteps):
+        """forward() through a CUDA graph cached per (input shape, number of timesteps, weights): the ~150 launches of a
+        noise prediction become one replay; inputs are copied into the graph's static buffers (timesteps stay on the
+        device, so any value replays).  The second call with a given signature captures, the first one runs eagerly
+        (it also lets the conv kernels measure their choices)."""
+        key = (tuple(x.shape), timesteps.numel(), str(x.device), self.precision, param_signature(self))
+        hit = self._fwd_graphs.get(key)
+        if hit is None:
+            if len(self._fwd_graphs) >= 4:
+                self._fwd_graphs.clear()
+            self._fwd_graphs[key] = "warm"
+            return self._forward_eager(x, timesteps)
+        if hit == "warm":
+            static_x = x.detach().to(torch.float32).clone()
+            static_t = timesteps.detach().to(device=x.device, dtype=torch.float32).clone()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = self._forward_eager(static_x, static_t)
+            hit = (g, static_x, static_t, static_out)
+            self._fwd_graphs[key] = hit
+        g, static_x, static_t, static_out = hit
+        static_x.copy_(x)
+        static_t.copy_(timesteps)
+        g.replay()
+        return static_out.clone()
 
 
 # ------------------------------------------------------------------------------------------

@@ -78,13 +78,26 @@ class Scheduler:
         dev = sample.device
         N, Cc = sample.shape[:2]
         cpad = ops.round_up(Cc, 4)
-        coef = torch.tensor([self.coef_row(int(timestep))], dtype=torch.float32).to(dev)
+        coef = self._coef_on(dev, int(timestep))
         x = ops.to_ndhwc(sample, cpad, torch.float32)
         e = ops.to_ndhwc(model_output, cpad, torch.float32)
         nz = None if noise is None else ops.to_ndhwc(noise, cpad, torch.float32)
         x0 = torch.empty_like(x)
         ops.scheduler_step(e, x, coef, None, cpad, noise=nz, x0_out=x0, seed=self._seed())
         return ops.to_ncdhw(x, Cc), ops.to_ncdhw(x0, Cc)
+
+    def _coef_on(self, dev, timestep: int, eta=None) -> torch.Tensor:
+        """coefficient row of one timestep on the device, cached: a fresh pageable upload per step() would block the
+        host until the stream drains"""
+        key = (str(dev), timestep, eta, getattr(self, "eta", None), self.num_inference_steps, self.prediction_type)
+        cache = self.__dict__.setdefault("_coef_cache", {})
+        t = cache.get(key)
+        if t is None:
+            if len(cache) > 4096:
+                cache.clear()
+            t = torch.tensor([self.coef_row(timestep)], dtype=torch.float32).to(dev)
+            cache[key] = t
+        return t
 
     _seed_state = 0
 
