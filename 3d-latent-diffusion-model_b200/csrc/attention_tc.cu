@@ -419,7 +419,6 @@ attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   const int nw = tileB_exists ? 2 : 1;
-  const bool ptm = (a.dbg & 2) != 0;   // B200LDM_ATTN_DBG=2: P through TMEM instead of shared memory
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -464,34 +463,6 @@ attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       ptx::mbar_wait(kv_full, 0, 11);
       ptx::tc_fence_after();
       for (int w = 0; w < nw; ++w) issue_s(w, 0);
-      if (ptm) {
-        // P lives in TMEM (bf16 pairs over the first BN/2 columns of S_w) and is the MMA's A operand: no P store to
-        // shared memory, no proxy fence; S_w(j+1) is queued right behind PV_w(j) (the tensor pipe runs them in order)
-        for (int j = 0; j < ntiles; ++j) {
-          const int s = j % STAGES;
-          const uint32_t vs = kv_smem + s * 2 * Cfg::kKVBytes + Cfg::kKVBytes;
-          for (int w = 0; w < nw; ++w) {
-            ptx::mbar_wait(p_full + 8 * w, (uint32_t)j & 1u, 14);
-            ptx::tc_fence_after();
-            const uint32_t tP = tmem + Cfg::kSCol + w * BN;
-            const uint32_t tO = tmem + Cfg::kOCol + w * D;
-#pragma unroll
-            for (int kk = 0; kk < BN / 16; ++kk) {
-              const uint64_t db = umma_desc_mn_sw128(vs + kk * 2048, Cfg::kKVSub, 1024);
-              ptx::umma_bf16_ts(tO, tP + kk * 8, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
-            }
-            ptx::umma_commit(pv_done + 8 * w);
-            if (w == nw - 1) ptx::umma_commit(kv_empty + 8 * s);
-            if (j + 1 < ntiles) {
-              if (w == 0) {
-                ptx::mbar_wait(kv_full + 8 * ((j + 1) % STAGES), (uint32_t)((j + 1) / STAGES) & 1u, 11);
-                ptx::tc_fence_after();
-              }
-              issue_s(w, j + 1);
-            }
-          }
-        }
-      } else
       for (int j = 0; j < ntiles; ++j) {
         const int s = j % STAGES;
         const uint32_t vs = kv_smem + s * 2 * Cfg::kKVBytes + Cfg::kKVBytes;
@@ -562,7 +533,7 @@ attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0 && !ptm) ptx::mbar_arrive(s_free + 8 * w);   // the tensor core may overwrite S_w with the next tile's scores
+        if (lane == 0) ptx::mbar_arrive(s_free + 8 * w);   // the tensor core may overwrite S_w with the next tile's scores
         if (tr) { t1 = clock64(); tc[1] += t1 - t0; t0 = t1; }
         const int kvalid = a.L - j * BN;
         if (kvalid < BN) {
@@ -611,22 +582,6 @@ attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         constexpr bool no_mufu = false;
 #endif
         float ps4[4] = {0.f, 0.f, 0.f, 0.f};
-        if (ptm) {
-#pragma unroll
-          for (int c32 = 0; c32 < BN / 32; ++c32) {
-            uint32_t pw[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const float p0 = ex2_approx(fmaf(sv[c32 * 32 + 2 * e], a.scale_log2, neg_m));
-              const float p1 = ex2_approx(fmaf(sv[c32 * 32 + 2 * e + 1], a.scale_log2, neg_m));
-              ps4[e & 3] += p0 + p1;
-              const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-              pw[e] = *reinterpret_cast<const uint32_t*>(&hb);
-            }
-            ptx::tmem_st16(tS + c32 * 16, pw);
-          }
-          ptx::tmem_st_wait();
-        } else {
 #pragma unroll
         for (int c8 = 0; c8 < BN / 8; ++c8) {
           uint32_t pk[4];
@@ -644,9 +599,8 @@ attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
           uint4* dst = reinterpret_cast<uint4*>(p_gen + sub * 16384 + row * 128 + ((cc ^ (row & 7)) << 4));
           *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-        }
         l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
-        if (!ptm) ptx::fence_proxy_async();
+        ptx::fence_proxy_async();
         ptx::tc_fence_before();
         ptx::mbar_arrive(p_full + 8 * w);
         if (tr) { t1 = clock64(); tc[5] += t1 - t0; }
