@@ -63,6 +63,11 @@ SIGNATURES = {
     "b200ldm_groupnorm_small": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _f32, _i32, _i32, _vp]),
     "b200ldm_fill_zero": (C.c_int, [_vp, _sz, _vp]),
     "b200ldm_attention": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _f32, _i32, _i32, _vp]),
+    "b200ldm_cross_attention": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _f32, _i32, _i32,
+                                          _vp]),
+    "b200ldm_layernorm": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _vp]),
+    "b200ldm_geglu": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
+    "b200ldm_embedding_add": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "b200ldm_tap_gather": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
                                      C.POINTER(SchedParams), _vp]),
     "b200ldm_upsample_nearest2x": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -41,6 +41,13 @@ class SamplingLoop:
         self.spatial = tuple(input_noise.shape[2:])
         self.mode = mode
         self.c_in = self.c_lat + (conditioning.shape[1] if mode == "concat" else 0)
+        # mode "crossattn": the conditioning is the cross-attention context [N, Lc, cross_attention_dim]; its padded
+        # compute-dtype token matrix lives in a fixed buffer the captured step reads
+        self.ctx = None
+        if mode == "crossattn" and conditioning is not None:
+            if not unet.with_conditioning:
+                raise ValueError("model should have with_conditioning = True if context is provided")
+            self.ctx = unet.context_tokens(conditioning.to(dev))
         if self.c_in != unet.in_channels:
             raise ValueError(f"UNet expects {unet.in_channels} input channels, sampling provides {self.c_in}")
         if self.c_lat % 4:
@@ -77,6 +84,8 @@ class SamplingLoop:
             self.coef.copy_(scheduler.coef_table(self.coef.device))
         if self.mode == "concat":
             ops.to_ndhwc(conditioning, _pad64(self.c_in), self.dtype, out=self.x_model, c_offset=self.c_lat)
+        elif self.ctx is not None and not _fresh:
+            self.unet.context_tokens(conditioning.to(self.ctx.device), out=self.ctx)
         if step_noise is not None:
             if step_noise.shape[0] != self.n_steps or tuple(step_noise.shape[1:]) != self.shape:
                 raise ValueError("step_noise must be [n_steps, *input_noise.shape]")
@@ -93,9 +102,9 @@ class SamplingLoop:
                 self._sched = ops.make_sched_params(self.x_t, self.coef, self.counter, self.c_lat, self.dtype,
                                                     noise=self.noise, noise_step_stride=self.noise_stride,
                                                     x_model=self.x_model, seed=self.seed_dev)
-            self.unet.forward_ndhwc(self.x_model, self.temb_cur, 0, sched=self._sched)
+            self.unet.forward_ndhwc(self.x_model, self.temb_cur, 0, sched=self._sched, ctx=self.ctx)
         else:
-            eps = self.unet.forward_ndhwc(self.x_model, self.temb_cur, 0)
+            eps = self.unet.forward_ndhwc(self.x_model, self.temb_cur, 0, ctx=self.ctx)
             ops.scheduler_step(eps, self.x_t, self.coef, self.counter, self.c_lat, noise=self.noise,
                                noise_step_stride=self.noise_stride, x_model=self.x_model, seed=self.seed_dev)
         ops.counter_add(self.counter, 1)
@@ -165,11 +174,11 @@ class DiffusionInferer:
             raise NotImplementedError(f"{mode} condition is not supported")
         if mode == "concat" and conditioning is None:
             raise ValueError("Conditioning must be supplied for if condition mode is concat.")
-        if mode == "crossattn" and conditioning is not None:
-            raise ValueError("model should have with_conditioning = True if context is provided")
         scheduler = scheduler or self.scheduler
         if not isinstance(diffusion_model, DiffusionModelUNet):
             raise TypeError("b200ldm inferers drive b200ldm.DiffusionModelUNet (there is no generic / CPU fallback)")
+        if mode == "crossattn" and conditioning is not None and not diffusion_model.with_conditioning:
+            raise ValueError("model should have with_conditioning = True if context is provided")
         if not input_noise.is_cuda:
             raise RuntimeError("b200ldm sampling needs CUDA tensors (there is no CPU fallback)")
         if seed is None:

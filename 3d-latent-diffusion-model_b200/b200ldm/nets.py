@@ -193,23 +193,32 @@ class ConvOnly(nn.Module):
 class Linear(nn.Module):
     """nn.Linear-shaped parameters; runs as a 1x1x1 conv (GEMM) in fp32 or bf16."""
 
-    def __init__(self, cin: int, cout: int):
+    def __init__(self, cin: int, cout: int, bias: bool = True):
         super().__init__()
         self.cin, self.cout = cin, cout
         self.weight = nn.Parameter(torch.empty(cout, cin))
-        self.bias = nn.Parameter(torch.empty(cout))
         nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
-        nn.init.uniform_(self.bias, -1.0 / cin ** 0.5, 1.0 / cin ** 0.5)
+        if bias:
+            self.bias = nn.Parameter(torch.empty(cout))
+            nn.init.uniform_(self.bias, -1.0 / cin ** 0.5, 1.0 / cin ** 0.5)
+        else:
+            self.register_parameter("bias", None)
         self._cache = PackedCache()
 
-    def packed(self, dtype):
+    def packed(self, dtype, cin_phys: int | None = None):
+        """(weights [1][round16(cout)][cin_phys], bias fp32 | None); cin_phys > cin: zero columns for a padded input."""
+        cin_phys = cin_phys or self.cin
+
         def build():
-            w = ops.repack_conv_weight(self.weight, ops.round_up(self.cout, 16), self.cin, dtype)
+            w = ops.repack_conv_weight(self.weight, ops.round_up(self.cout, 16), cin_phys, dtype)
+            if self.bias is None:
+                return w, None
             b = torch.zeros(ops.round_up(self.cout, 16), dtype=torch.float32, device=self.weight.device)
             b[: self.cout] = self.bias.detach().float()
             return w, b
 
-        return self._cache.get(dtype, (self.weight, self.bias), build)
+        ps = (self.weight,) if self.bias is None else (self.weight, self.bias)
+        return self._cache.get((dtype, cin_phys), ps, build)
 
 
 class GroupNorm(nn.Module):
@@ -280,6 +289,126 @@ class SpatialAttentionBlock(nn.Module):
         return self.attn.run(self.norm.run(x, silu=False), x)
 
 
+class LayerNorm(nn.Module):
+    def __init__(self, channels: int, eps: float = 1e-5):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(channels))
+        self.bias = nn.Parameter(torch.zeros(channels))
+
+    def run(self, x2d):
+        return ops.layernorm(x2d, self.weight.detach(), self.bias.detach(), self.eps)
+
+
+class XAttention(nn.Module):
+    """attn1 / attn2 of MONAI DiffusionUNetTransformerBlock (SABlock / CrossAttentionBlock with qkv_bias=False):
+    q from the tokens, k/v from the context (the tokens themselves for attn1).  attn1 runs one fused QKV GEMM,
+    attn2 one Q GEMM + one fused KV GEMM over the context; out_proj carries the residual in its epilogue."""
+
+    def __init__(self, hidden: int, heads: int, head_dim: int, context_dim: int | None = None):
+        super().__init__()
+        inner = heads * head_dim
+        self.hidden, self.inner, self.heads, self.head_dim = hidden, inner, heads, head_dim
+        self.scale = head_dim ** -0.5
+        self.context_dim = context_dim
+        self.to_q = Linear(hidden, inner, bias=False)
+        self.to_k = Linear(context_dim or hidden, inner, bias=False)
+        self.to_v = Linear(context_dim or hidden, inner, bias=False)
+        self.out_proj = Linear(inner, hidden)
+        self._cache = PackedCache()
+
+    def _packed_cat(self, key, linears, dtype, cin_phys):
+        ps = [l.weight for l in linears]
+
+        def build():
+            w = torch.cat(ps, dim=0).detach()
+            return ops.repack_conv_weight(w, w.shape[0], cin_phys, dtype)
+
+        return self._cache.get((key, dtype, cin_phys), ps, build)
+
+    def run(self, xn, residual, B: int, L: int, ctx=None):
+        """xn, residual: [B*L, hidden]; ctx: None (self attention) or [B*Lc, pad64(context_dim)] context tokens."""
+        dt = xn.dtype
+        if ctx is None:
+            wqkv = self._packed_cat("qkv", (self.to_q, self.to_k, self.to_v), dt, self.hidden)
+            qkv = ops.linear(xn, wqkv, None, 3 * self.inner)
+            att = ops.attention(qkv.reshape(B, L, 3 * self.inner), self.heads, self.head_dim, self.scale)
+        else:
+            wq, _ = self.to_q.packed(dt)
+            wkv = self._packed_cat("kv", (self.to_k, self.to_v), dt, ctx.shape[-1])
+            q = ops.linear(xn, wq, None, self.inner)
+            kv = ops.linear(ctx, wkv, None, 2 * self.inner)
+            att = ops.cross_attention(q.reshape(B, L, self.inner), kv.reshape(B, ctx.shape[0] // B, 2 * self.inner),
+                                      self.heads, self.head_dim, self.scale)
+        wo, bo = self.out_proj.packed(dt)
+        return ops.linear(att.reshape(B * L, self.inner), wo, bo, self.hidden, residual=residual)
+
+
+class GEGLUMLP(nn.Module):
+    """MONAI MLPBlock(act="GEGLU"): linear1 -> value * gelu(gate) -> linear2 (+ residual in the GEMM epilogue)."""
+
+    def __init__(self, hidden: int, mlp_dim: int):
+        super().__init__()
+        self.linear1 = Linear(hidden, mlp_dim * 2)
+        self.linear2 = Linear(mlp_dim, hidden)
+
+    def run(self, xn, residual):
+        w1, b1 = self.linear1.packed(xn.dtype)
+        w2, b2 = self.linear2.packed(xn.dtype)
+        h = ops.geglu(ops.linear(xn, w1, b1, self.linear1.cout))
+        return ops.linear(h, w2, b2, self.linear2.cout, residual=residual)
+
+
+class TransformerBlock(nn.Module):
+    def __init__(self, channels: int, heads: int, head_dim: int, cross_attention_dim: int | None):
+        super().__init__()
+        self.attn1 = XAttention(channels, heads, head_dim)
+        self.ff = GEGLUMLP(channels, channels * 4)
+        self.attn2 = XAttention(channels, heads, head_dim, cross_attention_dim)
+        self.norm1, self.norm2, self.norm3 = LayerNorm(channels), LayerNorm(channels), LayerNorm(channels)
+
+    def run(self, t, B: int, L: int, ctx):
+        t = self.attn1.run(self.norm1.run(t), t, B, L)
+        t = self.attn2.run(self.norm2.run(t), t, B, L, ctx)
+        return self.ff.run(self.norm3.run(t), t)
+
+
+class SpatialTransformer(nn.Module):
+    """MONAI SpatialTransformer (attention levels of a with_conditioning=True UNet): GroupNorm -> 1x1x1 proj_in ->
+    transformer blocks over the D*H*W tokens (NDHWC activations ARE the token matrix, no permute) -> 1x1x1 proj_out
+    (zero-init) + residual."""
+
+    def __init__(self, channels: int, heads: int, head_dim: int, num_layers: int, groups: int, eps: float,
+                 cross_attention_dim: int | None):
+        super().__init__()
+        inner = heads * head_dim
+        if inner % 64:
+            raise NotImplementedError("b200ldm SpatialTransformer needs heads * head_dim to be a multiple of 64")
+        self.norm = GroupNorm(groups, channels, eps)
+        self.proj_in = ConvOnly(channels, inner, 1, 1, 0)
+        self.transformer_blocks = nn.ModuleList(
+            [TransformerBlock(inner, heads, head_dim, cross_attention_dim) for _ in range(num_layers)])
+        self.proj_out = zero_module(ConvOnly(inner, channels, 1, 1, 0))
+
+    def run(self, x, ctx):
+        shp = x.shape
+        B = shp[0]
+        t = self.proj_in.run(self.norm.run(x, silu=False))
+        inner = t.shape[-1]
+        L = t.numel() // (B * inner)
+        t2 = t.reshape(B * L, inner)
+        for blk in self.transformer_blocks:
+            t2 = blk.run(t2, B, L, ctx)
+        return self.proj_out.run(t2.reshape(shp[:-1] + (inner,)), residual=x, want_stats=True)
+
+
+def _make_attn(cout, head_ch, groups, eps, xattn):
+    """xattn None: SpatialAttentionBlock; (num_layers, cross_attention_dim): SpatialTransformer."""
+    if xattn is None:
+        return SpatialAttentionBlock(cout, head_ch, groups, eps)
+    return SpatialTransformer(cout, cout // head_ch, head_ch, xattn[0], groups, eps, xattn[1])
+
+
 class NearestUp(nn.Module):
     """UpSample(mode="nontrainable", nearest x2) + post conv; children `upsample_non_trainable`, `postconv`."""
 
@@ -337,26 +466,26 @@ class _UNetUp(nn.Module):
 
 
 class _DownBlock(nn.Module):
-    def __init__(self, cin, cout, temb, n_res, groups, eps, add_down, attn, head_ch):
+    def __init__(self, cin, cout, temb, n_res, groups, eps, add_down, attn, head_ch, xattn=None):
         super().__init__()
         self.resnets = nn.ModuleList([UNetResBlock(cin if j == 0 else cout, cout, temb, groups, eps)
                                       for j in range(n_res)])
         if attn:
-            self.attentions = nn.ModuleList([SpatialAttentionBlock(cout, head_ch, groups, eps) for _ in range(n_res)])
+            self.attentions = nn.ModuleList([_make_attn(cout, head_ch, groups, eps, xattn) for _ in range(n_res)])
         self.has_attn = attn
         self.downsampler = _DownOp(cout) if add_down else None
 
 
 class _MidBlock(nn.Module):
-    def __init__(self, ch, temb, groups, eps, head_ch):
+    def __init__(self, ch, temb, groups, eps, head_ch, xattn=None):
         super().__init__()
         self.resnet_1 = UNetResBlock(ch, ch, temb, groups, eps)
-        self.attention = SpatialAttentionBlock(ch, head_ch, groups, eps)
+        self.attention = _make_attn(ch, head_ch, groups, eps, xattn)
         self.resnet_2 = UNetResBlock(ch, ch, temb, groups, eps)
 
 
 class _UpBlock(nn.Module):
-    def __init__(self, cin, prev, cout, temb, n_res, groups, eps, add_up, attn, head_ch):
+    def __init__(self, cin, prev, cout, temb, n_res, groups, eps, add_up, attn, head_ch, xattn=None):
         super().__init__()
         blocks = []
         for j in range(n_res):
@@ -365,7 +494,7 @@ class _UpBlock(nn.Module):
             blocks.append(UNetResBlock(res_in + skip_ch, cout, temb, groups, eps))
         self.resnets = nn.ModuleList(blocks)
         if attn:
-            self.attentions = nn.ModuleList([SpatialAttentionBlock(cout, head_ch, groups, eps) for _ in range(n_res)])
+            self.attentions = nn.ModuleList([_make_attn(cout, head_ch, groups, eps, xattn) for _ in range(n_res)])
         self.has_attn = attn
         self.upsampler = _UNetUp(cout) if add_up else None
 
@@ -401,10 +530,15 @@ class DiffusionModelUNet(nn.Module):
         super().__init__()
         if spatial_dims != 3:
             raise ValueError("b200ldm implements the 3-D hot path only (spatial_dims=3)")
-        if with_conditioning or cross_attention_dim is not None:
-            raise NotImplementedError("cross-attention conditioning is not on the reference's hot path (SURVEY.md 8f)")
-        if resblock_updown or num_class_embeds is not None:
-            raise NotImplementedError("resblock_updown / class embeddings are not used by any reference config")
+        if with_conditioning and cross_attention_dim is None:
+            raise ValueError("DiffusionModelUNet expects dimension of the cross-attention conditioning "
+                             "(cross_attention_dim) when using with_conditioning.")
+        if cross_attention_dim is not None and not with_conditioning:
+            raise ValueError("DiffusionModelUNet expects with_conditioning=True when specifying the cross_attention_dim.")
+        if resblock_updown:
+            raise NotImplementedError("resblock_updown is not used by any reference config")
+        if dropout_cattn > 1.0 or dropout_cattn < 0.0:
+            raise ValueError("Dropout cannot be negative or >1.0!")
         if any(c % norm_num_groups for c in channels):
             raise ValueError("DiffusionModelUNet expects all channels being multiple of norm_num_groups")
         if len(channels) != len(attention_levels):
@@ -422,18 +556,23 @@ class DiffusionModelUNet(nn.Module):
         self._fwd_graphs = {}
         self.block_out_channels = list(channels)
         self.with_conditioning = with_conditioning
+        self.cross_attention_dim = cross_attention_dim
         self.precision = precision or default_precision()
         temb = channels[0] * 4
+        xattn = (transformer_num_layers, cross_attention_dim) if with_conditioning else None
 
         self.conv_in = ConvOnly(in_channels, channels[0])
         self.time_embed = nn.Sequential(Linear(channels[0], temb), nn.SiLU(), Linear(temb, temb))
+        self.num_class_embeds = num_class_embeds
+        if num_class_embeds is not None:
+            self.class_embedding = nn.Embedding(num_class_embeds, temb)
         self.down_blocks = nn.ModuleList()
         cout = channels[0]
         for i in range(L):
             cin, cout = cout, channels[i]
             self.down_blocks.append(_DownBlock(cin, cout, temb, nres[i], norm_num_groups, norm_eps, i != L - 1,
-                                               bool(attention_levels[i]), head[i]))
-        self.middle_block = _MidBlock(channels[-1], temb, norm_num_groups, norm_eps, head[-1])
+                                               bool(attention_levels[i]), head[i], xattn))
+        self.middle_block = _MidBlock(channels[-1], temb, norm_num_groups, norm_eps, head[-1], xattn)
         self.up_blocks = nn.ModuleList()
         rc, rn = list(reversed(channels)), list(reversed(nres))
         ra, rh = list(reversed(attention_levels)), list(reversed(head))
@@ -442,7 +581,7 @@ class DiffusionModelUNet(nn.Module):
             prev, cout = cout, rc[i]
             cin = rc[min(i + 1, L - 1)]
             self.up_blocks.append(_UpBlock(cin, prev, cout, temb, rn[i] + 1, norm_num_groups, norm_eps, i != L - 1,
-                                           bool(ra[i]), rh[i]))
+                                           bool(ra[i]), rh[i], xattn))
         self.out = nn.Sequential(GroupNorm(norm_num_groups, channels[0], norm_eps), nn.SiLU(),
                                  zero_module(ConvOnly(channels[0], out_channels, terminal=True)))
         self._cache = PackedCache()
@@ -464,9 +603,12 @@ class DiffusionModelUNet(nn.Module):
             o += r.cout
         return offs, o
 
-    def time_embedding_table(self, timesteps: torch.Tensor) -> torch.Tensor:
+    def time_embedding_table(self, timesteps: torch.Tensor, class_labels: torch.Tensor | None = None) -> torch.Tensor:
         """[n_t] -> fp32 [n_t, sum(C_out over ResNet blocks)]: time_emb_proj_i(SiLU(time_embed(sincos(t)))) for every
-        block i, computed by one fused GEMM (the 19 M=1 GEMVs are independent of x)."""
+        block i, computed by one fused GEMM (the 19 M=1 GEMVs are independent of x).  With
+        num_class_embeds the class embedding of row r's label is added to the time embedding first."""
+        if self.num_class_embeds is not None and class_labels is None:
+            raise ValueError("class_labels should be provided when num_class_embeds > 0")
         rbs = self.resblocks()
         params = [p for r in rbs for p in (r.time_emb_proj.weight, r.time_emb_proj.bias)]
 
@@ -482,12 +624,36 @@ class DiffusionModelUNet(nn.Module):
         w2, b2 = l2.packed(torch.float32)
         h = ops.linear(t_emb, w0, b0, l0.cout)
         h = ops.linear(ops.silu_f32(h), w2, b2, l2.cout)
+        if self.num_class_embeds is not None:
+            labels = class_labels.to(device=h.device, dtype=torch.int64).reshape(-1)
+            if labels.numel() != h.shape[0]:
+                if h.shape[0] != 1:
+                    raise ValueError("class_labels must have one entry per timestep row")
+                h = h.expand(labels.numel(), -1).contiguous()
+            h = ops.embedding_add(h, self.class_embedding.weight.detach().float().contiguous(), labels.contiguous())
         return ops.linear(ops.silu_f32(h), wall, ball, total)
 
+    def context_tokens(self, context: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """[B, Lc, cross_attention_dim] (any float dtype) -> [B*Lc, pad64(dim)] in the compute dtype, zero padded
+        (the K/V projections read it through the same TMA path as every other GEMM operand)."""
+        if context.ndim != 3 or context.shape[-1] != self.cross_attention_dim:
+            raise ValueError(f"context must be [B, L, {self.cross_attention_dim}], got {tuple(context.shape)}")
+        B, Lc, Dc = context.shape
+        src = context.detach().to(torch.float32).reshape(B * Lc, Dc, 1, 1, 1).contiguous()
+        o = None if out is None else out.reshape(B * Lc, 1, 1, 1, -1)
+        return ops.to_ndhwc(src, _pad64(Dc), _PREC[self.precision], out=o).reshape(B * Lc, _pad64(Dc))
+
     # ---- NDHWC core
-    def forward_ndhwc(self, x, temb_all, temb_stride: int, sched=None):
-        """x: [N,D,H,W,pad64(in_channels)] (bf16|fp32); temb_all: fp32 [n_t, total] rows (n_t = 1 -> stride 0).
+    def forward_ndhwc(self, x, temb_all, temb_stride: int, sched=None, ctx=None):
+        """x: [N,D,H,W,pad64(in_channels)] (bf16|fp32); temb_all: fp32 [n_t, total] rows (n_t = 1 -> stride 0);
+        ctx: context tokens from `context_tokens` (with_conditioning=True models only).
         Returns eps [N,D,H,W,round16(out_channels)]."""
+        if self.with_conditioning and ctx is None:
+            raise ValueError("with_conditioning=True: a context tensor is required (cross-attention conditioning)")
+
+        def attend(a, h):
+            return a.run(h, ctx) if self.with_conditioning else a.run(h)
+
         offs, _ = self._temb_layout()
         it = iter(range(len(offs)))
 
@@ -501,20 +667,20 @@ class DiffusionModelUNet(nn.Module):
             for j, r in enumerate(blk.resnets):
                 h = r.run(h, temb_for(), temb_stride)
                 if blk.has_attn:
-                    h = blk.attentions[j].run(h)
+                    h = attend(blk.attentions[j], h)
                 skips.append(h)
             if blk.downsampler is not None:
                 h = blk.downsampler.op.run(h, want_stats=True)
                 skips.append(h)
         mb = self.middle_block
         h = mb.resnet_1.run(h, temb_for(), temb_stride)
-        h = mb.attention.run(h)
+        h = attend(mb.attention, h)
         h = mb.resnet_2.run(h, temb_for(), temb_stride)
         for blk in self.up_blocks:
             for j, r in enumerate(blk.resnets):
                 h = r.run(h, temb_for(), temb_stride, x2=skips.pop())
                 if blk.has_attn:
-                    h = blk.attentions[j].run(h)
+                    h = attend(blk.attentions[j], h)
             if blk.upsampler is not None:
                 h = blk.upsampler.upsample.run(h)
         h = self.out[0].run(h, silu=True)
@@ -524,51 +690,68 @@ class DiffusionModelUNet(nn.Module):
                 mid_block_additional_residual=None):
         if context is not None and not self.with_conditioning:
             raise ValueError("model should have with_conditioning = True if context is provided")
-        if class_labels is not None or down_block_additional_residuals is not None \
-                or mid_block_additional_residual is not None:
-            raise NotImplementedError("class labels / ControlNet residuals are not on the reference's hot path")
+        if down_block_additional_residuals is not None or mid_block_additional_residual is not None:
+            raise NotImplementedError("ControlNet residuals are not on the reference's hot path")
+        if self.num_class_embeds is not None and class_labels is None:
+            raise ValueError("class_labels should be provided when num_class_embeds > 0")
+        if self.num_class_embeds is None:
+            class_labels = None
         if x.ndim != 5 or x.shape[1] != self.in_channels:
             raise ValueError(f"expected [B,{self.in_channels},D,H,W], got {tuple(x.shape)}")
         if timesteps.ndim != 1:
             raise ValueError("Timesteps should be a 1d-array")
         if timesteps.numel() not in (1, x.shape[0]):
             raise ValueError("timesteps must have 1 or batch elements")
+        if context is not None and context.shape[0] != x.shape[0]:
+            raise ValueError("context must have one row of tokens per batch element")
         with torch.no_grad():
             if FORWARD_GRAPH and x.is_cuda and not torch.cuda.is_current_stream_capturing():
-                return self._forward_graphed(x, timesteps)
-            return self._forward_eager(x, timesteps)
+                return self._forward_graphed(x, timesteps, context, class_labels)
+            return self._forward_eager(x, timesteps, context, class_labels)
 
-    def _forward_eager(self, x, timesteps):
+    def _forward_eager(self, x, timesteps, context=None, class_labels=None):
         dt = _PREC[self.precision]
         xa = ops.to_ndhwc(x, _pad64(self.in_channels), dt)
-        temb_all = self.time_embedding_table(timesteps.to(device=x.device, dtype=torch.float32))
-        stride = 0 if timesteps.numel() == 1 else temb_all.shape[1]
-        eps = self.forward_ndhwc(xa, temb_all, stride)
+        if class_labels is not None and timesteps.numel() == 1 and x.shape[0] > 1:
+            timesteps = timesteps.expand(x.shape[0])
+        temb_all = self.time_embedding_table(timesteps.to(device=x.device, dtype=torch.float32), class_labels)
+        stride = 0 if temb_all.shape[0] == 1 else temb_all.shape[1]
+        ctx = None if context is None else self.context_tokens(context.to(x.device))
+        eps = self.forward_ndhwc(xa, temb_all, stride, ctx=ctx)
         return ops.to_ncdhw(eps, self.out_channels)
 
-    def _forward_graphed(self, x, timesteps):
-        """forward() through a CUDA graph cached per (input shape, number of timesteps, weights): the ~150 launches of a
-        noise prediction become one replay; inputs are copied into the graph's static buffers (timesteps stay on the
-        device, so any value replays).  The second call with a given signature captures, the first one runs eagerly
-        (it also lets the conv kernels measure their choices)."""
-        key = (tuple(x.shape), timesteps.numel(), str(x.device), self.precision, param_signature(self))
+    def _forward_graphed(self, x, timesteps, context=None, class_labels=None):
+        """forward() through a CUDA graph cached per (input shapes, number of timesteps, weights): the ~150 launches of
+        a noise prediction become one replay; inputs are copied into the graph's static buffers (timesteps, context
+        and class labels stay on the device, so any value replays).  The second call with a given signature captures,
+        the first one runs eagerly (it also lets the conv kernels measure their choices)."""
+        key = (tuple(x.shape), timesteps.numel(), None if context is None else tuple(context.shape),
+               None if class_labels is None else class_labels.numel(), str(x.device), self.precision,
+               param_signature(self))
         hit = self._fwd_graphs.get(key)
         if hit is None:
             if len(self._fwd_graphs) >= 4:
                 self._fwd_graphs.clear()
             self._fwd_graphs[key] = "warm"
-            return self._forward_eager(x, timesteps)
+            return self._forward_eager(x, timesteps, context, class_labels)
         if hit == "warm":
             static_x = x.detach().to(torch.float32).clone()
             static_t = timesteps.detach().to(device=x.device, dtype=torch.float32).clone()
+            static_c = None if context is None else context.detach().to(device=x.device, dtype=torch.float32).clone()
+            static_l = None if class_labels is None else class_labels.detach().to(device=x.device,
+                                                                                 dtype=torch.int64).clone()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                static_out = self._forward_eager(static_x, static_t)
-            hit = (g, static_x, static_t, static_out)
+                static_out = self._forward_eager(static_x, static_t, static_c, static_l)
+            hit = (g, static_x, static_t, static_c, static_l, static_out)
             self._fwd_graphs[key] = hit
-        g, static_x, static_t, static_out = hit
+        g, static_x, static_t, static_c, static_l, static_out = hit
         static_x.copy_(x)
         static_t.copy_(timesteps)
+        if static_c is not None:
+            static_c.copy_(context)
+        if static_l is not None:
+            static_l.copy_(class_labels)
         g.replay()
         return static_out.clone()
 

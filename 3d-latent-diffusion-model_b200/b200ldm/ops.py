@@ -244,6 +244,65 @@ def attention(qkv, heads: int, head_dim: int, scale: float, engine: int = ENGINE
     return o
 
 
+def cross_attention(q, kv, heads: int, head_dim: int, scale: float, engine: int = ENGINE_AUTO):
+    """q: [B, Lq, H*d]; kv: [B, Lk, 2*H*d] fused key/value projections of the context -> [B, Lq, H*d]."""
+    _need_cuda(q, kv)
+    lib = _lib.load()
+    B, Lq, Cc = q.shape
+    Lk = kv.shape[1]
+    assert Cc == heads * head_dim and kv.shape == (B, Lk, 2 * Cc) and q.is_contiguous() and kv.is_contiguous()
+    assert q.dtype == kv.dtype
+    o = torch.empty((B, Lq, Cc), dtype=q.dtype, device=q.device)
+    base = kv.data_ptr()
+    ev = PROFILER.start() if PROFILER is not None else None
+    _lib.check(lib.b200ldm_cross_attention(q.data_ptr(), base, base + Cc * kv.element_size(), o.data_ptr(), B, heads,
+                                           Lq, Lk, head_dim, Cc, 2 * Cc, float(scale), dtype_code(q.dtype), engine,
+                                           _stream()), "cross_attention")
+    if ev is not None:
+        PROFILER.stop("attention", f"B{B} H{heads} Lq{Lq} Lk{Lk} d{head_dim}", 4.0 * B * heads * Lq * Lk * head_dim, ev)
+    return o
+
+
+def layernorm(x2d, gamma, beta, eps: float = 1e-5):
+    """nn.LayerNorm over the last axis of [M, C] tokens (gamma / beta fp32)."""
+    _need_cuda(x2d, gamma, beta)
+    M, Cc = x2d.shape
+    assert x2d.is_contiguous() and gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    y = torch.empty_like(x2d)
+    ev = PROFILER.start() if PROFILER is not None else None
+    _lib.check(_lib.load().b200ldm_layernorm(x2d.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), M, Cc,
+                                             float(eps), dtype_code(x2d.dtype), _stream()), "layernorm")
+    if ev is not None:
+        PROFILER.stop("layernorm", f"C{Cc} M{M}", 2.0 * x2d.numel() * x2d.element_size(), ev)
+    return y
+
+
+def geglu(h2d):
+    """[M, 2J] -> [M, J]: value half * gelu(gate half) (MONAI MLPBlock act="GEGLU")."""
+    _need_cuda(h2d)
+    M, J2 = h2d.shape
+    assert h2d.is_contiguous() and J2 % 16 == 0
+    y = torch.empty((M, J2 // 2), dtype=h2d.dtype, device=h2d.device)
+    ev = PROFILER.start() if PROFILER is not None else None
+    _lib.check(_lib.load().b200ldm_geglu(h2d.data_ptr(), y.data_ptr(), M, J2 // 2, dtype_code(h2d.dtype), _stream()),
+               "geglu")
+    if ev is not None:
+        PROFILER.stop("geglu", f"J{J2 // 2} M{M}", 1.5 * h2d.numel() * h2d.element_size(), ev)
+    return y
+
+
+def embedding_add(a, table, idx):
+    """a [n, dim] fp32 + table[idx] (class embedding onto the time embedding); idx int64 on the device."""
+    _need_cuda(a, table, idx)
+    n, dim = a.shape
+    assert a.dtype == torch.float32 and table.dtype == torch.float32 and idx.dtype == torch.int64
+    assert a.is_contiguous() and table.is_contiguous() and idx.numel() == n and table.shape[1] == dim
+    out = torch.empty_like(a)
+    _lib.check(_lib.load().b200ldm_embedding_add(a.data_ptr(), table.data_ptr(), idx.data_ptr(), out.data_ptr(), n, dim,
+                                                 table.shape[0], _stream()), "embedding_add")
+    return out
+
+
 def tap_gather(z, bias, cp: int, cy: int, sched=None, want_y: bool = True):
     """y[v][co] = bias[co] + sum_tap z[v + shift(tap)][tap*cp + co]: second half of a narrow-output 3x3x3 conv.
     sched: a SchedParams (make_sched_params) -> the gathered tensor is the noise prediction and the scheduler update is

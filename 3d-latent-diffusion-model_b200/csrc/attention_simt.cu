@@ -11,7 +11,7 @@ constexpr int kAttThreads = 128;
 template <typename T, int DS>
 __global__ void __launch_bounds__(kAttThreads)
 attention_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ o,
-                      int H, int L, int d, long long ld, float scale, int KT) {
+                      int H, int L, int Lk, int d, long long ld, long long ldkv, float scale, int KT) {
   extern __shared__ float smem[];
   float* Ks = smem;                 // [KT][d]
   float* Vs = smem + (size_t)KT * d;
@@ -32,12 +32,12 @@ attention_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
   }
   float m = -INFINITY, l = 0.f;
 
-  for (int k0 = 0; k0 < L; k0 += KT) {
-    const int kn = min(KT, L - k0);
+  for (int k0 = 0; k0 < Lk; k0 += KT) {
+    const int kn = min(KT, Lk - k0);
     __syncthreads();
     for (int i = threadIdx.x; i < kn * d; i += kAttThreads) {
       const int r = i / d, c = i - r * d;
-      const size_t g = ((size_t)b * L + k0 + r) * ld + head_off + c;
+      const size_t g = ((size_t)b * Lk + k0 + r) * ldkv + head_off + c;
       Ks[i] = to_f32<T>(k[g]);
       Vs[i] = to_f32<T>(v[g]);
     }
@@ -67,8 +67,8 @@ attention_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
 }
 
 template <typename T>
-static int launch_attention_simt(const void* q, const void* k, const void* v, void* o, int B, int H, int L, int d,
-                                 long long ld, float scale, cudaStream_t st) {
+static int launch_attention_simt(const void* q, const void* k, const void* v, void* o, int B, int H, int L, int Lk,
+                                 int d, long long ld, long long ldkv, float scale, cudaStream_t st) {
   const int DS = (d % 64 == 0) ? 64 : 32;
   const int dsplit = d / DS;
   B2_REQUIRE(d % 32 == 0 && dsplit <= 32 && (dsplit & (dsplit - 1)) == 0, B200LDM_BAD_SHAPE,
@@ -81,35 +81,42 @@ static int launch_attention_simt(const void* q, const void* k, const void* v, vo
     B2_CHECK_CUDA(cudaFuncSetAttribute(attention_simt_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
     attention_simt_kernel<T, 64><<<grid, kAttThreads, smem, st>>>((const T*)q, (const T*)k, (const T*)v, (T*)o, H, L,
-                                                                 d, ld, scale, KT);
+                                                                 Lk, d, ld, ldkv, scale, KT);
   } else {
     attention_simt_kernel<T, 32><<<grid, kAttThreads, smem, st>>>((const T*)q, (const T*)k, (const T*)v, (T*)o, H, L,
-                                                                 d, ld, scale, KT);
+                                                                 Lk, d, ld, ldkv, scale, KT);
   }
   B2_LAUNCH_CHECK();
   return B200LDM_OK;
 }
 
-int attention_tcgen05(const void* q, const void* k, const void* v, void* o, int B, int H, int L, int d, long long ld,
-                      float scale, cudaStream_t st);
+int attention_tcgen05(const void* q, const void* k, const void* v, void* o, int B, int H, int L, int Lk, int d,
+                      long long ld, long long ldkv, float scale, cudaStream_t st);
 bool attention_tcgen05_supported(int d);
 
 }  // namespace b200ldm
 
+extern "C" int b200ldm_cross_attention(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t H,
+                                       int32_t Lq, int32_t Lk, int32_t d, int64_t ldq, int64_t ldkv, float scale,
+                                       int32_t dtype, int32_t engine, b200ldm_stream stream) {
+  using namespace b200ldm;
+  B2_REQUIRE(q && k && v && o, B200LDM_BAD_ARG, "attention: null pointer");
+  B2_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0 && d > 0 && ldq >= (int64_t)H * d && ldkv >= (int64_t)H * d,
+             B200LDM_BAD_SHAPE, "attention: bad shape");
+  if (engine == B200LDM_ENGINE_AUTO)
+    engine = (dtype == B200LDM_BF16 && attention_tcgen05_supported(d)) ? B200LDM_ENGINE_TCGEN05 : B200LDM_ENGINE_SIMT;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (engine == B200LDM_ENGINE_TCGEN05) {
+    B2_REQUIRE(dtype == B200LDM_BF16, B200LDM_BAD_ARG, "tcgen05 attention needs bf16");
+    return attention_tcgen05(q, k, v, o, B, H, Lq, Lk, d, ldq, ldkv, scale, st);
+  }
+  if (dtype == B200LDM_BF16) return launch_attention_simt<__nv_bfloat16>(q, k, v, o, B, H, Lq, Lk, d, ldq, ldkv, scale, st);
+  if (dtype == B200LDM_F32) return launch_attention_simt<float>(q, k, v, o, B, H, Lq, Lk, d, ldq, ldkv, scale, st);
+  return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);
+}
+
 extern "C" int b200ldm_attention(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t H, int32_t L,
                                  int32_t d, int64_t ld, float scale, int32_t dtype, int32_t engine,
                                  b200ldm_stream stream) {
-  using namespace b200ldm;
-  B2_REQUIRE(q && k && v && o, B200LDM_BAD_ARG, "attention: null pointer");
-  B2_REQUIRE(B > 0 && H > 0 && L > 0 && d > 0 && ld >= (int64_t)H * d, B200LDM_BAD_SHAPE, "attention: bad shape");
-  if (engine == B200LDM_ENGINE_AUTO)
-    engine = (dtype == B200LDM_BF16 && attention_tcgen05_supported(d)) ? B200LDM_ENGINE_TCGEN05 : B200LDM_ENGINE_SIMT;
-  if (engine == B200LDM_ENGINE_TCGEN05) {
-    B2_REQUIRE(dtype == B200LDM_BF16, B200LDM_BAD_ARG, "tcgen05 attention needs bf16");
-    return attention_tcgen05(q, k, v, o, B, H, L, d, ld, scale, (cudaStream_t)stream);
-  }
-  if (dtype == B200LDM_BF16)
-    return launch_attention_simt<__nv_bfloat16>(q, k, v, o, B, H, L, d, ld, scale, (cudaStream_t)stream);
-  if (dtype == B200LDM_F32) return launch_attention_simt<float>(q, k, v, o, B, H, L, d, ld, scale, (cudaStream_t)stream);
-  return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);
+  return b200ldm_cross_attention(q, k, v, o, B, H, L, L, d, ld, ld, scale, dtype, engine, stream);
 }

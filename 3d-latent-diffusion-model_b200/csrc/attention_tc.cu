@@ -24,7 +24,8 @@ struct AttnMaps {
 };
 
 struct AttnArgs {
-  int H, L, d;
+  int H, L, d;       // L = queries per (batch, head)
+  int Lk;            // keys / values per (batch, head): == L for self attention, the context length for cross attention
   float scale_log2;  // softmax scale * log2(e)
   __nv_bfloat16* o;  // [B][L][H*d]
   unsigned long long* trace;  // debug (b200ldm_debug_set_conv_trace): per-CTA cycle counters of the softmax warps
@@ -101,7 +102,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128;
   const int h = blockIdx.y, b = blockIdx.z;
-  const int ntiles = (a.L + BN - 1) / BN;
+  const int ntiles = (a.Lk + BN - 1) / BN;
   const int col0 = h * D;
 
   if (warp == 0 && lane == 0) {
@@ -231,7 +232,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       ptx::mbar_arrive(s_empty + 8 * (j & 1));  // S buffer may be overwritten by tile j+2
       if (tr) { t1 = clock64(); tc[1] += t1 - t0; t0 = t1; }
 
-      const int kvalid = a.L - j * BN;  // keys in this tile that exist
+      const int kvalid = a.Lk - j * BN;  // keys in this tile that exist
       if (kvalid < BN) {                // last tile only (warp-uniform)
 #pragma unroll
         for (int i = 0; i < BN; ++i)
@@ -397,7 +398,7 @@ attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256;
   const int h = blockIdx.y, b = blockIdx.z;
-  const int ntiles = (a.L + BN - 1) / BN;
+  const int ntiles = (a.Lk + BN - 1) / BN;
   const int col0 = h * D;
   const bool tileB_exists = q0 + 128 < a.L;   // CTA-uniform: the second query tile may be entirely past L
 
@@ -535,7 +536,7 @@ attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(s_free + 8 * w);   // the tensor core may overwrite S_w with the next tile's scores
         if (tr) { t1 = clock64(); tc[1] += t1 - t0; t0 = t1; }
-        const int kvalid = a.L - j * BN;
+        const int kvalid = a.Lk - j * BN;
         if (kvalid < BN) {
 #pragma unroll
           for (int i = 0; i < BN; ++i)
@@ -676,16 +677,16 @@ static int make_qkv_map(CUtensorMap* m, const void* base, int cols, int L, int B
 }
 
 template <int D, int BN>
-static int launch_attention_tc(const void* q, const void* k, const void* v, void* o, int B, int H, int L, long long ld,
-                               float scale, cudaStream_t st) {
+static int launch_attention_tc(const void* q, const void* k, const void* v, void* o, int B, int H, int L, int Lk,
+                               long long ld, long long ldkv, float scale, cudaStream_t st) {
   using Cfg = AttnCfg<D, BN>;
   AttnMaps maps;
   int rc;
   if ((rc = make_qkv_map(&maps.q, q, H * D, L, B, ld, 128))) return rc;
-  if ((rc = make_qkv_map(&maps.k, k, H * D, L, B, ld, BN))) return rc;
-  if ((rc = make_qkv_map(&maps.v, v, H * D, L, B, ld, BN))) return rc;
+  if ((rc = make_qkv_map(&maps.k, k, H * D, Lk, B, ldkv, BN))) return rc;
+  if ((rc = make_qkv_map(&maps.v, v, H * D, Lk, B, ldkv, BN))) return rc;
   static const int dbg = [] { const char* e = getenv("B200LDM_ATTN_DBG"); return e ? atoi(e) : 0; }();
-  AttnArgs a{H, L, D, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o), g_attn_trace, dbg};
+  AttnArgs a{H, L, D, Lk, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o), g_attn_trace, dbg};
   static bool attr_done = false;
   if (!attr_done) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -699,16 +700,16 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
 }
 
 template <int D, int BN, int OCC>
-static int launch_attention_tc2(const void* q, const void* k, const void* v, void* o, int B, int H, int L, long long ld,
-                                float scale, cudaStream_t st) {
+static int launch_attention_tc2(const void* q, const void* k, const void* v, void* o, int B, int H, int L, int Lk,
+                                long long ld, long long ldkv, float scale, cudaStream_t st) {
   using Cfg = Attn2Cfg<D, BN, OCC>;
   AttnMaps maps;
   int rc;
   if ((rc = make_qkv_map(&maps.q, q, H * D, L, B, ld, 128))) return rc;
-  if ((rc = make_qkv_map(&maps.k, k, H * D, L, B, ld, BN))) return rc;
-  if ((rc = make_qkv_map(&maps.v, v, H * D, L, B, ld, BN))) return rc;
+  if ((rc = make_qkv_map(&maps.k, k, H * D, Lk, B, ldkv, BN))) return rc;
+  if ((rc = make_qkv_map(&maps.v, v, H * D, Lk, B, ldkv, BN))) return rc;
   static const int dbg = [] { const char* e = getenv("B200LDM_ATTN_DBG"); return e ? atoi(e) : 0; }();
-  AttnArgs a{H, L, D, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o), g_attn_trace, dbg};
+  AttnArgs a{H, L, D, Lk, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o), g_attn_trace, dbg};
   static bool attr_done = false;
   if (!attr_done) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<D, BN, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -730,27 +731,28 @@ static const int g_attn_v = [] {
 
 bool attention_tcgen05_supported(int d) { return d == 64 || d == 128 || d == 256; }
 
-int attention_tcgen05(const void* q, const void* k, const void* v, void* o, int B, int H, int L, int d, long long ld,
-                      float scale, cudaStream_t st) {
+int attention_tcgen05(const void* q, const void* k, const void* v, void* o, int B, int H, int L, int Lk, int d,
+                      long long ld, long long ldkv, float scale, cudaStream_t st) {
   B2_REQUIRE(attention_tcgen05_supported(d), B200LDM_BAD_SHAPE, "tcgen05 attention supports head dim 64/128/256 (got %d)",
              d);
-  B2_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && ld % 8 == 0, B200LDM_BAD_ALIGN,
-             "attention: pointers / row stride must be 16-byte aligned");
+  B2_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && ld % 8 == 0 && ldkv % 8 == 0,
+             B200LDM_BAD_ALIGN, "attention: pointers / row strides must be 16-byte aligned");
   // head dim 64: the one-query-tile kernel with 64-key tiles runs TWO CTAs per SM (96 KB smem, 256 TMEM columns each)
   // and beats the two-tile ping-pong kernel by 7-19 % (0.406 vs 0.436 ms at B8 H4 L5544): its two softmax warps per
   // sub-partition belong to independent CTAs and never fall into lock-step.  Head dim 128 keeps the ping-pong kernel.
-  const bool pingpong = L > 128 && ((d == 128 && g_attn_v != 1) || (d == 64 && g_attn_v == 2));
+  // Cross attention (Lk = context length, usually one short tile) always takes the one-query-tile kernel.
+  const bool pingpong = L > 128 && Lk > 128 && ((d == 128 && g_attn_v != 1) || (d == 64 && g_attn_v == 2));
   if (pingpong) {
     // d = 64: B200LDM_ATTN_OCC=2 runs 64-key tiles with two CTAs per SM (four softmax warps per sub-partition)
     static const int occ = [] { const char* e = getenv("B200LDM_ATTN_OCC"); return e ? atoi(e) : 1; }();
-    if (d == 64 && occ == 2) return launch_attention_tc2<64, 64, 2>(q, k, v, o, B, H, L, ld, scale, st);
-    if (d == 64) return launch_attention_tc2<64, 128, 1>(q, k, v, o, B, H, L, ld, scale, st);
-    return launch_attention_tc2<128, 64, 1>(q, k, v, o, B, H, L, ld, scale, st);
+    if (d == 64 && occ == 2) return launch_attention_tc2<64, 64, 2>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
+    if (d == 64) return launch_attention_tc2<64, 128, 1>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
+    return launch_attention_tc2<128, 64, 1>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
   }
-  if (d == 64 && L > 128) return launch_attention_tc<64, 64>(q, k, v, o, B, H, L, ld, scale, st);
-  if (d == 64) return launch_attention_tc<64, 128>(q, k, v, o, B, H, L, ld, scale, st);
-  if (d == 128) return launch_attention_tc<128, 128>(q, k, v, o, B, H, L, ld, scale, st);
-  return launch_attention_tc<256, 64>(q, k, v, o, B, H, L, ld, scale, st);
+  if (d == 64 && Lk > 128) return launch_attention_tc<64, 64>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
+  if (d == 64) return launch_attention_tc<64, 128>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
+  if (d == 128) return launch_attention_tc<128, 128>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
+  return launch_attention_tc<256, 64>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
 }
 
 }  // namespace b200ldm

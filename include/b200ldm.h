@@ -171,6 +171,27 @@ int b200ldm_attention(const void* q, const void* k, const void* v, void* o, int3
                       int32_t L, int32_t d, int64_t ld, float scale, int32_t dtype, int32_t engine,
                       b200ldm_stream stream);
 
+/* Cross attention (MONAI CrossAttentionBlock inside SpatialTransformer, with_conditioning=True; the reference's
+ * commented-out `mode="crossattn"` call, 3d_ldm/train_diffusion.py:314-321): queries [B][Lq] with
+ * row stride ldq, keys/values [B][Lk] with row stride ldkv (the context projections), o: [B][Lq][H*d] dense.
+ * b200ldm_attention(L, ld) == b200ldm_cross_attention(L, L, ld, ld). */
+int b200ldm_cross_attention(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t H, int32_t Lq,
+                            int32_t Lk, int32_t d, int64_t ldq, int64_t ldkv, float scale, int32_t dtype,
+                            int32_t engine, b200ldm_stream stream);
+
+/* Token-major helpers of MONAI DiffusionUNetTransformerBlock (replace nn.LayerNorm and the
+ * GEGLU gate of MLPBlock(act="GEGLU")):
+ *   layernorm: y[m][:] = (x[m][:] - mean_m) * rsqrt(var_m + eps) * gamma + beta over the C channels of each of M rows
+ *              (biased variance, like torch); C % 8 == 0, C <= 4096; gamma/beta fp32.
+ *   geglu:     y[m][j] = h[m][j] * gelu_erf(h[m][J + j]),  h: [M][2J], y: [M][J], J % 8 == 0. */
+int b200ldm_layernorm(const void* x, void* y, const float* gamma, const float* beta, int64_t M, int32_t C, float eps,
+                      int32_t dtype, b200ldm_stream stream);
+int b200ldm_geglu(const void* h, void* y, int64_t M, int32_t J, int32_t dtype, b200ldm_stream stream);
+/* out[r][:] = a[r][:] + table[idx[r]][:], fp32: the class embedding added to the time embedding
+ * (DiffusionModelUNet num_class_embeds / class_labels); idx int64 on the device. */
+int b200ldm_embedding_add(const float* a, const float* table, const int64_t* idx, float* out, int32_t n_rows,
+                          int32_t dim, int32_t n_classes, b200ldm_stream stream);
+
 /* Second half of a narrow-output 3x3x3 conv (SURVEY.md 8a a2 `out.2`, a4 decoder `conv_out`; replaces F.conv3d there):
  * the conv is run as a 1x1x1 GEMM z[v][tap*cp + co] = sum_ci w[tap][co][ci] x[v][ci] (b200ldm_conv3d, ksize 1, weights
  * stacked [27*cp][Cin]) so the input is read once instead of 27 times, then

@@ -87,6 +87,96 @@ class SpatialAttentionBlock(nn.Module):
         return t + res
 
 
+class _Attention(nn.Module):
+    """Shared core of MONAI SABlock / CrossAttentionBlock as DiffusionUNetTransformerBlock builds them
+    (qkv_bias=False, include_fc=True, separate linears): q from x, k/v from `context` (x itself when None)."""
+
+    def __init__(self, hidden: int, heads: int, head_dim: int, context_dim: int | None = None):
+        super().__init__()
+        inner = heads * head_dim
+        self.heads, self.head_dim, self.scale = heads, head_dim, head_dim ** -0.5
+        self.to_q = nn.Linear(hidden, inner, bias=False)
+        self.to_k = nn.Linear(context_dim or hidden, inner, bias=False)
+        self.to_v = nn.Linear(context_dim or hidden, inner, bias=False)
+        self.out_proj = nn.Linear(inner, hidden)
+
+    def forward(self, x, context=None):
+        ctx = x if context is None else context
+        b, n, _ = x.shape
+        h, d = self.heads, self.head_dim
+        q = self.to_q(x).view(b, n, h, d).permute(0, 2, 1, 3)
+        k = self.to_k(ctx).view(b, ctx.shape[1], h, d).permute(0, 2, 1, 3)
+        v = self.to_v(ctx).view(b, ctx.shape[1], h, d).permute(0, 2, 1, 3)
+        att = (torch.einsum("bhxd,bhyd->bhxy", q, k) * self.scale).softmax(dim=-1)
+        y = torch.einsum("bhxy,bhyd->bhxd", att, v).permute(0, 2, 1, 3).reshape(b, n, h * d)
+        return self.out_proj(y)
+
+
+class _GEGLUMLP(nn.Module):
+    """MONAI MLPBlock(act="GEGLU"): linear1 -> (value, gate) halves -> value * gelu(gate) -> linear2 (dropout 0)."""
+
+    def __init__(self, hidden: int, mlp_dim: int):
+        super().__init__()
+        self.linear1 = nn.Linear(hidden, mlp_dim * 2)
+        self.linear2 = nn.Linear(mlp_dim, hidden)
+
+    def forward(self, x):
+        val, gate = self.linear1(x).chunk(2, dim=-1)
+        return self.linear2(val * F.gelu(gate))
+
+
+class TransformerBlock(nn.Module):
+    """MONAI DiffusionUNetTransformerBlock: self attention, cross attention, GEGLU feed-forward, each pre-LayerNormed
+    and residual.  [MONAI-recall >= 1.4; the reference only has the commented-out call, 3d_ldm/train_diffusion.py:314-321]"""
+
+    def __init__(self, channels: int, heads: int, head_dim: int, cross_attention_dim: int | None):
+        super().__init__()
+        self.attn1 = _Attention(channels, heads, head_dim)
+        self.ff = _GEGLUMLP(channels, channels * 4)
+        self.attn2 = _Attention(channels, heads, head_dim, cross_attention_dim)
+        self.norm1 = nn.LayerNorm(channels)
+        self.norm2 = nn.LayerNorm(channels)
+        self.norm3 = nn.LayerNorm(channels)
+
+    def forward(self, x, context=None):
+        x = self.attn1(self.norm1(x)) + x
+        x = self.attn2(self.norm2(x), context=context) + x
+        return self.ff(self.norm3(x)) + x
+
+
+class SpatialTransformer(nn.Module):
+    """MONAI SpatialTransformer: GN -> 1x1x1 proj_in -> tokens -> transformer blocks -> 1x1x1 proj_out (zero-init)
+    -> + residual.  Replaces SpatialAttentionBlock at attention levels when with_conditioning=True."""
+
+    def __init__(self, channels: int, heads: int, head_dim: int, num_layers: int, groups: int, eps: float,
+                 cross_attention_dim: int | None):
+        super().__init__()
+        inner = heads * head_dim
+        self.norm = nn.GroupNorm(groups, channels, eps=eps, affine=True)
+        self.proj_in = ConvOnly(channels, inner, 1, 1, 0)
+        self.transformer_blocks = nn.ModuleList(
+            [TransformerBlock(inner, heads, head_dim, cross_attention_dim) for _ in range(num_layers)])
+        self.proj_out = zero_module(ConvOnly(inner, channels, 1, 1, 0))
+
+    def forward(self, x, context=None):
+        res = x
+        b, _, d, h, w = x.shape
+        t = self.proj_in(self.norm(x))
+        inner = t.shape[1]
+        t = t.permute(0, 2, 3, 4, 1).reshape(b, d * h * w, inner)
+        for blk in self.transformer_blocks:
+            t = blk(t, context=context)
+        t = t.reshape(b, d, h, w, inner).permute(0, 4, 1, 2, 3).contiguous()
+        return self.proj_out(t) + res
+
+
+def _make_attn(cout, head_ch, groups, eps, xattn):
+    """xattn = None: plain SpatialAttentionBlock; else (num_layers, cross_attention_dim): SpatialTransformer."""
+    if xattn is None:
+        return SpatialAttentionBlock(cout, head_ch, groups, eps)
+    return SpatialTransformer(cout, cout // head_ch, head_ch, xattn[0], groups, eps, xattn[1])
+
+
 class _NearestUp(nn.Module):
     """MONAI UpSample(mode="nontrainable", interp_mode="nearest", scale 2) + post conv;
     children named `upsample_non_trainable` (no params) and `postconv`."""
@@ -152,24 +242,22 @@ class _UNetUp(nn.Module):
 
 
 class _DownBlock(nn.Module):
-    def __init__(self, cin, cout, temb, n_res, groups, eps, add_down, attn, head_ch):
+    def __init__(self, cin, cout, temb, n_res, groups, eps, add_down, attn, head_ch, xattn=None):
         super().__init__()
         self.resnets = nn.ModuleList(
             [UNetResBlock(cin if j == 0 else cout, cout, temb, groups, eps) for j in range(n_res)]
         )
         if attn:
-            self.attentions = nn.ModuleList(
-                [SpatialAttentionBlock(cout, head_ch, groups, eps) for _ in range(n_res)]
-            )
-        self.has_attn = attn
+            self.attentions = nn.ModuleList([_make_attn(cout, head_ch, groups, eps, xattn) for _ in range(n_res)])
+        self.has_attn, self.xattn = attn, xattn is not None
         self.downsampler = _DownOp(cout) if add_down else None
 
-    def forward(self, h, emb):
+    def forward(self, h, emb, context=None):
         outs = []
         for j, r in enumerate(self.resnets):
             h = r(h, emb)
             if self.has_attn:
-                h = self.attentions[j](h).contiguous()
+                h = (self.attentions[j](h, context) if self.xattn else self.attentions[j](h)).contiguous()
             outs.append(h)
         if self.downsampler is not None:
             h = self.downsampler(h)
@@ -178,18 +266,21 @@ class _DownBlock(nn.Module):
 
 
 class _MidBlock(nn.Module):
-    def __init__(self, ch, temb, groups, eps, head_ch):
+    def __init__(self, ch, temb, groups, eps, head_ch, xattn=None):
         super().__init__()
         self.resnet_1 = UNetResBlock(ch, ch, temb, groups, eps)
-        self.attention = SpatialAttentionBlock(ch, head_ch, groups, eps)
+        self.attention = _make_attn(ch, head_ch, groups, eps, xattn)
         self.resnet_2 = UNetResBlock(ch, ch, temb, groups, eps)
+        self.xattn = xattn is not None
 
-    def forward(self, h, emb):
-        return self.resnet_2(self.attention(self.resnet_1(h, emb)), emb)
+    def forward(self, h, emb, context=None):
+        h = self.resnet_1(h, emb)
+        h = self.attention(h, context) if self.xattn else self.attention(h)
+        return self.resnet_2(h, emb)
 
 
 class _UpBlock(nn.Module):
-    def __init__(self, cin, prev, cout, temb, n_res, groups, eps, add_up, attn, head_ch):
+    def __init__(self, cin, prev, cout, temb, n_res, groups, eps, add_up, attn, head_ch, xattn=None):
         super().__init__()
         blocks = []
         for j in range(n_res):
@@ -198,18 +289,16 @@ class _UpBlock(nn.Module):
             blocks.append(UNetResBlock(res_in + skip_ch, cout, temb, groups, eps))
         self.resnets = nn.ModuleList(blocks)
         if attn:
-            self.attentions = nn.ModuleList(
-                [SpatialAttentionBlock(cout, head_ch, groups, eps) for _ in range(n_res)]
-            )
-        self.has_attn = attn
+            self.attentions = nn.ModuleList([_make_attn(cout, head_ch, groups, eps, xattn) for _ in range(n_res)])
+        self.has_attn, self.xattn = attn, xattn is not None
         self.upsampler = _UNetUp(cout) if add_up else None
 
-    def forward(self, h, skips, emb):
+    def forward(self, h, skips, emb, context=None):
         for j, r in enumerate(self.resnets):
             h = torch.cat([h, skips.pop()], dim=1)
             h = r(h, emb)
             if self.has_attn:
-                h = self.attentions[j](h).contiguous()
+                h = (self.attentions[j](h, context) if self.xattn else self.attentions[j](h)).contiguous()
         if self.upsampler is not None:
             h = self.upsampler(h)
         return h
@@ -245,8 +334,13 @@ class DiffusionModelUNet(nn.Module):
         super().__init__()
         if spatial_dims != 3:
             raise ValueError("oracle restates the 3-D path only")
-        if with_conditioning or resblock_updown or num_class_embeds is not None:
+        if resblock_updown:
             raise NotImplementedError("not used by any reference config (SURVEY.md 8f)")
+        if with_conditioning and cross_attention_dim is None:
+            raise ValueError("DiffusionModelUNet expects dimension of the cross-attention conditioning "
+                             "(cross_attention_dim) when using with_conditioning.")
+        if cross_attention_dim is not None and not with_conditioning:
+            raise ValueError("DiffusionModelUNet expects with_conditioning=True when specifying the cross_attention_dim.")
         if any(c % norm_num_groups for c in channels):
             raise ValueError("DiffusionModelUNet expects all channels being multiple of norm_num_groups")
         if len(channels) != len(attention_levels):
@@ -260,9 +354,13 @@ class DiffusionModelUNet(nn.Module):
         self.block_out_channels = list(channels)
         self.with_conditioning = with_conditioning
         temb = channels[0] * 4
+        xattn = (transformer_num_layers, cross_attention_dim) if with_conditioning else None
 
         self.conv_in = ConvOnly(in_channels, channels[0], 3, 1, 1)
         self.time_embed = nn.Sequential(nn.Linear(channels[0], temb), nn.SiLU(), nn.Linear(temb, temb))
+        self.num_class_embeds = num_class_embeds
+        if num_class_embeds is not None:
+            self.class_embedding = nn.Embedding(num_class_embeds, temb)
 
         self.down_blocks = nn.ModuleList()
         cout = channels[0]
@@ -270,9 +368,9 @@ class DiffusionModelUNet(nn.Module):
             cin, cout = cout, channels[i]
             self.down_blocks.append(
                 _DownBlock(cin, cout, temb, nres[i], norm_num_groups, norm_eps, i != L - 1,
-                           bool(attention_levels[i]), head[i])
+                           bool(attention_levels[i]), head[i], xattn)
             )
-        self.middle_block = _MidBlock(channels[-1], temb, norm_num_groups, norm_eps, head[-1])
+        self.middle_block = _MidBlock(channels[-1], temb, norm_num_groups, norm_eps, head[-1], xattn)
 
         self.up_blocks = nn.ModuleList()
         rc, rn = list(reversed(channels)), list(reversed(nres))
@@ -283,7 +381,7 @@ class DiffusionModelUNet(nn.Module):
             cin = rc[min(i + 1, L - 1)]
             self.up_blocks.append(
                 _UpBlock(cin, prev, cout, temb, rn[i] + 1, norm_num_groups, norm_eps, i != L - 1,
-                         bool(ra[i]), rh[i])
+                         bool(ra[i]), rh[i], xattn)
             )
         self.out = nn.Sequential(
             nn.GroupNorm(norm_num_groups, channels[0], eps=norm_eps, affine=True),
@@ -297,18 +395,22 @@ class DiffusionModelUNet(nn.Module):
             raise ValueError("model should have with_conditioning = True if context is provided")
         t_emb = get_timestep_embedding(timesteps, self.block_out_channels[0]).to(dtype=x.dtype)
         emb = self.time_embed(t_emb)
+        if self.num_class_embeds is not None:
+            if class_labels is None:
+                raise ValueError("class_labels should be provided when num_class_embeds > 0")
+            emb = emb + self.class_embedding(class_labels).to(dtype=x.dtype)
         h = self.conv_in(x)
         skips = [h]
         for blk in self.down_blocks:
-            h, outs = blk(h, emb)
+            h, outs = blk(h, emb, context)
             skips.extend(outs)
         if down_block_additional_residuals is not None:
             skips = [s + r for s, r in zip(skips, down_block_additional_residuals)]
-        h = self.middle_block(h, emb)
+        h = self.middle_block(h, emb, context)
         if mid_block_additional_residual is not None:
             h = h + mid_block_additional_residual
         for blk in self.up_blocks:
-            h = blk(h, skips, emb)
+            h = blk(h, skips, emb, context)
         return self.out(h)
 
 
@@ -484,7 +586,9 @@ def randomize_parameters(model: nn.Module, seed: int = 1234) -> nn.Module:
             m.weight.copy_(torch.randn(m.weight.shape, generator=g) / math.sqrt(fan_in))
             if m.bias is not None:
                 m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.02)
-        elif isinstance(m, nn.GroupNorm):
+        elif isinstance(m, (nn.GroupNorm, nn.LayerNorm)):
             m.weight.copy_(1.0 + 0.1 * torch.randn(m.weight.shape, generator=g))
             m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+        elif isinstance(m, nn.Embedding):
+            m.weight.copy_(torch.randn(m.weight.shape, generator=g))
     return model

@@ -432,6 +432,75 @@ def test_attention_tcgen05_peaked_softmax():
     assert e <= 1e-2, e
 
 
+def _xatt_ref(qm, kv, H, d):
+    B, Lq, _ = qm.shape
+    Lk = kv.shape[1]
+    qq = qm.double().view(B, Lq, H, d).permute(0, 2, 1, 3)
+    kk, vv = (kv.double()[..., i * H * d:(i + 1) * H * d].reshape(B, Lk, H, d).permute(0, 2, 1, 3) for i in range(2))
+    att = torch.softmax(qq @ kk.transpose(-1, -2) * d ** -0.5, dim=-1)
+    return (att @ vv).permute(0, 2, 1, 3).reshape(B, Lq, H * d)
+
+
+# B, H, Lq, Lk, d: context of one token, a ragged single tile, several 64-key tiles (d = 64 two-CTA kernel), head dims
+# 128 / 256, more keys than queries
+XATT_CASES = [(2, 2, 300, 1, 64), (2, 2, 384, 7, 64), (1, 4, 130, 77, 64), (2, 2, 200, 333, 64), (1, 2, 257, 50, 128),
+              (1, 2, 300, 400, 128), (1, 1, 190, 100, 256), (2, 2, 5, 9, 64)]
+
+
+@pytest.mark.parametrize("case", XATT_CASES, ids=lambda c: f"B{c[0]}H{c[1]}Lq{c[2]}Lk{c[3]}d{c[4]}")
+def test_cross_attention_tcgen05_bf16(case):
+    from b200ldm import ops
+    B, H, Lq, Lk, d = case
+    qm, kv = q(rnd((B, Lq, H * d), 24), torch.bfloat16), q(rnd((B, Lk, 2 * H * d), 25), torch.bfloat16)
+    o = ops.cross_attention(qm.to(DEV).bfloat16(), kv.to(DEV).bfloat16(), H, d, d ** -0.5, engine=ops.ENGINE_TCGEN05)
+    e = relerr(o.float(), _xatt_ref(qm, kv, H, d))
+    assert e <= 1e-2, e
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("case", [(2, 2, 70, 7, 32), (1, 2, 130, 45, 64), (1, 1, 33, 200, 128)],
+                         ids=lambda c: f"B{c[0]}H{c[1]}Lq{c[2]}Lk{c[3]}d{c[4]}")
+def test_cross_attention_simt(case, dtype):
+    from b200ldm import ops
+    B, H, Lq, Lk, d = case
+    qm, kv = q(rnd((B, Lq, H * d), 26), dtype), q(rnd((B, Lk, 2 * H * d), 27), dtype)
+    o = ops.cross_attention(qm.to(DEV).to(dtype), kv.to(DEV).to(dtype), H, d, d ** -0.5, engine=ops.ENGINE_SIMT)
+    e = relerr(o.float(), _xatt_ref(qm, kv, H, d))
+    assert e <= (2e-5 if dtype == torch.float32 else 6e-3), e
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("shape", [(5, 64), (1000, 128), (777, 320), (64, 1024), (9, 2048), (3, 4096)],
+                         ids=lambda s: f"M{s[0]}C{s[1]}")
+def test_layernorm(shape, dtype):
+    from b200ldm import ops
+    M, Cc = shape
+    x = q(rnd((M, Cc), 28) * 3.0 + 1.5, dtype)
+    g, b = 1.0 + 0.1 * rnd((Cc,), 29), 0.1 * rnd((Cc,), 30)
+    y = ops.layernorm(x.to(DEV).to(dtype), g.to(DEV), b.to(DEV), 1e-5)
+    ref = F.layer_norm(x.double(), (Cc,), g.double(), b.double(), 1e-5)
+    e = relerr(y.float(), ref)
+    assert e <= (2e-6 if dtype == torch.float32 else 5e-3), e
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_geglu(dtype):
+    from b200ldm import ops
+    h = q(rnd((333, 2 * 512), 31) * 2.0, dtype)
+    y = ops.geglu(h.to(DEV).to(dtype))
+    ref = h[:, :512].double() * F.gelu(h[:, 512:].double())
+    e = relerr(y.float(), ref)
+    assert e <= (2e-6 if dtype == torch.float32 else 5e-3), e
+
+
+def test_embedding_add():
+    from b200ldm import ops
+    a, table = rnd((3, 256), 32), rnd((5, 256), 33)
+    idx = torch.tensor([4, 0, 2])
+    got = ops.embedding_add(a.to(DEV), table.to(DEV), idx.to(DEV))
+    assert torch.equal(got.cpu(), a + table[idx])
+
+
 # ------------------------------------------------------------------------------------------
 # element-wise family
 # ------------------------------------------------------------------------------------------

@@ -90,6 +90,7 @@ def test_define_instance_on_reference_style_config(cfg):
 def test_state_dict_keys_and_shapes_match_oracle():
     import b200ldm
     for ours, ref in ((b200ldm.DiffusionModelUNet(**gc.UNET_KW), oracle.DiffusionModelUNet(**gc.UNET_KW)),
+                      (b200ldm.DiffusionModelUNet(**gc.XATTN_UNET_KW), oracle.DiffusionModelUNet(**gc.XATTN_UNET_KW)),
                       (b200ldm.AutoencoderKL(**gc.AE_KW), oracle.AutoencoderKL(**gc.AE_KW))):
         a, b = ours.state_dict(), ref.state_dict()
         assert list(a.keys()) == list(b.keys())
@@ -108,6 +109,13 @@ def test_constructor_errors_match_reference_surface():
     u = b200ldm.DiffusionModelUNet(**gc.UNET_KW)
     with pytest.raises(ValueError):
         u(torch.zeros((1, 8) + gc.LATENT), torch.tensor([1.0]), context=torch.zeros(1, 1, 4))
+    with pytest.raises(ValueError):   # with_conditioning without a context width / a width without with_conditioning
+        b200ldm.DiffusionModelUNet(**{**gc.XATTN_UNET_KW, "cross_attention_dim": None})
+    with pytest.raises(ValueError):
+        b200ldm.DiffusionModelUNet(**{**gc.UNET_KW, "cross_attention_dim": 8})
+    xu = b200ldm.DiffusionModelUNet(**gc.XATTN_UNET_KW)
+    with pytest.raises(ValueError):   # class embeddings configured, labels missing
+        xu(torch.zeros((1, 4) + gc.LATENT), torch.tensor([1.0]), context=torch.zeros(1, 2, 24))
 
 
 @pytest.mark.parametrize("pred", ["epsilon", "sample", "v_prediction"])

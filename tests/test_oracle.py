@@ -144,3 +144,42 @@ def test_inferer_concat_requires_conditioning():
         inf.sample(torch.zeros((1, 4) + gc.LATENT), gc.tiny_ae(), gc.tiny_unet(), s, mode="concat")
     with pytest.raises(NotImplementedError):
         inf.sample(torch.zeros((1, 4) + gc.LATENT), gc.tiny_ae(), gc.tiny_unet(), s, mode="nope")
+
+
+XGOLD = os.path.join(os.path.dirname(__file__), "golden", "xattn_cases.pt")
+
+
+def test_cross_attention_golden_and_context_sensitivity():
+    """with_conditioning=True (SpatialTransformer + class embedding): the oracle equals its committed
+    fixture, the context and the class label both move the prediction, and a context the attention cannot tell apart
+    (every token identical) gives the same result for any context length (softmax over equal keys = the value)."""
+    gold = torch.load(XGOLD, weights_only=True)
+    with torch.no_grad():
+        unet, x, ts, ctx, labels = gc.tiny_xattn_case()
+        eps = unet(x, ts, context=ctx, class_labels=labels)
+        assert torch.allclose(eps, gold["xattn_unet_eps"], atol=2e-5, rtol=1e-4)
+        assert (unet(x, ts, context=ctx.flip(0), class_labels=labels) - eps).abs().max() > 1e-3
+        assert (unet(x, ts, context=ctx, class_labels=labels.flip(0)) - eps).abs().max() > 1e-3
+        one = ctx[:, :1]
+        a = unet(x, ts, context=one, class_labels=labels)
+        b = unet(x, ts, context=one.expand(-1, 5, -1).contiguous(), class_labels=labels)
+        assert torch.allclose(a, b, atol=1e-5, rtol=1e-5)
+        _, img, lat = gc.tiny_xattn_sampling_case("ddpm")
+        assert torch.allclose(lat, gold["xattn_sample_latent"], atol=2e-4, rtol=1e-3)
+        assert torch.allclose(img, gold["xattn_sample_image"], atol=2e-3, rtol=1e-3)
+
+
+def test_cross_attention_constructor_surface():
+    with pytest.raises(ValueError):
+        oracle.DiffusionModelUNet(**{**gc.XATTN_UNET_KW, "cross_attention_dim": None})
+    with pytest.raises(ValueError):
+        oracle.DiffusionModelUNet(**{**gc.UNET_KW, "cross_attention_dim": 8})
+    u = gc.tiny_xattn_unet()
+    with pytest.raises(ValueError):  # num_class_embeds set, labels missing
+        u(torch.zeros((1, 4) + gc.LATENT), torch.tensor([1.0]), context=torch.zeros(1, 2, 24))
+    keys = [k for k in u.state_dict() if k.startswith("middle_block.attention.")]
+    assert "middle_block.attention.transformer_blocks.1.attn2.to_k.weight" in keys
+    assert "middle_block.attention.transformer_blocks.0.attn1.to_q.bias" not in keys       # qkv_bias=False
+    assert u.state_dict()["middle_block.attention.transformer_blocks.0.attn2.to_k.weight"].shape == (128, 24)
+    assert u.state_dict()["middle_block.attention.transformer_blocks.0.ff.linear1.weight"].shape == (1024, 128)
+    assert u.state_dict()["class_embedding.weight"].shape == (5, 256)
