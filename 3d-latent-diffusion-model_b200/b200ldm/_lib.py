@@ -37,7 +37,7 @@ class SchedParams(C.Structure):
         ("x_model", C.c_void_p), ("coef", C.c_void_p), ("counter", C.c_void_p),
         ("n_vox", C.c_int64), ("noise_step_stride", C.c_int64),
         ("C", C.c_int32), ("C_eps", C.c_int32), ("C_model", C.c_int32), ("dtype", C.c_int32),
-        ("seed", C.c_uint64), ("seed_dev", C.c_void_p),
+        ("seed", C.c_uint64), ("seed_dev", C.c_void_p), ("var_pred", C.c_void_p), ("var_coef", C.c_void_p),
     ]
 
 

@@ -60,6 +60,14 @@ class SamplingLoop:
         self.temb_table = unet.time_embedding_table(ts)                            # [n_steps, total]
         self.temb_cur = torch.empty((1, self.temb_table.shape[1]), dtype=torch.float32, device=dev)
         self.coef = scheduler.coef_table(dev).clone()
+        # learned variance (DDPMScheduler variance_type "learned" / "learned_range"): the UNet predicts 2 * c_lat channels
+        # and the second half scales each element's noise; that update runs in the standalone scheduler kernel
+        self.var_coef = None
+        if unet.out_channels == 2 * self.c_lat and getattr(scheduler, "learned_variance", False):
+            self.var_coef = scheduler.var_coef_table(dev).clone()
+        elif unet.out_channels != self.c_lat:
+            raise ValueError(f"UNet predicts {unet.out_channels} channels for a {self.c_lat}-channel latent "
+                             "(twice the channels needs a learned variance_type)")
         self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.noise, self.noise_stride = None, 0
@@ -82,6 +90,8 @@ class SamplingLoop:
             ops.to_ndhwc(input_noise, self.c_lat, torch.float32, out=self.x_t)
             ops.to_ndhwc(input_noise, _pad64(self.c_in), self.dtype, out=self.x_model)
             self.coef.copy_(scheduler.coef_table(self.coef.device))
+            if self.var_coef is not None:
+                self.var_coef.copy_(scheduler.var_coef_table(self.coef.device))
         if self.mode == "concat":
             ops.to_ndhwc(conditioning, _pad64(self.c_in), self.dtype, out=self.x_model, c_offset=self.c_lat)
         elif self.ctx is not None and not _fresh:
@@ -96,7 +106,7 @@ class SamplingLoop:
 
     def _body(self):
         ops.select_row(self.temb_table, self.counter, self.temb_cur)
-        if FUSE_SCHED and self.unet.out[2].conv.tap_expanded(self.x_model):
+        if FUSE_SCHED and self.var_coef is None and self.unet.out[2].conv.tap_expanded(self.x_model):
             # the scheduler update runs inside the UNet's last kernel (the output conv's tap gather) on the fp32 sums
             if self._sched is None:
                 self._sched = ops.make_sched_params(self.x_t, self.coef, self.counter, self.c_lat, self.dtype,
@@ -106,7 +116,8 @@ class SamplingLoop:
         else:
             eps = self.unet.forward_ndhwc(self.x_model, self.temb_cur, 0, ctx=self.ctx)
             ops.scheduler_step(eps, self.x_t, self.coef, self.counter, self.c_lat, noise=self.noise,
-                               noise_step_stride=self.noise_stride, x_model=self.x_model, seed=self.seed_dev)
+                               noise_step_stride=self.noise_stride, x_model=self.x_model, seed=self.seed_dev,
+                               var_offset=self.c_lat if self.var_coef is not None else 0, var_coef=self.var_coef)
         ops.counter_add(self.counter, 1)
 
     def _capture(self):
@@ -154,7 +165,8 @@ class DiffusionInferer:
         then costs T graph replays and nothing else (capture and its allocator traffic were 0.2-1.1 s per call)."""
         key = (id(unet), param_signature(unet), unet.precision, tuple(input_noise.shape), str(input_noise.device),
                None if conditioning is None else tuple(conditioning.shape), mode,
-               tuple(int(t) for t in scheduler.timesteps), step_noise is not None)
+               tuple(int(t) for t in scheduler.timesteps), step_noise is not None,
+               getattr(scheduler, "variance_type", None))
         loop = self._loops.get(key)
         if loop is None:
             while len(self._loops) >= self.MAX_CACHED_LOOPS:

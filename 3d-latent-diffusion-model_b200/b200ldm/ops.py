@@ -386,10 +386,12 @@ def counter_add(counter, delta: int = 1):
 
 
 def make_sched_params(x_t, coef, counter, c: int, dtype: torch.dtype, eps=None, noise=None, noise_step_stride: int = 0,
-                      x0_out=None, x_model=None, seed=0):
+                      x0_out=None, x_model=None, seed=0, var_offset: int = 0, var_coef=None):
     """b200ldm_sched_params for `scheduler_step` or for the fused update inside `tap_gather`.  The returned struct holds
-    raw pointers: keep the tensors alive (the sampling loop owns them for its whole life)."""
-    _need_cuda(eps, x_t, coef, noise, x_model)
+    raw pointers: keep the tensors alive (the sampling loop owns them for its whole life).
+    var_coef ([n_steps, 2] fp32) + var_offset: learned variance, the predicted variance sits `var_offset` channels
+    into `eps` (the second half of the model output)."""
+    _need_cuda(eps, x_t, coef, noise, x_model, var_coef)
     seed_dev = None
     if torch.is_tensor(seed):
         _need_cuda(seed)
@@ -400,16 +402,19 @@ def make_sched_params(x_t, coef, counter, c: int, dtype: torch.dtype, eps=None, 
         counter=_ptr(counter), n_vox=x_t.numel() // c, noise_step_stride=noise_step_stride, C=c,
         C_eps=c if eps is None else eps.shape[-1], C_model=0 if x_model is None else x_model.shape[-1],
         dtype=dtype_code(dtype), seed=seed, seed_dev=_ptr(seed_dev))
-    p._keep = (eps, x_t, noise, x0_out, x_model, coef, counter, seed_dev)
+    if var_coef is not None:
+        assert eps is not None and 0 < var_offset and var_offset + c <= eps.shape[-1] and var_coef.dtype == torch.float32
+        p.var_pred, p.var_coef = eps.data_ptr() + var_offset * eps.element_size(), var_coef.data_ptr()
+    p._keep = (eps, x_t, noise, x0_out, x_model, coef, counter, seed_dev, var_coef)
     return p
 
 
 def scheduler_step(eps, x_t, coef, counter, c: int, noise=None, noise_step_stride: int = 0, x0_out=None, x_model=None,
-                   seed=0):
+                   seed=0, var_offset: int = 0, var_coef=None):
     """In-place x_t <- step(eps, x_t); eps [.., C_eps] NDHWC, x_t fp32 [.., C] NDHWC.
     seed: int, or a device int64[1] tensor read by the kernel (a captured graph then serves any seed)."""
     p = make_sched_params(x_t, coef, counter, c, eps.dtype, eps=eps, noise=noise, noise_step_stride=noise_step_stride,
-                          x0_out=x0_out, x_model=x_model, seed=seed)
+                          x0_out=x0_out, x_model=x_model, seed=seed, var_offset=var_offset, var_coef=var_coef)
     _lib.check(_lib.load().b200ldm_scheduler_step(C.byref(p), _stream()), "scheduler_step")
 
 

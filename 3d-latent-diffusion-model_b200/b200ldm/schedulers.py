@@ -71,25 +71,45 @@ class Scheduler:
         rows = [self.coef_row(int(t)) for t in self.timesteps]
         return torch.tensor(rows, dtype=torch.float32).to(device).contiguous()
 
+    learned_variance = False   # DDPMScheduler(variance_type="learned" | "learned_range") sets it
+
+    def var_coef_row(self, timestep: int) -> list[float]:
+        raise NotImplementedError
+
+    def var_coef_table(self, device) -> torch.Tensor:
+        """[n_steps, 2] rows {A, B}: per-element noise scale sqrt(A * predicted_variance + B) (include/b200ldm.h)."""
+        rows = [self.var_coef_row(int(t)) for t in self.timesteps]
+        return torch.tensor(rows, dtype=torch.float32).to(device).contiguous()
+
     def _step_kernel(self, model_output, timestep, sample, noise):
         """NCDHW fp32 tensors in, (prev_sample, pred_original_sample) out."""
-        if model_output.shape != sample.shape:
-            raise ValueError("model_output and sample must have the same shape (learned variance is unsupported)")
         dev = sample.device
         N, Cc = sample.shape[:2]
         cpad = ops.round_up(Cc, 4)
-        coef = self._coef_on(dev, int(timestep))
+        split = self.learned_variance and model_output.shape[1] == 2 * Cc \
+            and tuple(model_output.shape[2:]) == tuple(sample.shape[2:])
+        if not split and model_output.shape != sample.shape:
+            raise ValueError("model_output and sample must have the same shape (twice the channels only with a learned "
+                             "variance_type)")
+        coef = self._coef_on(dev, int(timestep), split=split)
         x = ops.to_ndhwc(sample, cpad, torch.float32)
-        e = ops.to_ndhwc(model_output, cpad, torch.float32)
+        var_coef = None
+        if split:   # [eps | predicted variance] side by side, each half padded to cpad channels
+            e = ops.to_ndhwc(model_output[:, :Cc], 2 * cpad, torch.float32)
+            ops.to_ndhwc(model_output[:, Cc:], 2 * cpad, torch.float32, out=e, c_offset=cpad)
+            var_coef = torch.tensor([self.var_coef_row(int(timestep))], dtype=torch.float32).to(dev)
+        else:
+            e = ops.to_ndhwc(model_output, cpad, torch.float32)
         nz = None if noise is None else ops.to_ndhwc(noise, cpad, torch.float32)
         x0 = torch.empty_like(x)
-        ops.scheduler_step(e, x, coef, None, cpad, noise=nz, x0_out=x0, seed=self._seed())
+        ops.scheduler_step(e, x, coef, None, cpad, noise=nz, x0_out=x0, seed=self._seed(), var_offset=cpad if split else 0,
+                           var_coef=var_coef)
         return ops.to_ncdhw(x, Cc), ops.to_ncdhw(x0, Cc)
 
-    def _coef_on(self, dev, timestep: int, eta=None) -> torch.Tensor:
+    def _coef_on(self, dev, timestep: int, eta=None, split: bool = False) -> torch.Tensor:
         """coefficient row of one timestep on the device, cached: a fresh pageable upload per step() would block the
         host until the stream drains"""
-        key = (str(dev), timestep, eta, getattr(self, "eta", None), self.num_inference_steps, self.prediction_type)
+        key = (str(dev), timestep, eta, getattr(self, "eta", None), self.num_inference_steps, self.prediction_type, split)
         cache = self.__dict__.setdefault("_coef_cache", {})
         t = cache.get(key)
         if t is None:
@@ -111,10 +131,11 @@ class DDPMScheduler(Scheduler):
                  clip_sample: bool = True, prediction_type: str = "epsilon", clip_sample_min: float = -1.0,
                  clip_sample_max: float = 1.0, **schedule_args):
         super().__init__(num_train_timesteps, schedule, **schedule_args)
-        if variance_type not in ("fixed_small", "fixed_large"):
-            raise NotImplementedError("learned variance types are not on the reference's hot path (SURVEY.md 8f)")
+        if variance_type not in ("fixed_small", "fixed_large", "learned", "learned_range"):
+            raise ValueError("Argument `variance_type` must be a member of `DDPMVarianceType`")
         if prediction_type not in self._PRED:
             raise ValueError("Argument `prediction_type` must be a member of DDPMPredictionType")
+        self.learned_variance = variance_type in ("learned", "learned_range")
         self.variance_type, self.clip_sample, self.prediction_type = variance_type, clip_sample, prediction_type
         self.clip_sample_values = [clip_sample_min, clip_sample_max]
 
@@ -125,7 +146,21 @@ class DDPMScheduler(Scheduler):
         a_t = self.alphas_cumprod[t]
         a_prev = self.alphas_cumprod[t - 1] if t > 0 else self.one
         var = (1 - a_prev) / (1 - a_t) * self.betas[t]
-        return torch.clamp(var, min=1e-20) if self.variance_type == "fixed_small" else self.betas[t]
+        if self.variance_type == "fixed_small":
+            return torch.clamp(var, min=1e-20)
+        # learned types WITHOUT a predicted variance fall through to the unclamped posterior variance (upstream)
+        return self.betas[t] if self.variance_type == "fixed_large" else var
+
+    def var_coef_row(self, t: int) -> list[float]:
+        """{A, B}: the model's predicted variance v gives the noise scale sqrt(A*v + B).  learned: the prediction IS the
+        variance; learned_range: v in [-1, 1] interpolates var_t .. beta_t, frac = (v + 1) / 2."""
+        if t == 0:
+            return [0.0, 0.0]
+        if self.variance_type == "learned":
+            return [1.0, 0.0]
+        a_t, a_prev = self.alphas_cumprod[t], self.alphas_cumprod[t - 1]
+        lo, hi = (1 - a_prev) / (1 - a_t) * self.betas[t], self.betas[t]
+        return [float((hi - lo) / 2), float((hi + lo) / 2)]
 
     def coef_row(self, t: int) -> list[float]:
         """{a_x, r, c_x0, c_xt, c_e, sigma, clip_lo, clip_hi} (include/b200ldm.h) in fp32 torch arithmetic that mirrors

@@ -195,6 +195,8 @@ __global__ void scheduler_step_kernel(const b200ldm_sched_params p) {
   const int qpv = p.C >> 2;  // 4-channel groups per voxel
   const long long quads = p.n_vox * qpv;
   const T* eps = reinterpret_cast<const T*>(p.eps);
+  const T* vp = reinterpret_cast<const T*>(p.var_pred);
+  const float var_a = vp ? p.var_coef[(size_t)step * 2] : 0.f, var_b = vp ? p.var_coef[(size_t)step * 2 + 1] : 0.f;
   T* xm = reinterpret_cast<T*>(p.x_model);
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < quads;
        q += (long long)gridDim.x * blockDim.x) {
@@ -213,11 +215,16 @@ __global__ void scheduler_step_kernel(const b200ldm_sched_params p) {
         philox_normal4(seed, (uint32_t)step, (uint64_t)q, z);
       }
     }
+    float sg[4] = {sigma, sigma, sigma, sigma};
+    if (vp && sigma != 0.f) {  // learned variance: per-element noise scale from the model's second output half
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sg[j] = sqrtf(fmaf(var_a, to_f32<T>(vp[(size_t)vox * p.C_eps + c + j]), var_b));
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float u = r_e * e[j];
       x0[j] = fminf(fmaxf(a_x != 0.f ? (x[j] + u) * a_x : u, lo), hi);
-      o[j] = c_x0 * x0[j] + c_xt * x[j] + c_eps * e[j] + sigma * z[j];
+      o[j] = c_x0 * x0[j] + c_xt * x[j] + c_eps * e[j] + sg[j] * z[j];
     }
     *reinterpret_cast<float4*>(p.x_t + xi) = make_float4(o[0], o[1], o[2], o[3]);
     if (p.x0_out) *reinterpret_cast<float4*>(p.x0_out + xi) = make_float4(x0[0], x0[1], x0[2], x0[3]);
@@ -469,6 +476,8 @@ int b200ldm_upsample_nearest2x(const void* x, void* y, int32_t N, int32_t D, int
 int b200ldm_tap_gather(const void* z, const float* bias, void* y, int32_t N, int32_t D, int32_t H, int32_t W, int32_t ldz,
                        int32_t cp, int32_t cy, int32_t dtype, const b200ldm_sched_params* sched, b200ldm_stream stream) {
   B2_REQUIRE(z && (y || sched) && N > 0 && D > 0 && H > 0 && W > 0, B200LDM_BAD_ARG, "tap_gather: bad arguments");
+  B2_REQUIRE(!sched || (!sched->var_pred && !sched->var_coef), B200LDM_BAD_ARG,
+             "tap_gather: the fused scheduler update does not take a learned variance (use b200ldm_scheduler_step)");
   B2_REQUIRE((cp == 1 || cp == 2 || cp == 4 || cp == 8 || cp == 16) && cy >= cp && cy % 8 == 0 && ldz >= 27 * cp &&
                  ldz % 8 == 0,
              B200LDM_BAD_SHAPE, "tap_gather: channels per tap must be 1/2/4/8/16, cy a multiple of 8 >= cp, ldz >= 27*cp");
@@ -548,6 +557,8 @@ int b200ldm_scheduler_step(const b200ldm_sched_params* p, b200ldm_stream stream)
   B2_REQUIRE(p->n_vox > 0 && p->C > 0 && p->C % 4 == 0 && p->C_eps >= p->C, B200LDM_BAD_SHAPE,
              "scheduler_step: C must be a positive multiple of 4 and <= C_eps");
   B2_REQUIRE(!p->x_model || p->C_model >= p->C, B200LDM_BAD_SHAPE, "scheduler_step: C_model < C");
+  B2_REQUIRE((p->var_pred == nullptr) == (p->var_coef == nullptr), B200LDM_BAD_ARG,
+             "scheduler_step: var_pred and var_coef go together (learned variance)");
   B2_REQUIRE(aligned16(p->x_t) && aligned16(p->noise) && aligned16(p->x0_out) && p->noise_step_stride % 4 == 0,
              B200LDM_BAD_ALIGN, "scheduler_step: fp32 buffers must be 16-byte aligned");
   const long long quads = p->n_vox * (p->C / 4);

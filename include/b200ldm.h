@@ -255,6 +255,13 @@ typedef struct b200ldm_sched_params_s {
   uint64_t seed;
   const uint64_t* seed_dev; /* optional device-side seed; when non-NULL it replaces `seed`, so one captured CUDA
                                graph of the denoising step can be replayed for a new batch with a new seed */
+  /* learned variance (DDPMScheduler variance_type "learned" / "learned_range"): var_pred points
+   * at the predicted-variance half of the model output (`dtype`, row stride C_eps like `eps`), var_coef at a device
+   * table [n_steps][2] fp32 rows {A, B}; the noise scale of element i becomes sqrt(A * var_pred[i] + B) (learned:
+   * A = 1, B = 0; learned_range: A = (beta_t - var_t) / 2, B = (beta_t + var_t) / 2) and the row's `sigma` only says
+   * whether noise is drawn at all (0 at t = 0).  Both NULL: fixed variance.  Not available fused into tap_gather. */
+  const void* var_pred;
+  const float* var_coef;
 } b200ldm_sched_params;
 int b200ldm_scheduler_step(const b200ldm_sched_params* p, b200ldm_stream stream);
 /* standalone Philox normal stream identical to the one scheduler_step draws (parity tests) */

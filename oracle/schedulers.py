@@ -44,8 +44,8 @@ class DDPMScheduler(Scheduler):
                  clip_sample=True, prediction_type="epsilon", clip_sample_min=-1.0, clip_sample_max=1.0,
                  **schedule_args):
         super().__init__(num_train_timesteps, schedule, **schedule_args)
-        if variance_type not in ("fixed_small", "fixed_large"):
-            raise ValueError("oracle restates fixed_small/fixed_large only (reference default fixed_small)")
+        if variance_type not in ("fixed_small", "fixed_large", "learned", "learned_range"):
+            raise ValueError("Argument `variance_type` must be a member of `DDPMVarianceType`")
         if prediction_type not in ("epsilon", "sample", "v_prediction"):
             raise ValueError("Argument `prediction_type` must be a member of DDPMPredictionType")
         self.variance_type, self.clip_sample, self.prediction_type = variance_type, clip_sample, prediction_type
@@ -59,20 +59,31 @@ class DDPMScheduler(Scheduler):
         ts = (np.arange(0, num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64)
         self.timesteps = torch.from_numpy(ts).to(device)
 
-    def _get_variance(self, t):
+    def _get_variance(self, t, predicted_variance=None):
+        """MONAI DDPMScheduler._get_variance [MONAI-recall]: the learned types use the second half of the model
+        output; without one they fall through to the unclamped posterior variance."""
         a_t = self.alphas_cumprod[t]
         a_prev = self.alphas_cumprod[t - 1] if t > 0 else self.one
         var = (1 - a_prev) / (1 - a_t) * self.betas[t]
         if self.variance_type == "fixed_small":
             var = torch.clamp(var, min=1e-20)
-        else:
+        elif self.variance_type == "fixed_large":
             var = self.betas[t]
+        elif self.variance_type == "learned" and predicted_variance is not None:
+            return predicted_variance
+        elif self.variance_type == "learned_range" and predicted_variance is not None:
+            min_log, max_log = var, self.betas[t]
+            frac = (predicted_variance + 1) / 2
+            var = frac * max_log + (1 - frac) * min_log
         return var
 
     def step(self, model_output, timestep, sample, generator=None, noise=None):
         """`noise` (extension for parity tests): if given it replaces the
         internally drawn randn so both sides consume identical per-step noise."""
         t = int(timestep)
+        predicted_variance = None
+        if model_output.shape[1] == sample.shape[1] * 2 and self.variance_type in ("learned", "learned_range"):
+            model_output, predicted_variance = torch.split(model_output, sample.shape[1], dim=1)
         a_t = self.alphas_cumprod[t]
         a_prev = self.alphas_cumprod[t - 1] if t > 0 else self.one  # t-1 even after set_timesteps(n<T)
         b_t, b_prev = 1 - a_t, 1 - a_prev
@@ -91,7 +102,7 @@ class DDPMScheduler(Scheduler):
             if noise is None:
                 noise = torch.randn(model_output.size(), dtype=model_output.dtype, layout=model_output.layout,
                                     generator=generator, device=model_output.device)
-            prev = prev + (self._get_variance(t) ** 0.5) * noise
+            prev = prev + (self._get_variance(t, predicted_variance) ** 0.5) * noise
         return prev, x0
 
 

@@ -381,3 +381,52 @@ def test_xattn_latent_sampling_vs_golden(precision):
     plain = port(gc.tiny_unet(), b200ldm.DiffusionModelUNet, gc.UNET_KW, precision)
     with pytest.raises(ValueError):   # context handed to a model without cross attention
         inf.sample(x_T.to(DEV), ae, plain, sched, conditioning=ctx.to(DEV), mode="crossattn", verbose=False)
+
+
+# ------------------------------------------------------------------------------------------
+# learned variance (DDPMScheduler variance_type "learned" / "learned_range")
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("vt", ["learned", "learned_range"])
+def test_scheduler_step_learned_variance_vs_oracle(vt):
+    import b200ldm
+    ours, ref = gc.make_scheduler(b200ldm, "ddpm", 10, variance_type=vt), gc.make_scheduler(oracle, "ddpm", 10, variance_type=vt)
+    g = gc.gen(17)
+    x, e, z = (torch.randn((2, 4) + gc.LATENT, generator=g) for _ in range(3))
+    v = torch.rand((2, 4) + gc.LATENT, generator=g) * (1.6 if vt == "learned_range" else 0.02) \
+        - (0.8 if vt == "learned_range" else 0.0)
+    out = torch.cat([e, v], dim=1)
+    for t in (900, 300, 0):
+        got, got0 = ours.step(out.to(DEV), t, x.to(DEV), noise=z.to(DEV))
+        want, want0 = ref.step(out, t, x, noise=z)
+        assert relerr(got, want) <= 2e-6 and relerr(got0, want0) <= 2e-6, (t, relerr(got, want))
+        plain, _ = ours.step(e.to(DEV), t, x.to(DEV), noise=z.to(DEV))     # falls back to the unclamped fixed variance
+        assert relerr(plain, ref.step(e, t, x, noise=z)[0]) <= 2e-6
+    with pytest.raises(ValueError):
+        gc.make_scheduler(b200ldm, "ddpm", 10).step(out.to(DEV), 900, x.to(DEV))   # 2C channels need a learned type
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sampling_with_learned_range_variance(precision):
+    """UNet with 2 x latent channels out + learned_range variance through inferer.sample (graph replay), vs the oracle."""
+    import b200ldm
+    kw = {**gc.UNET_KW, "out_channels": 8}
+    r_unet = oracle.randomize_parameters(oracle.DiffusionModelUNet(**kw), 99).eval()
+    r_ae = gc.tiny_ae()
+    unet = port(r_unet, b200ldm.DiffusionModelUNet, kw, precision)
+    ae = port(r_ae, b200ldm.AutoencoderKL, gc.AE_KW, precision)
+    n = 4
+    sched = gc.make_scheduler(b200ldm, "ddpm", n, variance_type="learned_range")
+    r_sched = gc.make_scheduler(oracle, "ddpm", n, variance_type="learned_range")
+    x_T, cond, step_noise = gc.sampling_inputs(n)
+    img, lat = b200ldm.LatentDiffusionInferer(sched, 1.0).sample(
+        x_T.to(DEV), ae, unet, sched, conditioning=cond.to(DEV), mode="concat", verbose=False,
+        step_noise=step_noise.to(DEV), return_latent=True)
+    want_img, want_lat = oracle.LatentDiffusionInferer(r_sched, 1.0).sample(
+        x_T, r_ae, r_unet, r_sched, conditioning=cond, mode="concat", verbose=False, step_noise=step_noise,
+        return_latent=True)
+    assert relerr(lat, want_lat) <= (2e-4 if precision == "fp32" else 5e-2), relerr(lat, want_lat)
+    assert psnr(img, want_img) >= (80.0 if precision == "fp32" else 40.0)
+    fixed = gc.make_scheduler(b200ldm, "ddpm", n)
+    with pytest.raises(ValueError):   # 2C-channel UNet with a fixed-variance scheduler
+        b200ldm.LatentDiffusionInferer(fixed, 1.0).sample(x_T.to(DEV), ae, unet, fixed, conditioning=cond.to(DEV),
+                                                          mode="concat", verbose=False)

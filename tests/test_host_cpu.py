@@ -32,10 +32,11 @@ def test_cabi_exports_every_declared_symbol(lib_built):
 def test_struct_layout_matches_header(lib_built):
     from b200ldm import _lib
     # the compiled structs are the reference: 8 pointers + 20 int32 + workspace ptr + int64 + chunk_stats ptr +
-    # 3 skip pointers + 2 int32 (conv), 7 pointers + 2 int64 + 4 int32 + uint64 + seed pointer (sched)
+    # 3 skip pointers + 2 int32 (conv), 7 pointers + 2 int64 + 4 int32 + uint64 + seed pointer + 2 learned-variance
+    # pointers (sched)
     lib = _lib.load()
     assert ctypes.sizeof(_lib.ConvParams) == lib.b200ldm_sizeof_params(0) == 8 * 8 + 20 * 4 + 8 + 8 + 8 + 3 * 8 + 2 * 4
-    assert ctypes.sizeof(_lib.SchedParams) == lib.b200ldm_sizeof_params(1) == 7 * 8 + 2 * 8 + 4 * 4 + 8 + 8
+    assert ctypes.sizeof(_lib.SchedParams) == lib.b200ldm_sizeof_params(1) == 7 * 8 + 2 * 8 + 4 * 4 + 8 + 8 + 2 * 8
 
 
 def test_no_cpu_fallback(lib_built):
@@ -138,14 +139,39 @@ def test_coef_table_reproduces_oracle_step(kind, n, pred):
             assert torch.allclose(x0, want0, atol=5e-5, rtol=2e-5)
 
 
+@pytest.mark.parametrize("vt", ["learned", "learned_range"])
+def test_learned_variance_rows_reproduce_oracle_step(vt):
+    """variance_type learned / learned_range: the per-element noise scale sqrt(A*v + B) of our
+    host-side rows == the oracle's step on a model output with twice the channels; without a predicted variance both
+    fall through to the unclamped posterior variance."""
+    import b200ldm
+    ours, ref = gc.make_scheduler(b200ldm, "ddpm", 10, variance_type=vt), gc.make_scheduler(oracle, "ddpm", 10, variance_type=vt)
+    assert ours.learned_variance
+    g = torch.Generator().manual_seed(5)
+    x, e, z = (torch.randn(1, 4, 3, 3, 3, generator=g) for _ in range(3))
+    v = torch.rand(1, 4, 3, 3, 3, generator=g) * (1.6 if vt == "learned_range" else 0.02) - (0.8 if vt == "learned_range" else 0.0)
+    for t in (900, 400, 0):
+        a_x, r, c0, ct, ce, sg, lo, hi = ours.coef_row(t)
+        A, B = ours.var_coef_row(t)
+        x0 = ((x + r * e) * a_x).clamp(lo, hi)
+        want, want0 = ref.step(torch.cat([e, v], dim=1), t, x, noise=z)
+        mine = c0 * x0 + ct * x + (0.0 if sg == 0 else (A * v + B) ** 0.5) * z
+        assert torch.allclose(mine, want, atol=5e-5, rtol=2e-5) and torch.allclose(x0, want0, atol=5e-5, rtol=2e-5)
+        want_plain, _ = ref.step(e, t, x, noise=z)       # no predicted variance: unclamped fixed-small value
+        assert torch.allclose(c0 * x0 + ct * x + sg * z, want_plain, atol=5e-5, rtol=2e-5)
+    with pytest.raises(ValueError):
+        b200ldm.DDPMScheduler(variance_type="nope")
+
+
 def test_scheduler_constructor_errors():
     import b200ldm
     with pytest.raises(ValueError):
         b200ldm.DDPMScheduler(prediction_type="nonsense")
     with pytest.raises(ValueError):
         b200ldm.DDIMScheduler(prediction_type="nonsense")
-    with pytest.raises(NotImplementedError):
-        b200ldm.DDPMScheduler(variance_type="learned_range")   # needs a 2C-channel UNet head: not in any reference config
+    assert b200ldm.DDPMScheduler(variance_type="learned_range").learned_variance
+    with pytest.raises(ValueError):
+        b200ldm.DDPMScheduler(variance_type="learned_rnage")
 
 
 def test_serving_batch_plan_and_surface():
