@@ -38,6 +38,7 @@ class SchedParams(C.Structure):
         ("n_vox", C.c_int64), ("noise_step_stride", C.c_int64),
         ("C", C.c_int32), ("C_eps", C.c_int32), ("C_model", C.c_int32), ("dtype", C.c_int32),
         ("seed", C.c_uint64), ("seed_dev", C.c_void_p), ("var_pred", C.c_void_p), ("var_coef", C.c_void_p),
+        ("philox_offset", C.c_int64),
     ]
 
 

@@ -386,7 +386,7 @@ def counter_add(counter, delta: int = 1):
 
 
 def make_sched_params(x_t, coef, counter, c: int, dtype: torch.dtype, eps=None, noise=None, noise_step_stride: int = 0,
-                      x0_out=None, x_model=None, seed=0, var_offset: int = 0, var_coef=None):
+                      x0_out=None, x_model=None, seed=0, var_offset: int = 0, var_coef=None, philox_offset: int = 0):
     """b200ldm_sched_params for `scheduler_step` or for the fused update inside `tap_gather`.  The returned struct holds
     raw pointers: keep the tensors alive (the sampling loop owns them for its whole life).
     var_coef ([n_steps, 2] fp32) + var_offset: learned variance, the predicted variance sits `var_offset` channels
@@ -401,7 +401,7 @@ def make_sched_params(x_t, coef, counter, c: int, dtype: torch.dtype, eps=None, 
         eps=_ptr(eps), x_t=_ptr(x_t), noise=_ptr(noise), x0_out=_ptr(x0_out), x_model=_ptr(x_model), coef=_ptr(coef),
         counter=_ptr(counter), n_vox=x_t.numel() // c, noise_step_stride=noise_step_stride, C=c,
         C_eps=c if eps is None else eps.shape[-1], C_model=0 if x_model is None else x_model.shape[-1],
-        dtype=dtype_code(dtype), seed=seed, seed_dev=_ptr(seed_dev))
+        dtype=dtype_code(dtype), seed=seed, seed_dev=_ptr(seed_dev), philox_offset=philox_offset)
     if var_coef is not None:
         assert eps is not None and 0 < var_offset and var_offset + c <= eps.shape[-1] and var_coef.dtype == torch.float32
         p.var_pred, p.var_coef = eps.data_ptr() + var_offset * eps.element_size(), var_coef.data_ptr()
@@ -410,11 +410,12 @@ def make_sched_params(x_t, coef, counter, c: int, dtype: torch.dtype, eps=None, 
 
 
 def scheduler_step(eps, x_t, coef, counter, c: int, noise=None, noise_step_stride: int = 0, x0_out=None, x_model=None,
-                   seed=0, var_offset: int = 0, var_coef=None):
+                   seed=0, var_offset: int = 0, var_coef=None, philox_offset: int = 0):
     """In-place x_t <- step(eps, x_t); eps [.., C_eps] NDHWC, x_t fp32 [.., C] NDHWC.
     seed: int, or a device int64[1] tensor read by the kernel (a captured graph then serves any seed)."""
     p = make_sched_params(x_t, coef, counter, c, eps.dtype, eps=eps, noise=noise, noise_step_stride=noise_step_stride,
-                          x0_out=x0_out, x_model=x_model, seed=seed, var_offset=var_offset, var_coef=var_coef)
+                          x0_out=x0_out, x_model=x_model, seed=seed, var_offset=var_offset, var_coef=var_coef,
+                          philox_offset=philox_offset)
     _lib.check(_lib.load().b200ldm_scheduler_step(C.byref(p), _stream()), "scheduler_step")
 
 

@@ -93,8 +93,13 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   const uint32_t v_empty = v_full + 8 * STAGES;      // [STAGES]
   const uint32_t s_full = v_empty + 8 * STAGES;      // [2]
   const uint32_t s_empty = s_full + 16;              // [2]
-  const uint32_t p_full = s_empty + 16;
-  const uint32_t pv_done = p_full + 8;               // [2]: PV of even / odd tiles (one per P buffer)
+  // p_full is per P buffer (tile parity), like pv_done: with ONE barrier for both buffers the softmax warps could
+  // complete the phases of tiles j and j+1 (j+1 only needs S_{j+1} and PV_{j-1}) while the MMA thread still waited
+  // for a late V_j; the thread then found the barrier two phases on, waited for the parity of tile j+2 - whose P
+  // needs PV_j - and the CTA deadlocked (seen as a 2 s mbarrier timeout under concurrent streams, and most likely the
+  // one unexplained launch failure of DESIGN.md section 6: V_0 is the third load of a CTA and can trail K_0 / K_1).
+  const uint32_t p_full = s_empty + 16;              // [2]
+  const uint32_t pv_done = p_full + 16;              // [2]: PV of even / odd tiles (one per P buffer)
   const uint32_t tmem_slot = pv_done + 16;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
@@ -114,6 +119,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
     }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(s_full + 8 * s, 1); ptx::mbar_init(s_empty + 8 * s, 128); }
     ptx::mbar_init(p_full, 128);
+    ptx::mbar_init(p_full + 8, 128);
     ptx::mbar_init(pv_done, 1);
     ptx::mbar_init(pv_done + 8, 1);
     ptx::fence_barrier_init();
@@ -180,7 +186,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         if (j + 1 < ntiles) issue_s(j + 1);
         const int s = j % STAGES;
         ptx::mbar_wait(v_full + 8 * s, (uint32_t)(j / STAGES) & 1u, 16);
-        ptx::mbar_wait(p_full, (uint32_t)j & 1u, 14);
+        ptx::mbar_wait(p_full + 8 * (j & 1), (uint32_t)(j >> 1) & 1u, 14);
         ptx::tc_fence_after();
         const uint32_t vs = v_smem + s * Cfg::kKVBytes;
         const uint32_t tO = tmem + Cfg::kOCol;
@@ -302,7 +308,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       l_sum += psum;
       ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the UMMA (async proxy)
       ptx::tc_fence_before();     // orders the TMEM rescale stores before the MMA warp's next PV
-      ptx::mbar_arrive(p_full);
+      ptx::mbar_arrive(p_full + 8 * (j & 1));
       if (tr) { t1 = clock64(); tc[5] += t1 - t0; }
     }
     if (tr) {

@@ -212,7 +212,7 @@ __global__ void scheduler_step_kernel(const b200ldm_sched_params p) {
         const float4 nz = *reinterpret_cast<const float4*>(p.noise + (size_t)step * p.noise_step_stride + xi);
         z[0] = nz.x; z[1] = nz.y; z[2] = nz.z; z[3] = nz.w;
       } else {
-        philox_normal4(seed, (uint32_t)step, (uint64_t)q, z);
+        philox_normal4(seed, (uint32_t)step, (uint64_t)(q + p.philox_offset), z);
       }
     }
     float sg[4] = {sigma, sigma, sigma, sigma};
@@ -311,7 +311,7 @@ __global__ void tap_gather_kernel(const T* __restrict__ z, const float* __restri
               const float4 nz = *reinterpret_cast<const float4*>(sp.noise + (size_t)step * sp.noise_step_stride + xi);
               zz[0] = nz.x; zz[1] = nz.y; zz[2] = nz.z; zz[3] = nz.w;
             } else {
-              philox_normal4(seed, (uint32_t)step, (uint64_t)(v * qpv + qi), zz);
+              philox_normal4(seed, (uint32_t)step, (uint64_t)(v * qpv + qi + sp.philox_offset), zz);
             }
           }
 #pragma unroll

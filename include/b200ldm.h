@@ -262,6 +262,8 @@ typedef struct b200ldm_sched_params_s {
    * whether noise is drawn at all (0 at t = 0).  Both NULL: fixed variance.  Not available fused into tap_gather. */
   const void* var_pred;
   const float* var_coef;
+  int64_t philox_offset;    /* added to the element-group index that keys the Philox stream: a batch processed as
+                               several sub-batch launches draws the same noise as one launch over the whole batch */
 } b200ldm_sched_params;
 int b200ldm_scheduler_step(const b200ldm_sched_params* p, b200ldm_stream stream);
 /* standalone Philox normal stream identical to the one scheduler_step draws (parity tests) */

@@ -33,10 +33,10 @@ def test_struct_layout_matches_header(lib_built):
     from b200ldm import _lib
     # the compiled structs are the reference: 8 pointers + 20 int32 + workspace ptr + int64 + chunk_stats ptr +
     # 3 skip pointers + 2 int32 (conv), 7 pointers + 2 int64 + 4 int32 + uint64 + seed pointer + 2 learned-variance
-    # pointers (sched)
+    # pointers + int64 Philox offset (sched)
     lib = _lib.load()
     assert ctypes.sizeof(_lib.ConvParams) == lib.b200ldm_sizeof_params(0) == 8 * 8 + 20 * 4 + 8 + 8 + 8 + 3 * 8 + 2 * 4
-    assert ctypes.sizeof(_lib.SchedParams) == lib.b200ldm_sizeof_params(1) == 7 * 8 + 2 * 8 + 4 * 4 + 8 + 8 + 2 * 8
+    assert ctypes.sizeof(_lib.SchedParams) == lib.b200ldm_sizeof_params(1) == 7 * 8 + 2 * 8 + 4 * 4 + 8 + 8 + 2 * 8 + 8
 
 
 def test_no_cpu_fallback(lib_built):
