@@ -606,10 +606,19 @@ static const int g_force_cl = [] {
 }();
 
 // B200LDM_CONV_KERNEL pins the kernel wherever it supports the problem: 0 = one CTA per tile (conv3d_tc_kernel),
-// 1 = persistent CTA pairs (conv_tc2.cu), 2 = persistent single CTAs (conv_tcp.cu); unset: measured / cost model
+// 1 = persistent CTA pairs (conv_tc2.cu), 2 = persistent single CTAs (conv_tcp.cu), 3 = persistent W-halo kernel
+// (conv_halo.cu); unset: measured / cost model
 static int g_tc2 = [] {
   const char* e = getenv("B200LDM_CONV_KERNEL");
   return e ? atoi(e) : -1;
+}();
+// B200LDM_CONV_HALO=1 adds the W-halo kernel (conv_halo.cu, kernel 3) to the measured candidates.  Off by default: it
+// moves 2.4x fewer bytes into the SM but is 12 % SLOWER on the 64-channel convs it was written for (1.385 vs 1.232 ms
+// at 8x80^3) - those are bound by the tensor core re-reading the 128 x 16 A tile from shared memory for every MMA,
+// not by L2 ingest; it won by 2 % on one shape (256 -> 128 at 40^3).
+static const int g_halo = [] {
+  const char* e = getenv("B200LDM_CONV_HALO");
+  return e ? atoi(e) : 0;
 }();
 void set_conv_kernel(int k) { g_tc2 = k; }   // tests: exercise every kernel in one process (b200ldm_debug_set_conv_kernel)
 
@@ -620,8 +629,10 @@ static const int g_force_splits = [] {
 
 struct ConvPlan {
   int bn, n_tiles, tn, td, th, tw, nb_n, nb_d, nb_h, nb_w, m_tiles, mt, cl, splits;
-  int tc2;     // kernel: 0 one CTA per tile, 1 persistent CTA pairs (conv_tc2.cu), 2 persistent single CTAs (conv_tcp.cu)
+  int tc2;     // kernel: 0 one CTA per tile, 1 persistent CTA pairs (conv_tc2.cu), 2 persistent single CTAs (conv_tcp.cu),
+               // 3 persistent W-halo kernel (conv_halo.cu)
   int tc2_ok;  // the problem is eligible for the persistent kernels
+  int halo_ok; // ... and for the W-halo kernel
   int split_ok, ctas1, iters;   // split-K allowed; CTAs of the one-CTA-per-tile kernel at splits = 1 (mt = 1); k-iterations
 };
 
@@ -757,6 +768,16 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
       if (it != g_choice.end()) choice = it->second;
     }
     pl.tc2 = tma_epi ? (choice & 15) : 0;
+    // kernel 3 (conv_halo.cu): its own tile geometry - one sample, 16 lines of 8 voxels
+    pl.halo_ok = (tma_epi && pl.bn <= 128 && p->ksize == 3 && p->stride == 1 && p->pad_lo == 1 && !p->upsample2x &&
+                  p->Wo >= 4) ? 1 : 0;
+    if (pl.tc2 == 3 && !pl.halo_ok) pl.tc2 = 0;
+    if (pl.tc2 == 3) {
+      pl.tn = 1; pl.tw = 8;
+      choose_halo_tile(p->Do, p->Ho, &pl.td, &pl.th);
+      pl.nb_n = p->N; pl.nb_d = ceil_div(p->Do, pl.td); pl.nb_h = ceil_div(p->Ho, pl.th); pl.nb_w = ceil_div(p->Wo, pl.tw);
+      pl.m_tiles = pl.nb_n * pl.nb_d * pl.nb_h * pl.nb_w;
+    }
     if (pl.tc2) { pl.mt = 1; pl.cl = 1; pl.splits = 1; }
     else {
       const int sp = (choice >> 4) & 255, mt = (choice >> 12) & 15, cl = choice >> 16;
@@ -843,6 +864,7 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
       int choices[24], nc = 0;
       choices[nc++] = 0;
       if (pl.tc2_ok) choices[nc++] = 2;
+      if (pl.halo_ok && g_halo) choices[nc++] = 3;
       if (pl.tc2_ok && getenv("B200LDM_CONV_TUNE_PAIRS")) choices[nc++] = 1;   // CTA pairs: measured slower almost everywhere
       // (2-CTA weight-multicast variants were candidates for big launches for a while: they never won by the 2 %
       // margin, and the one intermittent launch failure of the round happened with them in the set - left out)
@@ -941,13 +963,14 @@ static int conv3d_run_plan(const b200ldm_conv3d_params* p, const ConvPlan& pl, c
   int rc;
   if (p->stride == 1) {
     const uint64_t C = p->C1;
-    rc = make_act_map(&maps.a[0], p->x, p->C1, p->W, p->H, p->D, p->N, C, W * C, H * W * C, D * H * W * C, a.tw,
+    const int atw = pl.tc2 == 3 ? a.tw + 2 : a.tw;   // W-halo kernel: each line is loaded with one voxel on either side
+    rc = make_act_map(&maps.a[0], p->x, p->C1, p->W, p->H, p->D, p->N, C, W * C, H * W * C, D * H * W * C, atw,
                       a.th, a.td, a.tn);
     if (rc) return rc;
     if (p->C2 > 0) {
       const uint64_t C2 = p->C2;
       rc = make_act_map(&maps.a[1], p->x2, p->C2, p->W, p->H, p->D, p->N, C2, W * C2, H * W * C2, D * H * W * C2,
-                        a.tw, a.th, a.td, a.tn);
+                        atw, a.th, a.td, a.tn);
       if (rc) return rc;
     } else {
       maps.a[1] = maps.a[0];
@@ -1016,6 +1039,12 @@ static int conv3d_run_plan(const b200ldm_conv3d_params* p, const ConvPlan& pl, c
   }
 
   const int m_tiles = pl.m_tiles, mt = pl.mt, cl = pl.cl;
+  if (pl.tc2 == 3) {
+    B2_REQUIRE(conv_halo_supported(bn, a), B200LDM_BAD_SHAPE, "conv3d: problem not eligible for the W-halo kernel");
+    rc = make_weight_map(&maps.w, p->w, Cin, cout_rows, taps, bn);
+    if (rc) return rc;
+    return launch_conv_halo(maps, a, bn, m_tiles, n_tiles, st);
+  }
   if (pl.tc2 == 2 && conv_tcp_supported(bn, a)) {
     rc = make_weight_map(&maps.w, p->w, Cin, cout_rows, taps, bn);
     if (rc) return rc;

@@ -55,4 +55,10 @@ int conv_tcp_mt(int bn);
 int launch_conv_tcp(const ConvTcMaps& maps, const ConvTcArgs& a, int bn, int m_tiles, int n_tiles, int zdim,
                     cudaStream_t st);
 
+// conv_halo.cu: persistent kernel for 3x3x3 stride-1 convs with Cout tiles of 64 / 128: W-halo activation boxes
+// (one TMA load serves the three kw taps through shifted UMMA views); tile = 1 x td x th x 8 voxels, td * th = 16
+bool conv_halo_supported(int bn, const ConvTcArgs& a);
+void choose_halo_tile(int Do, int Ho, int* td, int* th);
+int launch_conv_halo(const ConvTcMaps& maps, const ConvTcArgs& a, int bn, int m_tiles, int n_tiles, cudaStream_t st);
+
 }  // namespace b200ldm

@@ -197,9 +197,13 @@ def test_conv3d_chunk_stats_feed_groupnorm(case):
 @pytest.mark.parametrize("shape", [(2, (6, 8, 4), 128, 256, 192, 64), (1, (9, 11, 7), 64, 128, 64, 0),
                                    (8, (4, 4, 4), 256, 256, 512, 256), (2, (16, 16, 16), 64, 64, 128, 0)],
                          ids=["two_src_skip", "odd", "batch_tile", "big"])
-def test_conv3d_fused_skip_conv(shape):
+@pytest.mark.parametrize("kernel", [-1, 3], ids=["auto", "w_halo"])
+def test_conv3d_fused_skip_conv(shape, kernel):
     """y = conv3(h) + conv1(cat(sx, sx2)) in one launch == the two convs of a ResNet block with a channel change"""
-    from b200ldm import ops
+    import ctypes
+    from b200ldm import _lib, ops
+    lib = _lib.load()
+    lib.b200ldm_debug_set_conv_kernel.argtypes = [ctypes.c_int]
     N, sp, C, Cout, S1, S2 = shape
     dtype = torch.bfloat16
     h = q(rnd((N, C) + sp, 91), dtype)
@@ -210,8 +214,12 @@ def test_conv3d_fused_skip_conv(shape):
     ref = F.conv3d(h.double(), w.double(), b.double(), padding=1) + F.conv3d(sx.double(), ws.double())
     wp = ops.repack_conv_weight(w.to(DEV), Cout, C, dtype)
     wsp = ops.repack_conv_weight(ws.to(DEV), Cout, S1 + S2, dtype)
-    y = ops.conv3d(to_act(h, dtype), wp, b.to(DEV), Cout, 3, 1, 1, 1,
-                   skip=(to_act(sx[:, :S1], dtype), to_act(sx[:, S1:], dtype) if S2 else None, wsp), want_stats=True)
+    lib.b200ldm_debug_set_conv_kernel(kernel)
+    try:
+        y = ops.conv3d(to_act(h, dtype), wp, b.to(DEV), Cout, 3, 1, 1, 1,
+                       skip=(to_act(sx[:, :S1], dtype), to_act(sx[:, S1:], dtype) if S2 else None, wsp), want_stats=True)
+    finally:
+        lib.b200ldm_debug_set_conv_kernel(-1)
     e = relerr(from_act(y, Cout), ref)
     assert e <= 1e-2, e
 
@@ -294,14 +302,17 @@ def test_tap_gather_fp32_exact():
     assert torch.allclose(y, want, atol=1e-5, rtol=1e-5)
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 2], ids=["tile_per_cta", "cta_pairs", "persistent"])
+@pytest.mark.parametrize("kernel", [0, 1, 2, 3], ids=["tile_per_cta", "cta_pairs", "persistent", "w_halo"])
 @pytest.mark.parametrize("case", [(2, (9, 11, 7), 128, 0, 256, 3, 1), (1, (8, 8, 8), 64, 64, 64, 3, 1), (2, (6, 10, 6), 64, 0, 128, 3, 2),
                                   (3, (5, 5, 5), 256, 0, 512, 1, 1), (1, (18, 22, 14), 64, 0, 64, 3, 1),
-                                  (8, (4, 4, 4), 128, 0, 192, 3, 1), (5, (3, 4, 2), 64, 64, 320, 3, 1)],
+                                  (8, (4, 4, 4), 128, 0, 192, 3, 1), (5, (3, 4, 2), 64, 64, 320, 3, 1),
+                                  (2, (16, 16, 16), 64, 0, 64, 3, 1), (1, (9, 11, 13), 128, 0, 128, 3, 1),
+                                  (3, (4, 20, 24), 128, 64, 64, 3, 1)],
                          ids=lambda c: f"N{c[0]}_{'x'.join(map(str, c[1]))}_C{c[2]}+{c[3]}->{c[4]}_k{c[5]}s{c[6]}")
 def test_conv3d_every_tensor_core_kernel(case, kernel):
-    """the three tcgen05 conv kernels (one CTA per tile, persistent CTA pairs, persistent single CTAs) pinned one by one:
-    same tensor, residual + time-embedding + GroupNorm chunk statistics included"""
+    """the tcgen05 conv kernels (one CTA per tile, persistent CTA pairs, persistent single CTAs, persistent W-halo) pinned
+    one by one (a kernel that does not take a problem leaves it to kernel 0): same tensor, residual + time-embedding +
+    GroupNorm chunk statistics included"""
     import ctypes
     from b200ldm import _lib, ops
     lib = _lib.load()
