@@ -430,3 +430,28 @@ def test_sampling_with_learned_range_variance(precision):
     with pytest.raises(ValueError):   # 2C-channel UNet with a fixed-variance scheduler
         b200ldm.LatentDiffusionInferer(fixed, 1.0).sample(x_T.to(DEV), ae, unet, fixed, conditioning=cond.to(DEV),
                                                           mode="concat", verbose=False)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sub_batch_streams_draw_the_same_noise(precision):
+    """SamplingLoop(batch_streams=n): the batch runs as n sub-batches on parallel graph branches; in-kernel Philox noise is
+    keyed by the element's index in the WHOLE batch (philox_offset), so the trajectory does not depend on the split."""
+    import b200ldm
+    from b200ldm.inferer import SamplingLoop
+    unet = port(gc.tiny_unet(), b200ldm.DiffusionModelUNet, gc.UNET_KW, precision)
+    sched = gc.make_scheduler(b200ldm, "ddpm", 4)
+    g = gc.gen(77)
+    x_T, cond = torch.randn((3, 4) + gc.LATENT, generator=g), torch.randn((3, 4) + gc.LATENT, generator=g)
+    outs = []
+    for n in (1, 2, 3):
+        loop = SamplingLoop(unet, sched, x_T.to(DEV), cond.to(DEV), "concat", seed=1234, use_graph=True, batch_streams=n)
+        assert len(loop.subs) == n and loop.subs[0][0] == 0 and loop.subs[-1][1] == 3
+        for _ in sched.timesteps:
+            loop.step()
+        outs.append(loop.latent_ncdhw())
+    tol = 1e-4 if precision == "fp32" else 2e-2
+    assert relerr(outs[1], outs[0]) <= tol and relerr(outs[2], outs[0]) <= tol
+    other = SamplingLoop(unet, sched, x_T.to(DEV), cond.to(DEV), "concat", seed=1235, use_graph=True, batch_streams=2)
+    for _ in sched.timesteps:
+        other.step()
+    assert relerr(other.latent_ncdhw(), outs[0]) > 5e-2      # ... and really depends on the seed
