@@ -642,3 +642,45 @@ def test_ae_sampling_and_mul_add():
     s_ref = torch.exp(lv.clamp(-30, 20) / 2)
     assert relerr(sig, s_ref) <= 1e-5 and relerr(z, mu + s_ref * nz) <= 1e-5
     assert relerr(ops.mul_add_f32(mu.to(DEV), lv.to(DEV), nz.to(DEV)), mu + lv * nz) <= 1e-6
+
+
+def test_abi_is_reentrant_across_threads_and_streams():
+    """SURVEY 8b "threading / streams": entry points are re-entrant across streams, the plan cache is mutex-guarded.
+    Four host threads, each on its own CUDA stream, run conv (two kernels) + GroupNorm + attention chains concurrently;
+    every thread must reproduce the single-threaded result."""
+    import threading
+    from b200ldm import ops
+    dtype = torch.bfloat16
+    x = to_act(q(rnd((2, 128, 9, 11, 7), 301), dtype), dtype)
+    w1 = ops.repack_conv_weight((rnd((128, 128, 3, 3, 3), 302) * (128 * 27) ** -0.5).to(DEV), 128, 128, dtype)
+    w2 = ops.repack_conv_weight((rnd((384, 128, 1, 1, 1), 303) * 128 ** -0.5).to(DEV), 384, 128, dtype)
+    gamma, beta = (1.0 + 0.1 * rnd((128,), 304)).to(DEV), (0.1 * rnd((128,), 305)).to(DEV)
+
+    def chain():
+        h = ops.conv3d(x, w1, None, 128, 3, 1, 1, 1, want_stats=True)
+        h = ops.groupnorm(h, gamma, beta, 32, 1e-6, True)
+        qkv = ops.conv3d(h, w2, None, 384, ksize=1, stride=1, pad_lo=0)
+        return ops.attention(qkv.reshape(2, 9 * 11 * 7, 384), 2, 64, 0.125).float()
+
+    want = chain()          # also settles the measured conv kernel choices
+    torch.cuda.synchronize()
+    outs, errs = [None] * 4, []
+
+    def worker(i):
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for _ in range(6):
+                    outs[i] = chain()
+            s.synchronize()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for o in outs:
+        assert relerr(o, want) <= 2e-2     # GroupNorm sums are atomics: not bitwise
