@@ -22,13 +22,14 @@ from .nets import AutoencoderKL, DiffusionModelUNet, _PREC, _pad64, param_signat
 
 USE_GRAPH = os.environ.get("B200LDM_CUDA_GRAPH", "1") != "0"
 FUSE_SCHED = os.environ.get("B200LDM_FUSE_SCHED", "1") != "0"
-# The volumes of a batch are independent, so the denoising step CAN run as BATCH_STREAMS sub-batches on parallel streams
-# (parallel branches of the captured graph), the idea being that one sub-batch's CTAs fill the SMs another leaves idle
-# in the partial last wave of a conv (256 CTAs on 148 SMs = 2 waves for 1.7 waves of work) or in a chain of small
-# kernels.  Measured on B200 (scripts/ab_streams.py, profiles/r01d_batch_streams_ab.log): 32g / 20^3 / batch 8 step
-# 6.17 ms with 1 stream, 6.28 with 2, 7.43 with 4 - half-batch convs need more split-K and re-read the weights, which
-# costs more than the overlap returns - so the default stays 1; the noise does not depend on the split.
-BATCH_STREAMS = int(os.environ.get("B200LDM_BATCH_STREAMS", "1"))
+# The volumes of a batch are independent, so the TOP resolution level of the UNet (conv_in, down block 0, the last up
+# block, the output conv) runs as BATCH_STREAMS sub-batches on parallel streams = parallel branches of the captured
+# graph (DiffusionModelUNet.forward_ndhwc(split=...)): one sub-batch's CTAs fill the SMs another leaves idle in the
+# partial last wave of a conv (8 x 20^3: 256 CTAs on 148 SMs = 2 waves for 1.7 waves of work).  Splitting the WHOLE
+# step was measured slower (profiles/r01d_batch_streams_ab.log: 6.17 -> 6.28 ms with 2 streams - the small levels need
+# more split-K and re-read the weights), so the lower levels stay on the whole batch.  The noise does not depend on
+# the split.
+BATCH_STREAMS = int(os.environ.get("B200LDM_BATCH_STREAMS", "2"))
 
 
 class SamplingLoop:
@@ -84,8 +85,11 @@ class SamplingLoop:
         self.graph = None
         self.launches_per_step = 0
         self.use_graph = use_graph and USE_GRAPH
-        # sub-batches [lo, hi) of the batch axis, one stream each (only worth it inside a captured graph)
+        # sub-batches [lo, hi) of the batch axis, one stream each (only worth it inside a captured graph and where the
+        # top level is big enough to fill the chip more than once: >= 2 x 148 tiles of 128 voxels)
         n_sub = BATCH_STREAMS if batch_streams is None else batch_streams
+        if batch_streams is None and input_noise.numel() // self.c_lat < 2 * 148 * 128:
+            n_sub = 1
         n_sub = max(1, min(n_sub, N)) if self.use_graph else 1
         cuts = [round(i * N / n_sub) for i in range(n_sub + 1)]
         self.subs = [(cuts[i], cuts[i + 1]) for i in range(n_sub)]
@@ -117,45 +121,33 @@ class SamplingLoop:
         self.seed_dev.fill_(int(seed) & (2 ** 63 - 1))
         self.counter.zero_()
 
-    def _sub_body(self, i: int):
-        """UNet + scheduler update of sub-batch i (volumes [lo, hi)); everything is per-volume, so slices along the
-        batch axis are independent problems on contiguous views of the state buffers."""
-        lo, hi = self.subs[i]
-        x_model, x_t = self.x_model[lo:hi], self.x_t[lo:hi]
-        noise = None if self.noise is None else self.noise[lo:]      # slab of step s = rows [s * N + lo, ...)
-        ctx = None
-        if self.ctx is not None:
-            lc = self.ctx.shape[0] // self.shape[0]
-            ctx = self.ctx[lo * lc:hi * lc]
-        # Philox element-group index of the sub-batch's first element: the noise does not depend on the split
-        poff = lo * (self.x_t[0].numel() // 4)
-        if FUSE_SCHED and self.var_coef is None and self.unet.out[2].conv.tap_expanded(self.x_model):
-            # the scheduler update runs inside the UNet's last kernel (the output conv's tap gather) on the fp32 sums
-            if self._sched[i] is None:
-                self._sched[i] = ops.make_sched_params(x_t, self.coef, self.counter, self.c_lat, self.dtype,
-                                                       noise=noise, noise_step_stride=self.noise_stride,
-                                                       x_model=x_model, seed=self.seed_dev, philox_offset=poff)
-            self.unet.forward_ndhwc(x_model, self.temb_cur, 0, sched=self._sched[i], ctx=ctx)
-        else:
-            eps = self.unet.forward_ndhwc(x_model, self.temb_cur, 0, ctx=ctx)
-            ops.scheduler_step(eps, x_t, self.coef, self.counter, self.c_lat, noise=noise,
-                               noise_step_stride=self.noise_stride, x_model=x_model, seed=self.seed_dev,
-                               philox_offset=poff, var_offset=self.c_lat if self.var_coef is not None else 0, var_coef=self.var_coef)
+    def _sub_sched(self, i: int):
+        """scheduler parameters of sub-batch i: batch slices of the state buffers (contiguous views), the Philox index
+        of its first element so the noise does not depend on the split"""
+        if self._sched[i] is None:
+            lo, hi = self.subs[i]
+            noise = None if self.noise is None else self.noise[lo:]      # slab of step s = rows [s * N + lo, ...)
+            self._sched[i] = ops.make_sched_params(self.x_t[lo:hi], self.coef, self.counter, self.c_lat, self.dtype,
+                                                   noise=noise, noise_step_stride=self.noise_stride,
+                                                   x_model=self.x_model[lo:hi], seed=self.seed_dev,
+                                                   philox_offset=lo * (self.x_t[0].numel() // 4))
+        return self._sched[i]
 
     def _body(self):
         ops.select_row(self.temb_table, self.counter, self.temb_cur)
-        if len(self.subs) == 1:
-            self._sub_body(0)
+        if FUSE_SCHED and self.var_coef is None and self.unet.out[2].conv.tap_expanded(self.x_model):
+            # the scheduler update runs inside the UNet's last kernel (the output conv's tap gather) on the fp32 sums
+            if len(self.subs) > 1:
+                self.unet.forward_ndhwc(self.x_model, self.temb_cur, 0, ctx=self.ctx,
+                                        sched=[self._sub_sched(i) for i in range(len(self.subs))],
+                                        split=(self.subs, self.side_streams))
+            else:
+                self.unet.forward_ndhwc(self.x_model, self.temb_cur, 0, sched=self._sub_sched(0), ctx=self.ctx)
         else:
-            cur = torch.cuda.current_stream()
-            for s in self.side_streams:
-                s.wait_stream(cur)
-            for i, s in enumerate(self.side_streams):
-                with torch.cuda.stream(s):
-                    self._sub_body(i + 1)
-            self._sub_body(0)
-            for s in self.side_streams:
-                cur.wait_stream(s)
+            eps = self.unet.forward_ndhwc(self.x_model, self.temb_cur, 0, ctx=self.ctx)
+            ops.scheduler_step(eps, self.x_t, self.coef, self.counter, self.c_lat, noise=self.noise,
+                               noise_step_stride=self.noise_stride, x_model=self.x_model, seed=self.seed_dev,
+                               var_offset=self.c_lat if self.var_coef is not None else 0, var_coef=self.var_coef)
         ops.counter_add(self.counter, 1)
 
     def _capture(self):

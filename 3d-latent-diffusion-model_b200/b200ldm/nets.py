@@ -102,7 +102,7 @@ class Conv(nn.Module):
         return self._cache.get((dtype, c1, c1_phys, cin_phys), (self.weight, self.bias), build)
 
     def run(self, x, x2=None, c1: int | None = None, temb=None, temb_stride: int = 0, residual=None, gn_stats=None,
-            gn_groups: int = 0, out_f32: bool = False, want_stats: bool = False, sched=None):
+            gn_groups: int = 0, out_f32: bool = False, want_stats: bool = False, sched=None, out=None, cstats_out=None):
         if self.tap_expanded(x) and x2 is None and temb is None and residual is None and gn_stats is None and not out_f32:
             return self._run_tap_expanded(x, sched)
         if sched is not None:
@@ -113,7 +113,7 @@ class Conv(nn.Module):
             w, b = self.packed(x.dtype, c1=c1, c1_phys=x.shape[-1], cin_phys=x.shape[-1] + x2.shape[-1])
         return ops.conv3d(x, w, b, self.cout_phys, self.ksize, self.stride, self.pad_lo, self.pad_hi, x2=x2, temb=temb,
                           temb_stride=temb_stride, residual=residual, gn_stats=gn_stats, gn_groups=gn_groups,
-                          out_f32=out_f32, want_stats=want_stats)
+                          out_f32=out_f32, want_stats=want_stats, out=out, cstats_out=cstats_out)
 
 
     def tap_expanded(self, x) -> bool:
@@ -644,47 +644,134 @@ class DiffusionModelUNet(nn.Module):
         return ops.to_ndhwc(src, _pad64(Dc), _PREC[self.precision], out=o).reshape(B * Lc, _pad64(Dc))
 
     # ---- NDHWC core
-    def forward_ndhwc(self, x, temb_all, temb_stride: int, sched=None, ctx=None):
+    def forward_ndhwc(self, x, temb_all, temb_stride: int, sched=None, ctx=None, split=None):
         """x: [N,D,H,W,pad64(in_channels)] (bf16|fp32); temb_all: fp32 [n_t, total] rows (n_t = 1 -> stride 0);
         ctx: context tokens from `context_tokens` (with_conditioning=True models only).
-        Returns eps [N,D,H,W,round16(out_channels)]."""
+        Returns eps [N,D,H,W,round16(out_channels)].
+
+        split = (cuts, side_streams): the TOP resolution level - conv_in, down block 0 with its down-sampler, the last
+        up block and the output conv - runs as len(cuts) sub-batches [lo, hi) on parallel streams (volumes are
+        independent); the lower levels run on the whole batch.  At 8 x 20^3 a top-level conv is 256 CTAs = two waves
+        for 1.7 waves of work; two half batches on two streams keep the SMs fed through each other's partial wave
+        (6 x (GroupNorm + conv): 1.01 -> 0.92 ms, scripts/ab_level0_streams.py), while the small levels would only pay
+        for a split (more split-K, weights read twice).  `sched` is then one b200ldm_sched_params per sub-batch and
+        the fused update is the only output (returns None)."""
         if self.with_conditioning and ctx is None:
             raise ValueError("with_conditioning=True: a context tensor is required (cross-attention conditioning)")
-
-        def attend(a, h):
-            return a.run(h, ctx) if self.with_conditioning else a.run(h)
-
+        N = x.shape[0]
         offs, _ = self._temb_layout()
-        it = iter(range(len(offs)))
+        toff = {id(r): o for r, o in zip(self.resblocks(), offs)}
+        lc = 0 if ctx is None else ctx.shape[0] // N
 
-        def temb_for():
-            i = next(it)
-            return temb_all[:, offs[i]:]  # pointer offset only; the kernel strides rows by temb_stride
+        def temb_for(r, lo=0):   # pointer offset only; the kernel strides rows by temb_stride
+            return temb_all[lo if temb_stride else 0:, toff[id(r)]:]
 
-        h = self.conv_in.run(x, want_stats=True)
-        skips = [h]
-        for blk in self.down_blocks:
-            for j, r in enumerate(blk.resnets):
-                h = r.run(h, temb_for(), temb_stride)
-                if blk.has_attn:
-                    h = attend(blk.attentions[j], h)
-                skips.append(h)
-            if blk.downsampler is not None:
-                h = blk.downsampler.op.run(h, want_stats=True)
-                skips.append(h)
-        mb = self.middle_block
-        h = mb.resnet_1.run(h, temb_for(), temb_stride)
-        h = attend(mb.attention, h)
-        h = mb.resnet_2.run(h, temb_for(), temb_stride)
-        for blk in self.up_blocks:
-            for j, r in enumerate(blk.resnets):
-                h = r.run(h, temb_for(), temb_stride, x2=skips.pop())
-                if blk.has_attn:
-                    h = attend(blk.attentions[j], h)
-            if blk.upsampler is not None:
-                h = blk.upsampler.upsample.run(h)
-        h = self.out[0].run(h, silu=True)
-        return self.out[2].run(h, sched=sched)   # sched: the scheduler update rides in the output conv's last kernel
+        def attend(a, h, lo=0, hi=N):
+            return a.run(h, ctx[lo * lc:hi * lc]) if self.with_conditioning else a.run(h)
+
+        def bslice(t, lo, hi):   # batch slice that keeps the per-sample GroupNorm chunk sums attached
+            v = t[lo:hi]
+            cs = getattr(t, "cstats", None)
+            if cs is not None:
+                v.cstats = cs.view(N, -1)[lo:hi].reshape(-1)
+            return v
+
+        blk0, blk_last = self.down_blocks[0], self.up_blocks[-1]
+
+        def head(lo, hi, down_out):
+            """conv_in + down block 0 for volumes [lo, hi); the down-sampled tensor lands in down_out[lo:hi]"""
+            h = self.conv_in.run(x[lo:hi], want_stats=True)
+            sk = [h]
+            for j, r in enumerate(blk0.resnets):
+                h = r.run(h, temb_for(r, lo), temb_stride)
+                if blk0.has_attn:
+                    h = attend(blk0.attentions[j], h, lo, hi)
+                sk.append(h)
+            if blk0.downsampler is not None:
+                if down_out is None:
+                    h = blk0.downsampler.op.run(h, want_stats=True)
+                else:
+                    full, cs, emitted = down_out
+                    h = blk0.downsampler.op.run(h, want_stats=True, out=full[lo:hi],
+                                                cstats_out=cs.view(N, -1)[lo:hi].reshape(-1))
+                    emitted.append(getattr(h, "cstats", None) is not None)   # split-K plans emit no chunk sums
+            return h, sk
+
+        def body(h, skips):
+            """down blocks 1.., middle block, every up block but the last - whole batch"""
+            for blk in self.down_blocks[1:]:
+                for j, r in enumerate(blk.resnets):
+                    h = r.run(h, temb_for(r), temb_stride)
+                    if blk.has_attn:
+                        h = attend(blk.attentions[j], h)
+                    skips.append(h)
+                if blk.downsampler is not None:
+                    h = blk.downsampler.op.run(h, want_stats=True)
+                    skips.append(h)
+            mb = self.middle_block
+            h = mb.resnet_1.run(h, temb_for(mb.resnet_1), temb_stride)
+            h = attend(mb.attention, h)
+            h = mb.resnet_2.run(h, temb_for(mb.resnet_2), temb_stride)
+            for blk in self.up_blocks[:-1]:
+                for j, r in enumerate(blk.resnets):
+                    h = r.run(h, temb_for(r), temb_stride, x2=skips.pop())
+                    if blk.has_attn:
+                        h = attend(blk.attentions[j], h)
+                if blk.upsampler is not None:
+                    h = blk.upsampler.upsample.run(h)
+            return h
+
+        def tail(h, sk, lo, hi, sp):
+            """last up block + output conv for volumes [lo, hi); sk: that sub-batch's top-level skips"""
+            for j, r in enumerate(blk_last.resnets):
+                h = r.run(h, temb_for(r, lo), temb_stride, x2=sk.pop())
+                if blk_last.has_attn:
+                    h = attend(blk_last.attentions[j], h, lo, hi)
+            if blk_last.upsampler is not None:
+                h = blk_last.upsampler.upsample.run(h)
+            h = self.out[0].run(h, silu=True)
+            return self.out[2].run(h, sched=sp)   # sched: the scheduler update rides in the output conv's last kernel
+
+        if split is None or blk0.downsampler is None:
+            if isinstance(sched, (list, tuple)):
+                raise ValueError("per-sub-batch scheduler parameters need a split (and a UNet with more than one level)")
+            h, top = head(0, N, None)
+            h = body(h, [h] if blk0.downsampler is not None else [])
+            return tail(h, top, 0, N, sched)
+
+        cuts, side = split
+        if len(cuts) != len(side) + 1 or not isinstance(sched, (list, tuple)) or len(sched) != len(cuts):
+            raise ValueError("split = (cuts, side_streams) needs one stream less than, and one sched per, sub-batch")
+        cur = torch.cuda.current_stream()
+        # down-sampled tensor of the whole batch, written slice by slice by the sub-batches' down-samplers
+        ds = blk0.downsampler.op.conv
+        osp = tuple(ops.conv_out_extent(v, 3, 2, ds.pad_lo, ds.pad_hi) for v in x.shape[1:4])
+        down_full = torch.empty((N,) + osp + (ds.cout_phys,), dtype=x.dtype, device=x.device)
+        down_out = (down_full, ops.zeros_f64(N * (ds.cout_phys // 8) * 2, x.device), [])
+        tops = [None] * len(cuts)
+
+        def fork(fn):
+            for s in side:
+                s.wait_stream(cur)
+            for i, s in enumerate(side):
+                with torch.cuda.stream(s):
+                    fn(i + 1)
+            fn(0)
+            for s in side:
+                cur.wait_stream(s)
+
+        def run_head(i):
+            _, tops[i] = head(cuts[i][0], cuts[i][1], down_out)
+        fork(run_head)
+        if all(down_out[2]):
+            down_full.cstats = down_out[1]
+        h = body(down_full, [down_full])
+
+        def run_tail(i):
+            lo, hi = cuts[i]
+            tail(bslice(h, lo, hi), tops[i], lo, hi, sched[i])
+        fork(run_tail)
+        return None
 
     def forward(self, x, timesteps, context=None, class_labels=None, down_block_additional_residuals=None,
                 mid_block_additional_residual=None):

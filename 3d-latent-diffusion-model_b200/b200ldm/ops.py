@@ -83,14 +83,16 @@ def conv_out_extent(n: int, k: int, stride: int, pad_lo: int, pad_hi: int) -> in
 def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo: int = 1, pad_hi: int | None = None,
            x2=None, temb=None, temb_stride: int = 0, residual=None, gn_stats=None, gn_groups: int = 0,
            out_f32: bool = False, engine: int = ENGINE_AUTO, upsample2x: bool = False, want_stats: bool = False,
-           skip=None):
+           skip=None, out=None, cstats_out=None):
     """y = conv3d(cat(x, x2)) + bias (+ temb) (+ residual); x: [N,D,H,W,C1] NDHWC.
     upsample2x: the conv runs on the nearest-x2-upsampled x without materialising it (bf16: phase-decomposed
     weights from repack_upconv_weight; fp32: ordinary weights).
     skip: (sx, sx2 | None, sw_packed): a 1x1x1 conv of cat(sx, sx2) accumulated into the same output (ResNet
     skip_connection fused as extra K iterations; `bias` must already include its bias).  bf16 only.
     want_stats: when the tensor-core epilogue can, it also accumulates per-8-channel (sum, sumsq) of y; the result is
-    attached as `y.cstats` and lets the following GroupNorm skip its statistics pass."""
+    attached as `y.cstats` and lets the following GroupNorm skip its statistics pass.
+    out / cstats_out: write into this (contiguous, e.g. a batch slice of a larger tensor) instead of allocating; the
+    statistics slice must arrive zeroed."""
     _need_cuda(x, x2, w_packed, bias, temb, residual)
     lib = _lib.load()
     N, D, H, W, C1 = x.shape
@@ -100,7 +102,11 @@ def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo
     up = 2 if upsample2x else 1
     Do, Ho, Wo = (conv_out_extent(up * v, ksize, stride, pad_lo, pad_hi) for v in (D, H, W))
     odt = torch.float32 if out_f32 else x.dtype
-    y = torch.empty((N, Do, Ho, Wo, cout), dtype=odt, device=x.device)
+    if out is None:
+        y = torch.empty((N, Do, Ho, Wo, cout), dtype=odt, device=x.device)
+    else:
+        assert tuple(out.shape) == (N, Do, Ho, Wo, cout) and out.dtype == odt and out.is_contiguous() and out.is_cuda
+        y = out
     p = _lib.ConvParams(
         x=_ptr(x), x2=_ptr(x2), w=_ptr(w_packed), bias=_ptr(bias), temb=_ptr(temb), residual=_ptr(residual),
         y=_ptr(y), gn_stats=_ptr(gn_stats), N=N, D=D, H=H, W=W, C1=C1, C2=C2, Cout=cout, Do=Do, Ho=Ho, Wo=Wo,
@@ -120,7 +126,11 @@ def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
     cstats = None
     if want_stats and FUSE_GN_STATS and lib.b200ldm_conv3d_emits_chunk_stats(C.byref(p)):
-        cstats = zeros_f64(N * (cout // 8) * 2, x.device)
+        if cstats_out is not None:
+            assert cstats_out.dtype == torch.float64 and cstats_out.numel() == N * (cout // 8) * 2
+            cstats = cstats_out
+        else:
+            cstats = zeros_f64(N * (cout // 8) * 2, x.device)
         p.chunk_stats = cstats.data_ptr()
     ev = PROFILER.start() if PROFILER is not None else None
     _lib.check(lib.b200ldm_conv3d(C.byref(p), _stream()), "conv3d")

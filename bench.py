@@ -216,6 +216,7 @@ def bench_unet_step(args, rank, world, local):
     loop = SamplingLoop(unet, sched, x_T.to(dev), None, "crossattn", seed=42 + 1000 * rank, use_graph=True)
     loop.step()                                   # capture (eager warm-up inside) - counts as warm-up step 1
     per_graph = loop.launches_per_step            # kernels recorded into the graph = launched per replay
+    loop_subs = list(loop.subs)                   # sub-batches of the top UNet level (parallel graph branches)
     for _ in range(max(args.warmup, 3) - 1):
         loop.step()
     with ClockSampler(local) as clk:
@@ -242,11 +243,16 @@ def bench_unet_step(args, rank, world, local):
 
     # ---- roofline leg: per-kernel CUDA events inside an eager step (same stream the kernels launch on)
     pk = peaks()
+    # (a single-stream loop: per-kernel events mean nothing while two sub-batch streams share the SMs)
+    prof_loop = SamplingLoop(unet, sched, x_T.to(dev), None, "crossattn", seed=42 + 1000 * rank, use_graph=False)
+    prof_loop._body()
+    torch.cuda.synchronize()
     ops.PROFILER = ops.KernelProfiler()
     n_prof = 2
     for _ in range(n_prof):
-        loop._body()
+        prof_loop._body()
     torch.cuda.synchronize()
+    del prof_loop
     kinds, by_tag = ops.PROFILER.summary()
     ops.PROFILER = None
     conv = kinds["conv3d"]
@@ -290,7 +296,7 @@ def bench_unet_step(args, rank, world, local):
             "config": {"workload": "unet_step_16g: config_train_16g UNet (256,256,512) denoise step + fused DDPM update",
                        "batch_per_gpu": BATCH, "latent": list(LATENT_16G), "parallelism": f"replica-per-gpu x{world}",
                        "l2": "inputs larger than L2 (weights 0.3 GB + 181 MB activations per layer vs 126 MB L2)",
-                       "cuda_graph": True},
+                       "cuda_graph": True, "batch_streams": len(loop_subs)},
             "step_tflops_algorithmic": step_tf, "frac_of_sustained_peak": step_tf / pk["bf16_sustained"],
             "e2e": {"value": e2e_value, "unit": "volume-steps/s", "h2d_bytes_per_step": nbytes,
                     "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},

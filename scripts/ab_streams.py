@@ -1,5 +1,6 @@
-"""A/B of the sub-batch stream split of the denoising step (B200LDM_BATCH_STREAMS): graph-replayed ms/step for the
-32g UNet at 20^3 (cfg 3) and the 16g UNet at 36x44x28 (cfg 2), batch 8, alternating 1 / 2 / 4 streams in one process.
+"""A/B of the sub-batch stream split of the denoising step (B200LDM_BATCH_STREAMS; since commit "top-level split" only
+the TOP resolution level of the UNet is split, before that the whole step): graph-replayed ms/step for the 32g UNet at
+20^3 (cfg 3) and the 16g UNet at 36x44x28 (cfg 2), batch 8, alternating 1 / 2 / 4 streams in one process.
 usage: python scripts/ab_streams.py [reps]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

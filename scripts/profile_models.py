@@ -20,7 +20,8 @@ sched = b200ldm.DDPMScheduler(**B.SCHED)
 c_lat = kw["out_channels"]
 x_T = torch.randn((batch, c_lat) + lat)
 cond = torch.randn((batch, kw["in_channels"] - c_lat) + lat).to(dev) if kw["in_channels"] > c_lat else None
-loop = SamplingLoop(unet, sched, x_T.to(dev), cond, "concat" if cond is not None else "crossattn", use_graph=True)
+loop = SamplingLoop(unet, sched, x_T.to(dev), cond, "concat" if cond is not None else "crossattn", use_graph=True,
+                    batch_streams=int(os.environ.get("PROFILE_STREAMS", "1")))
 
 
 def report(title, fn, n=2):
