@@ -36,6 +36,8 @@ FUSE_UPSAMPLE = os.environ.get("B200LDM_FUSE_UPSAMPLE", "1") != "0"
 TAP_EXPAND = os.environ.get("B200LDM_TAP_EXPAND", "1") != "0"
 # DiffusionModelUNet.forward (the public module call) replays a cached CUDA graph from the second call of a signature on
 FORWARD_GRAPH = os.environ.get("B200LDM_FORWARD_GRAPH", "1") != "0"
+# sub-batch streams of the top UNet level inside the captured forward graph (see forward_ndhwc(split=...))
+FORWARD_STREAMS = int(os.environ.get("B200LDM_BATCH_STREAMS", "2"))
 # ResNet 1x1x1 skip_connection / nin_shortcut accumulated inside conv2 (extra K iterations) on the tensor-core path
 FUSE_SKIP = os.environ.get("B200LDM_FUSE_SKIP", "1") != "0"
 
@@ -104,7 +106,7 @@ class Conv(nn.Module):
     def run(self, x, x2=None, c1: int | None = None, temb=None, temb_stride: int = 0, residual=None, gn_stats=None,
             gn_groups: int = 0, out_f32: bool = False, want_stats: bool = False, sched=None, out=None, cstats_out=None):
         if self.tap_expanded(x) and x2 is None and temb is None and residual is None and gn_stats is None and not out_f32:
-            return self._run_tap_expanded(x, sched)
+            return self._run_tap_expanded(x, sched, out)
         if sched is not None:
             raise RuntimeError("the fused scheduler update needs the stacked-tap output conv (Conv.tap_expanded)")
         if x2 is None:
@@ -121,7 +123,7 @@ class Conv(nn.Module):
         return (TAP_EXPAND and self.terminal and self.cout <= 16 and self.ksize == 3 and self.stride == 1
                 and self.pad_lo == 1 and self.pad_hi == 1 and x.dtype == torch.bfloat16)
 
-    def _run_tap_expanded(self, x, sched=None):
+    def _run_tap_expanded(self, x, sched=None, out=None):
         """3x3x3 conv with <= 16 output channels = 1x1x1 GEMM to 27*cp stacked tap outputs + gather (ops.tap_gather);
         sched: the scheduler update is applied by the gather kernel and the conv output is not materialised."""
         cin_phys = x.shape[-1]
@@ -141,7 +143,7 @@ class Conv(nn.Module):
 
         wz, b = self._cache.get(("tapexp", x.dtype, cin_phys), (self.weight, self.bias), build)
         z = ops.conv3d(x, wz, None, nz, ksize=1, stride=1, pad_lo=0)
-        return ops.tap_gather(z, b, cp, self.cout_phys, sched=sched, want_y=sched is None)
+        return ops.tap_gather(z, b, cp, self.cout_phys, sched=sched, want_y=sched is None, out=out)
 
     def run_with_skip(self, x, skip_conv: "Conv", sx, sx2=None, want_stats: bool = False):
         """self(x) + skip_conv(cat(sx, sx2)) in ONE kernel: the 1x1x1 skip conv is a few more K iterations into the same
@@ -654,8 +656,8 @@ class DiffusionModelUNet(nn.Module):
         independent); the lower levels run on the whole batch.  At 8 x 20^3 a top-level conv is 256 CTAs = two waves
         for 1.7 waves of work; two half batches on two streams keep the SMs fed through each other's partial wave
         (6 x (GroupNorm + conv): 1.01 -> 0.92 ms, scripts/ab_level0_streams.py), while the small levels would only pay
-        for a split (more split-K, weights read twice).  `sched` is then one b200ldm_sched_params per sub-batch and
-        the fused update is the only output (returns None)."""
+        for a split (more split-K, weights read twice).  `sched` is then one b200ldm_sched_params per sub-batch (the
+        fused update is the only output, returns None) or None (returns the prediction of the whole batch)."""
         if self.with_conditioning and ctx is None:
             raise ValueError("with_conditioning=True: a context tensor is required (cross-attention conditioning)")
         N = x.shape[0]
@@ -721,7 +723,7 @@ class DiffusionModelUNet(nn.Module):
                     h = blk.upsampler.upsample.run(h)
             return h
 
-        def tail(h, sk, lo, hi, sp):
+        def tail(h, sk, lo, hi, sp, out=None):
             """last up block + output conv for volumes [lo, hi); sk: that sub-batch's top-level skips"""
             for j, r in enumerate(blk_last.resnets):
                 h = r.run(h, temb_for(r, lo), temb_stride, x2=sk.pop())
@@ -730,7 +732,7 @@ class DiffusionModelUNet(nn.Module):
             if blk_last.upsampler is not None:
                 h = blk_last.upsampler.upsample.run(h)
             h = self.out[0].run(h, silu=True)
-            return self.out[2].run(h, sched=sp)   # sched: the scheduler update rides in the output conv's last kernel
+            return self.out[2].run(h, sched=sp, out=out)   # sched: the scheduler update rides in this conv's last kernel
 
         if split is None or blk0.downsampler is None:
             if isinstance(sched, (list, tuple)):
@@ -740,7 +742,8 @@ class DiffusionModelUNet(nn.Module):
             return tail(h, top, 0, N, sched)
 
         cuts, side = split
-        if len(cuts) != len(side) + 1 or not isinstance(sched, (list, tuple)) or len(sched) != len(cuts):
+        if len(cuts) != len(side) + 1 or (sched is not None and (not isinstance(sched, (list, tuple))
+                                                                 or len(sched) != len(cuts))):
             raise ValueError("split = (cuts, side_streams) needs one stream less than, and one sched per, sub-batch")
         cur = torch.cuda.current_stream()
         # down-sampled tensor of the whole batch, written slice by slice by the sub-batches' down-samplers
@@ -767,11 +770,17 @@ class DiffusionModelUNet(nn.Module):
             down_full.cstats = down_out[1]
         h = body(down_full, [down_full])
 
+        eps = None
+        if sched is None:   # no fused scheduler update: the sub-batches write batch slices of one prediction tensor
+            oc = self.out[2].conv
+            eps = torch.empty(tuple(x.shape[:4]) + (oc.cout_phys,), dtype=x.dtype, device=x.device)
+
         def run_tail(i):
             lo, hi = cuts[i]
-            tail(bslice(h, lo, hi), tops[i], lo, hi, sched[i])
+            tail(bslice(h, lo, hi), tops[i], lo, hi, None if sched is None else sched[i],
+                 None if eps is None else eps[lo:hi])
         fork(run_tail)
-        return None
+        return eps
 
     def forward(self, x, timesteps, context=None, class_labels=None, down_block_additional_residuals=None,
                 mid_block_additional_residual=None):
@@ -804,8 +813,25 @@ class DiffusionModelUNet(nn.Module):
         temb_all = self.time_embedding_table(timesteps.to(device=x.device, dtype=torch.float32), class_labels)
         stride = 0 if temb_all.shape[0] == 1 else temb_all.shape[1]
         ctx = None if context is None else self.context_tokens(context.to(x.device))
-        eps = self.forward_ndhwc(xa, temb_all, stride, ctx=ctx)
+        eps = self.forward_ndhwc(xa, temb_all, stride, ctx=ctx, split=self._forward_split(xa))
         return ops.to_ncdhw(eps, self.out_channels)
+
+    def _forward_split(self, xa):
+        """(cuts, side streams) for the top-level sub-batch split of forward_ndhwc, or None: only inside a graph capture
+        (parallel branches; in eager mode the launch overhead of a second stream buys nothing) and only where the
+        top level fills the chip more than once (same rule as the sampling loop)."""
+        n, vox = xa.shape[0], xa.shape[1] * xa.shape[2] * xa.shape[3]
+        live = torch.cuda.is_current_stream_capturing() or self.__dict__.get("_warm_split", False)
+        if (FORWARD_STREAMS < 2 or n < 2 or n * vox < 2 * 148 * 128 or not live
+                or not self.out[2].conv.tap_expanded(xa) or self.down_blocks[0].downsampler is None):
+            return None
+        k = min(FORWARD_STREAMS, n)
+        cuts = [round(i * n / k) for i in range(k + 1)]
+        side = self.__dict__.setdefault("_side_streams", {})
+        key = (str(xa.device), k)
+        if key not in side:
+            side[key] = [torch.cuda.Stream(device=xa.device) for _ in range(k - 1)]
+        return [(cuts[i], cuts[i + 1]) for i in range(k)], side[key]
 
     def _forward_graphed(self, x, timesteps, context=None, class_labels=None):
         """forward() through a CUDA graph cached per (input shapes, number of timesteps, weights): the ~150 launches of
@@ -827,6 +853,14 @@ class DiffusionModelUNet(nn.Module):
             static_c = None if context is None else context.detach().to(device=x.device, dtype=torch.float32).clone()
             static_l = None if class_labels is None else class_labels.detach().to(device=x.device,
                                                                                  dtype=torch.int64).clone()
+            # one eager pass in the captured configuration (sub-batch streams): the conv kernels measure their choices
+            # for the sub-batch shapes now - a capturing stream can only use the cost model
+            self._warm_split = True
+            try:
+                self._forward_eager(static_x, static_t, static_c, static_l)
+            finally:
+                self._warm_split = False
+            torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 static_out = self._forward_eager(static_x, static_t, static_c, static_l)

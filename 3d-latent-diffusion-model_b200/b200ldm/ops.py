@@ -313,14 +313,19 @@ def embedding_add(a, table, idx):
     return out
 
 
-def tap_gather(z, bias, cp: int, cy: int, sched=None, want_y: bool = True):
+def tap_gather(z, bias, cp: int, cy: int, sched=None, want_y: bool = True, out=None):
     """y[v][co] = bias[co] + sum_tap z[v + shift(tap)][tap*cp + co]: second half of a narrow-output 3x3x3 conv.
     sched: a SchedParams (make_sched_params) -> the gathered tensor is the noise prediction and the scheduler update is
     applied in the same kernel; with want_y=False the prediction itself is never written (returns None)."""
     _need_cuda(z, bias)
     N, D, H, W, ldz = z.shape
     assert z.is_contiguous()
-    y = torch.empty((N, D, H, W, cy), dtype=z.dtype, device=z.device) if (want_y or sched is None) else None
+    y = None
+    if out is not None:
+        assert tuple(out.shape) == (N, D, H, W, cy) and out.dtype == z.dtype and out.is_contiguous() and out.is_cuda
+        y = out
+    elif want_y or sched is None:
+        y = torch.empty((N, D, H, W, cy), dtype=z.dtype, device=z.device)
     ev = PROFILER.start() if PROFILER is not None else None
     _lib.check(_lib.load().b200ldm_tap_gather(z.data_ptr(), _ptr(bias), _ptr(y), N, D, H, W, ldz, cp, cy,
                                               dtype_code(z.dtype), None if sched is None else C.byref(sched), _stream()),
