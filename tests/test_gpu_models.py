@@ -455,3 +455,23 @@ def test_sub_batch_streams_draw_the_same_noise(precision):
     for _ in sched.timesteps:
         other.step()
     assert relerr(other.latent_ncdhw(), outs[0]) > 5e-2      # ... and really depends on the seed
+
+
+def test_xattn_unet_realistic_widths_bf16():
+    """cross-attention conditioning at realistic widths: 512-channel transformer level (8 heads of 64 -> the tcgen05
+    attention kernels for both the 216-token self attention and the 77-token context), 768-wide context, GEGLU width
+    2048, two-row LayerNorm chunks - bf16 engine against the fp32 oracle on the CPU."""
+    import b200ldm
+    kw = dict(spatial_dims=3, in_channels=8, out_channels=8, channels=(256, 512), attention_levels=(False, True),
+              num_head_channels=(0, 64), num_res_blocks=1, norm_num_groups=32, norm_eps=1e-6, with_conditioning=True,
+              cross_attention_dim=768, transformer_num_layers=1)
+    ref = oracle.randomize_parameters(oracle.DiffusionModelUNet(**kw), 31).eval()
+    g = gc.gen(32)
+    x, ctx = torch.randn((2, 8, 12, 12, 12), generator=g), torch.randn((2, 77, 768), generator=g)
+    ts = torch.tensor([250.0, 731.0])
+    with torch.no_grad():
+        want = ref(x, ts, context=ctx)
+    m = port(ref, b200ldm.DiffusionModelUNet, kw, "bf16")
+    got = m(x.to(DEV), ts.to(DEV), context=ctx.to(DEV))
+    e = relerr(got, want)
+    assert e <= EPS_TOL["bf16"], e
