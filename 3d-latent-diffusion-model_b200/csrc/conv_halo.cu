@@ -1,20 +1,23 @@
 // conv_halo.cu - persistent tcgen05 implicit-GEMM Conv3d (3x3x3, stride 1, pad 1) for NARROW outputs (Cout tile 64 or
-// 128: the AutoencoderKL's 64/128-channel convs at full image resolution), where conv_tcp.cu is bound by the bytes an
-// SM can ingest from L2 (~72 B/clk): with a 64-column tile every k-iteration stages 2 x 16 KB of activations for 256
-// tensor cycles, 156 B/clk.  Here one TMA load brings a W-HALO box - the 8-voxel lines of the tile plus one voxel on
-// either side, 10 x 128 B per line - and the three kw taps read it through three shifted views: the UMMA descriptor
-// starts kw rows (kw * 128 B) into the stage and steps 1280 B between 8-row groups (one line each).  That is legal
-// because both TMA and UMMA derive the SWIZZLE_128B XOR from absolute shared-memory address bits, so a row is found
-// where the TMA put it whatever the view's origin.  Activation traffic per tap drops from 16 KB to 6.7 KB per
-// sub-tile; weights travel in their own, finer ring (one 64 x BN tile per tap).
+// 128: the AutoencoderKL's 64/128-channel convs at full image resolution).  Two things bound conv_tcp.cu there:
+//   * bytes into the SM: with a 64-column tile every k-iteration stages 2 x 16 KB of activations for ~400 tensor
+//     cycles, above the ~72 B/clk an SM ingests from L2;
+//   * the single MMA-issuing thread: a barrier wait + tcgen05.commit pair costs it ~250 cycles and building a
+//     descriptor with shifts and masks ~85 cycles per MMA - more than an N <= 128 instruction takes to execute
+//     (scripts/conv_dry.py: with loads and epilogue switched off the kernel was no faster).
+// Here one TMA load brings a W-HALO box - the 8-voxel lines of the tile plus one voxel on either side, 10 x 128 B per
+// line - and the three kw taps read it through three shifted views: the UMMA descriptor starts kw rows (kw * 128 B) into
+// the box and steps 1280 B between 8-row groups (one line each).  That is legal because both TMA and UMMA derive the
+// SWIZZLE_128B XOR from absolute shared-memory address bits, so a row is found where the TMA put it whatever the
+// view's origin, and it costs nothing (scripts/micro/umma_rate.cu: 48 cycles per M128 N64 K16 instruction either
+// way).  A stage = the MT halo boxes of a (kd, kh, chunk) group + the weight tiles of its three taps under ONE barrier
+// pair, i.e. 24 MMAs per wait / commit, and descriptors step by one 32-bit add (ptx::umma_bf16_lohi).
 //
-// MEASURED (profiles/r01d_conv_halo_vs_persistent.log): correct on every test shape, but NOT faster - 64 -> 64 at
-// 8 x 80^3 takes 1.385 ms against 1.232 ms for conv_tcp.cu, 128 -> 128 is a tie.  With 2.4x fewer bytes entering the
-// SM and the same time, L2 ingest is not what bounds narrow tiles: an SS-mode tcgen05.mma re-reads its 128 x 16 A tile
-// from shared memory (~64 cycles) whatever N is, so an N = 64 instruction takes ~80-90 cycles instead of 32 and an
-// N = 128 one ~96 instead of 64 (N = 256: 128 = the MMA floor).  The kernel is therefore opt-in (B200LDM_CONV_HALO=1
-// adds it to the measured candidates, B200LDM_CONV_KERNEL=3 pins it); it stays as the tested shifted-view building
-// block for a weights-as-A (transposed) formulation, which is what would lift the 64/128-channel convs.
+// MEASURED (profiles/r01e_conv_halo.log): 64 -> 64 at 8 x 80^3 0.82 ms = 1108 TFLOP/s against 1.25 ms for conv_tcp.cu -
+// the N = 64 instruction rate (48 cycles instead of the 32-cycle floor, 66.6 %) is now the bound; 128 -> 128 at
+// 8 x 40^3 0.30 ms = 1518 TFLOP/s against 0.38 ms.  (Its first version - two rings, a barrier pair per tap, descriptors
+// rebuilt per MMA - was 12 % SLOWER than conv_tcp.cu although it moved 2.4x fewer bytes: the issuer, not L2, set the
+// pace.)
 //
 // Everything else follows conv_tcp.cu: one CTA per SM walks the tile list, two TMEM accumulator sets (the epilogue of
 // tile i overlaps the main loop of tile i+1), the same epilogue math (bias / temb / residual / GroupNorm chunk sums,
@@ -40,26 +43,26 @@ template <int BN, int MT>
 struct ConvHaloCfg {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kAStage = MT * kHaloABytes;
+  // ONE ring: a stage = the MT halo boxes of a (kd, kh, chunk) group + the weight tiles of its three kw taps, filled
+  // under one barrier and released by one commit.  The single MMA-issuing thread pays ~250 cycles per barrier wait +
+  // commit pair; with a pair per tap (8 instructions of 48 cycles for BN = 64) that overhead, not the tensor pipe,
+  // set the pace.
+  static constexpr int kStageBytes = kAStage + 3 * kBBytes;
   static constexpr int kOutBytes = MT * 16384;       // per sub-tile ONE [128 rows x 64 ch] bf16 staging buffer
   static constexpr int kBarBytes = 512;
   static constexpr int kFlagBytes = MT * 512;
   static constexpr int kTail = 1024 /*align slack*/ + kBarBytes + kFlagBytes;
   static constexpr int kBudget = 232448 - kOutBytes - kTail;
-  // both rings must cover the TMA round trip (~2-3 K cycles under load): three halo stages = 9 taps of lookahead, and
-  // the weight ring gets everything that is left (9 tiles for BN = 64, 4 for BN = 128); with 4 weight tiles of 256
-  // tensor cycles each the BN = 64 kernel was latency-bound on the weights and no faster than conv_tcp.cu
-  static constexpr int kAStages = 3;
-  static constexpr int kBStagesMax = (kBudget - kAStages * kAStage) / kBBytes;
-  static constexpr int kBStages = kBStagesMax > 12 ? 12 : kBStagesMax;
+  static constexpr int kStages = kBudget / kStageBytes > 4 ? 4 : kBudget / kStageBytes;
   static constexpr int kAccCols = MT * BN;
   static constexpr int kTmemCols = 2 * kAccCols;
   static constexpr int kThreads = 64 + MT * 128;
-  static constexpr int kSmemBytes = kAStages * kAStage + kBStages * kBBytes + kOutBytes + kTail;
-  static_assert(kBStages >= 3, "weight ring depth");
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + kTail;
+  static_assert(kStages >= 2, "pipeline depth");
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols >= 32, "TMEM columns");
   static_assert(kSmemBytes <= 232448, "shared memory budget");
-  static_assert(kAStage % 1024 == 0 && kHaloABytes % 1024 == 0 && kBBytes % 1024 == 0, "1024-byte swizzle alignment");
-  static_assert(2 * (kAStages + kBStages) * 8 + 32 + MT * 8 + 8 <= kBarBytes, "barrier area");
+  static_assert(kStageBytes % 1024 == 0 && kHaloABytes % 1024 == 0 && kBBytes % 1024 == 0, "1024-byte swizzle alignment");
+  static_assert(2 * kStages * 8 + 32 + MT * 8 + 8 <= kBarBytes, "barrier area");
 };
 
 struct HaloTile {
@@ -78,19 +81,17 @@ template <int BN, int MT>
 __global__ void __launch_bounds__(ConvHaloCfg<BN, MT>::kThreads, 1)
 conv3d_halo_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
   using Cfg = ConvHaloCfg<BN, MT>;
-  constexpr int SA = Cfg::kAStages, SB = Cfg::kBStages;
+  constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  const uint32_t a_base = smem_base;                              // A ring: stage s at + s * kAStage
-  const uint32_t b_base = a_base + SA * Cfg::kAStage;             // B ring: stage s at + s * kBBytes
-  const uint32_t out_base = b_base + SB * Cfg::kBBytes;
+  const uint32_t a_base = smem_base;                              // stage s at + s * kStageBytes: MT halo boxes ...
+  const uint32_t b_base = a_base + Cfg::kAStage;                  // ... then the three weight tiles
+  const uint32_t out_base = smem_base + STAGES * Cfg::kStageBytes;
   const uint32_t bar_base = out_base + Cfg::kOutBytes;
-  const uint32_t afull = bar_base;                       // [SA]
-  const uint32_t aempty = afull + 8 * SA;                // [SA]
-  const uint32_t bfull = aempty + 8 * SA;                // [SB]
-  const uint32_t bempty = bfull + 8 * SB;                // [SB]
-  const uint32_t tfull_bar = bempty + 8 * SB;            // [2] accumulator set complete
+  const uint32_t full_bar = bar_base;                    // [STAGES]
+  const uint32_t empty_bar = full_bar + 8 * STAGES;      // [STAGES]
+  const uint32_t tfull_bar = empty_bar + 8 * STAGES;     // [2] accumulator set complete
   const uint32_t tempty_bar = tfull_bar + 16;            // [2] accumulator set drained (MT*4 warp arrivals)
   const uint32_t res_bar = tempty_bar + 16;              // [MT] residual tile landed in the staging buffer
   const uint32_t tmem_slot = res_bar + 8 * MT;
@@ -109,8 +110,7 @@ conv3d_halo_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) 
     ptx::prefetch_tmap(&maps.w);
     ptx::prefetch_tmap(&maps.a[0]);
     ptx::prefetch_tmap(&maps.y[0]);
-    for (int s = 0; s < SA; ++s) { ptx::mbar_init(afull + 8 * s, 1); ptx::mbar_init(aempty + 8 * s, 1); }
-    for (int s = 0; s < SB; ++s) { ptx::mbar_init(bfull + 8 * s, 1); ptx::mbar_init(bempty + 8 * s, 1); }
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(full_bar + 8 * s, 1); ptx::mbar_init(empty_bar + 8 * s, 1); }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(tfull_bar + 8 * i, 1);
       ptx::mbar_init(tempty_bar + 8 * i, MT * 4);
@@ -127,52 +127,42 @@ conv3d_halo_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) 
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      uint32_t ia = 0, ib = 0;   // running stage counters of the two rings
+      uint32_t itg = 0;
       for (int wk = blockIdx.x; wk < total; wk += gridDim.x) {
         const int x = wk % work_x, co0 = (wk / work_x) * BN;
         HaloTile c[MT];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) c[mt] = halo_box(a, x * MT + mt);
-        for (int g = 0; g < groups; ++g) {
+        for (int g = 0; g < groups + nskip; ++g, ++itg) {
+          const int s = (int)(itg % STAGES);
+          ptx::mbar_wait(empty_bar + 8 * s, ((itg / STAGES) & 1u) ^ 1u, 0);
+          const uint32_t full = full_bar + 8 * s;
+          const uint32_t sa = a_base + s * Cfg::kStageBytes, sb = b_base + s * Cfg::kStageBytes;
+          if (g >= groups) {   // fused 1x1x1 skip conv: plain 128-row boxes, one tap
+            const int sc = g - groups;
+            const bool second = sc >= a.nsk1;
+            const CUtensorMap* m = second ? &maps.s[1] : &maps.s[0];
+            ptx::mbar_expect_tx(full, (uint32_t)MT * 16384u + (uint32_t)Cfg::kBBytes);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+              ptx::tma_load_5d(sa + mt * kHaloABytes, m, full, (second ? sc - a.nsk1 : sc) * 64, c[mt].w0, c[mt].h0,
+                               c[mt].d0, c[mt].n0);
+            ptx::tma_load_3d(sb, &maps.sw, full, sc * 64, co0, 0);
+            continue;
+          }
           const int kdh = g / nchunks, chunk = g - kdh * nchunks;
           const int kd = kdh / 3, kh = kdh - kd * 3;
           const bool second = chunk >= a.nchunk1;
           const CUtensorMap* m = second ? &maps.a[1] : &maps.a[0];
           const int c0 = (second ? chunk - a.nchunk1 : chunk) * 64;
-          {
-            const int s = (int)(ia % SA);
-            ptx::mbar_wait(aempty + 8 * s, ((ia / SA) & 1u) ^ 1u, 0);
-            const uint32_t full = afull + 8 * s;
-            ptx::mbar_expect_tx(full, (uint32_t)MT * kHaloABytes);
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-              ptx::tma_load_5d(a_base + s * Cfg::kAStage + mt * kHaloABytes, m, full, c0, c[mt].w0 - 1,
-                               c[mt].h0 + kh - 1, c[mt].d0 + kd - 1, c[mt].n0);
-            ++ia;
-          }
-#pragma unroll 1
-          for (int kw = 0; kw < 3; ++kw, ++ib) {
-            const int s = (int)(ib % SB);
-            ptx::mbar_wait(bempty + 8 * s, ((ib / SB) & 1u) ^ 1u, 6);
-            ptx::mbar_expect_tx(bfull + 8 * s, (uint32_t)Cfg::kBBytes);
-            ptx::tma_load_3d(b_base + s * Cfg::kBBytes, &maps.w, bfull + 8 * s, chunk * 64, co0, kdh * 3 + kw);
-          }
-        }
-        for (int sc = 0; sc < nskip; ++sc, ++ia, ++ib) {   // fused 1x1x1 skip conv: plain 128-row boxes, one tap
-          const bool second = sc >= a.nsk1;
-          const CUtensorMap* m = second ? &maps.s[1] : &maps.s[0];
-          const int s = (int)(ia % SA);
-          ptx::mbar_wait(aempty + 8 * s, ((ia / SA) & 1u) ^ 1u, 0);
-          const uint32_t full = afull + 8 * s;
-          ptx::mbar_expect_tx(full, (uint32_t)MT * 16384u);
+          ptx::mbar_expect_tx(full, (uint32_t)MT * kHaloABytes + 3u * (uint32_t)Cfg::kBBytes);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
-            ptx::tma_load_5d(a_base + s * Cfg::kAStage + mt * kHaloABytes, m, full, (second ? sc - a.nsk1 : sc) * 64,
-                             c[mt].w0, c[mt].h0, c[mt].d0, c[mt].n0);
-          const int sb = (int)(ib % SB);
-          ptx::mbar_wait(bempty + 8 * sb, ((ib / SB) & 1u) ^ 1u, 6);
-          ptx::mbar_expect_tx(bfull + 8 * sb, (uint32_t)Cfg::kBBytes);
-          ptx::tma_load_3d(b_base + sb * Cfg::kBBytes, &maps.sw, bfull + 8 * sb, sc * 64, co0, 0);
+            ptx::tma_load_5d(sa + mt * kHaloABytes, m, full, c0, c[mt].w0 - 1, c[mt].h0 + kh - 1, c[mt].d0 + kd - 1,
+                             c[mt].n0);
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)
+            ptx::tma_load_3d(sb + kw * Cfg::kBBytes, &maps.w, full, chunk * 64, co0, kdh * 3 + kw);
         }
       }
     }
@@ -180,51 +170,45 @@ conv3d_halo_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) 
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN);
-      uint32_t ia = 0, ib = 0, tile = 0;
+      // descriptor low words step by one add (ptx::umma_bf16_lohi); the halo views use SBO = one line = 1280 B
+      constexpr uint32_t ahi = ptx::umma_desc_hi_sw128(kHaloLineBytes), bhi = ptx::umma_desc_hi_sw128();
+      const uint32_t a_lo0 = ptx::umma_desc_lo_sw128(a_base), b_lo0 = ptx::umma_desc_lo_sw128(b_base);
+      uint32_t itg = 0, tile = 0;
       for (int wk = blockIdx.x; wk < total; wk += gridDim.x, ++tile) {
         const uint32_t acc = tile & 1u, use = tile >> 1;
         ptx::mbar_wait(tempty_bar + 8 * acc, (use & 1u) ^ 1u, 5);   // the epilogue drained this accumulator set
         ptx::tc_fence_after();
         const uint32_t td = tmem_base + acc * Cfg::kAccCols;
-        uint32_t first = 0;   // 0 until the first MMA of the tile has been issued
-        for (int g = 0; g < groups; ++g, ++ia) {
-          const int s = (int)(ia % SA);
-          ptx::mbar_wait(afull + 8 * s, (ia / SA) & 1u, 1);
-          const uint32_t sa = a_base + s * Cfg::kAStage;
-#pragma unroll 1
-          for (int kw = 0; kw < 3; ++kw, ++ib) {
-            const int sb_i = (int)(ib % SB);
-            ptx::mbar_wait(bfull + 8 * sb_i, (ib / SB) & 1u, 7);
-            ptx::tc_fence_after();
-            const uint32_t sb = b_base + sb_i * Cfg::kBBytes;
+        uint32_t s = itg % STAGES, ph = (itg / STAGES) & 1u;
+        for (int g = 0; g < groups + nskip; ++g, ++itg) {
+          ptx::mbar_wait(full_bar + 8 * s, ph, 1);
+          ptx::tc_fence_after();
+          const uint32_t a_lo = a_lo0 + s * (uint32_t)(Cfg::kStageBytes >> 4);
+          const uint32_t b_lo = b_lo0 + s * (uint32_t)(Cfg::kStageBytes >> 4);
+          if (g < groups) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  ptx::umma_bf16_lohi(td + mt * BN,
+                                      a_lo + (uint32_t)((mt * kHaloABytes + kw * kHaloRowBytes + k * 32) >> 4),
+                                      b_lo + (uint32_t)((kw * Cfg::kBBytes + k * 32) >> 4), ahi, bhi, idesc,
+                                      (g > 0 || kw > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+          } else {
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                ptx::umma_bf16(td + mt * BN,
-                               ptx::umma_desc_k_sw128(sa + mt * kHaloABytes + kw * kHaloRowBytes + k * 32, kHaloLineBytes),
-                               ptx::umma_desc_k_sw128(sb + k * 32), idesc, (first | (uint32_t)k) ? 1u : 0u);
+                ptx::umma_bf16_lohi(td + mt * BN, a_lo + (uint32_t)((mt * kHaloABytes + k * 32) >> 4),
+                                    b_lo + (uint32_t)(k * 2), bhi, bhi, idesc, 1u);
             }
-            first = 1;
-            ptx::umma_commit(bempty + 8 * sb_i);   // weight tile free once these MMAs retire
           }
-          ptx::umma_commit(aempty + 8 * s);        // halo box free once all three taps have read it
-        }
-        for (int sc = 0; sc < nskip; ++sc, ++ia, ++ib) {
-          const int s = (int)(ia % SA), sb_i = (int)(ib % SB);
-          ptx::mbar_wait(afull + 8 * s, (ia / SA) & 1u, 1);
-          ptx::mbar_wait(bfull + 8 * sb_i, (ib / SB) & 1u, 7);
-          ptx::tc_fence_after();
-          const uint32_t sa = a_base + s * Cfg::kAStage, sb = b_base + sb_i * Cfg::kBBytes;
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::umma_bf16(td + mt * BN, ptx::umma_desc_k_sw128(sa + mt * kHaloABytes + k * 32),
-                             ptx::umma_desc_k_sw128(sb + k * 32), idesc, 1u);
-          }
-          ptx::umma_commit(bempty + 8 * sb_i);
-          ptx::umma_commit(aempty + 8 * s);
+          ptx::umma_commit(empty_bar + 8 * s);   // stage free once these MMAs retire
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         ptx::umma_commit(tfull_bar + 8 * acc);   // accumulator set complete: wake the epilogue warps
       }

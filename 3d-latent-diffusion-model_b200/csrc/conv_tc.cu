@@ -612,13 +612,12 @@ static int g_tc2 = [] {
   const char* e = getenv("B200LDM_CONV_KERNEL");
   return e ? atoi(e) : -1;
 }();
-// B200LDM_CONV_HALO=1 adds the W-halo kernel (conv_halo.cu, kernel 3) to the measured candidates.  Off by default: it
-// moves 2.4x fewer bytes into the SM but is 12 % SLOWER on the 64-channel convs it was written for (1.385 vs 1.232 ms
-// at 8x80^3) - those are bound by the tensor core re-reading the 128 x 16 A tile from shared memory for every MMA,
-// not by L2 ingest; it won by 2 % on one shape (256 -> 128 at 40^3).
+// B200LDM_CONV_HALO=0 keeps the W-halo kernel (conv_halo.cu, kernel 3) out of the measured candidates.  It is the
+// fastest kernel for 3x3x3 stride-1 convs with Cout tiles of 64 / 128 (64 -> 64 at 8 x 80^3: 0.82 ms against 1.25 ms
+// for conv_tcp.cu, 128 -> 128 at 8 x 40^3: 0.30 against 0.38 ms).
 static const int g_halo = [] {
   const char* e = getenv("B200LDM_CONV_HALO");
-  return e ? atoi(e) : 0;
+  return e ? atoi(e) : 1;
 }();
 void set_conv_kernel(int k) { g_tc2 = k; }   // tests: exercise every kernel in one process (b200ldm_debug_set_conv_kernel)
 
@@ -954,7 +953,7 @@ static int conv3d_run_plan(const b200ldm_conv3d_params* p, const ConvPlan& pl, c
   a.trace = g_conv_trace;
   {
     const char* e = getenv("B200LDM_CONV_ASHIFT");
-    a.ashift = (e && p->stride == 1 && a.rows_box + atoi(e) <= 128) ? atoi(e) : 0;
+    a.ashift = (e && p->stride == 1 && (a.rows_box + atoi(e) <= 128 || pl.tc2 == 2)) ? atoi(e) : 0;
   }
 
   ConvTcMaps maps;

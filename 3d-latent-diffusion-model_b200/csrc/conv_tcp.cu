@@ -110,7 +110,10 @@ conv3d_tcp_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)MT * (uint32_t)a.rows_box * 128u + (uint32_t)Cfg::kBBytes;
+      // debug (B200LDM_CONV_ASHIFT, timing only - results are wrong): bit 0 = no activation loads, bit 1 = no weight
+      // loads, bit 2 (epilogue warps) = hand the accumulator back without draining it
+      const bool dry_a = (a.ashift & 1) != 0, dry_b = (a.ashift & 2) != 0;
+      const uint32_t tx_bytes = (dry_a ? 0u : (uint32_t)MT * (uint32_t)a.rows_box * 128u) + (dry_b ? 0u : (uint32_t)Cfg::kBBytes);
       uint32_t itg = 0;
       for (int wk = blockIdx.x; wk < total; wk += gridDim.x) {
         int x, co0, phase;
@@ -125,6 +128,7 @@ conv3d_tcp_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
           const uint32_t full = full_bar + 8 * s;
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
           const uint32_t sb = sa + MT * kABytes;
+          if (dry_a && dry_b) { ptx::mbar_arrive(full); continue; }
           ptx::mbar_expect_tx(full, tx_bytes);
           if (it >= iters_main) {
             const int sc = it - iters_main;
@@ -150,10 +154,12 @@ conv3d_tcp_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
             const bool second = chunk >= a.nchunk1;
             const CUtensorMap* m = second ? &maps.a[1] : &maps.a[0];
             const int c0 = (second ? chunk - a.nchunk1 : chunk) * 64;
+            if (!dry_a) {
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-              ptx::tma_load_5d(sa + mt * kABytes, m, full, c0, c[mt].w0 + kw - pad_w, c[mt].h0 + kh - pad_h,
-                               c[mt].d0 + kd - pad_d, c[mt].n0);
+              for (int mt = 0; mt < MT; ++mt)
+                ptx::tma_load_5d(sa + mt * kABytes, m, full, c0, c[mt].w0 + kw - pad_w, c[mt].h0 + kh - pad_h,
+                                 c[mt].d0 + kd - pad_d, c[mt].n0);
+            }
           } else {
             const int od = kd - a.pad_lo, oh = kh - a.pad_lo, ow = kw - a.pad_lo;
             const int pd = od & 1, ph2 = oh & 1, pw = ow & 1;
@@ -163,7 +169,7 @@ conv3d_tcp_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
               ptx::tma_load_5d(sa + mt * kABytes, m, full, chunk * 64, c[mt].w0 + ((ow - pw) >> 1),
                                c[mt].h0 + ((oh - ph2) >> 1), c[mt].d0 + ((od - pd) >> 1), c[mt].n0);
           }
-          ptx::tma_load_3d(sb, &maps.w, full, chunk * 64, co0, wtap);
+          if (!dry_b) ptx::tma_load_3d(sb, &maps.w, full, chunk * 64, co0, wtap);
         }
       }
     }
@@ -171,27 +177,31 @@ conv3d_tcp_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN);
+      constexpr uint32_t dhi = ptx::umma_desc_hi_sw128();
+      // descriptor low words: base of stage 0, then one add per stage / sub-tile / k-slice (see umma_bf16_lohi)
+      const uint32_t a_lo0 = ptx::umma_desc_lo_sw128(smem_base);
+      const uint32_t b_lo0 = ptx::umma_desc_lo_sw128(smem_base + MT * kABytes);
       uint32_t itg = 0, tile = 0;
       for (int wk = blockIdx.x; wk < total; wk += gridDim.x, ++tile) {
         const uint32_t acc = tile & 1u, use = tile >> 1;
         ptx::mbar_wait(tempty_bar + 8 * acc, (use & 1u) ^ 1u, 5);   // the epilogue drained this accumulator set
         ptx::tc_fence_after();
         const uint32_t td = tmem_base + acc * Cfg::kAccCols;
+        uint32_t s = itg % STAGES, ph = (itg / STAGES) & 1u;
         for (int it = 0; it < iters_total; ++it, ++itg) {
-          const int s = (int)(itg % STAGES);
-          const uint32_t ph = (itg / STAGES) & 1u;
           ptx::mbar_wait(full_bar + 8 * s, ph, 1);
           ptx::tc_fence_after();
-          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
-          const uint32_t sb = sa + MT * kABytes;
+          const uint32_t a_lo = a_lo0 + s * (uint32_t)(Cfg::kStageBytes >> 4);
+          const uint32_t b_lo = b_lo0 + s * (uint32_t)(Cfg::kStageBytes >> 4);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              ptx::umma_bf16(td + mt * BN, ptx::umma_desc_k_sw128(sa + mt * kABytes + k * 32),
-                             ptx::umma_desc_k_sw128(sb + k * 32), idesc, (it > 0 || k > 0) ? 1u : 0u);
+              ptx::umma_bf16_lohi(td + mt * BN, a_lo + (uint32_t)((mt * kABytes + k * 32) >> 4), b_lo + (uint32_t)(k * 2),
+                                  dhi, dhi, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
           ptx::umma_commit(empty_bar + 8 * s);   // stage free once these MMAs retire
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         ptx::umma_commit(tfull_bar + 8 * acc);   // accumulator set complete: wake the epilogue warps
       }
@@ -231,6 +241,12 @@ conv3d_tcp_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
       }
       ptx::mbar_wait_long(tfull_bar + 8 * acc, use & 1u, 2);
       ptx::tc_fence_after();
+      if (a.ashift & 4) {   // debug: no epilogue work at all
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty_bar + 8 * acc);
+        continue;
+      }
 #pragma unroll 1
       for (int g = 0; g < gmax; ++g, ++gcount) {
         const uint32_t b = gcount & 1u;

@@ -186,6 +186,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same instruction with the operand descriptors given as (low word, shared high word).  For a SWIZZLE_128B K-major
+// tile the low word is ((smem address & 0x3FFFF) >> 4) | 1 << 16 and the high word a constant, so stepping to another
+// stage / sub-tile / k-slice is ONE 32-bit add on a precomputed base instead of the shift-mask-or chain of
+// umma_desc_k_sw128 - the single MMA-issuing thread is latency-bound on exactly that chain (~85 cycles per MMA, more
+// than an N <= 128 instruction takes to execute, scripts/conv_dry.py).
+__device__ __forceinline__ uint32_t umma_desc_lo_sw128(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+}
+__host__ __device__ constexpr uint32_t umma_desc_hi_sw128(uint32_t sbo_bytes = 1024) {
+  return (sbo_bytes >> 4) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi,
+                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // A operand from TMEM (tcgen05.mma ... [d], [a_tmem], bdesc, idesc, p)
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
