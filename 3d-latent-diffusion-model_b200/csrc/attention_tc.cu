@@ -164,19 +164,26 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, BN);
       constexpr uint32_t idesc_o = ptx::umma_idesc_bf16_bmn(128, D);
+      // operand descriptors as (low word, constant high word): stepping to another stage / 64-column block / k-slice
+      // is one 32-bit add (ptx::umma_bf16_lohi) - this thread is latency-bound on descriptor arithmetic otherwise
+      constexpr uint32_t khi = ptx::umma_desc_hi_sw128();      // K-major SWIZZLE_128B (Q, K, P), SBO 1024
+      const uint32_t q_lo = ptx::umma_desc_lo_sw128(q_smem);
+      const uint32_t k_lo0 = ptx::umma_desc_lo_sw128(k_smem);
+      const uint32_t p_lo0 = ptx::umma_desc_lo_sw128(p_smem);
+      // V: MN-major SWIZZLE_128B, LBO = one 64-column block (kKVSub), SBO = 1024
+      const uint32_t v_lo0 = ((v_smem & 0x3FFFFu) >> 4) | ((uint32_t)((Cfg::kKVSub >> 4) & 0x3FFF) << 16);
       auto issue_s = [&](int j) {
         const int s = j % STAGES;
         ptx::mbar_wait(k_full + 8 * s, (uint32_t)(j / STAGES) & 1u, 11);
         if (j >= 2) ptx::mbar_wait(s_empty + 8 * (j & 1), (uint32_t)((j >> 1) - 1) & 1u, 12);
         ptx::tc_fence_after();
-        const uint32_t ks = k_smem + s * Cfg::kKVBytes;
+        const uint32_t k_lo = k_lo0 + (uint32_t)s * (uint32_t)(Cfg::kKVBytes >> 4);
         const uint32_t tS = tmem + Cfg::kSCol0 + (j & 1) * BN;
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint64_t da = ptx::umma_desc_k_sw128(q_smem + (kk >> 2) * 16384 + (kk & 3) * 32);
-          const uint64_t db = ptx::umma_desc_k_sw128(ks + (kk >> 2) * Cfg::kKVSub + (kk & 3) * 32);
-          ptx::umma_bf16(tS, da, db, idesc_s, kk > 0 ? 1u : 0u);
-        }
+        for (int kk = 0; kk < D / 16; ++kk)
+          ptx::umma_bf16_lohi(tS, q_lo + (uint32_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
+                              k_lo + (uint32_t)(((kk >> 2) * Cfg::kKVSub + (kk & 3) * 32) >> 4), khi, khi, idesc_s,
+                              kk > 0 ? 1u : 0u);
         ptx::umma_commit(s_full + 8 * (j & 1));
         ptx::umma_commit(k_empty + 8 * s);   // K_j is free once S_j retires
       };
@@ -188,14 +195,13 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         ptx::mbar_wait(v_full + 8 * s, (uint32_t)(j / STAGES) & 1u, 16);
         ptx::mbar_wait(p_full + 8 * (j & 1), (uint32_t)(j >> 1) & 1u, 14);
         ptx::tc_fence_after();
-        const uint32_t vs = v_smem + s * Cfg::kKVBytes;
+        const uint32_t v_lo = v_lo0 + (uint32_t)s * (uint32_t)(Cfg::kKVBytes >> 4);
+        const uint32_t p_lo = p_lo0 + (uint32_t)(j & 1) * (uint32_t)(Cfg::kPBytes >> 4);
         const uint32_t tO = tmem + Cfg::kOCol;
 #pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk) {
-          const uint64_t da = ptx::umma_desc_k_sw128(p_smem + (j & 1) * Cfg::kPBytes + (kk >> 2) * 16384 + (kk & 3) * 32);
-          const uint64_t db = umma_desc_mn_sw128(vs + kk * 2048, Cfg::kKVSub, 1024);
-          ptx::umma_bf16(tO, da, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
-        }
+        for (int kk = 0; kk < BN / 16; ++kk)
+          ptx::umma_bf16_lohi(tO, p_lo + (uint32_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
+                              v_lo + (uint32_t)((kk * 2048) >> 4), khi, khi, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
         ptx::umma_commit(v_empty + 8 * s);   // V_j is free once PV_j retires
         ptx::umma_commit(pv_done + 8 * (j & 1));
       }

@@ -174,27 +174,30 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN);
+      constexpr uint32_t dhi = ptx::umma_desc_hi_sw128();
+      // descriptor low words: stage 0, then one add per stage / sub-tile / k-slice (ptx::umma_bf16_lohi) - building each
+      // descriptor with shifts and masks costs this single thread ~85 cycles per MMA (conv_halo.cu header)
+      const uint32_t a_lo0 = ptx::umma_desc_lo_sw128(smem_base + a.ashift * 128);
+      const uint32_t b_lo0 = ptx::umma_desc_lo_sw128(smem_base + MT * kABytes);
+      uint32_t s = 0, ph = 0;
       for (int it = it0; it < it1; ++it) {
-        const int s = (it - it0) % STAGES;
-        const uint32_t ph = (uint32_t)((it - it0) / STAGES) & 1u;
         ptx::mbar_wait(bar_base + 8 * s, ph, 1);
         ptx::tc_fence_after();
         if (trc && it == it0) trc[1] = clock64();
-        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
-        const uint32_t sb = sa + MT * kABytes;
+        const uint32_t a_lo = a_lo0 + s * (uint32_t)(Cfg::kStageBytes >> 4);
+        const uint32_t b_lo = b_lo0 + s * (uint32_t)(Cfg::kStageBytes >> 4);
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = ptx::umma_desc_k_sw128(sa + mt * kABytes + a.ashift * 128 + k * 32);
-            const uint64_t db = ptx::umma_desc_k_sw128(sb + k * 32);
-            ptx::umma_bf16(tmem_base + mt * BN, da, db, idesc, (it > it0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16_lohi(tmem_base + mt * BN, a_lo + (uint32_t)((mt * kABytes + k * 32) >> 4),
+                                b_lo + (uint32_t)(k * 2), dhi, dhi, idesc, (it > it0 || k > 0) ? 1u : 0u);
           if (it == it1 - 1) ptx::umma_commit(tmem_full_bar + 8 * mt);  // this accumulator is complete
         }
         // frees the smem stage (in every CTA of the cluster) when the MMAs retire
         if (CL == 1) ptx::umma_commit(bar_base + 8 * (STAGES + s));
         else ptx::umma_commit_mcast(bar_base + 8 * (STAGES + s), (uint16_t)((1u << CL) - 1));
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
       if (trc) trc[2] = clock64();
     }
