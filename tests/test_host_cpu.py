@@ -264,3 +264,27 @@ def test_nifti_roundtrip(tmp_path):
     # first index fastest on disk (what nibabel writes for a C-ordered array of this shape)
     first = np.frombuffer(raw, dtype="<f4", count=5, offset=352)
     assert np.array_equal(first, vol[:, 0, 0, 0])
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the driver's reference arm): rank 0 prints ONE JSON line with the same metric / unit /
+    config keys as the GPU arm plus impl / cpu_baseline / a zero-copy e2e block; other ranks exit 0 without output."""
+    import json
+    import subprocess
+    import sys
+    bench = os.path.join(ROOT, "bench.py")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "unet_denoise_volume_steps_per_sec"
+    assert d["unit"] == "volume-steps/s" and d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["config"]["workload"].startswith("unet_step_16g")
+    r1 = subprocess.run([sys.executable, bench, "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                        capture_output=True, text=True, env={**env, "RANK": "1", "WORLD_SIZE": "2"}, timeout=600)
+    assert r1.returncode == 0 and not [l for l in r1.stdout.splitlines() if l.startswith("{")]
