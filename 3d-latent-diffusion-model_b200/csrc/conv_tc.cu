@@ -632,7 +632,7 @@ static const int g_force_splits = [] {
 struct ConvPlan {
   int bn, n_tiles, tn, td, th, tw, nb_n, nb_d, nb_h, nb_w, m_tiles, mt, cl, splits;
   int tc2;     // kernel: 0 one CTA per tile, 1 persistent CTA pairs (conv_tc2.cu), 2 persistent single CTAs (conv_tcp.cu),
-               // 3 persistent W-halo kernel (conv_halo.cu)
+               // 3 persistent W-halo kernel (conv_halo.cu), 4 conv_tcp.cu with two epilogue warp sets
   int tc2_ok;  // the problem is eligible for the persistent kernels
   int halo_ok; // ... and for the W-halo kernel
   int split_ok, ctas1, iters;   // split-K allowed; CTAs of the one-CTA-per-tile kernel at splits = 1 (mt = 1); k-iterations
@@ -774,6 +774,7 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
     pl.halo_ok = (tma_epi && pl.bn <= 128 && p->ksize == 3 && p->stride == 1 && p->pad_lo == 1 && !p->upsample2x &&
                   p->Wo >= 4) ? 1 : 0;
     if (pl.tc2 == 3 && !pl.halo_ok) pl.tc2 = 0;
+    if (pl.tc2 == 4 && pl.bn != 256) pl.tc2 = 2;   // the wide-epilogue variant exists for the 128 x 256 tile only
     if (pl.tc2 == 3) {
       pl.tn = 1; pl.tw = 8;
       choose_halo_tile(p->Do, p->Ho, &pl.td, &pl.th);
@@ -867,6 +868,7 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
       choices[nc++] = 0;
       if (pl.tc2_ok) choices[nc++] = 2;
       if (pl.halo_ok && g_halo) choices[nc++] = 3;
+      if (pl.tc2_ok && pl.bn == 256) choices[nc++] = 4;   // persistent kernel with two epilogue warp sets
       if (pl.tc2_ok && getenv("B200LDM_CONV_TUNE_PAIRS")) choices[nc++] = 1;   // CTA pairs: measured slower almost everywhere
       // (2-CTA weight-multicast variants were candidates for big launches for a while: they never won by the 2 %
       // margin, and the one intermittent launch failure of the round happened with them in the set - left out)
@@ -1047,10 +1049,10 @@ static int conv3d_run_plan(const b200ldm_conv3d_params* p, const ConvPlan& pl, c
     if (rc) return rc;
     return launch_conv_halo(maps, a, bn, m_tiles, n_tiles, st);
   }
-  if (pl.tc2 == 2 && conv_tcp_supported(bn, a)) {
+  if ((pl.tc2 == 2 || pl.tc2 == 4) && conv_tcp_supported(bn, a)) {
     rc = make_weight_map(&maps.w, p->w, Cin, cout_rows, taps, bn);
     if (rc) return rc;
-    return launch_conv_tcp(maps, a, bn, m_tiles, n_tiles, a.up ? 8 : 1, st);
+    return launch_conv_tcp(maps, a, bn, m_tiles, n_tiles, a.up ? 8 : 1, st, pl.tc2 == 4);
   }
   if (pl.tc2 == 1 && conv_tc2_supported(bn, a)) {
     // each CTA of a pair stages half of the weight tile

@@ -52,8 +52,9 @@ int launch_conv_tc2(const ConvTcMaps& maps, const ConvTcArgs& a, int bn, int m_t
 // tile i+1); MT sub-tiles per CTA = conv_tcp_mt(bn)
 bool conv_tcp_supported(int bn, const ConvTcArgs& a);
 int conv_tcp_mt(int bn);
+// wide_epilogue (Cout tile 256 only): two epilogue warp sets drain alternate 64-column groups (kernel choice 4)
 int launch_conv_tcp(const ConvTcMaps& maps, const ConvTcArgs& a, int bn, int m_tiles, int n_tiles, int zdim,
-                    cudaStream_t st);
+                    cudaStream_t st, bool wide_epilogue = false);
 
 // conv_halo.cu: persistent kernel for 3x3x3 stride-1 convs with Cout tiles of 64 / 128: W-halo activation boxes
 // (one TMA load serves the three kw taps through shifted UMMA views); tile = 1 x td x th x 8 voxels, td * th = 16

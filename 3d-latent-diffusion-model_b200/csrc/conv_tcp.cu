@@ -19,19 +19,23 @@
 
 namespace b200ldm {
 
-template <int BN, int MT>
+// EW: epilogue warp SETS per sub-tile (4 warps each, one per TMEM lane quarter); set h drains the 64-column groups
+// g = h, h + EW, ... of its sub-tile through its own staging buffers.  EW = 2 for the 128 x 256 tile doubles the drain
+// rate where the main loop is short (1x1x1 projections: 4-16 k-iterations against ~10 K cycles of epilogue).
+template <int BN, int MT, int EW = 1>
 struct ConvTcpCfg {
+  static constexpr int kSets = MT * EW;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = MT * kABytes + kBBytes;
-  static constexpr int kOutBytes = MT * 2 * 16384;   // per sub-tile: two [128 rows x 64 ch] bf16 staging buffers
+  static constexpr int kOutBytes = kSets * 2 * 16384;   // per set: two [128 rows x 64 ch] bf16 staging buffers
   static constexpr int kBarBytes = 512;
-  static constexpr int kFlagBytes = MT * 512;        // per sub-tile: row-valid flags + per-chunk partial sums
+  static constexpr int kFlagBytes = kSets * 512;        // per set: row-valid flags + per-chunk partial sums
   static constexpr int kTail = 1024 /*align slack*/ + kBarBytes + kFlagBytes;
   static constexpr int kBudget = 232448 - kOutBytes - kTail;
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
   static constexpr int kAccCols = MT * BN;           // one accumulator set
   static constexpr int kTmemCols = 2 * kAccCols;
-  static constexpr int kThreads = 64 + MT * 128;     // warp0 TMA, warp1 MMA + TMEM owner, MT*4 epilogue warps
+  static constexpr int kThreads = 64 + kSets * 128;  // warp0 TMA, warp1 MMA + TMEM owner, 4 epilogue warps per set
   static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + kTail;
   static_assert(kStages >= 3, "pipeline depth");
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols >= 32, "TMEM columns");
@@ -59,10 +63,11 @@ __device__ __forceinline__ TcpTile tcp_box(const ConvTcArgs& a, int t) {
   return c;
 }
 
-template <int BN, int MT>
-__global__ void __launch_bounds__(ConvTcpCfg<BN, MT>::kThreads, 1)
+template <int BN, int MT, int EW>
+__global__ void __launch_bounds__(ConvTcpCfg<BN, MT, EW>::kThreads, 1)
 conv3d_tcp_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
-  using Cfg = ConvTcpCfg<BN, MT>;
+  using Cfg = ConvTcpCfg<BN, MT, EW>;
+  constexpr int SETS = Cfg::kSets;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -72,9 +77,9 @@ conv3d_tcp_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
   const uint32_t full_bar = bar_base;                    // [STAGES]
   const uint32_t empty_bar = bar_base + 8 * STAGES;      // [STAGES]
   const uint32_t tfull_bar = bar_base + 16 * STAGES;     // [2] accumulator set complete
-  const uint32_t tempty_bar = tfull_bar + 16;            // [2] accumulator set drained (MT*4 warp arrivals)
-  const uint32_t res_bar = tempty_bar + 16;              // [MT][2] residual tile landed in staging buffer
-  const uint32_t tmem_slot = res_bar + 8 * MT * 2;
+  const uint32_t tempty_bar = tfull_bar + 16;            // [2] accumulator set drained (SETS*4 warp arrivals)
+  const uint32_t res_bar = tempty_bar + 16;              // [SETS][2] residual tile landed in staging buffer
+  const uint32_t tmem_slot = res_bar + 8 * SETS * 2;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
   uint8_t* flag_gen = smem_gen + (bar_base - smem_base) + Cfg::kBarBytes;
 
@@ -96,9 +101,9 @@ conv3d_tcp_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(tfull_bar + 8 * i, 1);
-      ptx::mbar_init(tempty_bar + 8 * i, MT * 4);
+      ptx::mbar_init(tempty_bar + 8 * i, SETS * 4);
     }
-    for (int i = 0; i < MT * 2; ++i) ptx::mbar_init(res_bar + 8 * i, 1);
+    for (int i = 0; i < SETS * 2; ++i) ptx::mbar_init(res_bar + 8 * i, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -209,14 +214,16 @@ conv3d_tcp_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
   } else {
     // =========================== epilogue (4 warps per sub-tile) ===========================
     constexpr int G = BN / 64;
-    const int mt = (warp - 2) >> 2;  // which sub-tile / accumulator of the set
+    const int es = (warp - 2) >> 2;  // epilogue warp set
+    const int mt = es % MT;          // which sub-tile / accumulator of the accumulator set
+    const int half = es / MT;        // this set drains the 64-column groups g = half, half + EW, ...
     const int q = warp & 3;          // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane;   // accumulator row == voxel slot in the box
     const bool issuer = (((warp - 2) & 3) == 0) && lane == 0;
-    const uint32_t my_out = out_base + (uint32_t)mt * 2 * 16384;
-    uint8_t* my_out_gen = smem_gen + (out_base - smem_base) + (size_t)mt * 2 * 16384;
-    const uint32_t my_res = res_bar + 8 * mt * 2;
-    uint8_t* vrow = flag_gen + mt * 512;                        // [128] row-valid flags
+    const uint32_t my_out = out_base + (uint32_t)es * 2 * 16384;
+    uint8_t* my_out_gen = smem_gen + (out_base - smem_base) + (size_t)es * 2 * 16384;
+    const uint32_t my_res = res_bar + 8 * es * 2;
+    uint8_t* vrow = flag_gen + es * 512;                        // [128] row-valid flags
     float* csum = reinterpret_cast<float*>(vrow + 128);         // [G*8][2]
     const bool do_stats = a.chunk_stats != nullptr;
     uint32_t tile = 0, gcount = 0, res_ph0 = 0, res_ph1 = 0;
@@ -247,8 +254,13 @@ conv3d_tcp_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
         if (lane == 0) ptx::mbar_arrive(tempty_bar + 8 * acc);
         continue;
       }
+      if (half >= gmax) {   // no group for this set in a narrow last Cout tile: hand the accumulator back untouched
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty_bar + 8 * acc);
+      }
 #pragma unroll 1
-      for (int g = 0; g < gmax; ++g, ++gcount) {
+      for (int g = half; g < gmax; g += EW, ++gcount) {
         const uint32_t b = gcount & 1u;
         const uint32_t stg = my_out + b * 16384;
         uint8_t* stg_gen = my_out_gen + b * 16384;
@@ -263,10 +275,10 @@ conv3d_tcp_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
             ptx::tma_load_5d(stg, &maps.r, my_res + 8 * b, co0 + g * 64, c.w0, c.h0, c.d0, c.n0);
           }
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");   // buffer b is free, flags are visible
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + es) : "memory");   // buffer b is free, flags are visible
         ptx::tmem_ld_wait();
-        if (g == gmax - 1) {
-          // every column of this accumulator is in registers: hand it back to the MMA issuer
+        if (g + EW >= gmax) {
+          // every column this set reads is in registers: hand the accumulator back to the MMA issuer
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(tempty_bar + 8 * acc);
@@ -322,7 +334,7 @@ conv3d_tcp_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
           }
         }
         ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA store
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + es) : "memory");
         if (issuer) {
           ptx::tma_store_5d(&maps.y[phase], stg, co0 + g * 64, c.w0, c.h0, c.d0, c.n0);
           ptx::tma_store_commit();
@@ -354,8 +366,8 @@ conv3d_tcp_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
         }
       }
       if (do_stats) {
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
-        if (row < gmax * 16 && c.n0 < a.N) {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + es) : "memory");
+        if (row < gmax * 16 && ((row >> 4) % EW) == half && c.n0 < a.N) {
           const int k = row >> 1, which = row & 1;   // chunk k of this Cout tile, 0 = sum / 1 = sumsq
           atomicAdd(a.chunk_stats + ((size_t)c.n0 * (a.Cout >> 3) + (co0 >> 3) + k) * 2 + which, (double)csum[row]);
         }
@@ -377,14 +389,14 @@ bool conv_tcp_supported(int bn, const ConvTcArgs& a) {
 }
 int conv_tcp_mt(int bn) { return bn == 256 ? 1 : 2; }
 
-template <int BN, int MT>
+template <int BN, int MT, int EW = 1>
 static int launch_tcp(const ConvTcMaps& maps, ConvTcArgs a, int m_tiles, int n_tiles, int zdim, cudaStream_t st) {
-  using Cfg = ConvTcpCfg<BN, MT>;
+  using Cfg = ConvTcpCfg<BN, MT, EW>;
   static int sms = 0;
   static std::once_flag once;
   static cudaError_t init_err = cudaSuccess;
   std::call_once(once, [] {
-    init_err = cudaFuncSetAttribute(conv3d_tcp_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    init_err = cudaFuncSetAttribute(conv3d_tcp_kernel<BN, MT, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::kSmemBytes);
     int dev = 0;
     cudaGetDevice(&dev);
@@ -394,15 +406,16 @@ static int launch_tcp(const ConvTcMaps& maps, ConvTcArgs a, int m_tiles, int n_t
   a.work_x = ceil_div(m_tiles, MT); a.work_y = n_tiles; a.work_z = zdim;
   const long long total = (long long)a.work_x * a.work_y * a.work_z;
   const unsigned grid = (unsigned)(total < sms ? total : sms);
-  conv3d_tcp_kernel<BN, MT><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps, a);
+  conv3d_tcp_kernel<BN, MT, EW><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps, a);
   B2_LAUNCH_CHECK();
   return B200LDM_OK;
 }
 
 int launch_conv_tcp(const ConvTcMaps& maps, const ConvTcArgs& a, int bn, int m_tiles, int n_tiles, int zdim,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool wide_epilogue) {
   switch (bn) {
-    case 256: return launch_tcp<256, 1>(maps, a, m_tiles, n_tiles, zdim, st);
+    case 256: return wide_epilogue ? launch_tcp<256, 1, 2>(maps, a, m_tiles, n_tiles, zdim, st)
+                                   : launch_tcp<256, 1>(maps, a, m_tiles, n_tiles, zdim, st);
     case 128: return launch_tcp<128, 2>(maps, a, m_tiles, n_tiles, zdim, st);
     case 64: return launch_tcp<64, 2>(maps, a, m_tiles, n_tiles, zdim, st);
   }

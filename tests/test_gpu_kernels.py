@@ -302,12 +302,13 @@ def test_tap_gather_fp32_exact():
     assert torch.allclose(y, want, atol=1e-5, rtol=1e-5)
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 2, 3], ids=["tile_per_cta", "cta_pairs", "persistent", "w_halo"])
+@pytest.mark.parametrize("kernel", [0, 1, 2, 3, 4], ids=["tile_per_cta", "cta_pairs", "persistent", "w_halo", "persistent_wide_epi"])
 @pytest.mark.parametrize("case", [(2, (9, 11, 7), 128, 0, 256, 3, 1), (1, (8, 8, 8), 64, 64, 64, 3, 1), (2, (6, 10, 6), 64, 0, 128, 3, 2),
                                   (3, (5, 5, 5), 256, 0, 512, 1, 1), (1, (18, 22, 14), 64, 0, 64, 3, 1),
                                   (8, (4, 4, 4), 128, 0, 192, 3, 1), (5, (3, 4, 2), 64, 64, 320, 3, 1),
                                   (2, (16, 16, 16), 64, 0, 64, 3, 1), (1, (9, 11, 13), 128, 0, 128, 3, 1),
-                                  (3, (4, 20, 24), 128, 64, 64, 3, 1)],
+                                  (3, (4, 20, 24), 128, 64, 64, 3, 1), (2, (1, 1, 300), 256, 0, 768, 1, 1),
+                                  (1, (6, 6, 6), 128, 128, 512, 3, 1)],
                          ids=lambda c: f"N{c[0]}_{'x'.join(map(str, c[1]))}_C{c[2]}+{c[3]}->{c[4]}_k{c[5]}s{c[6]}")
 def test_conv3d_every_tensor_core_kernel(case, kernel):
     """the tcgen05 conv kernels (one CTA per tile, persistent CTA pairs, persistent single CTAs, persistent W-halo) pinned
