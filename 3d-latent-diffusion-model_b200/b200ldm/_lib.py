@@ -27,7 +27,7 @@ class ConvParams(C.Structure):
         ("engine", C.c_int32), ("out_f32", C.c_int32), ("upsample2x", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("chunk_stats", C.c_void_p),
         ("skip_x", C.c_void_p), ("skip_x2", C.c_void_p), ("skip_w", C.c_void_p),
-        ("skip_C1", C.c_int32), ("skip_C2", C.c_int32),
+        ("skip_C1", C.c_int32), ("skip_C2", C.c_int32), ("chunk_width", C.c_int32),
     ]
 
 
@@ -60,6 +60,8 @@ SIGNATURES = {
                                           _i32, _vp]),
     "b200ldm_groupnorm_apply_chunked": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _f32,
                                                   _i32, _i32, _vp]),
+    "b200ldm_groupnorm_apply_chunked_w": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32,
+                                                    _f32, _i32, _i32, _i32, _vp]),
     "b200ldm_groupnorm_small_fits": (C.c_int, [_i64, _i32, _i32, _i32]),
     "b200ldm_groupnorm_small": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _f32, _i32, _i32, _vp]),
     "b200ldm_fill_zero": (C.c_int, [_vp, _sz, _vp]),

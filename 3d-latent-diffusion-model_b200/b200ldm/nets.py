@@ -89,6 +89,16 @@ class Conv(nn.Module):
         self.cout_phys = ops.round_up(cout, 16) if terminal else _pad64(cout)
         self.terminal = terminal
         self._cache = PackedCache()
+        # groups of the GroupNorm that consumes this conv's output (set by the owning network): with fewer than 8
+        # channels per group (AutoencoderKL: 64 / 128 channels in 32 groups) the epilogue's statistics are emitted
+        # per group instead of per 8 channels, so that GroupNorm still needs no statistics pass
+        self.stats_groups = None
+
+    def stats_width(self) -> int:
+        g = self.stats_groups
+        if g and self.cout % g == 0 and self.cout // g in (2, 4) and self.cout % 64 == 0:
+            return self.cout // g
+        return 8
 
     def packed(self, dtype, c1: int | None = None, c1_phys: int | None = None, cin_phys: int | None = None):
         """(weights [k^3][cout_phys][cin_phys], bias fp32 [cout_phys]); c1/c1_phys describe a concat split."""
@@ -115,7 +125,8 @@ class Conv(nn.Module):
             w, b = self.packed(x.dtype, c1=c1, c1_phys=x.shape[-1], cin_phys=x.shape[-1] + x2.shape[-1])
         return ops.conv3d(x, w, b, self.cout_phys, self.ksize, self.stride, self.pad_lo, self.pad_hi, x2=x2, temb=temb,
                           temb_stride=temb_stride, residual=residual, gn_stats=gn_stats, gn_groups=gn_groups,
-                          out_f32=out_f32, want_stats=want_stats, out=out, cstats_out=cstats_out)
+                          out_f32=out_f32, want_stats=want_stats, out=out, cstats_out=cstats_out,
+                          stats_width=self.stats_width())
 
 
     def tap_expanded(self, x) -> bool:
@@ -160,7 +171,7 @@ class Conv(nn.Module):
 
         b = self._cache.get(("bias+skip",), (self.bias, skip_conv.bias), build)
         return ops.conv3d(x, w, b, self.cout_phys, self.ksize, self.stride, self.pad_lo, self.pad_hi,
-                          skip=(sx, sx2, sw), want_stats=want_stats)
+                          skip=(sx, sx2, sw), want_stats=want_stats, stats_width=self.stats_width())
 
     def run_upsampled(self, x):
         """conv(nearest_upsample_x2(x)) without materialising the upsampled tensor: on the tensor-core
@@ -177,8 +188,10 @@ class Conv(nn.Module):
         else:
             w, b = self.packed(x.dtype, cin_phys=cin_phys)
             if not FUSE_UPSAMPLE:
-                return ops.conv3d(ops.upsample_nearest2x(x), w, b, self.cout_phys, 3, 1, 1, 1, want_stats=True)
-        return ops.conv3d(x, w, b, self.cout_phys, 3, 1, 1, 1, upsample2x=True, want_stats=True)
+                return ops.conv3d(ops.upsample_nearest2x(x), w, b, self.cout_phys, 3, 1, 1, 1, want_stats=True,
+                                  stats_width=self.stats_width())
+        return ops.conv3d(x, w, b, self.cout_phys, 3, 1, 1, 1, upsample2x=True, want_stats=True,
+                          stats_width=self.stats_width())
 
 
 class ConvOnly(nn.Module):
@@ -676,6 +689,7 @@ class DiffusionModelUNet(nn.Module):
             cs = getattr(t, "cstats", None)
             if cs is not None:
                 v.cstats = cs.view(N, -1)[lo:hi].reshape(-1)
+                v.cstats_width = getattr(t, "cstats_width", 8)
             return v
 
         blk0, blk_last = self.down_blocks[0], self.up_blocks[-1]
@@ -1023,6 +1037,9 @@ class AutoencoderKL(nn.Module):
         self.quant_conv_mu = ConvOnly(latent_channels, latent_channels, 1, 1, 0, terminal=True)
         self.quant_conv_log_sigma = ConvOnly(latent_channels, latent_channels, 1, 1, 0, terminal=True)
         self.post_quant_conv = ConvOnly(latent_channels, latent_channels, 1, 1, 0)
+        for m in self.modules():   # every conv here feeds a GroupNorm with norm_num_groups groups (or nothing)
+            if isinstance(m, Conv):
+                m.stats_groups = norm_num_groups
 
     # ---- NDHWC cores
     def decode_ndhwc(self, z):

@@ -83,7 +83,7 @@ def conv_out_extent(n: int, k: int, stride: int, pad_lo: int, pad_hi: int) -> in
 def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo: int = 1, pad_hi: int | None = None,
            x2=None, temb=None, temb_stride: int = 0, residual=None, gn_stats=None, gn_groups: int = 0,
            out_f32: bool = False, engine: int = ENGINE_AUTO, upsample2x: bool = False, want_stats: bool = False,
-           skip=None, out=None, cstats_out=None):
+           skip=None, out=None, cstats_out=None, stats_width: int = 8):
     """y = conv3d(cat(x, x2)) + bias (+ temb) (+ residual); x: [N,D,H,W,C1] NDHWC.
     upsample2x: the conv runs on the nearest-x2-upsampled x without materialising it (bf16: phase-decomposed
     weights from repack_upconv_weight; fp32: ordinary weights).
@@ -91,6 +91,8 @@ def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo
     skip_connection fused as extra K iterations; `bias` must already include its bias).  bf16 only.
     want_stats: when the tensor-core epilogue can, it also accumulates per-8-channel (sum, sumsq) of y; the result is
     attached as `y.cstats` and lets the following GroupNorm skip its statistics pass.
+    stats_width: channels per statistics entry (8; 2 or 4 = the group width of a following GroupNorm with fewer than
+    8 channels per group - the persistent kernels emit those for Cout tiles <= 128); attached as `y.cstats_width`.
     out / cstats_out: write into this (contiguous, e.g. a batch slice of a larger tensor) instead of allocating; the
     statistics slice must arrive zeroed."""
     _need_cuda(x, x2, w_packed, bias, temb, residual)
@@ -111,7 +113,8 @@ def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo
         x=_ptr(x), x2=_ptr(x2), w=_ptr(w_packed), bias=_ptr(bias), temb=_ptr(temb), residual=_ptr(residual),
         y=_ptr(y), gn_stats=_ptr(gn_stats), N=N, D=D, H=H, W=W, C1=C1, C2=C2, Cout=cout, Do=Do, Ho=Ho, Wo=Wo,
         ksize=ksize, stride=stride, pad_lo=pad_lo, temb_stride=temb_stride, gn_groups=gn_groups,
-        dtype=dtype_code(x.dtype), engine=engine, out_f32=int(out_f32), upsample2x=int(upsample2x))
+        dtype=dtype_code(x.dtype), engine=engine, out_f32=int(out_f32), upsample2x=int(upsample2x),
+        chunk_width=stats_width if want_stats else 0)
     if skip is not None:
         sx, sx2, sw = skip
         _need_cuda(sx, sx2, sw)
@@ -127,15 +130,15 @@ def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo
     cstats = None
     if want_stats and FUSE_GN_STATS and lib.b200ldm_conv3d_emits_chunk_stats(C.byref(p)):
         if cstats_out is not None:
-            assert cstats_out.dtype == torch.float64 and cstats_out.numel() == N * (cout // 8) * 2
+            assert cstats_out.dtype == torch.float64 and cstats_out.numel() == N * (cout // stats_width) * 2
             cstats = cstats_out
         else:
-            cstats = zeros_f64(N * (cout // 8) * 2, x.device)
+            cstats = zeros_f64(N * (cout // stats_width) * 2, x.device)
         p.chunk_stats = cstats.data_ptr()
     ev = PROFILER.start() if PROFILER is not None else None
     _lib.check(lib.b200ldm_conv3d(C.byref(p), _stream()), "conv3d")
     if cstats is not None:
-        y.cstats = cstats
+        y.cstats, y.cstats_width = cstats, stats_width
     if ev is not None:
         # algorithmic FLOPs of the (padded) problem the kernel ran: 2*M*Cout*Cin*k^3
         # (fused upsample on tensor cores: 8 of the 27 taps are executed per output voxel - EXECUTED flops)
@@ -200,13 +203,16 @@ def groupnorm(x, gamma, beta, groups: int, eps: float, silu: bool, x2=None, stat
     dt = dtype_code(x.dtype)
     nbytes = float(N * S * (C1 + C2) * x.element_size())
     cs1, cs2 = getattr(x, "cstats", None), (None if x2 is None else getattr(x2, "cstats", None))
-    if stats is None and cs1 is not None and (x2 is None or cs2 is not None) and ((C1 + C2) // groups) % 8 == 0:
+    cw = getattr(x, "cstats_width", 8)
+    if (stats is None and cs1 is not None and (x2 is None or (cs2 is not None and getattr(x2, "cstats_width", 8) == cw))
+            and ((C1 + C2) // groups) % cw == 0 and C1 % cw == 0):
         # statistics already accumulated by the producing conv(s): one pass only
         y = torch.empty(x.shape[:-1] + (C1 + C2,), dtype=x.dtype, device=x.device)
         ev = PROFILER.start() if PROFILER is not None else None
-        _lib.check(lib.b200ldm_groupnorm_apply_chunked(_ptr(x), _ptr(x2), y.data_ptr(), cs1.data_ptr(), _ptr(cs2),
-                                                       gamma.data_ptr(), beta.data_ptr(), N, S, C1, C2, groups,
-                                                       float(eps), int(silu), dt, _stream()), "groupnorm_apply_chunked")
+        _lib.check(lib.b200ldm_groupnorm_apply_chunked_w(_ptr(x), _ptr(x2), y.data_ptr(), cs1.data_ptr(), _ptr(cs2),
+                                                         gamma.data_ptr(), beta.data_ptr(), N, S, C1, C2, groups,
+                                                         float(eps), int(silu), dt, cw, _stream()),
+                   "groupnorm_apply_chunked")
         if ev is not None:
             PROFILER.stop("gn_apply", f"C{C1 + C2} S{S}", 2.0 * nbytes, ev)
         return y

@@ -50,7 +50,7 @@ struct ConvHaloCfg {
   static constexpr int kStageBytes = kAStage + 3 * kBBytes;
   static constexpr int kOutBytes = MT * 16384;       // per sub-tile ONE [128 rows x 64 ch] bf16 staging buffer
   static constexpr int kBarBytes = 512;
-  static constexpr int kFlagBytes = MT * 512;
+  static constexpr int kFlagBytes = MT * 768;
   static constexpr int kTail = 1024 /*align slack*/ + kBarBytes + kFlagBytes;
   static constexpr int kBudget = 232448 - kOutBytes - kTail;
   static constexpr int kStages = kBudget / kStageBytes > 4 ? 4 : kBudget / kStageBytes;
@@ -224,9 +224,10 @@ conv3d_halo_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) 
     uint8_t* stg_gen = smem_gen + (out_base - smem_base) + (size_t)mt * 16384;
     uint8_t* rowp = stg_gen + (size_t)row * 128;
     const uint32_t my_res = res_bar + 8 * mt;
-    uint8_t* vrow = flag_gen + mt * 512;                        // [128] row-valid flags
+    uint8_t* vrow = flag_gen + mt * 768;                        // [128] row-valid flags
     float* csum = reinterpret_cast<float*>(vrow + 128);         // [G*8][2]
     const bool do_stats = a.chunk_stats != nullptr;
+    const int ns = 8 / a.cw;   // sub-sums per 8-channel chunk (chunk width 8, 4 or 2)
     uint32_t tile = 0, res_ph = 0;
     int t = row;
     const int rw = t % a.tw; t /= a.tw;
@@ -243,7 +244,7 @@ conv3d_halo_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) 
       const int gmax = min(G, (a.Cout - co0 + 63) / 64);   // 64-channel groups present in this Cout tile
       if (do_stats) {
         vrow[row] = valid ? 1 : 0;
-        if (row < G * 16) csum[row] = 0.f;
+        if (row < G * 16 * ns) csum[row] = 0.f;
       }
       ptx::mbar_wait_long(tfull_bar + 8 * acc, use & 1u, 2);
       ptx::tc_fence_after();
@@ -325,7 +326,7 @@ conv3d_halo_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) 
         if (do_stats) {
           // thread (slice = row>>3, chunk = row&7) sums 8 rows x 8 channels of the staged tile
           const int cch = row & 7, slice = row >> 3;
-          float s1 = 0.f, s2 = 0.f;
+          float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};   // per channel PAIR of the 8-channel chunk
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = slice * 8 + i;
@@ -335,25 +336,34 @@ conv3d_halo_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) 
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 t2 = __bfloat1622float2(hp[e]);
-                s1 += t2.x + t2.y;
-                s2 = fmaf(t2.x, t2.x, fmaf(t2.y, t2.y, s2));
+                s1[e] += t2.x + t2.y;
+                s2[e] = fmaf(t2.x, t2.x, fmaf(t2.y, t2.y, s2[e]));
               }
             }
           }
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 8); s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 16); s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-          if (lane < 8) {
-            atomicAdd(&csum[(g * 8 + lane) * 2], s1);
-            atomicAdd(&csum[(g * 8 + lane) * 2 + 1], s2);
+          // fold the pair sums to the chunk width: ns = 8 / cw sub-sums per 8-channel chunk (1, 2 or 4)
+          if (ns <= 2) { s1[0] += s1[1]; s2[0] += s2[1]; s1[1] = s1[2] + s1[3]; s2[1] = s2[2] + s2[3]; }
+          if (ns == 1) { s1[0] += s1[1]; s2[0] += s2[1]; }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i < ns) {   // warp-uniform
+              float a1 = s1[i], a2 = s2[i];
+              a1 += __shfl_xor_sync(0xffffffffu, a1, 8); a2 += __shfl_xor_sync(0xffffffffu, a2, 8);
+              a1 += __shfl_xor_sync(0xffffffffu, a1, 16); a2 += __shfl_xor_sync(0xffffffffu, a2, 16);
+              if (lane < 8) {
+                atomicAdd(&csum[((g * 8 + lane) * ns + i) * 2], a1);
+                atomicAdd(&csum[((g * 8 + lane) * ns + i) * 2 + 1], a2);
+              }
+            }
           }
           // the statistics read the staged tile: with ONE staging buffer the next group's writes must wait for them
           asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
         }
       }
       if (do_stats) {
-        if (row < gmax * 16 && c.n0 < a.N) {
+        if (row < gmax * 16 * ns && c.n0 < a.N) {
           const int k = row >> 1, which = row & 1;   // chunk k of this Cout tile, 0 = sum / 1 = sumsq
-          atomicAdd(a.chunk_stats + ((size_t)c.n0 * (a.Cout >> 3) + (co0 >> 3) + k) * 2 + which, (double)csum[row]);
+          atomicAdd(a.chunk_stats + ((size_t)c.n0 * (a.Cout / a.cw) + co0 / a.cw + k) * 2 + which, (double)csum[row]);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");   // csum is re-zeroed at the top of the next tile
       }

@@ -796,11 +796,16 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
 }
 
 // 1 when this exact problem runs the TMA epilogue with one sample per tile and no split-K, i.e. can emit chunk stats
+static int chunk_width_of(const b200ldm_conv3d_params* p) { return p->chunk_width ? p->chunk_width : 8; }
+// chunk sums finer than 8 channels exist in the persistent kernels (conv_tcp.cu, conv_halo.cu) with Cout tiles <= 128
+static bool plan_emits_width(const ConvPlan& pl, int cw) {
+  return cw == 8 || ((cw == 2 || cw == 4) && pl.bn <= 128 && (pl.tc2 == 2 || pl.tc2 == 3));
+}
 int conv3d_tcgen05_emits_chunk_stats(const b200ldm_conv3d_params* p) {
   if (p->dtype != B200LDM_BF16 || p->C1 % 64 || p->C2 % 64 || p->Cout % 64 || p->out_f32 || p->gn_stats) return 0;
   if (g_legacy_epilogue) return 0;
   const ConvPlan pl = plan_conv(p);
-  return (pl.splits == 1 && pl.tn == 1 && pl.bn >= 64) ? 1 : 0;   // holds for both tensor-core kernels
+  return (pl.splits == 1 && pl.tn == 1 && pl.bn >= 64 && plan_emits_width(pl, chunk_width_of(p))) ? 1 : 0;
 }
 
 long long conv3d_tcgen05_workspace_bytes(const b200ldm_conv3d_params* p) {
@@ -893,7 +898,7 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
         if (cp.splits > 1 && (!p->workspace || p->workspace_bytes < (long long)cp.splits * M_total * p->Cout * 4)) continue;
         b200ldm_conv3d_params q = *p;
         // statistics are accumulated by atomics: tuning launches must not add to the caller's buffer
-        if (cp.splits > 1 || cp.tn != 1) q.chunk_stats = nullptr;
+        if (cp.splits > 1 || cp.tn != 1 || !plan_emits_width(cp, chunk_width_of(p))) q.chunk_stats = nullptr;
         for (int rep = 0; rep < 3 && rc == B200LDM_OK; ++rep) {
           if (rep == 1) cudaEventRecord(e0, st);
           rc = conv3d_run_plan(&q, cp, st);
@@ -909,7 +914,8 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
       cudaEventDestroy(e1);
       if (rc != B200LDM_OK) return rc;
       if (p->chunk_stats)   // undo what the tuning launches accumulated
-        B2_CHECK_CUDA(cudaMemsetAsync(p->chunk_stats, 0, (size_t)p->N * (p->Cout / 8) * 2 * sizeof(double), st));
+        B2_CHECK_CUDA(cudaMemsetAsync(p->chunk_stats, 0,
+                                      (size_t)p->N * (p->Cout / chunk_width_of(p)) * 2 * sizeof(double), st));
       remember_choice(key, best);
       if (getenv("B200LDM_CONV_AUTOTUNE_LOG"))
         fprintf(stderr, "b200ldm autotune: %d+%d->%d k%d s%d%s%s%s @%dx%dx%dx%d: model plan %.3f ms, persistent %.3f ms, "
@@ -920,7 +926,7 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
       // the caller asked workspace_bytes / emits_chunk_stats before this call: honour that contract now (no stats
       // where it was told there would be none), later calls see the remembered choice
       ConvPlan run = plan_conv(p, best);
-      if (p->chunk_stats && (run.splits > 1 || run.tn != 1)) run = pl;
+      if (p->chunk_stats && (run.splits > 1 || run.tn != 1 || !plan_emits_width(run, chunk_width_of(p)))) run = pl;
       if (run.splits > 1 && (!p->workspace || p->workspace_bytes < (long long)run.splits * M_total * p->Cout * 4)) run = pl;
       return conv3d_run_plan(p, run, st);
     }
@@ -1016,8 +1022,9 @@ static int conv3d_run_plan(const b200ldm_conv3d_params* p, const ConvPlan& pl, c
   a.tma_epilogue = (!a.out_f32 && p->Cout % 64 == 0 && !p->gn_stats && bn >= 64 && g_legacy_epilogue == 0) ? 1 : 0;
   if (a.up) B2_REQUIRE(a.tma_epilogue, B200LDM_BAD_SHAPE, "fused upsample conv needs the TMA epilogue");
   a.chunk_stats = p->chunk_stats;
+  a.cw = chunk_width_of(p);
   if (p->chunk_stats)
-    B2_REQUIRE(a.tma_epilogue && pl.tn == 1 && pl.splits == 1, B200LDM_BAD_ARG,
+    B2_REQUIRE(a.tma_epilogue && pl.tn == 1 && pl.splits == 1 && plan_emits_width(pl, a.cw), B200LDM_BAD_ARG,
                "conv3d: chunk_stats not available for this problem (ask b200ldm_conv3d_emits_chunk_stats first)");
   if (a.tma_epilogue) {
     const uint64_t Co = p->Cout, Wo = p->Wo, Ho = p->Ho, Do = p->Do;

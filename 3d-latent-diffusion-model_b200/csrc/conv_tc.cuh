@@ -30,7 +30,8 @@ struct ConvTcArgs {
   const void* residual;
   void* y;
   double* gn_stats;
-  double* chunk_stats;        // [N][Cout/8][2] (sum, sumsq) per 8-channel chunk of y, accumulated by the TMA epilogue
+  double* chunk_stats;        // [N][Cout/cw][2] (sum, sumsq) per cw-channel chunk of y, accumulated by the TMA epilogue
+  int cw;                     // chunk width: 8, or 2 / 4 (conv_tcp.cu / conv_halo.cu with Cout tiles <= 128 only)
   int up;                     // 1: nearest-x2 upsample fused as 8 phase convs of 2x2x2 taps (blockIdx.z = phase)
   int splits;                 // split-K: blockIdx.z handles k-iterations [z*I/S, (z+1)*I/S) and writes fp32 slab z
   long long slab_elems;       // elements per fp32 slab (N*Do*Ho*Wo*Cout)

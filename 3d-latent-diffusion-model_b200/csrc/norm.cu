@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kNormThreads, MINB)
 gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict__ y,
                 const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                 long long S, int C1, int C2, int G, float eps, int silu, int vox_per_block, double inv_cnt_arg,
-                const double* __restrict__ cst1, const double* __restrict__ cst2) {
+                const double* __restrict__ cst1, const double* __restrict__ cst2, int cw) {
   const int n = gridDim.y - 1 - blockIdx.y;   // back to front, see gn_stats_kernel
   const int C = C1 + C2;
   const int vecs = C >> 3;
@@ -103,11 +103,12 @@ gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict
     if (g != g_prev) {
       double sum1, sum2;
       if (cst1) {
-        // assemble the group from per-8-channel chunk sums; chunks [0, C1/8) live in cst1, the rest in cst2
+        // assemble the group from per-cw-channel chunk sums (cw = 8, or 2 / 4 = the group width of narrow tensors);
+        // chunks [0, C1/cw) live in cst1, the rest in cst2
         sum1 = 0.0; sum2 = 0.0;
-        const int k0 = (g * cpg) >> 3, k1 = ((g + 1) * cpg) >> 3, kc1 = C1 >> 3;
+        const int k0 = (g * cpg) / cw, k1 = ((g + 1) * cpg) / cw, kc1 = C1 / cw;
         for (int k = k0; k < k1; ++k) {
-          const double* e2 = k < kc1 ? cst1 + ((size_t)n * kc1 + k) * 2 : cst2 + ((size_t)n * (C2 >> 3) + (k - kc1)) * 2;
+          const double* e2 = k < kc1 ? cst1 + ((size_t)n * kc1 + k) * 2 : cst2 + ((size_t)n * (C2 / cw) + (k - kc1)) * 2;
           sum1 += e2[0]; sum2 += e2[1];
         }
       } else {
@@ -260,13 +261,17 @@ int b200ldm_groupnorm_stats(const void* x, const void* x2, double* stats, int32_
 
 static int gn_apply_impl(const void* x, const void* x2, void* y, const double* stats, const double* cst1,
                          const double* cst2, const float* gamma, const float* beta, int32_t N, int64_t S, int32_t C1,
-                         int32_t C2, int32_t G, float eps, int32_t silu, int32_t dtype, b200ldm_stream stream) {
+                         int32_t C2, int32_t G, float eps, int32_t silu, int32_t dtype, b200ldm_stream stream,
+                         int32_t cw = 8) {
   using namespace b200ldm;
   B2_REQUIRE(x && y && (stats || cst1) && gamma && beta && N > 0 && S > 0, B200LDM_BAD_ARG,
              "groupnorm_apply: bad arguments");
   if (cst1)
-    B2_REQUIRE(G > 0 && (C1 + C2) % G == 0 && ((C1 + C2) / G) % 8 == 0 && ((C2 > 0) == (cst2 != nullptr)),
-               B200LDM_BAD_SHAPE, "groupnorm_apply_chunked: channels/group must be a multiple of 8 and cstats2 match x2");
+    B2_REQUIRE(G > 0 && (C1 + C2) % G == 0 && (cw == 2 || cw == 4 || cw == 8) && ((C1 + C2) / G) % cw == 0 &&
+                   C1 % cw == 0 && ((C2 > 0) == (cst2 != nullptr)),
+               B200LDM_BAD_SHAPE,
+               "groupnorm_apply_chunked: channels/group must be a multiple of the chunk width (2, 4 or 8) and cstats2 "
+               "match x2");
   B2_REQUIRE(aligned16(x) && aligned16(y) && aligned16(x2), B200LDM_BAD_ALIGN,
              "groupnorm_apply: x/y must be 16-byte aligned");
   B2_REQUIRE(C1 > 0 && C1 % 8 == 0 && C2 >= 0 && C2 % 8 == 0 && ((C2 > 0) == (x2 != nullptr)), B200LDM_BAD_SHAPE,
@@ -279,7 +284,7 @@ static int gn_apply_impl(const void* x, const void* x2, void* y, const double* s
 #define GN_APPLY_BF16(U, B)                                                                                      \
   gn_apply_kernel<__nv_bfloat16, U, B><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(                         \
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)x2, (__nv_bfloat16*)y, stats, gamma, beta, S, C1, C2, G, eps, \
-      silu, vpb, inv_cnt, cst1, cst2)
+      silu, vpb, inv_cnt, cst1, cst2, cw)
   if (dtype == B200LDM_BF16) {
     switch (variant) {
       case 1: GN_APPLY_BF16(1, 8); break;
@@ -293,7 +298,7 @@ static int gn_apply_impl(const void* x, const void* x2, void* y, const double* s
   } else if (dtype == B200LDM_F32)
     gn_apply_kernel<float, 4, 3><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(
         (const float*)x, (const float*)x2, (float*)y, stats, gamma, beta, S, C1, C2, G, eps, silu, vpb, inv_cnt, cst1,
-        cst2);
+        cst2, cw);
   else
     return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);
   B2_LAUNCH_CHECK();
@@ -313,6 +318,15 @@ int b200ldm_groupnorm_apply_chunked(const void* x, const void* x2, void* y, cons
                                     b200ldm_stream stream) {
   B2_REQUIRE(cstats1, B200LDM_BAD_ARG, "groupnorm_apply_chunked: null cstats1");
   return gn_apply_impl(x, x2, y, nullptr, cstats1, cstats2, gamma, beta, N, S, C1, C2, G, eps, silu, dtype, stream);
+}
+
+int b200ldm_groupnorm_apply_chunked_w(const void* x, const void* x2, void* y, const double* cstats1,
+                                      const double* cstats2, const float* gamma, const float* beta, int32_t N,
+                                      int64_t S, int32_t C1, int32_t C2, int32_t G, float eps, int32_t silu,
+                                      int32_t dtype, int32_t chunk_width, b200ldm_stream stream) {
+  B2_REQUIRE(cstats1, B200LDM_BAD_ARG, "groupnorm_apply_chunked: null cstats1");
+  return gn_apply_impl(x, x2, y, nullptr, cstats1, cstats2, gamma, beta, N, S, C1, C2, G, eps, silu, dtype, stream,
+                       chunk_width);
 }
 
 int b200ldm_groupnorm_small_fits(int64_t S, int32_t C, int32_t G, int32_t dtype) {

@@ -109,6 +109,9 @@ typedef struct {
   const void* skip_x2;
   const void* skip_w;
   int32_t skip_C1, skip_C2;
+  int32_t chunk_width;   /* channels per `chunk_stats` entry: 0 / 8 (default), or 2 / 4 = the group width of a following
+                            GroupNorm with fewer than 8 channels per group (AutoencoderKL, 64 / 128 channels in 32
+                            groups); chunk_stats is then [N][Cout/chunk_width][2].  Ask emits_chunk_stats. */
 } b200ldm_conv3d_params;
 
 int b200ldm_conv3d(const b200ldm_conv3d_params* p, b200ldm_stream stream);
@@ -155,6 +158,11 @@ int b200ldm_groupnorm_apply_chunked(const void* x, const void* x2, void* y, cons
 /* statistics + normalisation (+SiLU) in ONE launch for tiny tensors (S <= 4096 voxels per sample, channels/group a
  * multiple of 8): one CTA per (group, sample).  Same math as stats + apply.  b200ldm_groupnorm_small_fits(S, C1 + C2, G,
  * dtype) == 1 says whether a tensor qualifies; the host side uses it up to 256 voxels, where it beats the pair. */
+/* the same with chunk sums per `chunk_width` (2, 4 or 8) channels - see b200ldm_conv3d_params.chunk_width */
+int b200ldm_groupnorm_apply_chunked_w(const void* x, const void* x2, void* y, const double* cstats1,
+                                      const double* cstats2, const float* gamma, const float* beta, int32_t N,
+                                      int64_t S, int32_t C1, int32_t C2, int32_t G, float eps, int32_t silu,
+                                      int32_t dtype, int32_t chunk_width, b200ldm_stream stream);
 int b200ldm_groupnorm_small_fits(int64_t S, int32_t C, int32_t G, int32_t dtype);
 int b200ldm_groupnorm_small(const void* x, const void* x2, void* y, const float* gamma, const float* beta, int32_t N,
                             int64_t S, int32_t C1, int32_t C2, int32_t G, float eps, int32_t silu, int32_t dtype,

@@ -685,3 +685,42 @@ def test_abi_is_reentrant_across_threads_and_streams():
     assert not errs, errs
     for o in outs:
         assert relerr(o, want) <= 2e-2     # GroupNorm sums are atomics: not bitwise
+
+
+@pytest.mark.parametrize("kernel", [2, 3], ids=["persistent", "w_halo"])
+@pytest.mark.parametrize("case", [(2, (8, 16, 16), 64, 64, 2), (1, (9, 11, 13), 128, 128, 4), (2, (6, 8, 16), 128, 64, 2),
+                                  (1, (8, 8, 8), 64, 128, 4)],
+                         ids=lambda c: f"N{c[0]}_{'x'.join(map(str, c[1]))}_C{c[2]}->{c[3]}_w{c[4]}")
+def test_conv3d_fine_chunk_stats_feed_groupnorm(case, kernel):
+    """GroupNorm statistics per 2 / 4 channels (AutoencoderKL: 64 / 128 channels in 32 groups) from the persistent
+    kernels' epilogues: the sums match the stored tensor and the following GroupNorm(+SiLU) needs no statistics pass."""
+    import ctypes
+    from b200ldm import _lib, ops
+    lib = _lib.load()
+    lib.b200ldm_debug_set_conv_kernel.argtypes = [ctypes.c_int]
+    N, sp, C, Cout, cw = case
+    x = q(rnd((N, C) + sp, 401), torch.bfloat16)
+    w = q(rnd((Cout, C, 3, 3, 3), 402) * (C * 27) ** -0.5, torch.bfloat16)
+    b = 0.1 * rnd((Cout,), 403)
+    res = q(rnd((N, Cout) + sp, 404), torch.bfloat16)
+    wp = ops.repack_conv_weight(w.to(DEV), Cout, C, torch.bfloat16)
+    lib.b200ldm_debug_set_conv_kernel(kernel)
+    try:
+        y = ops.conv3d(to_act(x, torch.bfloat16), wp, b.to(DEV), Cout, 3, 1, 1, 1, residual=to_act(res, torch.bfloat16),
+                       want_stats=True, stats_width=cw)
+    finally:
+        lib.b200ldm_debug_set_conv_kernel(-1)
+    ref = F.conv3d(x.double(), w.double(), b.double(), padding=1) + res.double()
+    assert relerr(from_act(y, Cout), ref) <= 1e-2
+    cs = getattr(y, "cstats", None)
+    assert cs is not None and y.cstats_width == cw and cs.numel() == N * (Cout // cw) * 2
+    yf = from_act(y, Cout).double()
+    want = torch.stack([yf.reshape(N, Cout // cw, cw, -1).sum(dim=(2, 3)), (yf ** 2).reshape(N, Cout // cw, cw, -1).sum(dim=(2, 3))], dim=-1)
+    assert relerr(cs.reshape(N, Cout // cw, 2).cpu(), want) <= 1e-4
+    groups = Cout // cw
+    gamma, beta = 1.0 + 0.1 * rnd((Cout,), 405), 0.1 * rnd((Cout,), 406)
+    launches = ops.launch_count()
+    got = ops.groupnorm(y, gamma.to(DEV), beta.to(DEV), groups, 1e-6, True)
+    assert ops.launch_count() - launches == 1                     # apply only: no statistics pass
+    gref = F.silu(F.group_norm(yf, groups, gamma.double(), beta.double(), eps=1e-6))
+    assert relerr(from_act(got, Cout), gref) <= 6e-3

@@ -35,7 +35,7 @@ def test_struct_layout_matches_header(lib_built):
     # 3 skip pointers + 2 int32 (conv), 7 pointers + 2 int64 + 4 int32 + uint64 + seed pointer + 2 learned-variance
     # pointers + int64 Philox offset (sched)
     lib = _lib.load()
-    assert ctypes.sizeof(_lib.ConvParams) == lib.b200ldm_sizeof_params(0) == 8 * 8 + 20 * 4 + 8 + 8 + 8 + 3 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.ConvParams) == lib.b200ldm_sizeof_params(0) == 8 * 8 + 20 * 4 + 8 + 8 + 8 + 3 * 8 + 2 * 4 + 2 * 4   # + chunk_width + tail padding
     assert ctypes.sizeof(_lib.SchedParams) == lib.b200ldm_sizeof_params(1) == 7 * 8 + 2 * 8 + 4 * 4 + 8 + 8 + 2 * 8 + 8
 
 
