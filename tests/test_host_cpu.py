@@ -288,3 +288,18 @@ def test_bench_reference_arm_contract():
     r1 = subprocess.run([sys.executable, bench, "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                         capture_output=True, text=True, env={**env, "RANK": "1", "WORLD_SIZE": "2"}, timeout=600)
     assert r1.returncode == 0 and not [l for l in r1.stdout.splitlines() if l.startswith("{")]
+
+
+def test_public_header_is_plain_c():
+    """include/b200ldm.h is the drop-in boundary: it must compile as C99 and as C++ on its own (no torch / CUDA types)."""
+    import shutil
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "b200ldm.h")
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                ["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    text = open(hdr).read()
+    assert "#include <torch" not in text and "at::" not in text and "c10::" not in text and "cuda_runtime" not in text
