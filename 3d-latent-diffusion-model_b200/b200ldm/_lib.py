@@ -51,6 +51,8 @@ SIGNATURES = {
     "b200ldm_launch_count": (C.c_uint64, []),
     "b200ldm_sizeof_params": (_sz, [_i32]),
     "b200ldm_conv3d": (C.c_int, [C.POINTER(ConvParams), _vp]),
+    "b200ldm_conv3d_tune": (C.c_int, [C.POINTER(ConvParams), _vp]),
+    "b200ldm_conv3d_tune_pending": (C.c_int, [C.POINTER(ConvParams)]),
     "b200ldm_conv3d_workspace_bytes": (C.c_int64, [C.POINTER(ConvParams)]),
     "b200ldm_conv3d_emits_chunk_stats": (C.c_int, [C.POINTER(ConvParams)]),
     "b200ldm_repack_conv_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -64,7 +64,7 @@ class SamplingLoop:
         # state
         self.x_t = ops.to_ndhwc(input_noise, self.c_lat, torch.float32)            # fp32 master [N,D,H,W,C]
         self.x_model = ops.to_ndhwc(input_noise, _pad64(self.c_in), self.dtype)     # UNet input buffer (padding = 0)
-        ts = torch.as_tensor([float(t) for t in scheduler.timesteps], dtype=torch.float32, device=dev)
+        ts = torch.as_tensor(scheduler.timesteps).to(device=dev, dtype=torch.float32)
         self.temb_table = unet.time_embedding_table(ts)                            # [n_steps, total]
         self.temb_cur = torch.empty((1, self.temb_table.shape[1]), dtype=torch.float32, device=dev)
         self.coef = scheduler.coef_table(dev).clone()
@@ -195,7 +195,7 @@ class DiffusionInferer:
         then costs T graph replays and nothing else (capture and its allocator traffic were 0.2-1.1 s per call)."""
         key = (id(unet), param_signature(unet), unet.precision, tuple(input_noise.shape), str(input_noise.device),
                None if conditioning is None else tuple(conditioning.shape), mode,
-               tuple(int(t) for t in scheduler.timesteps), step_noise is not None,
+               tuple(torch.as_tensor(scheduler.timesteps).tolist()), step_noise is not None,   # one transfer, not T
                getattr(scheduler, "variance_type", None))
         loop = self._loops.get(key)
         if loop is None:
@@ -224,12 +224,15 @@ class DiffusionInferer:
         if not input_noise.is_cuda:
             raise RuntimeError("b200ldm sampling needs CUDA tensors (there is no CPU fallback)")
         if seed is None:
-            seed = int(torch.initial_seed()) & (2 ** 63 - 1)
+            # a fresh noise stream per call, drawn from (and advancing) torch's global generator like the reference's
+            # per-step torch.randn does: torch.manual_seed(s) still makes a whole run reproducible, and two consecutive
+            # calls never share their z_1..z_T (torch.initial_seed() is constant for the process - ADVICE r01)
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         loop = self._loop_for(diffusion_model, scheduler, input_noise, conditioning, mode, step_noise, seed)
         intermediates = []
-        for t in scheduler.timesteps:
+        for t in torch.as_tensor(scheduler.timesteps).tolist():
             loop.step()
-            if save_intermediates and int(t) % intermediate_steps == 0:
+            if save_intermediates and t % intermediate_steps == 0:
                 intermediates.append(loop.latent_ncdhw())
         image = loop.latent_ncdhw()
         if _return_loop:

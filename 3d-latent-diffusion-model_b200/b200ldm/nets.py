@@ -96,7 +96,7 @@ class Conv(nn.Module):
 
     def stats_width(self) -> int:
         g = self.stats_groups
-        if g and self.cout % g == 0 and self.cout // g in (2, 4) and self.cout % 64 == 0:
+        if g and self.cout % g == 0 and self.cout // g in (2, 4) and self.cout_phys % 64 == 0:
             return self.cout // g
         return 8
 
@@ -242,10 +242,29 @@ class GroupNorm(nn.Module):
         self.groups, self.channels, self.eps = groups, channels, eps
         self.weight = nn.Parameter(torch.ones(channels))
         self.bias = nn.Parameter(torch.zeros(channels))
+        self._cache = PackedCache()
 
     def run(self, x, silu: bool, x2=None, stats=None):
-        return ops.groupnorm(x, self.weight.detach(), self.bias.detach(), self.groups, self.eps, silu, x2=x2,
-                             stats=stats)
+        cphys = x.shape[-1] + (0 if x2 is None else x2.shape[-1])
+        if cphys == self.channels:
+            return ops.groupnorm(x, self.weight.detach(), self.bias.detach(), self.groups, self.eps, silu, x2=x2,
+                                 stats=stats)
+        # channel-padded activation (a 32-channel level lives in a 64-channel tensor whose upper half is exactly zero,
+        # config_train_stable.json:13-27): the kernel sees cphys / (channels per group) groups - the real ones followed by
+        # all-zero padding groups - with gamma = beta = 0 on the padding, so padded channels stay exactly zero
+        cpg = self.channels // self.groups
+        if x2 is not None or stats is not None or cphys % cpg:
+            raise NotImplementedError("GroupNorm over channel-padded tensors: single source, no pre-reduced statistics")
+
+        def build():
+            g = torch.zeros(cphys, dtype=torch.float32, device=self.weight.device)
+            b = torch.zeros(cphys, dtype=torch.float32, device=self.weight.device)
+            g[: self.channels] = self.weight.detach().float()
+            b[: self.channels] = self.bias.detach().float()
+            return g, b
+
+        g, b = self._cache.get(("padded", cphys), (self.weight, self.bias), build)
+        return ops.groupnorm(x, g, b, cphys // cpg, self.eps, silu)
 
 
 def zero_module(m: nn.Module) -> nn.Module:
@@ -474,10 +493,13 @@ class _DownOp(nn.Module):
         self.op = ConvOnly(ch, ch, 3, 2, 1)
 
 
-class _UNetUp(nn.Module):
-    def __init__(self, ch):
-        super().__init__()
-        self.upsample = NearestUp(ch)
+def _alias_upsampler_keys(state_dict, prefix, *_):
+    """load_state_dict pre-hook.  MONAI >= 1.4 names the post-upsample conv of a UNet up block
+    `up_blocks.{i}.upsampler.postconv.conv.*` (WrappedUpsample subclasses UpSample - an nn.Sequential with children
+    `upsample_non_trainable`, `postconv` - and is assigned to `upsampler` itself); that is what state_dict() emits.
+    The nested spelling `up_blocks.{i}.upsampler.upsample.postconv.conv.*` loads as an alias."""
+    for k in [k for k in state_dict if k.startswith(prefix) and ".upsampler.upsample." in k]:
+        state_dict[k.replace(".upsampler.upsample.", ".upsampler.")] = state_dict.pop(k)
 
 
 class _DownBlock(nn.Module):
@@ -511,7 +533,43 @@ class _UpBlock(nn.Module):
         if attn:
             self.attentions = nn.ModuleList([_make_attn(cout, head_ch, groups, eps, xattn) for _ in range(n_res)])
         self.has_attn = attn
-        self.upsampler = _UNetUp(cout) if add_up else None
+        self.upsampler = NearestUp(cout) if add_up else None
+
+
+def load_old_state_dict(module: nn.Module, old_state_dict: dict, verbose: bool = False) -> None:
+    """MONAI's `load_old_state_dict` (both nets have it since the MONAI-Generative merge): ingest a checkpoint written by
+    the pre-1.4 `generative` package.  Its attention blocks kept `to_q / to_k / to_v / proj_attn` directly on the block
+    (now `attn.to_q ... attn.out_proj`), transformer blocks called their output projection `to_out.0` (now `out_proj`),
+    and the post-upsample conv was `conv` (now `postconv`).  Everything else has the same name.  Strict: a key that is
+    still missing afterwards raises from load_state_dict."""
+    old = dict(old_state_dict)
+    new = module.state_dict()
+    if all(k in new for k in old):
+        module.load_state_dict(old)
+        return
+    renamed = {}
+    for k in new:
+        if k in old:
+            renamed[k] = old.pop(k)
+            continue
+        cand = k
+        if ".attn.out_proj." in k and "transformer_blocks" not in k:
+            cand = k.replace(".attn.out_proj.", ".proj_attn.")
+        elif ".attn.to_" in k and "transformer_blocks" not in k:
+            cand = k.replace(".attn.to_", ".to_")
+        elif ".out_proj." in k and "transformer_blocks" in k:
+            cand = k.replace(".out_proj.", ".to_out.0.")
+        elif "postconv" in k:
+            cand = k.replace("postconv", "conv")
+        if cand in old:
+            renamed[k] = old.pop(cand)
+    if verbose:
+        for k in new:
+            if k not in renamed:
+                print(f"key {k} not found in old state dict")
+        for k in old:
+            print(f"key {k} of the old state dict is unused")
+    module.load_state_dict(renamed, strict=True)
 
 
 def _per_level(v, n):
@@ -569,6 +627,7 @@ class DiffusionModelUNet(nn.Module):
                              "as `channels`.")
         self.in_channels, self.out_channels = in_channels, out_channels
         self._fwd_graphs = {}
+        self._register_load_state_dict_pre_hook(_alias_upsampler_keys)
         self.block_out_channels = list(channels)
         self.with_conditioning = with_conditioning
         self.cross_attention_dim = cross_attention_dim
@@ -600,6 +659,9 @@ class DiffusionModelUNet(nn.Module):
         self.out = nn.Sequential(GroupNorm(norm_num_groups, channels[0], norm_eps), nn.SiLU(),
                                  zero_module(ConvOnly(channels[0], out_channels, terminal=True)))
         self._cache = PackedCache()
+
+    def load_old_state_dict(self, old_state_dict: dict, verbose: bool = False) -> None:
+        load_old_state_dict(self, old_state_dict, verbose)
 
     # ---- time embedding (always fp32: tiny M, and it keeps t-conditioning exact in both modes)
     def resblocks(self):
@@ -734,7 +796,7 @@ class DiffusionModelUNet(nn.Module):
                     if blk.has_attn:
                         h = attend(blk.attentions[j], h)
                 if blk.upsampler is not None:
-                    h = blk.upsampler.upsample.run(h)
+                    h = blk.upsampler.run(h)
             return h
 
         def tail(h, sk, lo, hi, sp, out=None):
@@ -744,7 +806,7 @@ class DiffusionModelUNet(nn.Module):
                 if blk_last.has_attn:
                     h = attend(blk_last.attentions[j], h, lo, hi)
             if blk_last.upsampler is not None:
-                h = blk_last.upsampler.upsample.run(h)
+                h = blk_last.upsampler.run(h)
             h = self.out[0].run(h, silu=True)
             return self.out[2].run(h, sched=sp, out=out)   # sched: the scheduler update rides in this conv's last kernel
 
@@ -1021,8 +1083,9 @@ class AutoencoderKL(nn.Module):
             raise ValueError("AutoencoderKL expects all channels being multiple of norm_num_groups")
         if len(channels) != len(attention_levels):
             raise ValueError("AutoencoderKL expects channels being same size of attention_levels")
-        if any(c % 64 for c in channels):
-            raise NotImplementedError("b200ldm AutoencoderKL needs channel counts that are multiples of 64")
+        if any(c % 8 for c in channels):
+            raise NotImplementedError("b200ldm AutoencoderKL needs channel counts that are multiples of 8 (levels narrower "
+                                      "than 64 channels run zero-padded to one 128-byte TMA row)")
         nres = _per_level(num_res_blocks, len(channels))
         if len(nres) != len(channels):
             raise ValueError("`num_res_blocks` should be a single integer or a tuple of integers with the same length "
@@ -1040,6 +1103,9 @@ class AutoencoderKL(nn.Module):
         for m in self.modules():   # every conv here feeds a GroupNorm with norm_num_groups groups (or nothing)
             if isinstance(m, Conv):
                 m.stats_groups = norm_num_groups
+
+    def load_old_state_dict(self, old_state_dict: dict, verbose: bool = False) -> None:
+        load_old_state_dict(self, old_state_dict, verbose)
 
     # ---- NDHWC cores
     def decode_ndhwc(self, z):

@@ -47,6 +47,8 @@ class KernelProfiler:
 PROFILER: KernelProfiler | None = None
 # GroupNorm statistics fused into the producing conv's epilogue (per-8-channel chunk sums)
 FUSE_GN_STATS = __import__("os").environ.get("B200LDM_FUSE_GN_STATS", "1") != "0"
+# conv kernel choice measured on first use (b200ldm_conv3d_tune); B200LDM_CONV_AUTOTUNE=0 also disables it inside the library
+AUTOTUNE = __import__("os").environ.get("B200LDM_CONV_AUTOTUNE", "1") != "0"
 GN_SMALL_MAX_S = int(__import__("os").environ.get("B200LDM_GN_SMALL_MAX_S", "256"))
 
 
@@ -123,6 +125,19 @@ def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo
         p.skip_C1, p.skip_C2 = sx.shape[-1], 0 if sx2 is None else sx2.shape[-1]
     assert x.is_contiguous() and (x2 is None or x2.is_contiguous())
     assert residual is None or (residual.is_contiguous() and residual.shape == y.shape and residual.dtype == odt)
+    if AUTOTUNE and lib.b200ldm_conv3d_tune_pending(C.byref(p)) and not torch.cuda.is_current_stream_capturing():
+        # first eager call of this problem signature: measure which kernel / split-K factor runs it fastest (the one
+        # synchronising entry point of the library, include/b200ldm.h); b200ldm_conv3d below - and every later call,
+        # captured or not - then runs the remembered choice and never synchronises
+        tws = lib.b200ldm_conv3d_workspace_bytes(C.byref(p))      # the largest candidate while tuning is pending
+        if tws > 0:
+            ws = torch.empty((tws,), dtype=torch.uint8, device=x.device)
+            p.workspace, p.workspace_bytes = ws.data_ptr(), tws
+        if want_stats and FUSE_GN_STATS:
+            scratch = zeros_f64(N * (cout // stats_width) * 2, x.device)
+            p.chunk_stats = scratch.data_ptr()
+        _lib.check(lib.b200ldm_conv3d_tune(C.byref(p), _stream()), "conv3d_tune")
+        p.workspace, p.workspace_bytes, p.chunk_stats = None, 0, None
     ws_bytes = lib.b200ldm_conv3d_workspace_bytes(C.byref(p))
     if ws_bytes > 0:  # split-K partial sums (small-M convs): caller-owned scratch
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)

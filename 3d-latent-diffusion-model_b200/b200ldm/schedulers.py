@@ -23,6 +23,15 @@ def _betas(schedule: str, T: int, beta_start: float = 1e-4, beta_end: float = 2e
     raise ValueError(f"unknown noise schedule {schedule!r}")
 
 
+def _randn_like_upstream(model_output, sample, generator) -> torch.Tensor:
+    """upstream: torch.randn(model_output.size(), dtype=model_output.dtype, layout=..., generator=generator,
+    device=model_output.device), taken after a learned-variance output has been split, i.e. always sample-shaped.
+    Drawn on the generator's own device (upstream requires it to be the tensor's device), so the same generator state
+    gives the same noise as MONAI."""
+    z = torch.randn(tuple(sample.shape), dtype=model_output.dtype, generator=generator, device=generator.device)
+    return z.to(sample.device)
+
+
 class Scheduler:
     def __init__(self, num_train_timesteps: int = 1000, schedule: str = "linear_beta", **schedule_args):
         self.num_train_timesteps = num_train_timesteps
@@ -67,9 +76,28 @@ class Scheduler:
     def coef_row(self, timestep: int) -> list[float]:
         raise NotImplementedError
 
+    def _state_key(self) -> tuple:
+        """everything a coefficient row depends on besides the timestep (attributes may be reassigned after construction)"""
+        return (self.num_inference_steps, self.prediction_type, bool(self.clip_sample), tuple(self.clip_sample_values),
+                getattr(self, "variance_type", None), getattr(self, "eta", None), getattr(self, "steps_offset", None))
+
+    def _memo_table(self, name: str, row_fn, device) -> torch.Tensor:
+        """[n_steps, k] table on `device`, built once per (scheduler state, timestep grid): a cached sample() call used to
+        redo ~1000 tensor-scalar operations here (each a device sync when `timesteps` lives on the GPU)"""
+        ts = tuple(torch.as_tensor(self.timesteps).tolist())
+        key = (name, str(device), ts, self._state_key())
+        memo = self.__dict__.setdefault("_table_memo", {})
+        t = memo.get(key)
+        if t is None:
+            if len(memo) >= 8:
+                memo.clear()
+            t = torch.tensor([row_fn(int(v)) for v in ts], dtype=torch.float32).to(device).contiguous()
+            memo[key] = t
+        return t
+
     def coef_table(self, device) -> torch.Tensor:
-        rows = [self.coef_row(int(t)) for t in self.timesteps]
-        return torch.tensor(rows, dtype=torch.float32).to(device).contiguous()
+        """[n_steps, 8] coefficient rows; memoised - callers copy it into their own buffers, never write it"""
+        return self._memo_table("coef", self.coef_row, device)
 
     learned_variance = False   # DDPMScheduler(variance_type="learned" | "learned_range") sets it
 
@@ -78,8 +106,7 @@ class Scheduler:
 
     def var_coef_table(self, device) -> torch.Tensor:
         """[n_steps, 2] rows {A, B}: per-element noise scale sqrt(A * predicted_variance + B) (include/b200ldm.h)."""
-        rows = [self.var_coef_row(int(t)) for t in self.timesteps]
-        return torch.tensor(rows, dtype=torch.float32).to(device).contiguous()
+        return self._memo_table("var_coef", self.var_coef_row, device)
 
     def _step_kernel(self, model_output, timestep, sample, noise):
         """NCDHW fp32 tensors in, (prev_sample, pred_original_sample) out."""
@@ -109,7 +136,7 @@ class Scheduler:
     def _coef_on(self, dev, timestep: int, eta=None, split: bool = False) -> torch.Tensor:
         """coefficient row of one timestep on the device, cached: a fresh pageable upload per step() would block the
         host until the stream drains"""
-        key = (str(dev), timestep, eta, getattr(self, "eta", None), self.num_inference_steps, self.prediction_type, split)
+        key = (str(dev), timestep, eta, split, self._state_key())
         cache = self.__dict__.setdefault("_coef_cache", {})
         t = cache.get(key)
         if t is None:
@@ -176,9 +203,12 @@ class DDPMScheduler(Scheduler):
         return [float(a_x), float(a_e), float(c0), float(ct), 0.0, float(sigma), float(lo), float(hi)]
 
     def step(self, model_output, timestep, sample, generator=None, noise=None):
-        """Same contract as upstream; `noise` (extension) supplies this step's N(0,I) draw for parity tests.
-        Without it the kernel draws Philox noise seeded from torch's global seed (generator is ignored)."""
+        """Same contract as upstream.  `generator`: this step's N(0,I) is drawn from it with torch.randn exactly as
+        upstream does (same generator state -> same noise as MONAI).  `noise` (extension) supplies the draw itself
+        (parity tests).  With neither, the kernel draws Philox noise seeded from torch's global seed."""
         t = int(timestep)
+        if noise is None and generator is not None and t > 0:
+            noise = _randn_like_upstream(model_output, sample, generator)
         return self._step_kernel(model_output, t, sample, noise if t > 0 else None)
 
 
@@ -199,7 +229,14 @@ class DDIMScheduler(Scheduler):
         self.set_timesteps(self.num_train_timesteps)
 
     def set_timesteps(self, num_inference_steps: int, device=None) -> None:
-        self.timesteps = torch.from_numpy(self._grid(num_inference_steps)).to(device)
+        grid = self._grid(num_inference_steps)
+        ratio = self.num_train_timesteps // num_inference_steps
+        if self.steps_offset >= ratio:
+            raise ValueError(
+                f"`steps_offset`: {self.steps_offset} cannot be greater than or equal to "
+                f"`num_train_timesteps // num_inference_steps : {ratio}` as this will cause timesteps to exceed"
+                f" the max train timestep.")
+        self.timesteps = torch.from_numpy(grid).to(device)
         self.timesteps += self.steps_offset
 
     def _get_variance(self, t: int, prev_t: int) -> torch.Tensor:
@@ -229,6 +266,8 @@ class DDIMScheduler(Scheduler):
 
     def step(self, model_output, timestep, sample, eta: float = 0.0, generator=None, noise=None):
         t = int(timestep)
+        if noise is None and generator is not None and eta > 0:
+            noise = _randn_like_upstream(model_output, sample, generator)
         old = self.eta
         self.eta = eta
         try:

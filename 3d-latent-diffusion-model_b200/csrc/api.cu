@@ -25,6 +25,23 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+  return d < kMaxDevices ? d : kMaxDevices - 1;
+}
+
+int sm_count() {
+  static std::atomic<int> n[kMaxDevices];
+  const int d = current_device();
+  int v = n[d].load(std::memory_order_relaxed);
+  if (v <= 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v <= 0) v = 148;
+    n[d].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 }  // namespace b200ldm
 
 extern "C" {

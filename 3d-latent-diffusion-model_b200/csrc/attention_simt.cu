@@ -103,8 +103,14 @@ extern "C" int b200ldm_cross_attention(const void* q, const void* k, const void*
   B2_REQUIRE(q && k && v && o, B200LDM_BAD_ARG, "attention: null pointer");
   B2_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0 && d > 0 && ldq >= (int64_t)H * d && ldkv >= (int64_t)H * d,
              B200LDM_BAD_SHAPE, "attention: bad shape");
-  if (engine == B200LDM_ENGINE_AUTO)
-    engine = (dtype == B200LDM_BF16 && attention_tcgen05_supported(d)) ? B200LDM_ENGINE_TCGEN05 : B200LDM_ENGINE_SIMT;
+  if (engine == B200LDM_ENGINE_AUTO) {
+    // bf16 is the tensor-core product path: a head dim without a tcgen05 instance is an error, never a silent drop to
+    // the CUDA-core validation engine (which stays reachable by asking for B200LDM_ENGINE_SIMT explicitly)
+    B2_REQUIRE(dtype != B200LDM_BF16 || attention_tcgen05_supported(d), B200LDM_BAD_SHAPE,
+               "attention: no tcgen05 kernel for head dim %d (32 / 64 / 128 / 256); the SIMT validation engine must be "
+               "requested explicitly", d);
+    engine = dtype == B200LDM_BF16 ? B200LDM_ENGINE_TCGEN05 : B200LDM_ENGINE_SIMT;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (engine == B200LDM_ENGINE_TCGEN05) {
     B2_REQUIRE(dtype == B200LDM_BF16, B200LDM_BAD_ARG, "tcgen05 attention needs bf16");

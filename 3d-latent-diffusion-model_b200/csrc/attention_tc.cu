@@ -70,9 +70,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int D, int BN>
+// DR = the real head dim.  DR == D except for head dim 32 (config_train_stable.json: num_head_channels 32), which runs
+// on the D = 64 tiles: the 64-column TMA box at (h / 2) * 64 holds heads 2h' and 2h'+1 side by side in one
+// SWIZZLE_128B row, S = Q K^T contracts only this head's two 16-column K-slices (descriptor offset (h & 1) * 64 B), PV
+// multiplies P_h by the whole 64-column V box (an N = 64 MMA costs the same ~46 cycles as N = 32,
+// profiles/r01e_umma_rate_microbench.log) and the epilogue stores this head's 32 columns of O.
+template <int D, int BN, int DR = D>
 __global__ void __launch_bounds__(kAttnThreads, AttnCfg<D, BN>::kOcc)
 attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
+  static_assert(DR == D || (D == 64 && DR == 32), "head dim 32 rides on the 64-column tiles");
   using Cfg = AttnCfg<D, BN>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -108,7 +114,9 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   const int q0 = blockIdx.x * 128;
   const int h = blockIdx.y, b = blockIdx.z;
   const int ntiles = (a.Lk + BN - 1) / BN;
-  const int col0 = h * D;
+  const int colh = h * DR;                    // this head's first column in the [.., H * DR] projections
+  const int col0 = DR == D ? colh : (colh & ~63);   // first column of the TMA boxes
+  const int kk0 = DR == D ? 0 : ((colh & 63) >> 4); // first 16-column K-slice of this head inside the box
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&maps.q); ptx::prefetch_tmap(&maps.k); ptx::prefetch_tmap(&maps.v);
@@ -180,10 +188,12 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         const uint32_t k_lo = k_lo0 + (uint32_t)s * (uint32_t)(Cfg::kKVBytes >> 4);
         const uint32_t tS = tmem + Cfg::kSCol0 + (j & 1) * BN;
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)
+        for (int k = 0; k < DR / 16; ++k) {
+          const int kk = k + kk0;
           ptx::umma_bf16_lohi(tS, q_lo + (uint32_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
                               k_lo + (uint32_t)(((kk >> 2) * Cfg::kKVSub + (kk & 3) * 32) >> 4), khi, khi, idesc_s,
-                              kk > 0 ? 1u : 0u);
+                              k > 0 ? 1u : 0u);
+        }
         ptx::umma_commit(s_full + 8 * (j & 1));
         ptx::umma_commit(k_empty + 8 * s);   // K_j is free once S_j retires
       };
@@ -331,10 +341,10 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
     ptx::tc_fence_after();
     const int qi = q0 + row;
     const float inv = 1.0f / l_sum;
-    __nv_bfloat16* orow = a.o + ((size_t)b * a.L + (qi < a.L ? qi : 0)) * ((size_t)a.H * D) + col0;
-    const uint32_t tO = tmem + lane_off + Cfg::kOCol;
+    __nv_bfloat16* orow = a.o + ((size_t)b * a.L + (qi < a.L ? qi : 0)) * ((size_t)a.H * DR) + colh;
+    const uint32_t tO = tmem + lane_off + Cfg::kOCol + (uint32_t)(colh - col0);   // this head's columns of O
 #pragma unroll
-    for (int c = 0; c < D; c += 16) {
+    for (int c = 0; c < DR; c += 16) {
       uint32_t r[16];
       ptx::tmem_ld16(tO + c, r);
       ptx::tmem_ld_wait();
@@ -688,25 +698,20 @@ static int make_qkv_map(CUtensorMap* m, const void* base, int cols, int L, int B
   return B200LDM_OK;
 }
 
-template <int D, int BN>
+template <int D, int BN, int DR = D>
 static int launch_attention_tc(const void* q, const void* k, const void* v, void* o, int B, int H, int L, int Lk,
                                long long ld, long long ldkv, float scale, cudaStream_t st) {
   using Cfg = AttnCfg<D, BN>;
   AttnMaps maps;
   int rc;
-  if ((rc = make_qkv_map(&maps.q, q, H * D, L, B, ld, 128))) return rc;
-  if ((rc = make_qkv_map(&maps.k, k, H * D, Lk, B, ldkv, BN))) return rc;
-  if ((rc = make_qkv_map(&maps.v, v, H * D, Lk, B, ldkv, BN))) return rc;
+  if ((rc = make_qkv_map(&maps.q, q, H * DR, L, B, ld, 128))) return rc;
+  if ((rc = make_qkv_map(&maps.k, k, H * DR, Lk, B, ldkv, BN))) return rc;
+  if ((rc = make_qkv_map(&maps.v, v, H * DR, Lk, B, ldkv, BN))) return rc;
   static const int dbg = [] { const char* e = getenv("B200LDM_ATTN_DBG"); return e ? atoi(e) : 0; }();
-  AttnArgs a{H, L, D, Lk, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o), g_attn_trace, dbg};
-  static bool attr_done = false;
-  if (!attr_done) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::kSmem));
-    attr_done = true;
-  }
+  AttnArgs a{H, L, DR, Lk, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o), g_attn_trace, dbg};
+  B2_SET_SMEM_ONCE(Cfg::kSmem, attention_tc_kernel<D, BN, DR>);
   dim3 grid((unsigned)ceil_div(L, 128), (unsigned)H, (unsigned)B);
-  attention_tc_kernel<D, BN><<<grid, kAttnThreads, Cfg::kSmem, st>>>(maps, a);
+  attention_tc_kernel<D, BN, DR><<<grid, kAttnThreads, Cfg::kSmem, st>>>(maps, a);
   B2_LAUNCH_CHECK();
   return B200LDM_OK;
 }
@@ -722,12 +727,7 @@ static int launch_attention_tc2(const void* q, const void* k, const void* v, voi
   if ((rc = make_qkv_map(&maps.v, v, H * D, Lk, B, ldkv, BN))) return rc;
   static const int dbg = [] { const char* e = getenv("B200LDM_ATTN_DBG"); return e ? atoi(e) : 0; }();
   AttnArgs a{H, L, D, Lk, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o), g_attn_trace, dbg};
-  static bool attr_done = false;
-  if (!attr_done) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<D, BN, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::kSmem));
-    attr_done = true;
-  }
+  B2_SET_SMEM_ONCE(Cfg::kSmem, attention_tc2_kernel<D, BN, OCC>);
   dim3 grid((unsigned)ceil_div(L, 256), (unsigned)H, (unsigned)B);
   attention_tc2_kernel<D, BN, OCC><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, a);
   B2_LAUNCH_CHECK();
@@ -741,12 +741,12 @@ static const int g_attn_v = [] {
   return e ? atoi(e) : 0;
 }();
 
-bool attention_tcgen05_supported(int d) { return d == 64 || d == 128 || d == 256; }
+bool attention_tcgen05_supported(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
 
 int attention_tcgen05(const void* q, const void* k, const void* v, void* o, int B, int H, int L, int Lk, int d,
                       long long ld, long long ldkv, float scale, cudaStream_t st) {
-  B2_REQUIRE(attention_tcgen05_supported(d), B200LDM_BAD_SHAPE, "tcgen05 attention supports head dim 64/128/256 (got %d)",
-             d);
+  B2_REQUIRE(attention_tcgen05_supported(d), B200LDM_BAD_SHAPE,
+             "tcgen05 attention supports head dim 32/64/128/256 (got %d)", d);
   B2_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && ld % 8 == 0 && ldkv % 8 == 0,
              B200LDM_BAD_ALIGN, "attention: pointers / row strides must be 16-byte aligned");
   // head dim 64: the one-query-tile kernel with 64-key tiles runs TWO CTAs per SM (96 KB smem, 256 TMEM columns each)
@@ -761,6 +761,8 @@ int attention_tcgen05(const void* q, const void* k, const void* v, void* o, int 
     if (d == 64) return launch_attention_tc2<64, 128, 1>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
     return launch_attention_tc2<128, 64, 1>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
   }
+  if (d == 32 && Lk > 128) return launch_attention_tc<64, 64, 32>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
+  if (d == 32) return launch_attention_tc<64, 128, 32>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
   if (d == 64 && Lk > 128) return launch_attention_tc<64, 64>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
   if (d == 64) return launch_attention_tc<64, 128>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
   if (d == 128) return launch_attention_tc<128, 128>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);

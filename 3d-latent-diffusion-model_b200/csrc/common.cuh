@@ -42,6 +42,26 @@ extern std::atomic<uint64_t> g_launches;
                              cudaGetErrorString(_e), __FILE__, __LINE__);                  \
   } while (0)
 
+// ---------------------------------------------------------------- per-device state (host)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize), the SM count and measured kernel choices belong to ONE device; a
+// process may drive several (a serving replica looping over GPUs, torch.cuda.set_device(1) after a run on device 0),
+// so every cached launch setup is keyed by the current device.
+constexpr int kMaxDevices = 64;
+int current_device();   // cudaGetDevice (thread-local, no driver round trip), clamped to [0, kMaxDevices)
+int sm_count();         // multiprocessors of the current device (cached per device; 148 on B200)
+
+// opt a kernel in to > 48 KB of dynamic shared memory once per device (thread-safe: the attribute call is idempotent,
+// the bit is only an optimisation).  Variadic so that template-ids with commas can be passed.
+#define B2_SET_SMEM_ONCE(bytes, ...)                                                                        \
+  do {                                                                                                      \
+    static std::atomic<uint64_t> _b2_done{0};                                                               \
+    const uint64_t _b2_bit = 1ull << ::b200ldm::current_device();                                           \
+    if (!(_b2_done.load(std::memory_order_acquire) & _b2_bit)) {                                            \
+      B2_CHECK_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes))); \
+      _b2_done.fetch_or(_b2_bit, std::memory_order_release);                                                \
+    }                                                                                                       \
+  } while (0)
+
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

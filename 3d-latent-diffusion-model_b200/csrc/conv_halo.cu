@@ -399,17 +399,8 @@ void choose_halo_tile(int Do, int Ho, int* td, int* th) {
 template <int BN, int MT>
 static int launch_halo(const ConvTcMaps& maps, ConvTcArgs a, int m_tiles, int n_tiles, cudaStream_t st) {
   using Cfg = ConvHaloCfg<BN, MT>;
-  static int sms = 0;
-  static std::once_flag once;
-  static cudaError_t init_err = cudaSuccess;
-  std::call_once(once, [] {
-    init_err = cudaFuncSetAttribute(conv3d_halo_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Cfg::kSmemBytes);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  });
-  B2_CHECK_CUDA(init_err);
+  B2_SET_SMEM_ONCE(Cfg::kSmemBytes, conv3d_halo_kernel<BN, MT>);
+  const int sms = sm_count();
   a.work_x = ceil_div(m_tiles, MT); a.work_y = n_tiles; a.work_z = 1;
   const long long total = (long long)a.work_x * a.work_y;
   const unsigned grid = (unsigned)(total < sms ? total : sms);

@@ -171,6 +171,8 @@ int conv3d_simt(const b200ldm_conv3d_params* p, cudaStream_t st) {
 }
 
 int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st);
+int conv3d_tcgen05_tune(const b200ldm_conv3d_params* p, cudaStream_t st);
+int conv3d_tcgen05_tune_pending(const b200ldm_conv3d_params* p);
 long long conv3d_tcgen05_workspace_bytes(const b200ldm_conv3d_params* p);
 int conv3d_tcgen05_emits_chunk_stats(const b200ldm_conv3d_params* p);
 
@@ -190,6 +192,24 @@ extern "C" int64_t b200ldm_conv3d_workspace_bytes(const b200ldm_conv3d_params* p
   if (engine == B200LDM_ENGINE_AUTO)
     engine = (p->dtype == B200LDM_BF16) ? B200LDM_ENGINE_TCGEN05 : B200LDM_ENGINE_SIMT;
   return engine == B200LDM_ENGINE_TCGEN05 ? (int64_t)b200ldm::conv3d_tcgen05_workspace_bytes(p) : 0;
+}
+
+static int conv3d_engine_of(const b200ldm_conv3d_params* p) {
+  if (p->engine != B200LDM_ENGINE_AUTO) return p->engine;
+  return p->dtype == B200LDM_BF16 ? B200LDM_ENGINE_TCGEN05 : B200LDM_ENGINE_SIMT;
+}
+
+extern "C" int b200ldm_conv3d_tune_pending(const b200ldm_conv3d_params* p) {
+  if (!p || conv3d_engine_of(p) != B200LDM_ENGINE_TCGEN05) return 0;
+  return b200ldm::conv3d_tcgen05_tune_pending(p);
+}
+
+extern "C" int b200ldm_conv3d_tune(const b200ldm_conv3d_params* p, b200ldm_stream stream) {
+  using namespace b200ldm;
+  B2_REQUIRE(p != nullptr, B200LDM_BAD_ARG, "null params");
+  B2_REQUIRE(p->x && p->w && p->y, B200LDM_BAD_ARG, "null x / w / y");
+  if (conv3d_engine_of(p) != B200LDM_ENGINE_TCGEN05) return B200LDM_OK;   // the validation engine has one kernel
+  return conv3d_tcgen05_tune(p, (cudaStream_t)stream);
 }
 
 extern "C" int b200ldm_conv3d(const b200ldm_conv3d_params* p, b200ldm_stream stream) {

@@ -529,12 +529,7 @@ template <int BN, int MT, int CL>
 static int launch_conv_tc(const ConvTcMaps& maps, const ConvTcArgs& args, int m_tiles, int n_tiles, int splits,
                           cudaStream_t st) {
   using Cfg = ConvTcCfg<BN, MT>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<BN, MT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  B2_SET_SMEM_ONCE(Cfg::kSmemBytes, conv3d_tc_kernel<BN, MT, CL>);
   const unsigned gx = (unsigned)(ceil_div(ceil_div(m_tiles, MT), CL) * CL);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(gx, (unsigned)n_tiles, (unsigned)splits);
@@ -694,6 +689,7 @@ static void remember_choice(const ConvKey& key, int choice) {
 // force_tc2: -1 = remembered measurement, else cost model; >= 0 = that choice (tuning runs).
 static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
   ConvPlan pl{};
+  const int SMS = sm_count();
   if (p->Cout % 256 == 0) pl.bn = 256;
   else if (p->Cout % 128 == 0) pl.bn = 128;
   else if (p->Cout % 64 == 0) pl.bn = 64;
@@ -731,8 +727,8 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
       const double overhead = 4000.0 + 5000.0 * mt;   // prologue + epilogue (10K cycles for two accumulators)
       const long long ctas = (long long)ceil_div(ceil_div(pl.m_tiles, mt), cl) * cl * pl.n_tiles * zmul;
       for (int sp = 1; sp <= 12; ++sp) {
-        if (sp > 1 && (!split_ok || cl != 1 || iters / sp < 16 || ctas >= 148)) break;
-        const double rounds = (double)ceil_div(ctas * sp, 148);
+        if (sp > 1 && (!split_ok || cl != 1 || iters / sp < 16 || ctas >= SMS)) break;
+        const double rounds = (double)ceil_div(ctas * sp, SMS);
         double t = rounds * (ceil_div(iters, sp) * cyc_iter + overhead);
         if (sp > 1) t += 6000.0;  // finalize launch + slab traffic
         if (cl == 2) t *= 0.99;   // multicast: slightly less L2 traffic chip-wide
@@ -760,7 +756,7 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
       const double main_loop = iters * ((mma > load ? mma : load) + 8.0);
       const double epi = 2000.0 * (pl.bn / 64);
       const long long work = (long long)ceil_div(pl.m_tiles, pmt) * pl.n_tiles * zmul;
-      const double t2 = ceil_div(work, 148) * (main_loop > epi ? main_loop : epi) + 3000.0 + epi;
+      const double t2 = ceil_div(work, SMS) * (main_loop > epi ? main_loop : epi) + 3000.0 + epi;
       choice = (g_tc2 > 0) ? g_tc2 : (t2 < best ? 2 : 0);
     }
     if (force_tc2 >= 0) choice = force_tc2;
@@ -808,20 +804,34 @@ int conv3d_tcgen05_emits_chunk_stats(const b200ldm_conv3d_params* p) {
   return (pl.splits == 1 && pl.tn == 1 && pl.bn >= 64 && plan_emits_width(pl, chunk_width_of(p))) ? 1 : 0;
 }
 
+// A measurement is pending for this problem: tuning is on, nothing is pinned, the problem has more than one candidate
+// (persistent kernels and / or split-K factors) and no choice has been remembered yet.
+static bool tune_pending(const b200ldm_conv3d_params* p, const ConvPlan& pl) {
+  const bool splittable = pl.split_ok && pl.ctas1 < sm_count() && pl.iters >= 16;
+  if (!g_autotune || g_tc2 >= 0 || !(pl.tc2_ok || splittable)) return false;
+  std::lock_guard<std::mutex> lk(g_choice_mu);
+  return g_choice.count(conv_key(p)) == 0;
+}
+
+static bool conv3d_tcgen05_eligible(const b200ldm_conv3d_params* p) {
+  return p->dtype == B200LDM_BF16 && p->C1 > 0 && p->C1 % 64 == 0 && p->C2 >= 0 && p->C2 % 64 == 0 && p->Cout > 0 &&
+         p->Cout % 8 == 0 && (p->ksize == 1 || p->ksize == 3) && (p->stride == 1 || p->stride == 2);
+}
+
+int conv3d_tcgen05_tune_pending(const b200ldm_conv3d_params* p) {
+  if (!conv3d_tcgen05_eligible(p)) return 0;
+  return tune_pending(p, plan_conv(p)) ? 1 : 0;
+}
+
 long long conv3d_tcgen05_workspace_bytes(const b200ldm_conv3d_params* p) {
   if (p->dtype != B200LDM_BF16 || p->C1 % 64 || p->C2 % 64 || p->Cout % 8) return 0;
   const ConvPlan pl = plan_conv(p);
   int splits = pl.splits;
-  if (g_autotune && g_tc2 < 0 && pl.split_ok && pl.ctas1 < 148 && pl.iters >= 16) {
-    bool known;
-    {
-      std::lock_guard<std::mutex> lk(g_choice_mu);
-      known = g_choice.count(conv_key(p)) != 0;
-    }
-    if (!known) {   // the first call measures split factors up to 16 (those that keep >= 8 k-iterations per CTA)
-      for (int sp = 16; sp > splits; --sp)
-        if (pl.iters / sp >= 8 && (long long)pl.m_tiles * pl.n_tiles * sp <= 2 * 148) { splits = sp; break; }
-    }
+  const int SMS = sm_count();
+  if (pl.split_ok && pl.ctas1 < SMS && pl.iters >= 16 && tune_pending(p, pl)) {
+    // b200ldm_conv3d_tune measures split factors up to 16 (those that keep >= 8 k-iterations per CTA)
+    for (int sp = 16; sp > splits; --sp)
+      if (pl.iters / sp >= 8 && (long long)pl.m_tiles * pl.n_tiles * sp <= 2 * SMS) { splits = sp; break; }
   }
   if (splits <= 1) return 0;
   return (long long)splits * p->N * p->Do * p->Ho * p->Wo * p->Cout * 4;
@@ -829,7 +839,7 @@ long long conv3d_tcgen05_workspace_bytes(const b200ldm_conv3d_params* p) {
 
 static int conv3d_run_plan(const b200ldm_conv3d_params* p, const ConvPlan& pl, cudaStream_t st);
 
-int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
+static int conv3d_tcgen05_validate(const b200ldm_conv3d_params* p) {
   B2_REQUIRE(p->dtype == B200LDM_BF16, B200LDM_BAD_ARG, "tcgen05 conv needs bf16 activations");
   B2_REQUIRE(p->ksize == 1 || p->ksize == 3, B200LDM_BAD_SHAPE, "ksize must be 1 or 3 (got %d)", p->ksize);
   B2_REQUIRE(p->stride == 1 || p->stride == 2, B200LDM_BAD_SHAPE, "stride must be 1 or 2 (got %d)", p->stride);
@@ -855,17 +865,33 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
                    !p->residual && !p->temb && p->Cout % 64 == 0 && p->Do == 2 * p->D && p->Ho == 2 * p->H &&
                    p->Wo == 2 * p->W,
                B200LDM_BAD_SHAPE, "fused upsample conv: needs k3 s1 p1, one source, bf16 out, Cout %% 64 == 0, out = 2x in");
+  return B200LDM_OK;
+}
+
+// Always asynchronous, capture-safe, no host read of device data: runs the remembered (measured) choice of this problem
+// signature if b200ldm_conv3d_tune has stored one, the cost model's plan otherwise.  It never measures.
+int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
+  if (int rc = conv3d_tcgen05_validate(p)) return rc;
+  return conv3d_run_plan(p, plan_conv(p), st);
+}
+
+// The explicit measuring entry point (b200ldm_conv3d_tune): times the candidate kernels / split factors for this exact
+// problem on the caller's own buffers with CUDA events, SYNCHRONISES on each, and remembers the winner for later
+// b200ldm_conv3d calls of the same signature.  `y` holds a valid result afterwards; `chunk_stats` (if given) is used as
+// scratch and left zeroed.  Not capture-safe by construction: refuses a capturing stream.
+int conv3d_tcgen05_tune(const b200ldm_conv3d_params* p, cudaStream_t st) {
+  if (int rc = conv3d_tcgen05_validate(p)) return rc;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  B2_CHECK_CUDA(cudaStreamIsCapturing(st, &cap));
+  B2_REQUIRE(cap == cudaStreamCaptureStatusNone, B200LDM_BAD_ARG,
+             "b200ldm_conv3d_tune synchronises: it cannot run on a capturing stream");
   const ConvPlan pl = plan_conv(p);
-  const bool splittable = pl.split_ok && pl.ctas1 < 148 && pl.iters >= 16;
-  if (g_autotune && g_tc2 < 0 && (pl.tc2_ok || splittable)) {
-    const ConvKey key = conv_key(p);
-    bool known;
+  if (!tune_pending(p, pl)) return B200LDM_OK;   // nothing to choose from, pinned, disabled, or already measured
+  const int SMS = sm_count();
+  const bool splittable = pl.split_ok && pl.ctas1 < SMS && pl.iters >= 16;
+  const ConvKey key = conv_key(p);
+  {
     {
-      std::lock_guard<std::mutex> lk(g_choice_mu);
-      known = g_choice.count(key) != 0;
-    }
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (!known && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
       // time the candidates on the caller's own buffers (the result is the same tensor every time): the cost model's
       // plan, the persistent kernel, and - for launches that cannot fill the chip - other split-K factors / tile
       // heights of the one-CTA-per-tile kernel
@@ -882,7 +908,7 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
         for (int mt = 1; mt <= 2; ++mt)
           for (int sp : sps) {
             const long long ctas = (long long)ceil_div(pl.m_tiles, mt) * pl.n_tiles * sp;
-            if (pl.iters / sp < 8 || ctas > 2 * 148 || (sp > 1 && ctas < 32)) continue;
+            if (pl.iters / sp < 8 || ctas > 2 * SMS || (sp > 1 && ctas < 32)) continue;
             choices[nc++] = (sp << 4) | (mt << 12);
           }
       }
@@ -898,7 +924,9 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
         if (cp.splits > 1 && (!p->workspace || p->workspace_bytes < (long long)cp.splits * M_total * p->Cout * 4)) continue;
         b200ldm_conv3d_params q = *p;
         // statistics are accumulated by atomics: tuning launches must not add to the caller's buffer
-        if (cp.splits > 1 || cp.tn != 1 || !plan_emits_width(cp, chunk_width_of(p))) q.chunk_stats = nullptr;
+        if (cp.splits > 1 || cp.tn != 1 || cp.bn < 64 || !plan_emits_width(cp, chunk_width_of(p)) || p->Cout % 64 ||
+            p->out_f32 || p->gn_stats || g_legacy_epilogue)
+          q.chunk_stats = nullptr;
         for (int rep = 0; rep < 3 && rc == B200LDM_OK; ++rep) {
           if (rep == 1) cudaEventRecord(e0, st);
           rc = conv3d_run_plan(&q, cp, st);
@@ -923,15 +951,9 @@ int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st) {
                 p->C1, p->C2, p->Cout, p->ksize, p->stride, p->upsample2x ? " up" : "", p->residual ? " +res" : "",
                 p->skip_x ? " +skip" : "", p->N, p->Do, p->Ho, p->Wo, ms0 / 2, ms_tcp / 2, ms_best / 2, best & 15,
                 (best >> 4) & 255, (best >> 12) & 15, best >> 16, nc);
-      // the caller asked workspace_bytes / emits_chunk_stats before this call: honour that contract now (no stats
-      // where it was told there would be none), later calls see the remembered choice
-      ConvPlan run = plan_conv(p, best);
-      if (p->chunk_stats && (run.splits > 1 || run.tn != 1 || !plan_emits_width(run, chunk_width_of(p)))) run = pl;
-      if (run.splits > 1 && (!p->workspace || p->workspace_bytes < (long long)run.splits * M_total * p->Cout * 4)) run = pl;
-      return conv3d_run_plan(p, run, st);
     }
   }
-  return conv3d_run_plan(p, pl, st);
+  return B200LDM_OK;
 }
 
 static int conv3d_run_plan(const b200ldm_conv3d_params* p, const ConvPlan& pl, cudaStream_t st) {
@@ -1094,7 +1116,7 @@ static int conv3d_run_plan(const b200ldm_conv3d_params* p, const ConvPlan& pl, c
   }
   if (rc || pl.splits == 1) return rc;
   const long long vecs = M_total * (p->Cout / 8);
-  const unsigned blocks = (unsigned)std::min<long long>((vecs + 255) / 256, 148LL * 16);
+  const unsigned blocks = (unsigned)std::min<long long>((vecs + 255) / 256, (long long)sm_count() * 16);
   splitk_finalize_kernel<<<blocks, 256, 0, st>>>(
       reinterpret_cast<const float*>(p->workspace), pl.splits, M_total * p->Cout, M_total, p->Cout,
       (long long)p->Do * p->Ho * p->Wo, p->bias, p->temb, p->temb_stride,

@@ -416,15 +416,12 @@ bool conv_tc2_supported(int bn, const ConvTcArgs& a) {
 template <int BN>
 static int launch_tc2(const ConvTcMaps& maps, ConvTcArgs a, int m_tiles, int n_tiles, int zdim, cudaStream_t st) {
   using Cfg = ConvTc2Cfg<BN>;
-  static int max_pairs = 0;
-  static std::once_flag once;
-  static cudaError_t init_err = cudaSuccess;
-  std::call_once(once, [] {
-    init_err = cudaFuncSetAttribute(conv3d_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (init_err != cudaSuccess) return;
-    int sms = 0, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  B2_SET_SMEM_ONCE(Cfg::kSmemBytes, conv3d_tc2_kernel<BN>);
+  static std::atomic<int> pairs_of[kMaxDevices];   // resident CTA pairs, per device
+  const int dev = current_device();
+  int max_pairs = pairs_of[dev].load(std::memory_order_relaxed);
+  if (max_pairs <= 0) {
+    const int sms = sm_count();
     cudaLaunchConfig_t q{};
     q.gridDim = dim3((unsigned)(sms & ~1), 1, 1);
     q.blockDim = dim3(Cfg::kThreads, 1, 1);
@@ -441,8 +438,8 @@ static int launch_tc2(const ConvTcMaps& maps, ConvTcArgs a, int m_tiles, int n_t
     max_pairs = n < sms / 2 ? n : sms / 2;
     const char* e = getenv("B200LDM_CONV_TC2_PAIRS");
     if (e && atoi(e) > 0 && atoi(e) < max_pairs) max_pairs = atoi(e);
-  });
-  B2_CHECK_CUDA(init_err);
+    pairs_of[dev].store(max_pairs, std::memory_order_relaxed);
+  }
   a.work_x = ceil_div(m_tiles, 2); a.work_y = n_tiles; a.work_z = zdim;
   a.trace = g_conv_trace2;
   {

@@ -402,17 +402,8 @@ int conv_tcp_mt(int bn) { return bn == 256 ? 1 : 2; }
 template <int BN, int MT, int EW = 1>
 static int launch_tcp(const ConvTcMaps& maps, ConvTcArgs a, int m_tiles, int n_tiles, int zdim, cudaStream_t st) {
   using Cfg = ConvTcpCfg<BN, MT, EW>;
-  static int sms = 0;
-  static std::once_flag once;
-  static cudaError_t init_err = cudaSuccess;
-  std::call_once(once, [] {
-    init_err = cudaFuncSetAttribute(conv3d_tcp_kernel<BN, MT, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Cfg::kSmemBytes);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  });
-  B2_CHECK_CUDA(init_err);
+  B2_SET_SMEM_ONCE(Cfg::kSmemBytes, conv3d_tcp_kernel<BN, MT, EW>);
+  const int sms = sm_count();
   a.work_x = ceil_div(m_tiles, MT); a.work_y = n_tiles; a.work_z = zdim;
   const long long total = (long long)a.work_x * a.work_y * a.work_z;
   const unsigned grid = (unsigned)(total < sms ? total : sms);

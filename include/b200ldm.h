@@ -114,7 +114,23 @@ typedef struct {
                             groups); chunk_stats is then [N][Cout/chunk_width][2].  Ask emits_chunk_stats. */
 } b200ldm_conv3d_params;
 
+/* Asynchronous on `stream`, capture-safe, never synchronises and never reads device data on the host: it runs the
+ * kernel choice b200ldm_conv3d_tune remembered for this problem signature, else the planner's cost model. */
 int b200ldm_conv3d(const b200ldm_conv3d_params* p, b200ldm_stream stream);
+/* Explicit autotuning (the ONLY entry point of this library that synchronises).  Several kernels can run a given
+ * problem (one CTA per tile with split-K factors, persistent, persistent W-halo ...); which one is fastest is measured
+ * once per problem signature: b200ldm_conv3d_tune times the candidates on the caller's own buffers with CUDA events
+ * (3 launches each, cudaEventSynchronize after each candidate) and remembers the winner for every later
+ * b200ldm_conv3d of the same signature (shapes, fused operands - not pointers) in this process.  Afterwards `y` holds the
+ * conv result and `chunk_stats` (scratch during tuning, if given) is zero.  `workspace` must cover
+ * b200ldm_conv3d_workspace_bytes(p) as asked BEFORE the call (it reports the largest candidate while a measurement is
+ * pending).  Must not be called on a capturing stream (returns B200LDM_BAD_ARG).  A no-op returning OK when nothing
+ * is pending.  b200ldm_conv3d_tune_pending: 1 if a call would measure (tuning enabled - B200LDM_CONV_AUTOTUNE != 0 -,
+ * the problem has more than one candidate, and no choice is remembered yet), else 0; pure host arithmetic.
+ * Choices are per GPU model (this library is sm_100a / B200 only) and shared by all devices of the process;
+ * B200LDM_CONV_TUNE_FILE=<path> persists them across processes. */
+int b200ldm_conv3d_tune(const b200ldm_conv3d_params* p, b200ldm_stream stream);
+int b200ldm_conv3d_tune_pending(const b200ldm_conv3d_params* p);
 /* bytes of `workspace` this exact problem needs (0 for most shapes; > 0 when the planner splits K over CTAs
  * because the output has too few tiles to fill 148 SMs).  Pure host arithmetic, no CUDA call. */
 int64_t b200ldm_conv3d_workspace_bytes(const b200ldm_conv3d_params* p);

@@ -16,6 +16,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+# upper bound on one materialised block of attention scores (see SelfAttention.forward)
+ATTN_SCORE_BYTES = 1 << 30
 
 # --------------------------------------------------------------------------------------
 # small building blocks
@@ -62,9 +64,15 @@ class SelfAttention(nn.Module):
             return t.view(b, n, h, d).permute(0, 2, 1, 3)  # [B,H,N,d]
 
         q, k, v = split(self.to_q(x)), split(self.to_k(x)), split(self.to_v(x))
-        att = torch.einsum("bhxd,bhyd->bhxy", q, k) * self.scale
-        att = att.softmax(dim=-1)
-        y = torch.einsum("bhxy,bhyd->bhxd", att, v)
+        # the softmax is per query row, so evaluating the rows in blocks is the same arithmetic; it only bounds the
+        # [B,H,rows,N] score matrix (64000 tokens x 64000 keys x 4 B = 16 GB in the 160^3 decoder) to ~1 GB
+        rows = max(1, min(n, ATTN_SCORE_BYTES // max(1, 4 * b * h * n)))
+        ys = []
+        for r0 in range(0, n, rows):
+            att = torch.einsum("bhxd,bhyd->bhxy", q[:, :, r0:r0 + rows], k) * self.scale
+            att = att.softmax(dim=-1)
+            ys.append(torch.einsum("bhxy,bhyd->bhxd", att, v))
+        y = ys[0] if len(ys) == 1 else torch.cat(ys, dim=2)
         y = y.permute(0, 2, 1, 3).reshape(b, n, c)
         return self.out_proj(y)
 
@@ -232,15 +240,6 @@ class _DownOp(nn.Module):
         return self.op(x)
 
 
-class _UNetUp(nn.Module):
-    def __init__(self, ch: int):
-        super().__init__()
-        self.upsample = _NearestUp(ch)
-
-    def forward(self, x):
-        return self.upsample(x)
-
-
 class _DownBlock(nn.Module):
     def __init__(self, cin, cout, temb, n_res, groups, eps, add_down, attn, head_ch, xattn=None):
         super().__init__()
@@ -291,7 +290,9 @@ class _UpBlock(nn.Module):
         if attn:
             self.attentions = nn.ModuleList([_make_attn(cout, head_ch, groups, eps, xattn) for _ in range(n_res)])
         self.has_attn, self.xattn = attn, xattn is not None
-        self.upsampler = _UNetUp(cout) if add_up else None
+        # MONAI >= 1.4: WrappedUpsample(UpSample) - an nn.Sequential with children `upsample_non_trainable` and `postconv` -
+        # is assigned to `upsampler` directly, so the conv's key is `up_blocks.{i}.upsampler.postconv.conv.*`
+        self.upsampler = _NearestUp(cout) if add_up else None
 
     def forward(self, h, skips, emb, context=None):
         for j, r in enumerate(self.resnets):
@@ -306,6 +307,14 @@ class _UpBlock(nn.Module):
 
 def _per_level(v, n):
     return list(v) if isinstance(v, (list, tuple)) else [v] * n
+
+
+def _alias_upsampler_keys(state_dict, prefix, *_):
+    """load_state_dict pre-hook: the post-upsample conv of a UNet up block is `up_blocks.{i}.upsampler.postconv.conv.*`
+    in MONAI >= 1.4 (WrappedUpsample subclasses UpSample and is assigned to `upsampler` itself); the nested spelling
+    `upsampler.upsample.postconv.conv.*` of SURVEY.md App. E is accepted as an alias, so either checkpoint loads."""
+    for k in [k for k in state_dict if k.startswith(prefix) and ".upsampler.upsample." in k]:
+        state_dict[k.replace(".upsampler.upsample.", ".upsampler.")] = state_dict.pop(k)
 
 
 class DiffusionModelUNet(nn.Module):
@@ -353,6 +362,7 @@ class DiffusionModelUNet(nn.Module):
         self.in_channels, self.out_channels = in_channels, out_channels
         self.block_out_channels = list(channels)
         self.with_conditioning = with_conditioning
+        self._register_load_state_dict_pre_hook(_alias_upsampler_keys)
         temb = channels[0] * 4
         xattn = (transformer_num_layers, cross_attention_dim) if with_conditioning else None
 

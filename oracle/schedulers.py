@@ -126,6 +126,9 @@ class DDIMScheduler(Scheduler):
             raise ValueError("`num_inference_steps` cannot be larger than `num_train_timesteps`")
         self.num_inference_steps = num_inference_steps
         ratio = self.num_train_timesteps // num_inference_steps
+        if self.steps_offset >= ratio:   # upstream raises here - also from the constructor's set_timesteps(T) for any offset > 0
+            raise ValueError(f"`steps_offset`: {self.steps_offset} cannot be greater than or equal to "
+                             f"`num_train_timesteps // num_inference_steps : {ratio}`")
         ts = (np.arange(0, num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64)
         self.timesteps = torch.from_numpy(ts).to(device)
         self.timesteps += self.steps_offset

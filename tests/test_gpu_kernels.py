@@ -345,6 +345,65 @@ def test_conv3d_every_tensor_core_kernel(case, kernel):
         assert relerr(cs.reshape(N, Cout // 8, 2).cpu(), want) <= 1e-4
 
 
+def test_conv3d_tuning_is_an_explicit_entry_point():
+    """ABI contract (SURVEY.md 8b threading row): b200ldm_conv3d never measures or synchronises -
+    it is capture-safe even for a problem signature nothing has been measured for; measuring is b200ldm_conv3d_tune,
+    which refuses a capturing stream, and after which the same signature is no longer pending."""
+    import ctypes as C
+    from b200ldm import _lib, ops
+    lib = _lib.load()
+    N, sp, Cin, Cout = 3, (5, 6, 7), 128, 192            # a signature no other test uses (fresh in this process)
+    x = to_act(q(rnd((N, Cin) + sp, 91), torch.bfloat16), torch.bfloat16)
+    w = q(rnd((Cout, Cin, 3, 3, 3), 92) * (Cin * 27) ** -0.5, torch.bfloat16)
+    wp = ops.repack_conv_weight(w.to(DEV), Cout, Cin, torch.bfloat16)
+    y = torch.empty((N,) + sp + (Cout,), dtype=torch.bfloat16, device=DEV)
+
+    def params():
+        p = _lib.ConvParams(x=x.data_ptr(), w=wp.data_ptr(), y=y.data_ptr(), N=N, D=sp[0], H=sp[1], W=sp[2], C1=Cin, C2=0,
+                            Cout=Cout, Do=sp[0], Ho=sp[1], Wo=sp[2], ksize=3, stride=1, pad_lo=1, dtype=_lib.BF16,
+                            engine=_lib.ENGINE_AUTO)
+        nbytes = lib.b200ldm_conv3d_workspace_bytes(C.byref(p))
+        ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=DEV)
+        p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
+        return p, ws
+
+    p, ws = params()
+    assert lib.b200ldm_conv3d_tune_pending(C.byref(p)) == 1
+    # 1. the plain entry point inside a stream capture, nothing measured yet: must succeed (cost-model plan, no sync)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        _lib.check(lib.b200ldm_conv3d(C.byref(p), torch.cuda.current_stream().cuda_stream), "conv3d")
+        # ... and the measuring entry point must refuse the capturing stream instead of synchronising it
+        assert lib.b200ldm_conv3d_tune(C.byref(p), torch.cuda.current_stream().cuda_stream) == 5   # BAD_ARG
+    assert lib.b200ldm_conv3d_tune_pending(C.byref(p)) == 1          # calling conv3d did not measure anything
+    g.replay()
+    torch.cuda.synchronize()
+    ref = F.conv3d(ops.to_ncdhw(x, Cin).double().cpu(), w.double(), padding=1)
+    assert relerr(from_act(y, Cout), ref) <= 1e-2
+    # 2. explicit tuning: result valid, signature settled, a second call is a no-op
+    y.zero_()
+    _lib.check(lib.b200ldm_conv3d_tune(C.byref(p), torch.cuda.current_stream().cuda_stream), "conv3d_tune")
+    torch.cuda.synchronize()
+    assert relerr(from_act(y, Cout), ref) <= 1e-2
+    assert lib.b200ldm_conv3d_tune_pending(C.byref(p)) == 0
+    before = ops.launch_count()
+    _lib.check(lib.b200ldm_conv3d_tune(C.byref(p), torch.cuda.current_stream().cuda_stream), "conv3d_tune")
+    assert ops.launch_count() == before
+    # 3. the remembered choice runs through the plain entry point (workspace re-asked: it may have shrunk)
+    p2, ws2 = params()
+    y.zero_()
+    _lib.check(lib.b200ldm_conv3d(C.byref(p2), torch.cuda.current_stream().cuda_stream), "conv3d")
+    torch.cuda.synchronize()
+    assert relerr(from_act(y, Cout), ref) <= 1e-2
+    # 4. ops.conv3d tunes a fresh signature on its first eager call
+    x4 = to_act(q(rnd((2, Cin) + (3, 5, 9), 93), torch.bfloat16), torch.bfloat16)
+    p4 = _lib.ConvParams(x=x4.data_ptr(), w=wp.data_ptr(), y=y.data_ptr(), N=2, D=3, H=5, W=9, C1=Cin, C2=0, Cout=Cout,
+                         Do=3, Ho=5, Wo=9, ksize=3, stride=1, pad_lo=1, dtype=_lib.BF16, engine=_lib.ENGINE_AUTO)
+    assert lib.b200ldm_conv3d_tune_pending(C.byref(p4)) == 1
+    ops.conv3d(x4, wp, None, Cout)
+    assert lib.b200ldm_conv3d_tune_pending(C.byref(p4)) == 0
+
+
 def test_conv3d_rejects_bad_arguments():
     from b200ldm import ops
     x = torch.zeros((1, 4, 4, 4, 48), dtype=torch.bfloat16, device=DEV)
@@ -415,8 +474,15 @@ def test_attention_simt(case, dtype):
     assert e <= (2e-5 if dtype == torch.float32 else 6e-3), e
 
 
-@pytest.mark.parametrize("case", ATT_CASES[:5] + [(8, 4, 5544, 64), (1, 1, 4096, 256), (2, 16, 64, 64)],
-                         ids=lambda c: f"B{c[0]}H{c[1]}L{c[2]}d{c[3]}")
+# beyond the SIMT list: BASELINE cfg 2 attention (B8 H4 L5544 d64), AutoencoderKL d = 256 at L = 4096, the d = 128
+# ping-pong kernel at L >= 4096 (config_train_multigpu / config_train_stable AutoencoderKL attention),
+# head dim 32 (config_train_stable.json:47) on the 64-column tiles: even / odd / many heads, short and long sequences
+TC_ATT_CASES = ATT_CASES[:5] + [(8, 4, 5544, 64), (1, 1, 4096, 256), (2, 16, 64, 64), (1, 1, 4096, 128),
+                                (2, 1, 4500, 128), (1, 2, 64, 32), (2, 3, 100, 32), (1, 16, 1000, 32), (2, 16, 125, 32),
+                                (1, 1, 300, 32)]
+
+
+@pytest.mark.parametrize("case", TC_ATT_CASES, ids=lambda c: f"B{c[0]}H{c[1]}L{c[2]}d{c[3]}")
 def test_attention_tcgen05_bf16(case):
     from b200ldm import ops
     B, H, L, d = case
@@ -429,6 +495,20 @@ def test_attention_tcgen05_bf16(case):
         ref = ops.attention(dev_qkv, H, d, d ** -0.5, engine=ops.ENGINE_SIMT).float()
     e = relerr(o.float(), ref)
     assert e <= 1e-2, e
+
+
+def test_attention_auto_engine_never_falls_back_to_simt():
+    """north_star: no silent CUDA-core fallback on the bf16 product path.  ENGINE_AUTO with a head
+    dim that has no tcgen05 instance raises; head dim 32 runs on tcgen05 and agrees with the explicit engine."""
+    from b200ldm import ops
+    qkv = q(rnd((1, 70, 3 * 2 * 96), 26), torch.bfloat16).to(DEV).to(torch.bfloat16)
+    with pytest.raises(RuntimeError, match="BAD_SHAPE"):
+        ops.attention(qkv, 2, 96, 96 ** -0.5)
+    ops.attention(qkv, 2, 96, 96 ** -0.5, engine=ops.ENGINE_SIMT)      # explicit validation engine still works
+    qkv32 = q(rnd((2, 200, 3 * 4 * 32), 27), torch.bfloat16).to(DEV).to(torch.bfloat16)
+    a = ops.attention(qkv32, 4, 32, 32 ** -0.5)
+    b = ops.attention(qkv32, 4, 32, 32 ** -0.5, engine=ops.ENGINE_TCGEN05)
+    assert torch.equal(a, b)
 
 
 def test_attention_tcgen05_peaked_softmax():
@@ -456,7 +536,7 @@ def _xatt_ref(qm, kv, H, d):
 # B, H, Lq, Lk, d: context of one token, a ragged single tile, several 64-key tiles (d = 64 two-CTA kernel), head dims
 # 128 / 256, more keys than queries
 XATT_CASES = [(2, 2, 300, 1, 64), (2, 2, 384, 7, 64), (1, 4, 130, 77, 64), (2, 2, 200, 333, 64), (1, 2, 257, 50, 128),
-              (1, 2, 300, 400, 128), (1, 1, 190, 100, 256), (2, 2, 5, 9, 64)]
+              (1, 2, 300, 400, 128), (1, 1, 190, 100, 256), (2, 2, 5, 9, 64), (2, 4, 150, 77, 32), (1, 3, 129, 200, 32)]
 
 
 @pytest.mark.parametrize("case", XATT_CASES, ids=lambda c: f"B{c[0]}H{c[1]}Lq{c[2]}Lk{c[3]}d{c[4]}")

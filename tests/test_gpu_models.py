@@ -179,6 +179,54 @@ def test_serving_generator_batches_requests():
     assert out.shape == (1, 1) + patch
 
 
+def test_unseeded_sample_calls_draw_fresh_noise():
+    """without `seed=` every sample() call must use a new per-step noise stream (the reference draws
+    fresh torch.randn at every step of every call, 3d_ldm/inference.py:91-99); torch.manual_seed still makes the whole
+    sequence reproducible."""
+    import b200ldm
+    unet = port(gc.tiny_unet(), b200ldm.DiffusionModelUNet, gc.UNET_KW, "bf16")
+    ae = port(gc.tiny_ae(), b200ldm.AutoencoderKL, gc.AE_KW, "bf16")
+    sched = gc.make_scheduler(b200ldm, "ddpm", 5)
+    x_T, cond, _ = gc.sampling_inputs(5)
+    inf = b200ldm.LatentDiffusionInferer(sched)
+    kw = dict(input_noise=x_T.to(DEV), autoencoder_model=ae, diffusion_model=unet, scheduler=sched,
+              conditioning=cond.to(DEV), mode="concat", verbose=False, return_latent=True)
+    torch.manual_seed(42)
+    _, a = inf.sample(**kw)
+    _, b = inf.sample(**kw)          # same x_T, same cached loop, no seed: must differ
+    assert relerr(a, b) > 5e-2, relerr(a, b)
+    torch.manual_seed(42)
+    _, a2 = inf.sample(**kw)
+    _, b2 = inf.sample(**kw)
+    assert relerr(a2, a) <= 2e-2 and relerr(b2, b) <= 2e-2
+    _, c = inf.sample(**kw, seed=7)
+    _, c2 = inf.sample(**kw, seed=7)
+    assert relerr(c, c2) <= 2e-2
+
+
+@pytest.mark.parametrize("kind", ["ddpm", "ddim"])
+def test_scheduler_step_honours_generator(kind):
+    """scheduler.step(..., generator=g) draws this step's noise from g with torch.randn exactly as upstream does, so the
+    same generator state gives the oracle's result (VERDICT r01 missing #5)."""
+    import b200ldm
+    ours, ref = gc.make_scheduler(b200ldm, kind, 10), gc.make_scheduler(oracle, kind, 10)
+    g0 = gc.gen(3)
+    x = torch.randn((2, 4) + gc.LATENT, generator=g0)
+    eps = torch.randn((2, 4) + gc.LATENT, generator=g0)
+    t = int(ours.timesteps[3])
+    extra = {"eta": 0.7} if kind == "ddim" else {}
+    want, want0 = ref.step(eps, t, x, generator=gc.gen(99), **extra)
+    got, got0 = ours.step(eps.to(DEV), t, x.to(DEV), generator=gc.gen(99), **extra)
+    assert relerr(got, want) <= 1e-5 and relerr(got0, want0) <= 1e-5
+    other, _ = ours.step(eps.to(DEV), t, x.to(DEV), generator=gc.gen(100), **extra)
+    assert relerr(other, want) > 1e-3
+    gd = torch.Generator(device=DEV).manual_seed(5)      # a generator that lives on the GPU, as upstream requires there
+    a, _ = ours.step(eps.to(DEV), t, x.to(DEV), generator=gd, **extra)
+    gd.manual_seed(5)
+    b, _ = ours.step(eps.to(DEV), t, x.to(DEV), generator=gd, **extra)
+    assert torch.equal(a, b)
+
+
 def test_sampling_fused_scheduler_equals_separate_kernel():
     """north_star (4): the scheduler update rides in the UNet's last kernel.  Same trajectory as with the separate
     scheduler kernel (which reads a bf16-rounded prediction instead of the fp32 sums)."""

@@ -99,6 +99,62 @@ def test_state_dict_keys_and_shapes_match_oracle():
         ours.load_state_dict(ref.state_dict())  # strict
 
 
+def test_upsampler_key_spellings_both_load_strict():
+    """MONAI >= 1.4 names the UNet's post-upsample conv `up_blocks.{i}.upsampler.postconv.conv.*`;
+    SURVEY.md App. E recalled `...upsampler.upsample.postconv.conv.*`.  state_dict() emits the former, both load strictly
+    (product and oracle), and a key that is neither still fails."""
+    import b200ldm
+    for mod in (b200ldm, oracle):
+        ref = oracle.randomize_parameters(oracle.DiffusionModelUNet(**gc.UNET_KW), 3)
+        sd = ref.state_dict()
+        flat = [k for k in sd if ".upsampler." in k]
+        assert flat and all(".upsampler.postconv.conv." in k for k in flat), flat
+        nested = {k.replace(".upsampler.postconv.", ".upsampler.upsample.postconv."): v for k, v in sd.items()}
+        assert any(".upsampler.upsample.postconv." in k for k in nested)
+        for variant in (sd, nested):
+            m = mod.DiffusionModelUNet(**gc.UNET_KW)
+            m.load_state_dict(variant)  # strict
+            for k in flat:
+                assert torch.equal(m.state_dict()[k], sd[k])
+        bad = {k.replace(".upsampler.postconv.", ".upsampler.wrong.postconv."): v for k, v in sd.items()}
+        with pytest.raises(RuntimeError):
+            mod.DiffusionModelUNet(**gc.UNET_KW).load_state_dict(bad)
+
+
+def test_load_old_state_dict_generative_format():
+    """checkpoints of the pre-1.4 `generative` package: attention linears directly on the block with `proj_attn`,
+    transformer `to_out.0`, post-upsample conv named `conv` (MONAI's load_old_state_dict surface)."""
+    import b200ldm
+
+    def to_old(sd):
+        out = {}
+        for k, v in sd.items():
+            if "transformer_blocks" in k:
+                k = k.replace(".out_proj.", ".to_out.0.")
+            else:
+                k = k.replace(".attn.out_proj.", ".proj_attn.").replace(".attn.to_", ".to_")
+            out[k.replace("postconv", "conv")] = v
+        return out
+
+    for cls, kw, seed in ((b200ldm.DiffusionModelUNet, gc.UNET_KW, 5), (b200ldm.DiffusionModelUNet, gc.XATTN_UNET_KW, 6),
+                          (b200ldm.AutoencoderKL, gc.AE_KW, 7)):
+        ref = oracle.randomize_parameters(getattr(oracle, cls.__name__)(**kw), seed)
+        sd = ref.state_dict()
+        old = to_old(sd)
+        assert set(old) != set(sd)
+        m = cls(**kw)
+        m.load_old_state_dict(old)
+        got = m.state_dict()
+        assert list(got) == list(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+        m2 = cls(**kw)
+        m2.load_old_state_dict(sd)   # already in the new format: plain load
+        assert all(torch.equal(m2.state_dict()[k], sd[k]) for k in sd)
+        broken = dict(old)
+        broken.pop(next(k for k in broken if "proj_attn" in k or "to_out" in k))
+        with pytest.raises(RuntimeError):
+            cls(**kw).load_old_state_dict(broken)
+
+
 def test_constructor_errors_match_reference_surface():
     import b200ldm
     with pytest.raises(ValueError):
@@ -172,6 +228,36 @@ def test_scheduler_constructor_errors():
     assert b200ldm.DDPMScheduler(variance_type="learned_range").learned_variance
     with pytest.raises(ValueError):
         b200ldm.DDPMScheduler(variance_type="learned_rnage")
+
+
+def test_ddim_steps_offset_check_and_coef_cache_keys():
+    """ADVICE r01: upstream's `steps_offset >= num_train_timesteps // num_inference_steps` ValueError (it fires from the
+    constructor's set_timesteps(T) for any offset > 0, for product and oracle alike); coefficient caches follow
+    attributes reassigned after construction."""
+    import b200ldm
+    for mod in (b200ldm, oracle):
+        with pytest.raises(ValueError):
+            mod.DDIMScheduler(num_train_timesteps=1000, steps_offset=1)
+        s = mod.DDIMScheduler(num_train_timesteps=1000)
+        s.steps_offset = 20
+        with pytest.raises(ValueError):
+            s.set_timesteps(50)
+        s.steps_offset = 19
+        s.set_timesteps(50)
+        assert int(s.timesteps[0]) == 999 and int(s.timesteps[-1]) == 19
+    s = b200ldm.DDPMScheduler(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0195)
+    s.set_timesteps(10)
+    k0 = s._state_key()
+    t0 = s.coef_table("cpu")
+    assert s.coef_table("cpu") is t0                       # memoised per (state, grid)
+    s.clip_sample_values = [-2.0, 2.0]
+    assert s._state_key() != k0
+    t1 = s.coef_table("cpu")
+    assert t1 is not t0 and float(t1[0, 6]) == -2.0 and float(t0[0, 6]) == -1.0
+    s.clip_sample = False
+    assert float(s.coef_table("cpu")[0, 7]) > 1e38
+    s.set_timesteps(20)
+    assert s.coef_table("cpu").shape[0] == 20
 
 
 def test_serving_batch_plan_and_surface():
