@@ -27,7 +27,7 @@ class ConvParams(C.Structure):
         ("engine", C.c_int32), ("out_f32", C.c_int32), ("upsample2x", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("chunk_stats", C.c_void_p),
         ("skip_x", C.c_void_p), ("skip_x2", C.c_void_p), ("skip_w", C.c_void_p),
-        ("skip_C1", C.c_int32), ("skip_C2", C.c_int32), ("chunk_width", C.c_int32),
+        ("skip_C1", C.c_int32), ("skip_C2", C.c_int32), ("chunk_width", C.c_int32), ("defer_finalize", C.c_int32),
     ]
 
 
@@ -55,6 +55,10 @@ SIGNATURES = {
     "b200ldm_conv3d_tune_pending": (C.c_int, [C.POINTER(ConvParams)]),
     "b200ldm_conv3d_workspace_bytes": (C.c_int64, [C.POINTER(ConvParams)]),
     "b200ldm_conv3d_emits_chunk_stats": (C.c_int, [C.POINTER(ConvParams)]),
+    "b200ldm_conv3d_splits": (C.c_int, [C.POINTER(ConvParams)]),
+    "b200ldm_conv3d_finalize": (C.c_int, [_vp, _i32, _i64, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "b200ldm_groupnorm_small_slabs": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32,
+                                                _i32, _i32, _f32, _i32, _vp]),
     "b200ldm_repack_conv_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200ldm_repack_upconv_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200ldm_groupnorm_stats": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp]),

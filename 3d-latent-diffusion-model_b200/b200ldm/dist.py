@@ -69,23 +69,35 @@ def gather_volumes(local: torch.Tensor, seeds: torch.Tensor, total: int):
 
 @torch.no_grad()
 def sample_sharded(inferer, autoencoder, unet, scheduler, total: int, latent_shape, base_seed: int = 42,
-                   conditioning=None, mode: str = "crossattn", device=None, gather: bool = True):
+                   conditioning=None, mode: str = "crossattn", device=None, gather: bool = True, noise=None,
+                   max_batch: int | None = None):
     """Generate `total` volumes across all ranks.  Rank r draws x_T for its shard from
     torch.Generator(cpu).manual_seed(rank_seed(base_seed, r, i)) (as inference.py draws noise on the CPU, :88-92),
-    samples + decodes them as one batch, then gathers.  Returns (volumes [total,...], seeds [total])."""
+    samples + decodes them - as one batch, or in chunks of `max_batch` volumes (every full chunk replays the same
+    captured graphs) - then gathers.  Returns (volumes [total,...], seeds [total]).
+    `noise` (optional): the x_T of ALL `total` volumes, host (pinned for an asynchronous upload) or device; the rank's
+    slice is used instead of drawing.  `conditioning` likewise covers all `total` volumes on either side."""
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     device = device or (torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cpu")
     lo, hi = shard_range(total, rank, world)
     seeds = [rank_seed(base_seed, rank, i) for i in range(hi - lo)]
-    noise = torch.stack([torch.randn(tuple(latent_shape), generator=torch.Generator("cpu").manual_seed(s))
-                         for s in seeds]) if seeds else torch.empty((0,) + tuple(latent_shape))
-    cond = None if conditioning is None else conditioning[lo:hi].to(device)
-    if hi > lo:
-        vols = inferer.sample(input_noise=noise.to(device), autoencoder_model=autoencoder, diffusion_model=unet,
-                              scheduler=scheduler, conditioning=cond, mode=mode, verbose=False, seed=seeds[0])
+    if noise is not None:
+        x_T = noise[lo:hi]
+    elif seeds:
+        x_T = torch.stack([torch.randn(tuple(latent_shape), generator=torch.Generator("cpu").manual_seed(s))
+                           for s in seeds])
     else:
-        vols = torch.empty((0,), device=device)
+        x_T = torch.empty((0,) + tuple(latent_shape))
+    step = max_batch if max_batch else max(1, hi - lo)
+    parts = []
+    for c0 in range(0, hi - lo, step):
+        c1 = min(c0 + step, hi - lo)
+        cond = None if conditioning is None else conditioning[lo + c0:lo + c1].to(device, non_blocking=True)
+        parts.append(inferer.sample(input_noise=x_T[c0:c1].to(device, non_blocking=True), autoencoder_model=autoencoder,
+                                    diffusion_model=unet, scheduler=scheduler, conditioning=cond, mode=mode,
+                                    verbose=False, seed=seeds[c0]))
+    vols = (parts[0] if len(parts) == 1 else torch.cat(parts)) if parts else torch.empty((0,), device=device)
     sd = torch.as_tensor(seeds, dtype=torch.int64, device=device)
     if not gather:
         return vols, sd

@@ -114,7 +114,8 @@ class Conv(nn.Module):
         return self._cache.get((dtype, c1, c1_phys, cin_phys), (self.weight, self.bias), build)
 
     def run(self, x, x2=None, c1: int | None = None, temb=None, temb_stride: int = 0, residual=None, gn_stats=None,
-            gn_groups: int = 0, out_f32: bool = False, want_stats: bool = False, sched=None, out=None, cstats_out=None):
+            gn_groups: int = 0, out_f32: bool = False, want_stats: bool = False, sched=None, out=None, cstats_out=None,
+            defer: bool = False):
         if self.tap_expanded(x) and x2 is None and temb is None and residual is None and gn_stats is None and not out_f32:
             return self._run_tap_expanded(x, sched, out)
         if sched is not None:
@@ -126,7 +127,7 @@ class Conv(nn.Module):
         return ops.conv3d(x, w, b, self.cout_phys, self.ksize, self.stride, self.pad_lo, self.pad_hi, x2=x2, temb=temb,
                           temb_stride=temb_stride, residual=residual, gn_stats=gn_stats, gn_groups=gn_groups,
                           out_f32=out_f32, want_stats=want_stats, out=out, cstats_out=cstats_out,
-                          stats_width=self.stats_width())
+                          stats_width=self.stats_width(), defer=defer)
 
 
     def tap_expanded(self, x) -> bool:
@@ -156,7 +157,7 @@ class Conv(nn.Module):
         z = ops.conv3d(x, wz, None, nz, ksize=1, stride=1, pad_lo=0)
         return ops.tap_gather(z, b, cp, self.cout_phys, sched=sched, want_y=sched is None, out=out)
 
-    def run_with_skip(self, x, skip_conv: "Conv", sx, sx2=None, want_stats: bool = False):
+    def run_with_skip(self, x, skip_conv: "Conv", sx, sx2=None, want_stats: bool = False, defer: bool = False):
         """self(x) + skip_conv(cat(sx, sx2)) in ONE kernel: the 1x1x1 skip conv is a few more K iterations into the same
         TMEM accumulator (no second launch, no residual round trip)."""
         w, _ = self.packed(x.dtype, cin_phys=x.shape[-1])
@@ -171,7 +172,7 @@ class Conv(nn.Module):
 
         b = self._cache.get(("bias+skip",), (self.bias, skip_conv.bias), build)
         return ops.conv3d(x, w, b, self.cout_phys, self.ksize, self.stride, self.pad_lo, self.pad_hi,
-                          skip=(sx, sx2, sw), want_stats=want_stats, stats_width=self.stats_width())
+                          skip=(sx, sx2, sw), want_stats=want_stats, stats_width=self.stats_width(), defer=defer)
 
     def run_upsampled(self, x):
         """conv(nearest_upsample_x2(x)) without materialising the upsampled tensor: on the tensor-core
@@ -309,7 +310,9 @@ class SABlock(nn.Module):
         att = ops.attention(qkv.reshape(B, L, 3 * Cc), self.heads, self.head_dim, self.scale)
         wo, bo = self.out_proj.packed(xn.dtype)
         # 1x1x1 conv on the 5-D view (keeps the per-sample axis so the epilogue can emit GroupNorm chunk stats)
-        return ops.conv3d(att.reshape(shp), wo, bo, Cc, ksize=1, stride=1, pad_lo=0, residual=residual, want_stats=True)
+        # defer: the block output goes straight into the next block's GroupNorm (see ops.PendingFinalize)
+        return ops.conv3d(att.reshape(shp), wo, bo, Cc, ksize=1, stride=1, pad_lo=0, residual=residual, want_stats=True,
+                          defer=True)
 
 
 class SpatialAttentionBlock(nn.Module):
@@ -476,15 +479,17 @@ class UNetResBlock(nn.Module):
         cpg = self.cout // self.groups
         if FUSE_GN_STATS and cpg >= 2 and (cpg & (cpg - 1)) == 0:
             stats = ops.zeros_f64(x.shape[0] * self.groups * 2, x.device)
+        # defer: a split-K conv (the 4^3 / 5^3 levels) leaves its finalize pass to the GroupNorm that consumes the tensor -
+        # norm2 right here for conv1, the next block's first GroupNorm for the block output (ops.PendingFinalize)
         h = self.conv1.run(h, temb=temb, temb_stride=temb_stride, gn_stats=stats, gn_groups=self.groups,
-                           want_stats=stats is None)
+                           want_stats=stats is None, defer=stats is None)
         h = self.norm2.run(h, silu=True, stats=stats)
         if isinstance(self.skip_connection, nn.Identity):
-            return self.conv2.run(h, residual=x, want_stats=True)
+            return self.conv2.run(h, residual=x, want_stats=True, defer=True)
         if FUSE_SKIP and h.dtype == torch.bfloat16:
-            return self.conv2.conv.run_with_skip(h, self.skip_connection.conv, x, x2, want_stats=True)
+            return self.conv2.conv.run_with_skip(h, self.skip_connection.conv, x, x2, want_stats=True, defer=True)
         res = self.skip_connection.run(x, x2=x2, c1=None if x2 is None else x.shape[-1])
-        return self.conv2.run(h, residual=res, want_stats=True)
+        return self.conv2.run(h, residual=res, want_stats=True, defer=True)
 
 
 class _DownOp(nn.Module):

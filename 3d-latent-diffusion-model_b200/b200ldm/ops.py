@@ -49,6 +49,8 @@ PROFILER: KernelProfiler | None = None
 FUSE_GN_STATS = __import__("os").environ.get("B200LDM_FUSE_GN_STATS", "1") != "0"
 # conv kernel choice measured on first use (b200ldm_conv3d_tune); B200LDM_CONV_AUTOTUNE=0 also disables it inside the library
 AUTOTUNE = __import__("os").environ.get("B200LDM_CONV_AUTOTUNE", "1") != "0"
+# split-K convs feeding a small-level GroupNorm leave their finalize pass to it (b200ldm_groupnorm_small_slabs)
+DEFER_FINALIZE = __import__("os").environ.get("B200LDM_DEFER_FINALIZE", "1") != "0"
 GN_SMALL_MAX_S = int(__import__("os").environ.get("B200LDM_GN_SMALL_MAX_S", "256"))
 
 
@@ -64,8 +66,34 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class PendingFinalize:
+    """A split-K conv launched with defer_finalize: its output tensor `y` is allocated but NOT written yet - the fp32
+    partial sums sit in `ws`.  The tensor carries this object as `y.pending` until someone sums the slabs: the GroupNorm
+    that consumes it (groupnorm -> b200ldm_groupnorm_small_slabs, one launch for finalize + statistics + normalise), or
+    `_ptr`, which every other op goes through and which runs the standalone finalize first."""
+
+    def __init__(self, ws, splits, bias, temb, temb_stride, residual, M, cout, vox_per_sample):
+        self.ws, self.splits, self.bias, self.temb, self.temb_stride = ws, splits, bias, temb, temb_stride
+        self.residual, self.M, self.cout, self.vox_per_sample = residual, M, cout, vox_per_sample
+
+
+def finalize(t: torch.Tensor) -> None:
+    pend = getattr(t, "pending", None)
+    if pend is None:
+        return
+    t.pending = None
+    _lib.check(_lib.load().b200ldm_conv3d_finalize(pend.ws.data_ptr(), pend.splits, pend.M, pend.cout,
+                                                   pend.vox_per_sample, _ptr(pend.bias), _ptr(pend.temb),
+                                                   pend.temb_stride, _ptr(pend.residual), t.data_ptr(), _stream()),
+               "conv3d_finalize")
+
+
 def _ptr(t) -> int | None:
-    return None if t is None else t.data_ptr()
+    if t is None:
+        return None
+    if getattr(t, "pending", None) is not None:
+        finalize(t)
+    return t.data_ptr()
 
 
 def _need_cuda(*ts):
@@ -85,7 +113,7 @@ def conv_out_extent(n: int, k: int, stride: int, pad_lo: int, pad_hi: int) -> in
 def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo: int = 1, pad_hi: int | None = None,
            x2=None, temb=None, temb_stride: int = 0, residual=None, gn_stats=None, gn_groups: int = 0,
            out_f32: bool = False, engine: int = ENGINE_AUTO, upsample2x: bool = False, want_stats: bool = False,
-           skip=None, out=None, cstats_out=None, stats_width: int = 8):
+           skip=None, out=None, cstats_out=None, stats_width: int = 8, defer: bool = False):
     """y = conv3d(cat(x, x2)) + bias (+ temb) (+ residual); x: [N,D,H,W,C1] NDHWC.
     upsample2x: the conv runs on the nearest-x2-upsampled x without materialising it (bf16: phase-decomposed
     weights from repack_upconv_weight; fp32: ordinary weights).
@@ -96,7 +124,9 @@ def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo
     stats_width: channels per statistics entry (8; 2 or 4 = the group width of a following GroupNorm with fewer than
     8 channels per group - the persistent kernels emit those for Cout tiles <= 128); attached as `y.cstats_width`.
     out / cstats_out: write into this (contiguous, e.g. a batch slice of a larger tensor) instead of allocating; the
-    statistics slice must arrive zeroed."""
+    statistics slice must arrive zeroed.
+    defer: the caller hands `y` straight to a GroupNorm (ops.groupnorm) - when the problem runs split-K the finalize
+    pass is left to that GroupNorm (see PendingFinalize); the returned tensor must not be viewed / sliced before."""
     _need_cuda(x, x2, w_packed, bias, temb, residual)
     lib = _lib.load()
     N, D, H, W, C1 = x.shape
@@ -139,9 +169,14 @@ def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo
         _lib.check(lib.b200ldm_conv3d_tune(C.byref(p), _stream()), "conv3d_tune")
         p.workspace, p.workspace_bytes, p.chunk_stats = None, 0, None
     ws_bytes = lib.b200ldm_conv3d_workspace_bytes(C.byref(p))
+    ws = None
     if ws_bytes > 0:  # split-K partial sums (small-M convs): caller-owned scratch
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
+    splits = 1
+    if defer and ws is not None and out is None and not out_f32 and DEFER_FINALIZE:
+        splits = lib.b200ldm_conv3d_splits(C.byref(p))
+        p.defer_finalize = 1 if splits > 1 else 0
     cstats = None
     if want_stats and FUSE_GN_STATS and lib.b200ldm_conv3d_emits_chunk_stats(C.byref(p)):
         if cstats_out is not None:
@@ -152,6 +187,8 @@ def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo
         p.chunk_stats = cstats.data_ptr()
     ev = PROFILER.start() if PROFILER is not None else None
     _lib.check(lib.b200ldm_conv3d(C.byref(p), _stream()), "conv3d")
+    if p.defer_finalize:
+        y.pending = PendingFinalize(ws, splits, bias, temb, temb_stride, residual, N * Do * Ho * Wo, cout, Do * Ho * Wo)
     if cstats is not None:
         y.cstats, y.cstats_width = cstats, stats_width
     if ev is not None:
@@ -217,6 +254,25 @@ def groupnorm(x, gamma, beta, groups: int, eps: float, silu: bool, x2=None, stat
     S = x.numel() // (N * C1)
     dt = dtype_code(x.dtype)
     nbytes = float(N * S * (C1 + C2) * x.element_size())
+    pend = getattr(x, "pending", None)
+    if pend is not None:
+        cpg = (C1 + C2) // groups
+        if (stats is None and x.dtype == torch.bfloat16 and S <= GN_SMALL_MAX_S and (C1 + C2) % groups == 0
+                and cpg % 8 == 0 and C1 % cpg == 0 and S * (cpg // 8) <= 2048):
+            # the producing split-K conv left its partial sums: finalize + statistics + normalise in ONE launch; it also
+            # writes the un-normalised tensor into x itself (later residual / skip reads see a finished tensor)
+            x.pending = None
+            y = torch.empty(x.shape[:-1] + (C1 + C2,), dtype=x.dtype, device=x.device)
+            ev = PROFILER.start() if PROFILER is not None else None
+            _lib.check(lib.b200ldm_groupnorm_small_slabs(
+                pend.ws.data_ptr(), pend.splits, _ptr(pend.bias), _ptr(pend.temb), pend.temb_stride, _ptr(pend.residual),
+                x.data_ptr(), _ptr(x2), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), N, S, C1, C2, groups,
+                float(eps), int(silu), _stream()), "groupnorm_small_slabs")
+            if ev is not None:
+                PROFILER.stop("gn_small", f"C{C1 + C2} S{S} +finalize x{pend.splits}",
+                              2.0 * nbytes + float(N * S * C1) * (4 * pend.splits + 2), ev)
+            return y
+        finalize(x)
     cs1, cs2 = getattr(x, "cstats", None), (None if x2 is None else getattr(x2, "cstats", None))
     cw = getattr(x, "cstats_width", 8)
     if (stats is None and cs1 is not None and (x2 is None or (cs2 is not None and getattr(x2, "cstats_width", 8) == cw))
@@ -348,7 +404,7 @@ def tap_gather(z, bias, cp: int, cy: int, sched=None, want_y: bool = True, out=N
     elif want_y or sched is None:
         y = torch.empty((N, D, H, W, cy), dtype=z.dtype, device=z.device)
     ev = PROFILER.start() if PROFILER is not None else None
-    _lib.check(_lib.load().b200ldm_tap_gather(z.data_ptr(), _ptr(bias), _ptr(y), N, D, H, W, ldz, cp, cy,
+    _lib.check(_lib.load().b200ldm_tap_gather(_ptr(z), _ptr(bias), _ptr(y), N, D, H, W, ldz, cp, cy,
                                               dtype_code(z.dtype), None if sched is None else C.byref(sched), _stream()),
                "tap_gather")
     if ev is not None:
@@ -361,7 +417,7 @@ def upsample_nearest2x(x):
     _need_cuda(x)
     N, D, H, W, Cc = x.shape
     y = torch.empty((N, 2 * D, 2 * H, 2 * W, Cc), dtype=x.dtype, device=x.device)
-    _lib.check(_lib.load().b200ldm_upsample_nearest2x(x.data_ptr(), y.data_ptr(), N, D, H, W, Cc,
+    _lib.check(_lib.load().b200ldm_upsample_nearest2x(_ptr(x), y.data_ptr(), N, D, H, W, Cc,
                                                       dtype_code(x.dtype), _stream()), "upsample")
     return y
 
@@ -391,7 +447,7 @@ def to_ncdhw(src: torch.Tensor, channels: int) -> torch.Tensor:
     c_src = src.shape[-1]
     S = src.numel() // (N * c_src)
     out = torch.empty((N, channels) + sp, dtype=torch.float32, device=src.device)
-    _lib.check(_lib.load().b200ldm_ndhwc_to_ncdhw(src.data_ptr(), out.data_ptr(), N, channels, S, c_src,
+    _lib.check(_lib.load().b200ldm_ndhwc_to_ncdhw(_ptr(src), out.data_ptr(), N, channels, S, c_src,
                                                   dtype_code(src.dtype), _stream()), "ndhwc_to_ncdhw")
     return out
 

@@ -70,12 +70,34 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Blackwell's two-wide fp32 instructions (SASS FFMA2 / FADD2) and the three-input maximum (FMNMX3): the softmax warps'
+// exp loop is bound by ISSUE slots before it is bound by the MUFU pipe (profiles/r01_attention_experiments.md: 11.4
+// cycles per MUFU.EX2 against the pipe's 8.0, with FFMA + FADD + 0.5 F2FP issued next to every exponential), so one
+// instruction per PAIR of scores for the scale-and-shift and for the row sum takes 2.5 -> 1.5 companion instructions
+// per exponential, and the row maximum needs 32 instead of 64 instructions per 64-key tile.
+__device__ __forceinline__ void ffma2_bcast(float& d0, float& d1, float a0, float a1, float s, float c) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\tmov.b64 rc, {%5, %5};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(s), "f"(c));
+}
+__device__ __forceinline__ void fadd2_acc(float& d0, float& d1, float a0, float a1) {
+  asm("{\n\t.reg .b64 ra, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rd, {%0, %1};\n\t"
+      "add.rn.f32x2 rd, rd, ra;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 // DR = the real head dim.  DR == D except for head dim 32 (config_train_stable.json: num_head_channels 32), which runs
 // on the D = 64 tiles: the 64-column TMA box at (h / 2) * 64 holds heads 2h' and 2h'+1 side by side in one
 // SWIZZLE_128B row, S = Q K^T contracts only this head's two 16-column K-slices (descriptor offset (h & 1) * 64 B), PV
 // multiplies P_h by the whole 64-column V box (an N = 64 MMA costs the same ~46 cycles as N = 32,
 // profiles/r01e_umma_rate_microbench.log) and the epilogue stores this head's 32 columns of O.
-template <int D, int BN, int DR = D>
+template <int D, int BN, int DR = D, bool PACKED = true>
 __global__ void __launch_bounds__(kAttnThreads, AttnCfg<D, BN>::kOcc)
 attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   static_assert(DR == D || (D == 64 && DR == 32), "head dim 32 rides on the 64-column tiles");
@@ -261,10 +283,18 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
           if (i >= kvalid) sv[i] = -INFINITY;
       }
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 chains: no 128-deep dependency
+      if constexpr (PACKED) {
 #pragma unroll
-      for (int i = 0; i < BN; i += 4) {
+        for (int i = 0; i < BN; i += 8) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], sv[i + u]);
+          for (int u = 0; u < 4; ++u) mx4[u] = fmax3(mx4[u], sv[i + u], sv[i + 4 + u]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < BN; i += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], sv[i + u]);
+        }
       }
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * a.scale_log2;  // scale > 0
       // lazy rescale: keep the old reference unless the max grew by more than 2^8 (warp-uniform decision)
@@ -304,23 +334,45 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       // lives at r*128 + ((c ^ (r & 7)) << 4) inside each [128 x 64-key] sub-tile).  One FFMA + one MUFU.EX2 per
       // element; the row sum is taken in fp32 over 4 independent chains.
       const float neg_m = -m_used;
-      float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+      float psum;
+      if constexpr (PACKED) {
+        float ps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // 4 independent two-wide sum chains
 #pragma unroll
-      for (int c8 = 0; c8 < BN / 8; ++c8) {
-        uint32_t pk[4];
+        for (int c8 = 0; c8 < BN / 8; ++c8) {
+          uint32_t pk[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float p0 = ex2_approx(fmaf(sv[c8 * 8 + 2 * e], a.scale_log2, neg_m));
-          const float p1 = ex2_approx(fmaf(sv[c8 * 8 + 2 * e + 1], a.scale_log2, neg_m));
-          ps4[e] += p0 + p1;
-          const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-          pk[e] = *reinterpret_cast<const uint32_t*>(&hb);
+          for (int e = 0; e < 4; ++e) {
+            float x0, x1;
+            ffma2_bcast(x0, x1, sv[c8 * 8 + 2 * e], sv[c8 * 8 + 2 * e + 1], a.scale_log2, neg_m);
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            fadd2_acc(ps[2 * e], ps[2 * e + 1], p0, p1);
+            const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+            pk[e] = *reinterpret_cast<const uint32_t*>(&hb);
+          }
+          const int sub = c8 >> 3, cc = c8 & 7;
+          uint4* dst = reinterpret_cast<uint4*>(p_gen + sub * 16384 + row * 128 + ((cc ^ (row & 7)) << 4));
+          *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-        const int sub = c8 >> 3, cc = c8 & 7;
-        uint4* dst = reinterpret_cast<uint4*>(p_gen + sub * 16384 + row * 128 + ((cc ^ (row & 7)) << 4));
-        *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        psum = ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
+      } else {
+        float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c8 = 0; c8 < BN / 8; ++c8) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float p0 = ex2_approx(fmaf(sv[c8 * 8 + 2 * e], a.scale_log2, neg_m));
+            const float p1 = ex2_approx(fmaf(sv[c8 * 8 + 2 * e + 1], a.scale_log2, neg_m));
+            ps4[e] += p0 + p1;
+            const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+            pk[e] = *reinterpret_cast<const uint32_t*>(&hb);
+          }
+          const int sub = c8 >> 3, cc = c8 & 7;
+          uint4* dst = reinterpret_cast<uint4*>(p_gen + sub * 16384 + row * 128 + ((cc ^ (row & 7)) << 4));
+          *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
       }
-      const float psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
       l_sum += psum;
       ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the UMMA (async proxy)
       ptx::tc_fence_before();     // orders the TMEM rescale stores before the MMA warp's next PV
@@ -709,9 +761,16 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
   if ((rc = make_qkv_map(&maps.v, v, H * DR, Lk, B, ldkv, BN))) return rc;
   static const int dbg = [] { const char* e = getenv("B200LDM_ATTN_DBG"); return e ? atoi(e) : 0; }();
   AttnArgs a{H, L, DR, Lk, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o), g_attn_trace, dbg};
-  B2_SET_SMEM_ONCE(Cfg::kSmem, attention_tc_kernel<D, BN, DR>);
+  // B200LDM_ATTN_PACKED=0: the scalar FFMA / FADD / FMNMX softmax loop (A/B against the two-wide instructions)
+  static const int packed = [] { const char* e = getenv("B200LDM_ATTN_PACKED"); return e ? atoi(e) : 1; }();
   dim3 grid((unsigned)ceil_div(L, 128), (unsigned)H, (unsigned)B);
-  attention_tc_kernel<D, BN, DR><<<grid, kAttnThreads, Cfg::kSmem, st>>>(maps, a);
+  if (packed) {
+    B2_SET_SMEM_ONCE(Cfg::kSmem, attention_tc_kernel<D, BN, DR, true>);
+    attention_tc_kernel<D, BN, DR, true><<<grid, kAttnThreads, Cfg::kSmem, st>>>(maps, a);
+  } else {
+    B2_SET_SMEM_ONCE(Cfg::kSmem, attention_tc_kernel<D, BN, DR, false>);
+    attention_tc_kernel<D, BN, DR, false><<<grid, kAttnThreads, Cfg::kSmem, st>>>(maps, a);
+  }
   B2_LAUNCH_CHECK();
   return B200LDM_OK;
 }

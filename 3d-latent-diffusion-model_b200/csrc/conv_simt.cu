@@ -173,6 +173,10 @@ int conv3d_simt(const b200ldm_conv3d_params* p, cudaStream_t st) {
 int conv3d_tcgen05(const b200ldm_conv3d_params* p, cudaStream_t st);
 int conv3d_tcgen05_tune(const b200ldm_conv3d_params* p, cudaStream_t st);
 int conv3d_tcgen05_tune_pending(const b200ldm_conv3d_params* p);
+int conv3d_tcgen05_splits(const b200ldm_conv3d_params* p);
+int conv3d_splitk_finalize(const float* slabs, int splits, long long M, int Cout, long long vox_per_sample,
+                           const float* bias, const float* temb, int temb_stride, const void* residual, void* y,
+                           cudaStream_t st);
 long long conv3d_tcgen05_workspace_bytes(const b200ldm_conv3d_params* p);
 int conv3d_tcgen05_emits_chunk_stats(const b200ldm_conv3d_params* p);
 
@@ -197,6 +201,18 @@ extern "C" int64_t b200ldm_conv3d_workspace_bytes(const b200ldm_conv3d_params* p
 static int conv3d_engine_of(const b200ldm_conv3d_params* p) {
   if (p->engine != B200LDM_ENGINE_AUTO) return p->engine;
   return p->dtype == B200LDM_BF16 ? B200LDM_ENGINE_TCGEN05 : B200LDM_ENGINE_SIMT;
+}
+
+extern "C" int b200ldm_conv3d_splits(const b200ldm_conv3d_params* p) {
+  if (!p || conv3d_engine_of(p) != B200LDM_ENGINE_TCGEN05) return 1;
+  return b200ldm::conv3d_tcgen05_splits(p);
+}
+
+extern "C" int b200ldm_conv3d_finalize(const float* slabs, int32_t splits, int64_t M, int32_t Cout,
+                                       int64_t vox_per_sample, const float* bias, const float* temb,
+                                       int32_t temb_stride, const void* residual, void* y, b200ldm_stream stream) {
+  return b200ldm::conv3d_splitk_finalize(slabs, splits, M, Cout, vox_per_sample, bias, temb, temb_stride, residual, y,
+                                         (cudaStream_t)stream);
 }
 
 extern "C" int b200ldm_conv3d_tune_pending(const b200ldm_conv3d_params* p) {

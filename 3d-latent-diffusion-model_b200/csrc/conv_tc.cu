@@ -823,6 +823,27 @@ int conv3d_tcgen05_tune_pending(const b200ldm_conv3d_params* p) {
   return tune_pending(p, plan_conv(p)) ? 1 : 0;
 }
 
+int conv3d_tcgen05_splits(const b200ldm_conv3d_params* p) {
+  if (!conv3d_tcgen05_eligible(p)) return 1;
+  return plan_conv(p).splits;
+}
+
+int conv3d_splitk_finalize(const float* slabs, int splits, long long M, int Cout, long long vox_per_sample,
+                           const float* bias, const float* temb, int temb_stride, const void* residual, void* y,
+                           cudaStream_t st) {
+  B2_REQUIRE(slabs && y && splits >= 1 && M > 0 && Cout > 0 && Cout % 8 == 0 && vox_per_sample > 0, B200LDM_BAD_ARG,
+             "conv3d_finalize: bad arguments");
+  B2_REQUIRE(aligned16(slabs) && aligned16(y) && aligned16(residual), B200LDM_BAD_ALIGN,
+             "conv3d_finalize: pointers must be 16-byte aligned");
+  const long long vecs = M * (Cout / 8);
+  const unsigned blocks = (unsigned)std::min<long long>((vecs + 255) / 256, (long long)sm_count() * 16);
+  splitk_finalize_kernel<<<blocks, 256, 0, st>>>(slabs, splits, M * Cout, M, Cout, vox_per_sample, bias, temb, temb_stride,
+                                                 reinterpret_cast<const __nv_bfloat16*>(residual),
+                                                 reinterpret_cast<__nv_bfloat16*>(y));
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
 long long conv3d_tcgen05_workspace_bytes(const b200ldm_conv3d_params* p) {
   if (p->dtype != B200LDM_BF16 || p->C1 % 64 || p->C2 % 64 || p->Cout % 8) return 0;
   const ConvPlan pl = plan_conv(p);
@@ -1115,6 +1136,7 @@ static int conv3d_run_plan(const b200ldm_conv3d_params* p, const ConvPlan& pl, c
                           : launch_conv_tc<16, 1, 1>(maps, a, m_tiles, n_tiles, sp, st);
   }
   if (rc || pl.splits == 1) return rc;
+  if (p->defer_finalize) return B200LDM_OK;   // the caller sums the slabs (b200ldm_conv3d_finalize / groupnorm_small_slabs)
   const long long vecs = M_total * (p->Cout / 8);
   const unsigned blocks = (unsigned)std::min<long long>((vecs + 255) / 256, (long long)sm_count() * 16);
   splitk_finalize_kernel<<<blocks, 256, 0, st>>>(

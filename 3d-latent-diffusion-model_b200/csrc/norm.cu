@@ -217,6 +217,101 @@ gn_small_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict
   }
 }
 
+// gn_small_kernel whose first source has not been finalised yet: it is still the fp32 split-K slabs of the conv that
+// produced it.  The CTA of (group, sample) sums the slabs for its cpg channels x S voxels, adds bias / temb / residual,
+// rounds to bf16 (the value every other consumer of the tensor sees - written to y_raw when asked), keeps those values in
+// registers, reduces the statistics and normalises from the registers: conv -> finalize -> GroupNorm becomes
+// conv -> GroupNorm at the 4^3 / 5^3 levels, where each launch costs about as much as the work in it.
+constexpr int kSlabItems = 8;   // 8-channel vectors per thread: S * (cpg / 8) <= 256 * 8
+__global__ void __launch_bounds__(kNormThreads)
+gn_small_slabs_kernel(const float* __restrict__ slabs, int splits, long long slab_elems, const float* __restrict__ bias,
+                      const float* __restrict__ temb, int temb_stride, const __nv_bfloat16* __restrict__ residual,
+                      __nv_bfloat16* __restrict__ y_raw, const __nv_bfloat16* __restrict__ x2,
+                      __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      int S, int C1, int C2, int G, float eps, int silu) {
+  __shared__ double red[2][kNormThreads / 32];
+  __shared__ float s_mean, s_rstd;
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int C = C1 + C2, cpg = C / G, vpg = cpg >> 3;
+  const int items = S * vpg;
+  const bool from_slabs = g * cpg < C1;       // no group straddles the sources (checked on the host)
+  float val[kSlabItems][8];
+  float a = 0.f, b = 0.f;
+#pragma unroll
+  for (int k = 0; k < kSlabItems; ++k) {
+    const int i = threadIdx.x + k * kNormThreads;
+    if (i < items) {
+      const int v = i / vpg, c = g * cpg + (i - v * vpg) * 8;
+      float f[8];
+      if (from_slabs) {
+        const size_t off = ((size_t)n * S + v) * C1 + c;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        for (int z = 0; z < splits; ++z) {
+          float t[8];
+          Vec8<float>::load(slabs + (size_t)z * slab_elems + off, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] += t[e];
+        }
+        if (bias) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] += __ldg(bias + c + e);
+        }
+        if (temb) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] += __ldg(temb + (size_t)n * temb_stride + c + e);
+        }
+        if (residual) {
+          float t[8];
+          Vec8<__nv_bfloat16>::load(residual + off, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] += t[e];
+        }
+        // same operation order and the same bf16 rounding as splitk_finalize_kernel: bit-identical tensor
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __bfloat162float(__float2bfloat16_rn(f[e]));
+        if (y_raw) Vec8<__nv_bfloat16>::store(y_raw + off, f);
+      } else {
+        Vec8<__nv_bfloat16>::load(x2 + ((size_t)n * S + v) * C2 + (c - C1), f);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { val[k][e] = f[e]; a += f[e]; b = fmaf(f[e], f[e], b); }
+    }
+  }
+  double da = (double)warp_sum(a), db = (double)warp_sum(b);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = da; red[1][threadIdx.x >> 5] = db; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int w = 0; w < kNormThreads / 32; ++w) { s1 += red[0][w]; s2 += red[1][w]; }
+    const double inv = 1.0 / ((double)S * cpg);
+    const double m = s1 * inv;
+    double var = fma(-m, m, s2 * inv);
+    if (var < 0.0) var = 0.0;
+    float r = rsqrtf((float)var + eps);
+    r = r * (1.5f - 0.5f * ((float)var + eps) * r * r);
+    s_mean = (float)m;
+    s_rstd = r;
+  }
+  __syncthreads();
+  const float mean = s_mean, rstd = s_rstd;
+#pragma unroll
+  for (int k = 0; k < kSlabItems; ++k) {
+    const int i = threadIdx.x + k * kNormThreads;
+    if (i < items) {
+      const int v = i / vpg, c = g * cpg + (i - v * vpg) * 8;
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float ga = __ldg(gamma + c + e) * rstd;
+        const float t = fmaf(val[k][e] - mean, ga, __ldg(beta + c + e));
+        f[e] = silu ? silu_for<__nv_bfloat16>(t) : t;
+      }
+      Vec8<__nv_bfloat16>::store(y + ((size_t)n * S + v) * C + c, f);
+    }
+  }
+}
+
 static int norm_geometry(int N, long long S, int C, int G, int* vox_per_block, dim3* grid) {
   B2_REQUIRE(C % 8 == 0 && C / 8 <= kNormThreads, B200LDM_BAD_SHAPE, "GroupNorm needs C %% 8 == 0 and C <= %d (got %d)",
              8 * kNormThreads, C);
@@ -353,6 +448,30 @@ int b200ldm_groupnorm_small(const void* x, const void* x2, void* y, const float*
                                                                             gamma, beta, (int)S, C1, C2, G, eps, silu);
   else
     return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
+int b200ldm_groupnorm_small_slabs(const float* slabs, int32_t splits, const float* bias, const float* temb,
+                                  int32_t temb_stride, const void* residual, void* y_raw, const void* x2, void* y,
+                                  const float* gamma, const float* beta, int32_t N, int64_t S, int32_t C1, int32_t C2,
+                                  int32_t G, float eps, int32_t silu, b200ldm_stream stream) {
+  using namespace b200ldm;
+  B2_REQUIRE(slabs && y && gamma && beta && splits >= 1 && N > 0 && S > 0 && S <= 4096, B200LDM_BAD_ARG,
+             "groupnorm_small_slabs: bad arguments");
+  B2_REQUIRE(C1 > 0 && C1 % 8 == 0 && C2 >= 0 && C2 % 8 == 0 && ((C2 > 0) == (x2 != nullptr)) && G > 0 &&
+                 (C1 + C2) % G == 0 && ((C1 + C2) / G) % 8 == 0 && C1 % ((C1 + C2) / G) == 0,
+             B200LDM_BAD_SHAPE,
+             "groupnorm_small_slabs: C1/C2 multiples of 8 matching x2, channels/group a multiple of 8 dividing C1");
+  B2_REQUIRE(S * (((C1 + C2) / G) / 8) <= (int64_t)kNormThreads * kSlabItems, B200LDM_BAD_SHAPE,
+             "groupnorm_small_slabs: a (group, sample) slab must fit the CTA's registers (S * cpg / 8 <= %d)",
+             kNormThreads * kSlabItems);
+  B2_REQUIRE(aligned16(slabs) && aligned16(y) && aligned16(x2) && aligned16(residual) && aligned16(y_raw),
+             B200LDM_BAD_ALIGN, "groupnorm_small_slabs: 16-byte alignment");
+  const dim3 grid((unsigned)G, (unsigned)N, 1);
+  gn_small_slabs_kernel<<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(
+      slabs, splits, (long long)N * S * C1, bias, temb, temb_stride, (const __nv_bfloat16*)residual,
+      (__nv_bfloat16*)y_raw, (const __nv_bfloat16*)x2, (__nv_bfloat16*)y, gamma, beta, (int)S, C1, C2, G, eps, silu);
   B2_LAUNCH_CHECK();
   return B200LDM_OK;
 }

@@ -13,9 +13,15 @@ Default workload (N = 1 .. 8, weak scaling, one replica + one batch per GPU):
   The same JSON line also carries "sampling": generated volumes/s of BASELINE.json configs[2] per GPU (full 1000-step
   DDPM sampling with the config_train_32g UNet at a 20^3 latent + AutoencoderKL decode to 80^3, batch 8 per GPU, final
   gather over NCCL) - the other half of BASELINE.json's metric (--no-sampling skips it, --sampling-T shortens it).
-`--workload sample_32g`: that sampling workload alone as the headline line (--T steps, --latent edge).
+  Every throughput fraction is quoted twice: on ALGORITHMIC FLOPs and on EXECUTED FLOPs (`frac_executed`:
+  the convs behind a nearest-x2 up-sampling run 8 of their 27 taps); the `sampling` object has its own `e2e` (host noise
+  in, gathered volumes back in pinned host memory) and `roofline`.
+`--workload sample_32g`: that sampling workload alone as the headline line (--T steps, --latent edge, --batch volumes per
+  call; `--scaling strong --total-volumes 64` shares BASELINE configs[2]'s 64 volumes between the GPUs).
 `--impl reference`: the CPU oracle (pure-PyTorch restatement of the MONAI path; the reference itself is not
-  installable here - DESIGN.md) timed on the host cores of the box on a bounded sample of the same workload.
+  installable here - DESIGN.md) timed on the host cores of the box with the GPU arm's config: as many of the batch's 8
+  volumes as fit a 200 s budget for the requested steps (all 8 when they fit).
+Default --steps: 100 denoise steps (a >= 2 s timed region, so the clock samples describe the region).
 """
 from __future__ import annotations
 
@@ -47,6 +53,90 @@ LATENT_16G = (36, 44, 28)   # diffusion patch [144,176,112] / 4 (3d_ldm/config/c
 BATCH = 8
 SCHED = dict(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0195)
 FLOP_PER_VOLUME_STEP_16G = 2969.7e9   # SURVEY.md 8d / BASELINE.md 5 (algorithmic, unpadded)
+
+
+# ---------------------------------------------------------------------------------------------- FLOP census
+# SURVEY.md App. F counting rules: conv 2*vox*Cout*Cin*k^3, linear 2MKN, attention core 4*N^2*C; restated here so the
+# bench can quote EXECUTED next to ALGORITHMIC work: the convs that follow a nearest-x2 up-sampling run 8 instead of 27
+# taps per output voxel on the tensor-core path (phase decomposition), so 19/27 of their algorithmic
+# FLOPs are never executed and must not be credited as throughput (VERDICT r01 bench hygiene #10).
+def _conv_f(cin, cout, sp, taps=27):
+    return 2.0 * math.prod(sp) * cin * cout * taps
+
+
+def _attn_f(c, sp):
+    n = math.prod(sp)
+    return 8.0 * n * c * c + 4.0 * n * n * c
+
+
+def _res_f(cin, cout, sp):
+    return _conv_f(cin, cout, sp) + _conv_f(cout, cout, sp) + (_conv_f(cin, cout, sp, 1) if cin != cout else 0.0)
+
+
+def unet_flops(kw, spatial, taps_up=27):
+    """FLOPs of one DiffusionModelUNet forward for ONE volume (time-embedding GEMVs left out: < 0.1 %)"""
+    ch, att = list(kw["channels"]), list(kw["attention_levels"])
+    L = len(ch)
+    nres = kw["num_res_blocks"]
+    nres = list(nres) if isinstance(nres, (list, tuple)) else [nres] * L
+    sps = [tuple(spatial)]
+    for _ in range(L - 1):
+        sps.append(tuple((v + 1) // 2 for v in sps[-1]))
+    f = _conv_f(kw["in_channels"], ch[0], sps[0])
+    skips, cout = [ch[0]], ch[0]
+    for i in range(L):
+        cin, cout = cout, ch[i]
+        for j in range(nres[i]):
+            f += _res_f(cin if j == 0 else cout, cout, sps[i]) + (_attn_f(cout, sps[i]) if att[i] else 0.0)
+            skips.append(cout)
+        if i != L - 1:
+            f += _conv_f(cout, cout, sps[i + 1])
+            skips.append(cout)
+    f += 2 * _res_f(ch[-1], ch[-1], sps[-1]) + _attn_f(ch[-1], sps[-1])
+    rc, rn, ra = ch[::-1], nres[::-1], att[::-1]
+    cout = rc[0]
+    for i in range(L):
+        prev, cout = cout, rc[i]
+        for j in range(rn[i] + 1):
+            f += _res_f((prev if j == 0 else cout) + skips.pop(), cout, sps[L - 1 - i])
+            f += _attn_f(cout, sps[L - 1 - i]) if ra[i] else 0.0
+        if i != L - 1:
+            f += _conv_f(cout, cout, sps[L - 2 - i], taps_up)
+    return f + _conv_f(ch[0], kw["out_channels"], sps[0])
+
+
+def decoder_flops(kw, latent_sp, taps_up=27):
+    """FLOPs of AutoencoderKL.decode for ONE volume"""
+    ch, att = list(kw["channels"]), list(kw["attention_levels"])
+    L = len(ch)
+    nres = kw["num_res_blocks"]
+    nres = list(nres) if isinstance(nres, (list, tuple)) else [nres] * L
+    rc, ra, rn = ch[::-1], att[::-1], nres[::-1]
+    sp, lc = tuple(latent_sp), kw["latent_channels"]
+    f = _conv_f(lc, lc, sp, 1) + _conv_f(lc, rc[0], sp)
+    if kw.get("with_decoder_nonlocal_attn", True):
+        f += 2 * _res_f(rc[0], rc[0], sp) + _attn_f(rc[0], sp)
+    cout = rc[0]
+    for i in range(L):
+        cin, cout = cout, rc[i]
+        for j in range(rn[i]):
+            f += _res_f(cin if j == 0 else cout, cout, sp) + (_attn_f(cout, sp) if ra[i] else 0.0)
+        if i != L - 1:
+            sp = tuple(2 * v for v in sp)
+            f += _conv_f(cout, cout, sp, taps_up)
+    return f + _conv_f(cout, kw["out_channels"], sp)
+
+
+def executed_fraction_unet(kw, spatial):
+    return unet_flops(kw, spatial, 8) / unet_flops(kw, spatial, 27)
+
+
+def config_16g(world):
+    """`config` of the headline line - the SAME dict on the GPU arm and on the --impl reference arm"""
+    return {"workload": "unet_step_16g: config_train_16g UNet (256,256,512) denoise step + DDPM scheduler update, "
+                        "BASELINE.json configs[1]",
+            "batch_per_gpu": BATCH, "latent": list(LATENT_16G), "parallelism": f"replica-per-gpu x{world}",
+            "l2": "inputs larger than L2 (weights 0.3 GB + 181 MB activations per layer vs 126 MB L2)"}
 
 
 def seeded_init(model, seed):
@@ -122,6 +212,18 @@ def peaks():
         return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "src": "fallback"}
 
 
+def roofline_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full capture
+    committed for THIS round (profiles/roofline_traffic.json, written by scripts/ncu_summary.py with the commit it was
+    taken at); None when there is none - a number from an older build would not describe the kernels being benched."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        return float(d["traffic_bytes_per_launch"]), {k: d.get(k) for k in ("kernel", "launch", "algorithmic_bytes_per_launch",
+                                                                            "source", "commit")}
+    except Exception:
+        return None, {"source": "no ncu --set full capture committed for this build (profiles/roofline_traffic.json)"}
+
+
 def dist_setup():
     from b200ldm import dist as bd
     rank, world, local = bd.init_from_env()
@@ -149,67 +251,137 @@ def timed_region(fn, steps, world):
 
 # ---------------------------------------------------------------------------------------------- CPU oracle legs
 def cpu_oracle_unet_step(threads, budget_s, n_timed=1, n_warm=1):
-    """Time the oracle UNet-16g denoise step (+ scheduler step) on the host for a bounded sample."""
+    """The oracle's UNet-16g denoise step (+ scheduler step) on the host cores for a bounded sample of the workload:
+    the largest number of the batch's 8 volumes (processed as ONE batch, full 36x44x28 latent) whose n_warm + n_timed
+    steps fit `budget_s` (all 8 when they fit - then the sample IS the workload), else one volume cropped."""
     import oracle
     torch.set_num_threads(threads)
     unet = oracle.randomize_parameters(oracle.DiffusionModelUNet(**UNET_16G), 1234).eval()
     sched = oracle.DDPMScheduler(**SCHED)
-    candidates = [(LATENT_16G, 1.0, "1 of the 8 volumes, full 36x44x28 latent, 1 denoise step"),
-                  ((16, 24, 16), 16 * 24 * 16 / (36 * 44 * 28), "1 volume cropped to a 16x24x16 latent (13.9% of the voxels), "
-                                                                "1 denoise step")]
     g = torch.Generator().manual_seed(0)
-    for lat, frac, desc in candidates:
-        x = torch.randn((1, 8) + lat, generator=g)
-        t0 = time.perf_counter()
+
+    def step(x):
         with torch.no_grad():
             eps = unet(x, torch.tensor([500.0]))
             sched.step(eps, 500, x)
-        probe = time.perf_counter() - t0
-        if probe * (n_timed + n_warm) <= budget_s or lat == candidates[-1][0]:
+
+    x1 = torch.randn((1, 8) + LATENT_16G, generator=g)
+    step(x1)                                       # first touch (allocator, oneDNN primitive cache)
+    t0 = time.perf_counter()
+    step(x1)
+    probe = time.perf_counter() - t0               # one volume, one step
+    n_steps = n_timed + n_warm
+    lat, frac, nvol = LATENT_16G, 1.0, 1
+    for n in (8, 4, 2, 1):
+        if probe * n * n_steps <= budget_s:
+            nvol = n
             break
+    else:
+        lat, frac = (16, 24, 16), 16 * 24 * 16 / (36 * 44 * 28)
+    x = torch.randn((nvol, 8) + lat, generator=g)
     times = []
-    for i in range(n_warm - 1 + n_timed):
+    for i in range(n_steps):
         t0 = time.perf_counter()
-        with torch.no_grad():
-            eps = unet(x, torch.tensor([500.0]))
-            sched.step(eps, 500, x)
-        dt = time.perf_counter() - t0
-        if i >= n_warm - 1:
-            times.append(dt)
+        step(x)
+        if i >= n_warm:
+            times.append(time.perf_counter() - t0)
     total = sum(times)
-    return {"value": frac * len(times) / total, "unit": "volume-steps/s", "cores": threads, "kind": "port",
-            "sample": desc + f" (full-volume equivalents by voxel count); {len(times)} timed"}, total / len(times)
+    if frac == 1.0:
+        desc = (f"{nvol} of the {BATCH} volumes as one batch, full 36x44x28 latent" if nvol < BATCH
+                else f"the whole batch of {BATCH} volumes, full 36x44x28 latent (the sample is the workload)")
+    else:
+        desc = "1 volume cropped to a 16x24x16 latent (13.9 % of the voxels; full-volume equivalents by voxel count)"
+    return {"value": frac * nvol * len(times) / total, "unit": "volume-steps/s", "cores": threads, "kind": "port",
+            "sample": desc + f", UNet forward + scheduler step; {len(times)} timed steps after {n_warm} warm-up, "
+                             f"{total:.1f} s of CPU work"}, total / len(times)
 
 
 def run_reference(args):
+    """--impl reference: the reference's own (CPU) implementation of the path.  MONAI is not installable offline, so this
+    is the oracle port (cpu_baseline.kind "port"), all host threads, on the GPU arm's config / metric / unit."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    cb, ms_step = cpu_oracle_unet_step(threads, budget_s=200.0, n_timed=args.steps, n_warm=max(1, args.warmup))
+    budget = float(os.environ.get("B200LDM_BENCH_REF_BUDGET_S", "200"))
+    cb, s_step = cpu_oracle_unet_step(threads, budget_s=budget, n_timed=args.steps, n_warm=max(1, args.warmup))
     line = {"impl": "reference", "metric": "unet_denoise_volume_steps_per_sec", "value": cb["value"],
-            "unit": "volume-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "unet_step_16g: config_train_16g UNet denoise step, latent 36x44x28 (CPU oracle, "
-                                   "bounded sample)", "batch_per_gpu": BATCH},
-            "cpu_baseline": cb,
+            "unit": "volume-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(1, args.warmup),
+            "ms_per_step": s_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_16g(args.gpus), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "volume-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------- GPU workloads
+def profile_eager_steps(body, n_prof=2):
+    """per-kernel CUDA events (on the launching stream) around every launch of `n_prof` eager steps; returns
+    (kinds, by_tag, ms per step summed over kernels).  `body` must already have run once (weights packed, convs tuned)."""
+    from b200ldm import ops
+    torch.cuda.synchronize()
+    ops.PROFILER = ops.KernelProfiler()
+    for _ in range(n_prof):
+        body()
+    torch.cuda.synchronize()
+    kinds, by_tag = ops.PROFILER.summary()
+    ops.PROFILER = None
+    for d in (kinds, by_tag):
+        for v in d.values():
+            v["ms"] /= n_prof
+            v["work"] /= n_prof
+            v["launches"] //= n_prof
+    return kinds, by_tag, sum(v["ms"] for v in kinds.values())
+
+
+def conv_roofline(kinds, by_tag, step_ms, pk, kernel_desc):
+    """roofline object of the dominant kernel family (the tcgen05 implicit-GEMM convs of one step): `achieved` =
+    EXECUTED FLOPs of all conv launches of a step / their summed CUDA-event durations"""
+    conv = kinds["conv3d"]
+    conv_tf = conv["work"] / (conv["ms"] * 1e-3) / 1e12
+    traffic, tsrc = roofline_traffic()
+    roof = {"bound": "tensor", "kernel": kernel_desc, "achieved": conv_tf, "peak": pk["bf16_sustained"],
+            "unit": "TFLOP/s", "frac": conv_tf / pk["bf16_sustained"],
+            "flops": "executed (fused nearest-x2 up-sampling convs counted with the 8 taps they run, not 27)",
+            "peak_source": f"{pk['src']} MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed inside a full step); "
+                           f"burst {pk['bf16_burst']:.0f}", "frac_of_burst": conv_tf / pk["bf16_burst"],
+            "traffic": traffic, "traffic_source": tsrc,
+            "launches_per_step": conv["launches"], "ms_per_step": conv["ms"], "share_of_step": conv["ms"] / step_ms}
+    top = sorted(((v["ms"], k) for k, v in by_tag.items() if k[0] == "conv3d"), reverse=True)[:4]
+    roof["top_shapes"] = [{"shape": k[1], "ms": by_tag[k]["ms"], "launches": by_tag[k]["launches"],
+                           "TFLOPs": by_tag[k]["work"] / (by_tag[k]["ms"] * 1e-3) / 1e12} for _, k in top]
+    return roof
+
+
+def kernel_breakdown(kinds, pk, graph_ms=None):
+    out = {k: {"ms_per_step": v["ms"], "launches_per_step": v["launches"]} for k, v in kinds.items()}
+    for k in ("gn_stats", "gn_apply", "gn_small", "tap_gather"):
+        if k in kinds and kinds[k]["ms"] > 0:
+            out[k]["GBps"] = kinds[k]["work"] / (kinds[k]["ms"] * 1e-3) / 1e9
+            out[k]["frac_hbm"] = out[k]["GBps"] / pk["hbm"]
+    for k in ("attention", "conv3d"):
+        if k in kinds:
+            out[k]["TFLOPs"] = kinds[k]["work"] / (kinds[k]["ms"] * 1e-3) / 1e12
+    total = sum(v["ms"] for v in kinds.values())
+    out["_sum_of_kernels_ms"] = total
+    if graph_ms is not None:
+        # what the per-kernel events do not see: helper kernels without a profiler hook (select_row, counter_add, fills),
+        # launch gaps, and - with sub-batch streams - the overlap the graph gains (negative = the graph is faster)
+        out["_graph_replay_ms"] = graph_ms
+        out["_unattributed_ms"] = graph_ms - total
+    return out
+
+
 def bench_unet_step(args, rank, world, local):
     import b200ldm
-    from b200ldm import ops
     from b200ldm.inferer import SamplingLoop
     dev = torch.device("cuda", local)
     unet = seeded_init(b200ldm.DiffusionModelUNet(**UNET_16G, precision="bf16"), 1234).to(dev).eval()
     sched = b200ldm.DDPMScheduler(**SCHED)
     g = torch.Generator().manual_seed(42 + 1000 * rank)
     x_T = torch.randn((BATCH, 8) + LATENT_16G, generator=g)
-    if args.steps + args.warmup + 2 > 1000:
+    warm = max(args.warmup, 3)
+    if args.steps + warm + 2 > 1000:
         raise SystemExit("steps + warmup must stay below the 1000-step DDPM schedule")
 
     # ---- device-resident leg: graph-replayed denoise steps
@@ -217,7 +389,7 @@ def bench_unet_step(args, rank, world, local):
     loop.step()                                   # capture (eager warm-up inside) - counts as warm-up step 1
     per_graph = loop.launches_per_step            # kernels recorded into the graph = launched per replay
     loop_subs = list(loop.subs)                   # sub-batches of the top UNet level (parallel graph branches)
-    for _ in range(max(args.warmup, 3) - 1):
+    for _ in range(warm - 1):
         loop.step()
     with ClockSampler(local) as clk:
         ms = timed_region(loop.step, args.steps, world)
@@ -234,70 +406,48 @@ def bench_unet_step(args, rank, world, local):
         prev, _ = sched.step(eps, 500, x)
         out_host.copy_(prev, non_blocking=True)
 
-    for _ in range(2):
+    for _ in range(3):
         e2e_step()
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 50))
     ms_e2e = timed_region(e2e_step, e2e_steps, world)
     e2e_value = world * BATCH * e2e_steps / (ms_e2e * 1e-3)
     nbytes = x_host.numel() * 4
 
-    # ---- roofline leg: per-kernel CUDA events inside an eager step (same stream the kernels launch on)
+    # ---- roofline leg: per-kernel CUDA events inside eager steps (a single-stream loop: per-kernel events mean nothing
+    # while two sub-batch streams share the SMs)
     pk = peaks()
-    # (a single-stream loop: per-kernel events mean nothing while two sub-batch streams share the SMs)
     prof_loop = SamplingLoop(unet, sched, x_T.to(dev), None, "crossattn", seed=42 + 1000 * rank, use_graph=False)
     prof_loop._body()
-    torch.cuda.synchronize()
-    ops.PROFILER = ops.KernelProfiler()
-    n_prof = 2
-    for _ in range(n_prof):
-        prof_loop._body()
-    torch.cuda.synchronize()
+    kinds, by_tag, step_ms_prof = profile_eager_steps(prof_loop._body)
     del prof_loop
-    kinds, by_tag = ops.PROFILER.summary()
-    ops.PROFILER = None
-    conv = kinds["conv3d"]
-    conv_tf = conv["work"] / (conv["ms"] * 1e-3) / 1e12
-    step_ms_prof = sum(v["ms"] for v in kinds.values()) / n_prof
-    roof = {"bound": "tensor", "kernel": "conv3d_tc_kernel (tcgen05 implicit GEMM, all conv launches of one step)",
-            "achieved": conv_tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": conv_tf / pk["bf16_sustained"],
-            "peak_source": f"{pk['src']} (sustained: kernels timed inside a full step)",
-            # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (256->256 k3 @8x36x44x28, 844 us,
-            # tensor pipe 83.5 %) from the committed ncu --set full capture; algorithmic in + out = 363 MB
-            "traffic": 330.2e6, "traffic_source": "profiles/r01b_ncu_full.md (per launch of conv3d_tc_kernel<256,2,1>)",
-            "launches_per_step": conv["launches"] // n_prof, "share_of_step": conv["ms"] / n_prof / step_ms_prof}
-    breakdown = {k: {"ms_per_step": v["ms"] / n_prof, "launches_per_step": v["launches"] // n_prof} for k, v in kinds.items()}
-    for k in ("gn_stats", "gn_apply"):
-        if k in kinds:
-            breakdown[k]["GBps"] = kinds[k]["work"] / (kinds[k]["ms"] * 1e-3) / 1e9
-            breakdown[k]["frac_hbm"] = breakdown[k]["GBps"] / pk["hbm"]
-    if "attention" in kinds:
-        breakdown["attention"]["TFLOPs"] = kinds["attention"]["work"] / (kinds["attention"]["ms"] * 1e-3) / 1e12
-    top = sorted(((v["ms"], k) for k, v in by_tag.items() if k[0] == "conv3d"), reverse=True)[:4]
-    roof["top_shapes"] = [{"shape": k[1], "ms": by_tag[k]["ms"] / n_prof,
-                           "TFLOPs": by_tag[k]["work"] / (by_tag[k]["ms"] * 1e-3) / 1e12} for _, k in top]
+    roof = conv_roofline(kinds, by_tag, step_ms_prof, pk,
+                         "tcgen05 implicit-GEMM conv kernels (conv3d_tc / conv3d_tcp / conv3d_halo), all conv launches "
+                         "of one denoise step")
+    breakdown = kernel_breakdown(kinds, pk, ms / args.steps)
 
-    # ---- second half of BASELINE.json's metric: generated volumes/s (full sampling + decode), one warm-up batch
+    # ---- second half of BASELINE.json's metric: generated volumes/s (full sampling + decode)
     sampling = None
     if not args.no_sampling:
         del loop
         torch.cuda.empty_cache()
-        ms_batch, _, _ = run_sampling(rank, world, local, args.sampling_T, 20, 1, 1)
-        sampling = sampling_summary(ms_batch, world, args.sampling_T, 20)
+        sampling = run_sampling(rank, world, local, args.sampling_T, 20, reps=1, warm=1, batch=BATCH,
+                                total=BATCH * world)
 
     if rank != 0:
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_oracle_unet_step(os.cpu_count() or 1, budget_s=30.0, n_timed=1, n_warm=1)
-    step_tf = FLOP_PER_VOLUME_STEP_16G * BATCH / (ms / args.steps * 1e-3) / 1e12
+    step_s = ms / args.steps * 1e-3
+    step_tf = FLOP_PER_VOLUME_STEP_16G * BATCH / step_s / 1e12
+    fx = executed_fraction_unet(UNET_16G, LATENT_16G)
     line = {"metric": "unet_denoise_volume_steps_per_sec", "value": value, "unit": "volume-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "unet_step_16g: config_train_16g UNet (256,256,512) denoise step + fused DDPM update",
-                       "batch_per_gpu": BATCH, "latent": list(LATENT_16G), "parallelism": f"replica-per-gpu x{world}",
-                       "l2": "inputs larger than L2 (weights 0.3 GB + 181 MB activations per layer vs 126 MB L2)",
-                       "cuda_graph": True, "batch_streams": len(loop_subs)},
+            "config": config_16g(world), "impl_detail": {"cuda_graph": True, "batch_streams": len(loop_subs)},
             "step_tflops_algorithmic": step_tf, "frac_of_sustained_peak": step_tf / pk["bf16_sustained"],
+            "step_tflops_executed": step_tf * fx, "frac_executed": step_tf * fx / pk["bf16_sustained"],
+            "executed_over_algorithmic_flops": fx,
             "e2e": {"value": e2e_value, "unit": "volume-steps/s", "h2d_bytes_per_step": nbytes,
                     "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
             "gpu_launches": per_graph * args.steps, "launches_per_step": per_graph,
@@ -310,12 +460,14 @@ FLOP_UNET_32G = {16: 465.6e9, 20: 914.5e9, 40: 7910.7e9}     # per volume per st
 FLOP_DEC_32G = {16: 888.7e9, 20: 1799.7e9, 40: 21738e9}      # per volume
 
 
-def run_sampling(rank, world, local, T, latent, reps, warm):
-    """BASELINE.json configs[2] per GPU: full DDPM latent sampling (config_train_32g UNet, concat conditioning) +
-    AutoencoderKL decode, batch 8 volumes per GPU, final NCCL gather of volumes and seeds.  Returns (ms per batch
-    [max over ranks], launches, clocks)."""
+def run_sampling(rank, world, local, T, latent, reps, warm, batch=BATCH, total=None, want_e2e=True, want_roofline=True):
+    """BASELINE.json configs[2]: full DDPM latent sampling (config_train_32g UNet, concat conditioning) + AutoencoderKL
+    decode + final NCCL gather of volumes and seeds.  `total` volumes are sharded over the ranks (weak scaling:
+    total = batch * world; strong scaling: total fixed) and every rank works through its shard in batches of `batch`.
+    Returns the `sampling` object of the bench line (rank 0; timing = max over ranks)."""
     import b200ldm
     from b200ldm import dist as bd, ops
+    from b200ldm.inferer import SamplingLoop
     dev = torch.device("cuda", local)
     unet = seeded_init(b200ldm.DiffusionModelUNet(**UNET_32G, precision="bf16"), 1234).to(dev).eval()
     ae = seeded_init(b200ldm.AutoencoderKL(**AE_32G, precision="bf16"), 4321).to(dev).eval()
@@ -323,63 +475,108 @@ def run_sampling(rank, world, local, T, latent, reps, warm):
     sched.set_timesteps(T)
     inf = b200ldm.LatentDiffusionInferer(sched, scale_factor=1.0)
     lat = (16, latent, latent, latent)
-    total = BATCH * world
-    cond = torch.randn((total, 16) + lat[1:], generator=torch.Generator().manual_seed(7))
+    total = total or batch * world
+    g = torch.Generator().manual_seed(7)
+    cond_host = torch.randn((total, 16) + lat[1:], generator=g).pin_memory()
+    noise_host = torch.randn((total,) + lat, generator=g).pin_memory()
+    cond_dev, noise_dev = cond_host.to(dev), noise_host.to(dev)
+    out_host = torch.empty((total, 1, 4 * latent, 4 * latent, 4 * latent), dtype=torch.float32).pin_memory()
     seed = [42]
 
-    def one():
-        seed[0] += 1   # a new batch of volumes every call (new x_T, new in-kernel noise stream)
-        return bd.sample_sharded(inf, ae, unet, sched, total, lat, base_seed=seed[0], conditioning=cond, mode="concat",
-                                 device=dev)
+    def resident():   # inputs already in HBM, result left in HBM
+        seed[0] += 1   # a new in-kernel noise stream every call
+        return bd.sample_sharded(inf, ae, unet, sched, total, lat, base_seed=seed[0], conditioning=cond_dev,
+                                 mode="concat", device=dev, noise=noise_dev, max_batch=batch)
+
+    def e2e():        # what inference.py does around the path: host noise in, volumes back on the host
+        seed[0] += 1
+        vols, _ = bd.sample_sharded(inf, ae, unet, sched, total, lat, base_seed=seed[0], conditioning=cond_host,
+                                    mode="concat", device=dev, noise=noise_host, max_batch=batch)
+        if rank == 0:
+            out_host.copy_(vols, non_blocking=True)
 
     for _ in range(warm):
-        one()
+        resident()
     l0 = ops.launch_count()
     with ClockSampler(local) as clk:
-        ms = timed_region(one, reps, world)
-    return ms / reps, (ops.launch_count() - l0) // reps, clk.summary()
-
-
-def sampling_summary(ms_batch, world, T, latent):
+        ms = timed_region(resident, reps, world) / reps
+    launches = (ops.launch_count() - l0) // reps
     pk = peaks()
-    vps = world * BATCH / (ms_batch * 1e-3)
-    out = {"metric": "generated_volumes_per_sec", "value": vps, "unit": "volumes/s", "ms_per_batch": ms_batch,
+    vps = total / (ms * 1e-3)
+    out = {"metric": "generated_volumes_per_sec", "value": vps, "unit": "volumes/s", "ms_per_batch": ms,
            "workload": f"sample_32g: DDPM {T}-step latent sampling + AutoencoderKL decode, latent {latent}^3 -> "
-                       f"{4 * latent}^3, concat conditioning, batch {BATCH}/GPU, final gather of volumes + seeds"}
+                       f"{4 * latent}^3, concat conditioning, {total} volumes over {world} GPU(s) in batches of {batch}, "
+                       "final gather of volumes + seeds (BASELINE.json configs[2])",
+           "volumes_total": total, "batch": batch, "gpu_launches": launches, "clocks": clk.summary()}
     if latent in FLOP_UNET_32G:
-        flop = BATCH * (T * FLOP_UNET_32G[latent] + FLOP_DEC_32G[latent])
-        out["tflops_algorithmic"] = flop / (ms_batch * 1e-3) / 1e12
+        per_gpu = total / world
+        flop = per_gpu * (T * FLOP_UNET_32G[latent] + FLOP_DEC_32G[latent])
+        fx_u = executed_fraction_unet(UNET_32G, (latent,) * 3)
+        fx_d = decoder_flops(AE_32G, (latent,) * 3, 8) / decoder_flops(AE_32G, (latent,) * 3, 27)
+        flop_x = per_gpu * (T * FLOP_UNET_32G[latent] * fx_u + FLOP_DEC_32G[latent] * fx_d)
+        out["tflops_algorithmic"] = flop / (ms * 1e-3) / 1e12
         out["frac_of_sustained_peak"] = out["tflops_algorithmic"] / pk["bf16_sustained"]
+        out["tflops_executed"] = flop_x / (ms * 1e-3) / 1e12
+        out["frac_executed"] = out["tflops_executed"] / pk["bf16_sustained"]
+    if want_e2e:
+        e2e()
+        ms_e2e = timed_region(e2e, 1, world)
+        out["e2e"] = {"value": total / (ms_e2e * 1e-3), "unit": "volumes/s", "ms_per_batch": ms_e2e,
+                      "h2d_bytes_per_step": (noise_host.numel() + cond_host.numel()) * 4,
+                      "d2h_bytes_per_step": out_host.numel() * 4,
+                      "what": "x_T and conditioning from pinned host memory, gathered volumes copied into pinned host "
+                              "memory on rank 0, all inside the timed region"}
+    if want_roofline:
+        # dominant kernel of the sampling workload: the convs of the 32g denoise step (T x per-step vs one decode)
+        nb = min(batch, (total + world - 1) // world)
+        pl = SamplingLoop(unet, sched, noise_dev[:nb], cond_dev[:nb], "concat", seed=1, use_graph=False)
+        pl._body()
+        kinds, by_tag, step_ms = profile_eager_steps(pl._body)
+        out["roofline"] = conv_roofline(kinds, by_tag, step_ms, pk,
+                                        "tcgen05 implicit-GEMM conv kernels, all conv launches of one 32g denoise step")
+        out["kernel_breakdown"] = kernel_breakdown(kinds, pk)
     return out
 
 
 def bench_sample(args, rank, world, local):
-    ms_batch, launches, clocks = run_sampling(rank, world, local, args.T, args.latent, args.steps, max(1, args.warmup))
+    total = args.total_volumes if args.scaling == "strong" else args.batch * world
+    sm = run_sampling(rank, world, local, args.T, args.latent, args.steps, max(1, args.warmup), batch=args.batch,
+                      total=total)
     if rank != 0:
         return
-    sm = sampling_summary(ms_batch, world, args.T, args.latent)
     line = {"metric": sm["metric"], "value": sm["value"], "unit": sm["unit"], "n_gpus": world, "steps": args.steps,
-            "warmup": max(1, args.warmup), "ms_per_step": ms_batch, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": sm["workload"], "batch_per_gpu": BATCH, "parallelism": f"batch-sharded x{world}"},
+            "warmup": max(1, args.warmup), "ms_per_step": sm["ms_per_batch"], "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": sm["workload"], "volumes_total": total, "batch": args.batch,
+                       "parallelism": f"batch-sharded x{world}",
+                       "l2": "inputs larger than L2 (1.3 GB of packed weights per step vs 126 MB L2)"},
             "tflops_algorithmic": sm.get("tflops_algorithmic"), "frac_of_sustained_peak": sm.get("frac_of_sustained_peak"),
-            "gpu_launches": launches * args.steps, "clocks": clocks}
+            "tflops_executed": sm.get("tflops_executed"), "frac_executed": sm.get("frac_executed"),
+            "e2e": sm.get("e2e"), "roofline": sm.get("roofline"), "kernel_breakdown": sm.get("kernel_breakdown"),
+            "gpu_launches": sm["gpu_launches"] * args.steps, "clocks": sm["clocks"]}
     print(json.dumps(line))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None,
+                    help="timed steps (default: 100 denoise steps = a >= 2 s timed region; sample_32g: 1 batch)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="unet_step_16g", choices=["unet_step_16g", "sample_32g"])
     ap.add_argument("--T", type=int, default=50, help="sample_32g: number of DDPM steps")
     ap.add_argument("--latent", type=int, default=20, help="sample_32g: latent edge")
+    ap.add_argument("--batch", type=int, default=BATCH, help="sample_32g: volumes per sampling call on one GPU")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="sample_32g: weak = --batch volumes per GPU; strong = --total-volumes shared by all GPUs")
+    ap.add_argument("--total-volumes", type=int, default=64, help="sample_32g --scaling strong (BASELINE configs[2]: 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sampling", action="store_true", help="skip the volumes/s leg of the default workload")
     ap.add_argument("--sampling-T", type=int, default=1000, help="DDPM steps of the volumes/s leg (reference: 1000)")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 1 if args.workload == "sample_32g" else (100 if args.impl == "b200" else 3)
     if args.impl == "reference":
         return run_reference(args)
     if not torch.cuda.is_available():

@@ -112,6 +112,12 @@ typedef struct {
   int32_t chunk_width;   /* channels per `chunk_stats` entry: 0 / 8 (default), or 2 / 4 = the group width of a following
                             GroupNorm with fewer than 8 channels per group (AutoencoderKL, 64 / 128 channels in 32
                             groups); chunk_stats is then [N][Cout/chunk_width][2].  Ask emits_chunk_stats. */
+  int32_t defer_finalize; /* 1: when this problem runs split-K (b200ldm_conv3d_splits(p) > 1) the launch stops after
+                            the fp32 partial sums: `workspace` then holds `splits` slabs [N*Do*Ho*Wo][Cout] and `y` is
+                            NOT written; bias / temb / residual are applied by whoever sums the slabs -
+                            b200ldm_conv3d_finalize, or b200ldm_groupnorm_small_slabs, which does it inside the following
+                            GroupNorm (the 4^3 / 5^3 UNet levels are chains of launch-bound kernels).  Ignored (y is
+                            written as usual) when the problem does not split. */
 } b200ldm_conv3d_params;
 
 /* Asynchronous on `stream`, capture-safe, never synchronises and never reads device data on the host: it runs the
@@ -137,6 +143,15 @@ int64_t b200ldm_conv3d_workspace_bytes(const b200ldm_conv3d_params* p);
 /* 1 if this exact problem can accumulate `chunk_stats` in its epilogue (bf16 tensor-core path, Cout % 64 == 0,
  * one sample per tile, no split-K), else 0.  Pure host arithmetic. */
 int b200ldm_conv3d_emits_chunk_stats(const b200ldm_conv3d_params* p);
+/* split-K factor this exact problem runs with right now (1 = no split; the remembered measured choice, else the cost
+ * model).  Pure host arithmetic. */
+int b200ldm_conv3d_splits(const b200ldm_conv3d_params* p);
+/* Second half of a split-K conv launched with defer_finalize = 1:
+ *   y[m][c] = bf16( sum_z slabs[z][m][c] + bias[c] + temb[(m / vox_per_sample) * temb_stride + c] + residual[m][c] )
+ * slabs: fp32 [splits][M][Cout] (the conv's workspace); bias / temb / residual may be NULL. */
+int b200ldm_conv3d_finalize(const float* slabs, int32_t splits, int64_t M, int32_t Cout, int64_t vox_per_sample,
+                            const float* bias, const float* temb, int32_t temb_stride, const void* residual, void* y,
+                            b200ldm_stream stream);
 
 /* src: fp32 [Cout][Cin][k][k][k] (PyTorch layout) -> dst: [k^3][Cout_pad][Cin_pad] in `dtype`,
  * zero padded; cin_offset lets a weight be split across padded concat sources:
@@ -183,6 +198,15 @@ int b200ldm_groupnorm_small_fits(int64_t S, int32_t C, int32_t G, int32_t dtype)
 int b200ldm_groupnorm_small(const void* x, const void* x2, void* y, const float* gamma, const float* beta, int32_t N,
                             int64_t S, int32_t C1, int32_t C2, int32_t G, float eps, int32_t silu, int32_t dtype,
                             b200ldm_stream stream);
+/* b200ldm_groupnorm_small whose first source is still the fp32 partial sums of a split-K conv (defer_finalize = 1):
+ * one launch sums the `splits` slabs [N*S][C1], adds bias / temb / residual (any may be NULL), rounds to bf16 exactly
+ * like b200ldm_conv3d_finalize, writes that un-normalised tensor to `y_raw` if it is not NULL (it is the ResNet block's
+ * output: a later residual / skip source), and GroupNorm(+SiLU)s cat(that, x2) into `y`.  bf16 only; needs
+ * b200ldm_groupnorm_small_fits(S, C1 + C2, G) and C1 % ((C1 + C2) / G) == 0 (no group straddles the two sources). */
+int b200ldm_groupnorm_small_slabs(const float* slabs, int32_t splits, const float* bias, const float* temb,
+                                  int32_t temb_stride, const void* residual, void* y_raw, const void* x2, void* y,
+                                  const float* gamma, const float* beta, int32_t N, int64_t S, int32_t C1, int32_t C2,
+                                  int32_t G, float eps, int32_t silu, b200ldm_stream stream);
 int b200ldm_fill_zero(void* p, size_t bytes, b200ldm_stream stream);
 
 /* ------------------------------------------------------------------------------------------

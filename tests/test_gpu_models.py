@@ -523,3 +523,82 @@ def test_xattn_unet_realistic_widths_bf16():
     got = m(x.to(DEV), ts.to(DEV), context=ctx.to(DEV))
     e = relerr(got, want)
     assert e <= EPS_TOL["bf16"], e
+
+
+# ------------------------------------------------------------------------------------------
+# the reference's other model configs (VERDICT r01 missing #3 / #4): config_train_stable.json (32-channel AutoencoderKL
+# levels with 16 groups, head dim 32 in the UNet) and config_train_multigpu.json / config_optimized.json (attention at
+# the 128-channel AutoencoderKL level + the decoder's non-local trio => d = 128 self-attention at (2s)^3 tokens)
+# ------------------------------------------------------------------------------------------
+STABLE_AE_KW = dict(spatial_dims=3, in_channels=1, out_channels=1, latent_channels=8, channels=[32, 64, 128],
+                    num_res_blocks=1, norm_num_groups=16, norm_eps=1e-6, attention_levels=[False, False, True],
+                    with_encoder_nonlocal_attn=False, with_decoder_nonlocal_attn=False)
+STABLE_UNET_KW = dict(spatial_dims=3, in_channels=16, out_channels=8, channels=[128, 256, 512],
+                      attention_levels=[False, False, True], num_head_channels=[0, 0, 32], num_res_blocks=1)
+MULTIGPU_AE_KW = dict(spatial_dims=3, in_channels=1, out_channels=1, latent_channels=16, channels=[64, 128, 256],
+                      num_res_blocks=2, norm_num_groups=32, norm_eps=1e-6, attention_levels=[False, True, True],
+                      with_encoder_nonlocal_attn=False, with_decoder_nonlocal_attn=True)
+OPTIMIZED_AE_KW = dict(MULTIGPU_AE_KW, channels=[128, 256, 256])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,kw,latent", [("stable", STABLE_AE_KW, (4, 6, 4)), ("multigpu", MULTIGPU_AE_KW, (6, 8, 4)),
+                                            ("optimized", OPTIMIZED_AE_KW, (4, 4, 6))])
+def test_autoencoder_other_reference_configs_vs_oracle(name, kw, latent, precision):
+    import b200ldm
+    ref = oracle.randomize_parameters(oracle.AutoencoderKL(**kw), 99).eval()
+    m = port(ref, b200ldm.AutoencoderKL, kw, precision)
+    z = torch.randn((2, kw["latent_channels"]) + latent, generator=gc.gen(31))
+    img = torch.rand((1, 1) + tuple(4 * v for v in latent), generator=gc.gen(32))
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    with torch.no_grad():
+        want_dec = ref.decode_stage_2_outputs(z)
+        want_mu, want_sigma = ref.encode(img)
+        want_rec = ref.reconstruct(img)
+    tol = 1e-4 if precision == "fp32" else 2e-2
+    e_dec = relerr(m.decode_stage_2_outputs(z.to(DEV)), want_dec)
+    mu, sigma = m.encode(img.to(DEV))
+    e_mu, e_rec = relerr(mu, want_mu), relerr(m.reconstruct(img.to(DEV)), want_rec)
+    print(f"AE {name}/{precision}: decode {e_dec:.2e} mu {e_mu:.2e} reconstruct {e_rec:.2e}")
+    assert e_dec <= tol and e_mu <= tol and e_rec <= 2 * tol, (e_dec, e_mu, e_rec)
+    assert relerr(sigma, want_sigma) <= (1e-3 if precision == "fp32" else 1e-1)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("latent", [(8, 12, 8), (24, 24, 24)], ids=["12tokens", "216tokens"])
+def test_unet_stable_config_head_dim_32_vs_oracle(latent, precision):
+    """config_train_stable.json:40-49: channels (128, 256, 512), attention only at the last level with 32-channel heads
+    (16 heads of head dim 32 - the tcgen05 kernel's 64-column tiles shared by head pairs), mid-block attention too"""
+    import b200ldm
+    ref = oracle.randomize_parameters(oracle.DiffusionModelUNet(**STABLE_UNET_KW), 77).eval()
+    m = port(ref, b200ldm.DiffusionModelUNet, STABLE_UNET_KW, precision)
+    x = torch.randn((2, 16) + latent, generator=gc.gen(33))
+    ts = torch.tensor([700.0, 3.0])
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    with torch.no_grad():
+        want = ref(x, ts)
+    e = relerr(m(x.to(DEV), ts.to(DEV)), want)
+    print(f"unet stable {latent}/{precision}: eps relerr {e:.3e}")
+    assert e <= EPS_TOL[precision], e
+
+
+def test_stable_config_sampling_psnr():
+    """config_train_stable end to end: DDPM-10 sampling with concat conditioning + decode, bf16 vs oracle >= 40 dB"""
+    import b200ldm
+    r_unet = oracle.randomize_parameters(oracle.DiffusionModelUNet(**STABLE_UNET_KW), 77).eval()
+    r_ae = oracle.randomize_parameters(oracle.AutoencoderKL(**STABLE_AE_KW), 99).eval()
+    unet = port(r_unet, b200ldm.DiffusionModelUNet, STABLE_UNET_KW, "bf16")
+    ae = port(r_ae, b200ldm.AutoencoderKL, STABLE_AE_KW, "bf16")
+    n, g = 10, gc.gen(34)
+    shp = (2, 8, 8, 12, 8)
+    x_T, cond = torch.randn(shp, generator=g), torch.randn(shp, generator=g)
+    step_noise = torch.randn((n,) + shp, generator=g)
+    s_ours, s_ref = gc.make_scheduler(b200ldm, "ddpm", n), gc.make_scheduler(oracle, "ddpm", n)
+    img = b200ldm.LatentDiffusionInferer(s_ours, 1.0).sample(
+        input_noise=x_T.to(DEV), autoencoder_model=ae, diffusion_model=unet, scheduler=s_ours,
+        conditioning=cond.to(DEV), mode="concat", verbose=False, step_noise=step_noise.to(DEV))
+    want = oracle.LatentDiffusionInferer(s_ref, 1.0).sample(x_T, r_ae, r_unet, s_ref, conditioning=cond, mode="concat",
+                                                            verbose=False, step_noise=step_noise)
+    p = psnr(img, want)
+    print(f"config_train_stable DDPM-10 sampling + decode, bf16: {p:.1f} dB")
+    assert img.shape == (2, 1, 32, 48, 32) and p >= 40.0, p

@@ -35,7 +35,7 @@ def test_struct_layout_matches_header(lib_built):
     # 3 skip pointers + 2 int32 (conv), 7 pointers + 2 int64 + 4 int32 + uint64 + seed pointer + 2 learned-variance
     # pointers + int64 Philox offset (sched)
     lib = _lib.load()
-    assert ctypes.sizeof(_lib.ConvParams) == lib.b200ldm_sizeof_params(0) == 8 * 8 + 20 * 4 + 8 + 8 + 8 + 3 * 8 + 2 * 4 + 2 * 4   # + chunk_width + tail padding
+    assert ctypes.sizeof(_lib.ConvParams) == lib.b200ldm_sizeof_params(0) == 8 * 8 + 20 * 4 + 8 + 8 + 8 + 3 * 8 + 2 * 4 + 2 * 4   # + chunk_width + defer_finalize
     assert ctypes.sizeof(_lib.SchedParams) == lib.b200ldm_sizeof_params(1) == 7 * 8 + 2 * 8 + 4 * 4 + 8 + 8 + 2 * 8 + 8
 
 
@@ -360,6 +360,7 @@ def test_bench_reference_arm_contract():
     import sys
     bench = os.path.join(ROOT, "bench.py")
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env["B200LDM_BENCH_REF_BUDGET_S"] = "6"      # keep the CPU suite short: one (cropped) volume instead of the batch
     r = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -371,6 +372,14 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["config"]["workload"].startswith("unet_step_16g")
+    sys.path.insert(0, ROOT)
+    import bench as bench_mod
+    assert d["config"] == bench_mod.config_16g(1)          # the GPU arm's config, key for key (driver: same_config)
+    # FLOP census used for the executed-vs-algorithmic fractions reproduces SURVEY.md 8d within 0.2 %
+    assert abs(bench_mod.unet_flops(bench_mod.UNET_16G, bench_mod.LATENT_16G) / 2969.7e9 - 1) < 2e-3
+    assert abs(bench_mod.unet_flops(bench_mod.UNET_32G, (20, 20, 20)) / 914.5e9 - 1) < 2e-3
+    assert abs(bench_mod.decoder_flops(bench_mod.AE_32G, (20, 20, 20)) / 1799.7e9 - 1) < 2e-3
+    assert 0.93 < bench_mod.executed_fraction_unet(bench_mod.UNET_16G, bench_mod.LATENT_16G) < 0.95
     r1 = subprocess.run([sys.executable, bench, "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                         capture_output=True, text=True, env={**env, "RANK": "1", "WORLD_SIZE": "2"}, timeout=600)
     assert r1.returncode == 0 and not [l for l in r1.stdout.splitlines() if l.startswith("{")]
