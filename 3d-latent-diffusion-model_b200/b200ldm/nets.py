@@ -789,7 +789,7 @@ class DiffusionModelUNet(nn.Module):
                         h = attend(blk.attentions[j], h)
                     skips.append(h)
                 if blk.downsampler is not None:
-                    h = blk.downsampler.op.run(h, want_stats=True)
+                    h = blk.downsampler.op.run(h, want_stats=True, defer=True)   # next consumer: a ResNet block's norm1
                     skips.append(h)
             mb = self.middle_block
             h = mb.resnet_1.run(h, temb_for(mb.resnet_1), temb_stride)

@@ -33,6 +33,7 @@ struct AttnArgs {
 };
 
 constexpr int kAttnThreads = 192;
+constexpr int kAttnPackedDefault = 1;   // B200LDM_ATTN_PACKED (see launch_attention_tc)
 
 template <int D, int BN>
 struct AttnCfg {
@@ -86,6 +87,42 @@ __device__ __forceinline__ void fadd2_acc(float& d0, float& d1, float a0, float 
       "add.rn.f32x2 rd, rd, ra;\n\tmov.b64 {%0, %1}, rd;\n\t}"
       : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
 }
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// 2^x for a PAIR of scores on the FMA / ALU pipes instead of the MUFU (FlashAttention-4's trick, here with the two-wide
+// instructions so that it costs 5.5 instead of 9 issue slots per element): x = n + f with n = round(x) taken from the
+// mantissa of x + 1.5 * 2^23, 2^f on [-0.5, 0.5] by a cubic (max relative error 7.5e-5, two orders below the bf16
+// rounding of P), and n added into the exponent field.  x is clamped at -125 so that the exponent cannot wrap (2^-125
+// stands in for 0: masked keys and hopeless scores contribute ~1e-38).  The kernel's exponentials are MUFU-bound (16 per
+// clock and SM against 4096 tensor FLOPs per clock and SM): a share of them moved here lowers that floor.
+__device__ __forceinline__ void exp2_poly2(float& p0, float& p1, float x0, float x1) {
+  constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23
+  x0 = fmaxf(x0, -125.0f);
+  x1 = fmaxf(x1, -125.0f);
+  float r0, r1, n0, n1, f0, f1, q0, q1;
+  fadd2(r0, r1, x0, x1, kMagic, kMagic);          // integer part lands in the low mantissa bits
+  fadd2(n0, n1, r0, r1, -kMagic, -kMagic);
+  fadd2(f0, f1, x0, x1, -n0, -n1);
+  ffma2(q0, q1, f0, f1, 0.05517164617776871f, 0.05517164617776871f, 0.2426111251115799f, 0.2426111251115799f);
+  ffma2(q0, q1, q0, q1, f0, f1, 0.6932609677314758f, 0.6932609677314758f);
+  ffma2(q0, q1, q0, q1, f0, f1, 0.9999280571937561f, 0.9999280571937561f);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(r0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23));
+}
+// which of every 8 consecutive score pairs take the polynomial path (spread out so MUFU and FMA work interleave)
+__device__ __forceinline__ constexpr bool poly_pair(int poly8, int q) {
+  return poly8 == 4 ? (q & 1) : poly8 == 3 ? (q == 2 || q == 5 || q == 7) : poly8 == 2 ? (q == 3 || q == 7)
+       : poly8 == 1 ? (q == 7) : false;
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -97,7 +134,9 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // SWIZZLE_128B row, S = Q K^T contracts only this head's two 16-column K-slices (descriptor offset (h & 1) * 64 B), PV
 // multiplies P_h by the whole 64-column V box (an N = 64 MMA costs the same ~46 cycles as N = 32,
 // profiles/r01e_umma_rate_microbench.log) and the epilogue stores this head's 32 columns of O.
-template <int D, int BN, int DR = D, bool PACKED = true>
+// PACKED: 0 = scalar FFMA / FADD softmax loop, 1 = two-wide fp32 instructions, 2 .. 5 = two-wide + (PACKED - 1) of every 8
+// score pairs exponentiated by exp2_poly2 instead of MUFU.EX2
+template <int D, int BN, int DR = D, int PACKED = 1>
 __global__ void __launch_bounds__(kAttnThreads, AttnCfg<D, BN>::kOcc)
 attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   static_assert(DR == D || (D == 64 && DR == 32), "head dim 32 rides on the 64-column tiles");
@@ -283,7 +322,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
           if (i >= kvalid) sv[i] = -INFINITY;
       }
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 chains: no 128-deep dependency
-      if constexpr (PACKED) {
+      if constexpr (PACKED != 0) {
 #pragma unroll
         for (int i = 0; i < BN; i += 8) {
 #pragma unroll
@@ -335,16 +374,21 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       // element; the row sum is taken in fp32 over 4 independent chains.
       const float neg_m = -m_used;
       float psum;
-      if constexpr (PACKED) {
+      if constexpr (PACKED != 0) {
         float ps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // 4 independent two-wide sum chains
 #pragma unroll
         for (int c8 = 0; c8 < BN / 8; ++c8) {
           uint32_t pk[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float x0, x1;
+            float x0, x1, p0, p1;
             ffma2_bcast(x0, x1, sv[c8 * 8 + 2 * e], sv[c8 * 8 + 2 * e + 1], a.scale_log2, neg_m);
-            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            if (poly_pair(PACKED - 1, (c8 & 1) * 4 + e)) {   // folds at compile time: both loops are fully unrolled
+              exp2_poly2(p0, p1, x0, x1);
+            } else {
+              p0 = ex2_approx(x0);
+              p1 = ex2_approx(x1);
+            }
             fadd2_acc(ps[2 * e], ps[2 * e + 1], p0, p1);
             const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
             pk[e] = *reinterpret_cast<const uint32_t*>(&hb);
@@ -761,16 +805,29 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
   if ((rc = make_qkv_map(&maps.v, v, H * DR, Lk, B, ldkv, BN))) return rc;
   static const int dbg = [] { const char* e = getenv("B200LDM_ATTN_DBG"); return e ? atoi(e) : 0; }();
   AttnArgs a{H, L, DR, Lk, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o), g_attn_trace, dbg};
-  // B200LDM_ATTN_PACKED=0: the scalar FFMA / FADD / FMNMX softmax loop (A/B against the two-wide instructions)
-  static const int packed = [] { const char* e = getenv("B200LDM_ATTN_PACKED"); return e ? atoi(e) : 1; }();
+  // B200LDM_ATTN_PACKED: 0 = scalar softmax loop, 1 = two-wide fp32 instructions, 2 .. 5 = + 1 .. 4 of every 8 score
+  // pairs through the polynomial exp2 (head dim 32 / 64 only: the wider heads are tensor-bound); default: measured best
+  static const int packed = [] { const char* e = getenv("B200LDM_ATTN_PACKED"); return e ? atoi(e) : kAttnPackedDefault; }();
   dim3 grid((unsigned)ceil_div(L, 128), (unsigned)H, (unsigned)B);
-  if (packed) {
-    B2_SET_SMEM_ONCE(Cfg::kSmem, attention_tc_kernel<D, BN, DR, true>);
-    attention_tc_kernel<D, BN, DR, true><<<grid, kAttnThreads, Cfg::kSmem, st>>>(maps, a);
+#define B2_ATTN_LAUNCH(MODE)                                                              \
+  do {                                                                                    \
+    B2_SET_SMEM_ONCE(Cfg::kSmem, attention_tc_kernel<D, BN, DR, MODE>);                   \
+    attention_tc_kernel<D, BN, DR, MODE><<<grid, kAttnThreads, Cfg::kSmem, st>>>(maps, a); \
+  } while (0)
+  if constexpr (D == 64) {
+    switch (packed) {
+      case 0: B2_ATTN_LAUNCH(0); break;
+      case 2: B2_ATTN_LAUNCH(2); break;
+      case 3: B2_ATTN_LAUNCH(3); break;
+      case 4: B2_ATTN_LAUNCH(4); break;
+      case 5: B2_ATTN_LAUNCH(5); break;
+      default: B2_ATTN_LAUNCH(1); break;
+    }
   } else {
-    B2_SET_SMEM_ONCE(Cfg::kSmem, attention_tc_kernel<D, BN, DR, false>);
-    attention_tc_kernel<D, BN, DR, false><<<grid, kAttnThreads, Cfg::kSmem, st>>>(maps, a);
+    if (packed == 0) B2_ATTN_LAUNCH(0);
+    else B2_ATTN_LAUNCH(1);
   }
+#undef B2_ATTN_LAUNCH
   B2_LAUNCH_CHECK();
   return B200LDM_OK;
 }

@@ -25,17 +25,47 @@ KEYS = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak
         ]
 
 
-def main(path):
+def _num(v):
+    return float(v.replace(",", ""))
+
+
+def _bytes(v, unit):
+    return _num(v) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+
+
+def main(path, traffic_json=None, algorithmic_bytes=None, commit=None, launch=None):
+    """python scripts/ncu_summary.py file.ncu-rep [--traffic-json profiles/roofline_traffic.json
+    --algorithmic-bytes N --commit SHA --launch "256->256 k3 @8x36x44x28"]: with --traffic-json the FIRST kernel of the
+    report becomes bench.py's roofline.traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch)."""
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
-    for r in rows[2:]:
+    for n, r in enumerate(rows[2:]):
         print("----", r[hdr.index("Kernel Name")][:100])
         for k in KEYS:
             if k in hdr:
                 i = hdr.index(k)
                 print(f"  {k:86s} {units[i]:14s} {r[i]}")
+        if traffic_json and n == 0:
+            import json
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            t = _bytes(r[ir], units[ir]) + _bytes(r[iw], units[iw])
+            it = hdr.index("gpu__time_duration.sum")
+            json.dump({"kernel": r[hdr.index("Kernel Name")][:120], "launch": launch, "traffic_bytes_per_launch": t,
+                       "algorithmic_bytes_per_launch": algorithmic_bytes, "duration": f"{r[it]} {units[it]}",
+                       "tensor_pipe_active_pct": r[hdr.index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")]
+                       if "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active" in hdr else None,
+                       "source": "ncu --set full --clock-control none, " + path.split("/")[-1], "commit": commit},
+                      open(traffic_json, "w"), indent=1)
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("rep")
+    ap.add_argument("--traffic-json")
+    ap.add_argument("--algorithmic-bytes", type=float)
+    ap.add_argument("--commit")
+    ap.add_argument("--launch")
+    a = ap.parse_args()
+    main(a.rep, a.traffic_json, a.algorithmic_bytes, a.commit, a.launch)
