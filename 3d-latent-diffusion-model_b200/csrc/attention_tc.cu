@@ -30,27 +30,43 @@ struct AttnArgs {
   __nv_bfloat16* o;  // [B][L][H*d]
   unsigned long long* trace;  // debug (b200ldm_debug_set_conv_trace): per-CTA cycle counters of the softmax warps
   int dbg;                    // debug: bit0 = exp2 replaced by a multiply (is the MUFU pipe the limiter?)
+  int stagger;                // cycles the softmax warps of every second CTA of an SM wait before their first tile (0: off)
 };
+
+// CTAs that have started on each SM so far (only its parity is used): two CTAs of the one-query-tile kernel share an
+// SM, and their softmax warps share the MUFU pipe of a sub-partition.  Launched together they run in lock-step - both in
+// the exp phase (MUFU at half rate each), then both in the MUFU-free part of a tile (clock64 trace, round 2: exp + P store
+// 885 cycles per tile against 512 for the pipe alone, 758 cycles of other work).  Starting every second CTA of an SM
+// half a tile late puts one CTA's exp phase next to the other's TMEM load / row maximum / barrier work.
+__device__ unsigned int g_attn_sm_arrivals[1024];
 
 constexpr int kAttnThreads = 192;
 constexpr int kAttnPackedDefault = 1;   // B200LDM_ATTN_PACKED (see launch_attention_tc)
+constexpr int kAttnPTmemDefault = 1;    // B200LDM_ATTN_PTMEM: P through TMEM for the 64-column kernels (+6 %, measured); the
+                                        // wider heads (tensor-bound, one CTA per SM) show no difference and keep shared memory
+constexpr int kAttnSBDefault = 0;       // B200LDM_ATTN_SB
+constexpr int kAttnStaggerDefault = 0;  // B200LDM_ATTN_STAGGER: start offset (cycles) of every second CTA of an SM
 
-template <int D, int BN>
+// SB: ONE S buffer (with P aliased onto it, i.e. PT) instead of two: BN + D = 128 TMEM columns and no P tiles in shared
+// memory (~64 KB), so THREE CTAs share an SM - three softmax warps per sub-partition.  A CTA's tiles are then strictly
+// serial (softmax_j -> PV_j -> S_{j+1} -> softmax_{j+1}); the other two CTAs fill the gaps.
+template <int D, int BN, bool SB = false>
 struct AttnCfg {
   static constexpr int kStages = (D == 64) ? 3 : 2;
   static constexpr int kQBytes = (D / 64) * 16384;
   static constexpr int kKVSub = BN * 128;             // one 64-column sub-tile of K or V
   static constexpr int kKVBytes = (D / 64) * kKVSub;  // K (or V) tile
-  static constexpr int kPBytes = (BN / 64) * 16384;   // one P tile; there are TWO (tile parity) so exp(j+1) never waits for PV(j)
+  static constexpr int kPBytes = SB ? 0 : (BN / 64) * 16384;   // one P tile; there are TWO (tile parity) so exp(j+1) never waits for PV(j)
   static constexpr int kSmem = kQBytes + kStages * 2 * kKVBytes + 2 * kPBytes + 1024 + 256;
+  static constexpr int kNB = SB ? 1 : 2;  // S (and P) buffers
   // 2*BN + D <= 256 columns and <= ~113 KB of smem (head dim 64 with 64-key tiles): TWO CTAs per SM, i.e. two
   // independent softmax warps per sub-partition that are never in lock-step
-  static constexpr int kOcc = (2 * BN + D <= 256 && kSmem <= 115712) ? 2 : 1;
-  static constexpr int kTmemCols = kOcc == 2 ? 256 : 512;
-  static constexpr int kSCol0 = 0;        // S buffers at columns [0, 2*BN)
-  static constexpr int kOCol = 2 * BN;    // O at [2*BN, 2*BN + D)
-  static_assert(2 * BN + D <= 512, "TMEM budget");
-  static_assert(kSmem <= 232448, "smem budget");
+  static constexpr int kOcc = SB ? 3 : ((2 * BN + D <= 256 && kSmem <= 115712) ? 2 : 1);
+  static constexpr int kTmemCols = SB ? 128 : (kOcc == 2 ? 256 : 512);
+  static constexpr int kSCol0 = 0;          // S buffers at columns [0, kNB*BN)
+  static constexpr int kOCol = kNB * BN;    // O at [kNB*BN, kNB*BN + D)
+  static_assert(kNB * BN + D <= kTmemCols, "TMEM budget");
+  static_assert(kSmem <= 232448 / kOcc, "smem budget");
 };
 
 // MN-major SWIZZLE_128B operand (V as landed by TMA: rows = keys (K dim), 64 head-dim columns per 128-byte row).
@@ -136,11 +152,23 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // profiles/r01e_umma_rate_microbench.log) and the epilogue stores this head's 32 columns of O.
 // PACKED: 0 = scalar FFMA / FADD softmax loop, 1 = two-wide fp32 instructions, 2 .. 5 = two-wide + (PACKED - 1) of every 8
 // score pairs exponentiated by exp2_poly2 instead of MUFU.EX2
-template <int D, int BN, int DR = D, int PACKED = 1>
-__global__ void __launch_bounds__(kAttnThreads, AttnCfg<D, BN>::kOcc)
+// PT: P goes back into TMEM (bf16 pairs over the first BN / 2 columns of the S buffer it came from) and is the A operand of
+// the PV MMA (tcgen05.mma with A in TMEM).  The head-dim-64 kernel is bound by SHARED-MEMORY bandwidth, not by MUFU or
+// issue slots (round 2: the exp phase can be made 15 % shorter, a third of the exponentials can leave the MUFU pipe, the
+// co-resident CTAs can be staggered - the kernel time does not move): per 64-key tile a CTA moves 16 KB (Q) + 8 KB (K) +
+// 16 KB (P) + 8 KB (V) of UMMA operand reads, 16 KB of P stores and 16 KB of TMA fills through a 128 B/clk port - 625
+// cycles, 1250 for the two CTAs of an SM, of a ~1600-cycle tile period (an N = 64 MMA's 48-cycle "instruction floor" IS
+// the 6 KB operand read).  P in TMEM removes 32 of those 80 KB.
+template <int D, int BN, int DR = D, int PACKED = 1, bool PT = false, bool SB = false>
+__global__ void __launch_bounds__(kAttnThreads, AttnCfg<D, BN, SB>::kOcc)
 attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   static_assert(DR == D || (D == 64 && DR == 32), "head dim 32 rides on the 64-column tiles");
-  using Cfg = AttnCfg<D, BN>;
+  static_assert(!SB || PT, "the single S buffer holds P as well");
+  using Cfg = AttnCfg<D, BN, SB>;
+  // buffer index / mbarrier phase parity of tile j: two buffers alternate (a barrier completes every second tile), one
+  // buffer completes a phase per tile
+  auto bf = [](int j) { return SB ? 0 : (j & 1); };
+  auto ph = [](int j) { return (uint32_t)(SB ? j : (j >> 1)) & 1u; };
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -194,10 +222,16 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (Cfg::kOcc >= 2 && a.stagger > 0 && threadIdx.x == 64) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tmem_slot_ptr[1] = atomicAdd(&g_attn_sm_arrivals[smid & 1023u], 1u);
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  const bool late = Cfg::kOcc >= 2 && a.stagger > 0 && (tmem_slot_ptr[1] & 1u);
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -244,10 +278,16 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       auto issue_s = [&](int j) {
         const int s = j % STAGES;
         ptx::mbar_wait(k_full + 8 * s, (uint32_t)(j / STAGES) & 1u, 11);
-        if (j >= 2) ptx::mbar_wait(s_empty + 8 * (j & 1), (uint32_t)((j >> 1) - 1) & 1u, 12);
+        if (!SB && j >= 2) {
+          // S_j overwrites the buffer of tile j - 2: free once the softmax warps hold S_{j-2} in registers - or, with P
+          // aliased onto it (PT), once PV_{j-2} has consumed that P.  (SB: S_j is issued right behind PV_{j-1}, the
+          // MMAs of one thread execute in issue order, so the WAR hazard on the shared buffer needs no barrier.)
+          if constexpr (PT) ptx::mbar_wait(pv_done + 8 * (j & 1), (uint32_t)((j >> 1) - 1) & 1u, 12);
+          else ptx::mbar_wait(s_empty + 8 * (j & 1), (uint32_t)((j >> 1) - 1) & 1u, 12);
+        }
         ptx::tc_fence_after();
         const uint32_t k_lo = k_lo0 + (uint32_t)s * (uint32_t)(Cfg::kKVBytes >> 4);
-        const uint32_t tS = tmem + Cfg::kSCol0 + (j & 1) * BN;
+        const uint32_t tS = tmem + Cfg::kSCol0 + bf(j) * BN;
 #pragma unroll
         for (int k = 0; k < DR / 16; ++k) {
           const int kk = k + kk0;
@@ -255,26 +295,36 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
                               k_lo + (uint32_t)(((kk >> 2) * Cfg::kKVSub + (kk & 3) * 32) >> 4), khi, khi, idesc_s,
                               k > 0 ? 1u : 0u);
         }
-        ptx::umma_commit(s_full + 8 * (j & 1));
+        ptx::umma_commit(s_full + 8 * bf(j));
         ptx::umma_commit(k_empty + 8 * s);   // K_j is free once S_j retires
       };
       ptx::mbar_wait(q_full, 0, 13);
       issue_s(0);
       for (int j = 0; j < ntiles; ++j) {
-        if (j + 1 < ntiles) issue_s(j + 1);
+        if (!SB && j + 1 < ntiles) issue_s(j + 1);
         const int s = j % STAGES;
         ptx::mbar_wait(v_full + 8 * s, (uint32_t)(j / STAGES) & 1u, 16);
-        ptx::mbar_wait(p_full + 8 * (j & 1), (uint32_t)(j >> 1) & 1u, 14);
+        ptx::mbar_wait(p_full + 8 * bf(j), ph(j), 14);
         ptx::tc_fence_after();
         const uint32_t v_lo = v_lo0 + (uint32_t)s * (uint32_t)(Cfg::kKVBytes >> 4);
         const uint32_t p_lo = p_lo0 + (uint32_t)(j & 1) * (uint32_t)(Cfg::kPBytes >> 4);
         const uint32_t tO = tmem + Cfg::kOCol;
+        if constexpr (PT) {
+          const uint32_t tP = tmem + Cfg::kSCol0 + bf(j) * BN;   // 16 keys = 8 columns of bf16 pairs per k-slice
 #pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk)
-          ptx::umma_bf16_lohi(tO, p_lo + (uint32_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
-                              v_lo + (uint32_t)((kk * 2048) >> 4), khi, khi, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < BN / 16; ++kk)
+            ptx::umma_bf16_ts(tO, tP + kk * 8,
+                              (static_cast<uint64_t>(khi) << 32) | static_cast<uint64_t>(v_lo + (uint32_t)((kk * 2048) >> 4)),
+                              idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < BN / 16; ++kk)
+            ptx::umma_bf16_lohi(tO, p_lo + (uint32_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
+                                v_lo + (uint32_t)((kk * 2048) >> 4), khi, khi, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+        }
         ptx::umma_commit(v_empty + 8 * s);   // V_j is free once PV_j retires
-        ptx::umma_commit(pv_done + 8 * (j & 1));
+        ptx::umma_commit(pv_done + 8 * bf(j));
+        if (SB && j + 1 < ntiles) issue_s(j + 1);   // queued right behind PV_j: it overwrites the P that PV_j reads
       }
     }
   } else {
@@ -292,14 +342,18 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
     constexpr bool tr = false;
 #endif
     long long tc[6] = {0, 0, 0, 0, 0, 0};
+    if (late) {   // every second CTA of this SM: start half a tile behind the co-resident CTA (see g_attn_sm_arrivals)
+      const long long t_s = clock64();
+      while (clock64() - t_s < a.stagger) {}
+    }
     const long long t_begin = tr ? clock64() : 0;
     for (int j = 0; j < ntiles; ++j) {
       long long t0 = tr ? clock64() : 0, t1;
       uint8_t* p_gen = p_base + (size_t)(j & 1) * Cfg::kPBytes;
-      ptx::mbar_wait(s_full + 8 * (j & 1), (uint32_t)(j >> 1) & 1u, 20);
+      ptx::mbar_wait(s_full + 8 * bf(j), ph(j), 20);
       ptx::tc_fence_after();
       if (tr) { t1 = clock64(); tc[0] += t1 - t0; t0 = t1; }
-      const uint32_t tS = tmem + lane_off + Cfg::kSCol0 + (j & 1) * BN;
+      const uint32_t tS = tmem + lane_off + Cfg::kSCol0 + bf(j) * BN;
       float sv[BN];  // RAW scores; the softmax scale is folded into the exp2 FFMA below
       {
         uint32_t r[BN / 32][32];   // every load in flight before the single wait
@@ -312,7 +366,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
           for (int i = 0; i < 32; ++i) sv[c * 32 + i] = __uint_as_float(r[c][i]);
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(s_empty + 8 * (j & 1));  // S buffer may be overwritten by tile j+2
+      if constexpr (!PT) ptx::mbar_arrive(s_empty + 8 * (j & 1));  // S buffer may be overwritten by tile j+2
       if (tr) { t1 = clock64(); tc[1] += t1 - t0; t0 = t1; }
 
       const int kvalid = a.Lk - j * BN;  // keys in this tile that exist
@@ -344,7 +398,8 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       // P is double-buffered by tile parity: writing P(j) only needs PV(j-2) (same buffer) to have retired, so this
       // tile's exp phase overlaps PV(j-1) - with a single buffer the chain softmax -> PV -> softmax serialised a
       // ~900-cycle MMA round trip behind every tile.  O itself is only touched when the lazy rescale fires.
-      if (j >= 2) ptx::mbar_wait(pv_done + 8 * (j & 1), (uint32_t)((j >> 1) - 1) & 1u, 21);
+      // (no pv_done wait for the P buffer: tcgen05.commit covers every earlier MMA of the issuing thread, S_j was issued
+      // after PV_{j-2}, so s_full(j) - waited for above - already implies that PV_{j-2} has retired and P(j & 1) is free)
       if (tr) { t1 = clock64(); tc[3] += t1 - t0; t0 = t1; }
       if (any_need) {
         if (need) {
@@ -353,7 +408,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
           l_sum *= alpha;
         }
         if (j > 0) {
-          ptx::mbar_wait(pv_done + 8 * ((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u, 23);  // PV_{j-1} retired: O is ours
+          ptx::mbar_wait(pv_done + 8 * bf(j - 1), ph(j - 1), 23);  // PV_{j-1} retired: O is ours
           ptx::tc_fence_after();
           const uint32_t tO = tmem + lane_off + Cfg::kOCol;
 #pragma unroll
@@ -373,54 +428,56 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       // lives at r*128 + ((c ^ (r & 7)) << 4) inside each [128 x 64-key] sub-tile).  One FFMA + one MUFU.EX2 per
       // element; the row sum is taken in fp32 over 4 independent chains.
       const float neg_m = -m_used;
-      float psum;
-      if constexpr (PACKED != 0) {
-        float ps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // 4 independent two-wide sum chains
-#pragma unroll
-        for (int c8 = 0; c8 < BN / 8; ++c8) {
-          uint32_t pk[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x0, x1, p0, p1;
-            ffma2_bcast(x0, x1, sv[c8 * 8 + 2 * e], sv[c8 * 8 + 2 * e + 1], a.scale_log2, neg_m);
-            if (poly_pair(PACKED - 1, (c8 & 1) * 4 + e)) {   // folds at compile time: both loops are fully unrolled
-              exp2_poly2(p0, p1, x0, x1);
-            } else {
-              p0 = ex2_approx(x0);
-              p1 = ex2_approx(x1);
-            }
-            fadd2_acc(ps[2 * e], ps[2 * e + 1], p0, p1);
-            const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-            pk[e] = *reinterpret_cast<const uint32_t*>(&hb);
-          }
-          const int sub = c8 >> 3, cc = c8 & 7;
-          uint4* dst = reinterpret_cast<uint4*>(p_gen + sub * 16384 + row * 128 + ((cc ^ (row & 7)) << 4));
-          *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      float ps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // 4 independent (two-wide) sum chains
+      // pair q = scores 2q, 2q+1 of this row -> P as one packed bf16x2 word; q is a compile-time constant after unrolling
+      auto exp_pair = [&](int q) -> uint32_t {
+        float x0, x1, p0, p1;
+        if constexpr (PACKED != 0) {
+          ffma2_bcast(x0, x1, sv[2 * q], sv[2 * q + 1], a.scale_log2, neg_m);
+        } else {
+          x0 = fmaf(sv[2 * q], a.scale_log2, neg_m);
+          x1 = fmaf(sv[2 * q + 1], a.scale_log2, neg_m);
         }
-        psum = ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
+        if (PACKED >= 2 && poly_pair(PACKED - 1, q & 7)) {
+          exp2_poly2(p0, p1, x0, x1);
+        } else {
+          p0 = ex2_approx(x0);
+          p1 = ex2_approx(x1);
+        }
+        if constexpr (PACKED != 0) {
+          fadd2_acc(ps[2 * (q & 3)], ps[2 * (q & 3) + 1], p0, p1);
+        } else {
+          ps[q & 3] += p0 + p1;
+        }
+        const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+        return *reinterpret_cast<const uint32_t*>(&hb);
+      };
+      if constexpr (PT) {
+        const uint32_t tP = tmem + lane_off + Cfg::kSCol0 + bf(j) * BN;   // over the columns S_j was read from
+#pragma unroll
+        for (int c32 = 0; c32 < BN / 32; ++c32) {
+          uint32_t pw[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pw[e] = exp_pair(c32 * 16 + e);
+          ptx::tmem_st16(tP + c32 * 16, pw);
+        }
+        ptx::tmem_st_wait();
       } else {
-        float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c8 = 0; c8 < BN / 8; ++c8) {
           uint32_t pk[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float p0 = ex2_approx(fmaf(sv[c8 * 8 + 2 * e], a.scale_log2, neg_m));
-            const float p1 = ex2_approx(fmaf(sv[c8 * 8 + 2 * e + 1], a.scale_log2, neg_m));
-            ps4[e] += p0 + p1;
-            const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-            pk[e] = *reinterpret_cast<const uint32_t*>(&hb);
-          }
+          for (int e = 0; e < 4; ++e) pk[e] = exp_pair(c8 * 4 + e);
           const int sub = c8 >> 3, cc = c8 & 7;
           uint4* dst = reinterpret_cast<uint4*>(p_gen + sub * 16384 + row * 128 + ((cc ^ (row & 7)) << 4));
           *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-        psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
       }
+      const float psum = ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
       l_sum += psum;
-      ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the UMMA (async proxy)
+      if constexpr (!PT) ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the UMMA (async proxy)
       ptx::tc_fence_before();     // orders the TMEM rescale stores before the MMA warp's next PV
-      ptx::mbar_arrive(p_full + 8 * (j & 1));
+      ptx::mbar_arrive(p_full + 8 * bf(j));
       if (tr) { t1 = clock64(); tc[5] += t1 - t0; }
     }
     if (tr) {
@@ -433,7 +490,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       }
     }
     // ---- epilogue: O / l -> bf16 -> global
-    ptx::mbar_wait(pv_done + 8 * ((ntiles - 1) & 1), (uint32_t)((ntiles - 1) >> 1) & 1u, 22);
+    ptx::mbar_wait(pv_done + 8 * bf(ntiles - 1), ph(ntiles - 1), 22);
     ptx::tc_fence_after();
     const int qi = q0 + row;
     const float inv = 1.0f / l_sum;
@@ -804,28 +861,57 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
   if ((rc = make_qkv_map(&maps.k, k, H * DR, Lk, B, ldkv, BN))) return rc;
   if ((rc = make_qkv_map(&maps.v, v, H * DR, Lk, B, ldkv, BN))) return rc;
   static const int dbg = [] { const char* e = getenv("B200LDM_ATTN_DBG"); return e ? atoi(e) : 0; }();
-  AttnArgs a{H, L, DR, Lk, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o), g_attn_trace, dbg};
+  static const int stagger = [] { const char* e = getenv("B200LDM_ATTN_STAGGER"); return e ? atoi(e) : kAttnStaggerDefault; }();
+  AttnArgs a{H, L, DR, Lk, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o), g_attn_trace, dbg, stagger};
   // B200LDM_ATTN_PACKED: 0 = scalar softmax loop, 1 = two-wide fp32 instructions, 2 .. 5 = + 1 .. 4 of every 8 score
   // pairs through the polynomial exp2 (head dim 32 / 64 only: the wider heads are tensor-bound); default: measured best
   static const int packed = [] { const char* e = getenv("B200LDM_ATTN_PACKED"); return e ? atoi(e) : kAttnPackedDefault; }();
   dim3 grid((unsigned)ceil_div(L, 128), (unsigned)H, (unsigned)B);
-#define B2_ATTN_LAUNCH(MODE)                                                              \
-  do {                                                                                    \
-    B2_SET_SMEM_ONCE(Cfg::kSmem, attention_tc_kernel<D, BN, DR, MODE>);                   \
-    attention_tc_kernel<D, BN, DR, MODE><<<grid, kAttnThreads, Cfg::kSmem, st>>>(maps, a); \
+  // B200LDM_ATTN_PTMEM: 1 = P through TMEM (A operand of the PV MMA from TMEM), 0 = P through shared memory;
+  // B200LDM_ATTN_SB: 1 = single S buffer + P through TMEM, three CTAs per SM (head dim 32 / 64 with 64-key tiles only)
+  static const int ptmem = [] { const char* e = getenv("B200LDM_ATTN_PTMEM"); return e ? atoi(e) : kAttnPTmemDefault; }();
+  static const int sbuf = [] { const char* e = getenv("B200LDM_ATTN_SB"); return e ? atoi(e) : kAttnSBDefault; }();
+  // B200LDM_ATTN_SMEM_PAD=<bytes>: extra dynamic shared memory per CTA (experiments: forces fewer CTAs per SM)
+  static const int smem_pad = [] { const char* e = getenv("B200LDM_ATTN_SMEM_PAD"); return e ? atoi(e) : 0; }();
+#define B2_ATTN_LAUNCH(MODE, PTM, SBF)                                                                         \
+  do {                                                                                                         \
+    using LCfg = AttnCfg<D, BN, SBF>;                                                                          \
+    B2_SET_SMEM_ONCE(LCfg::kSmem + smem_pad, attention_tc_kernel<D, BN, DR, MODE, PTM, SBF>);                  \
+    attention_tc_kernel<D, BN, DR, MODE, PTM, SBF><<<grid, kAttnThreads, LCfg::kSmem + smem_pad, st>>>(maps, a); \
   } while (0)
+  if constexpr (D == 64 && BN == 64) {
+    if (sbuf) {
+      switch (packed) {
+        case 0: B2_ATTN_LAUNCH(0, true, true); break;
+        case 3: B2_ATTN_LAUNCH(3, true, true); break;
+        case 4: B2_ATTN_LAUNCH(4, true, true); break;
+        default: B2_ATTN_LAUNCH(1, true, true); break;
+      }
+      B2_LAUNCH_CHECK();
+      return B200LDM_OK;
+    }
+  }
   if constexpr (D == 64) {
-    switch (packed) {
-      case 0: B2_ATTN_LAUNCH(0); break;
-      case 2: B2_ATTN_LAUNCH(2); break;
-      case 3: B2_ATTN_LAUNCH(3); break;
-      case 4: B2_ATTN_LAUNCH(4); break;
-      case 5: B2_ATTN_LAUNCH(5); break;
-      default: B2_ATTN_LAUNCH(1); break;
+    if (ptmem) {
+      switch (packed) {
+        case 0: B2_ATTN_LAUNCH(0, true, false); break;
+        case 3: B2_ATTN_LAUNCH(3, true, false); break;
+        case 4: B2_ATTN_LAUNCH(4, true, false); break;
+        case 5: B2_ATTN_LAUNCH(5, true, false); break;
+        default: B2_ATTN_LAUNCH(1, true, false); break;
+      }
+    } else {
+      switch (packed) {
+        case 0: B2_ATTN_LAUNCH(0, false, false); break;
+        case 3: B2_ATTN_LAUNCH(3, false, false); break;
+        case 4: B2_ATTN_LAUNCH(4, false, false); break;
+        case 5: B2_ATTN_LAUNCH(5, false, false); break;
+        default: B2_ATTN_LAUNCH(1, false, false); break;
+      }
     }
   } else {
-    if (packed == 0) B2_ATTN_LAUNCH(0);
-    else B2_ATTN_LAUNCH(1);
+    if (ptmem > 1) { if (packed == 0) B2_ATTN_LAUNCH(0, true, false); else B2_ATTN_LAUNCH(1, true, false); }   // =2: forced
+    else { if (packed == 0) B2_ATTN_LAUNCH(0, false, false); else B2_ATTN_LAUNCH(1, false, false); }
   }
 #undef B2_ATTN_LAUNCH
   B2_LAUNCH_CHECK();
@@ -842,7 +928,7 @@ static int launch_attention_tc2(const void* q, const void* k, const void* v, voi
   if ((rc = make_qkv_map(&maps.k, k, H * D, Lk, B, ldkv, BN))) return rc;
   if ((rc = make_qkv_map(&maps.v, v, H * D, Lk, B, ldkv, BN))) return rc;
   static const int dbg = [] { const char* e = getenv("B200LDM_ATTN_DBG"); return e ? atoi(e) : 0; }();
-  AttnArgs a{H, L, D, Lk, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o), g_attn_trace, dbg};
+  AttnArgs a{H, L, D, Lk, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o), g_attn_trace, dbg, 0};
   B2_SET_SMEM_ONCE(Cfg::kSmem, attention_tc2_kernel<D, BN, OCC>);
   dim3 grid((unsigned)ceil_div(L, 256), (unsigned)H, (unsigned)B);
   attention_tc2_kernel<D, BN, OCC><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, a);
