@@ -45,6 +45,7 @@ constexpr int kAttnPackedDefault = 1;   // B200LDM_ATTN_PACKED (see launch_atten
 constexpr int kAttnPTmemDefault = 1;    // B200LDM_ATTN_PTMEM: P through TMEM for the 64-column kernels (+6 %, measured); the
                                         // wider heads (tensor-bound, one CTA per SM) show no difference and keep shared memory
 constexpr int kAttnSBDefault = 0;       // B200LDM_ATTN_SB
+constexpr int kAttnQTmemDefault = 1;    // B200LDM_ATTN_QTMEM: Q in TMEM too (+3-4 % on top of P in TMEM, measured)
 constexpr int kAttnStaggerDefault = 0;  // B200LDM_ATTN_STAGGER: start offset (cycles) of every second CTA of an SM
 
 // SB: ONE S buffer (with P aliased onto it, i.e. PT) instead of two: BN + D = 128 TMEM columns and no P tiles in shared
@@ -159,11 +160,17 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // 16 KB (P) + 8 KB (V) of UMMA operand reads, 16 KB of P stores and 16 KB of TMA fills through a 128 B/clk port - 625
 // cycles, 1250 for the two CTAs of an SM, of a ~1600-cycle tile period (an N = 64 MMA's 48-cycle "instruction floor" IS
 // the 6 KB operand read).  P in TMEM removes 32 of those 80 KB.
-template <int D, int BN, int DR = D, int PACKED = 1, bool PT = false, bool SB = false>
+// QT: the query tile lives in TMEM too (D / 2 columns of bf16 pairs next to O; the softmax warps copy it there from the TMA
+// landing zone once per CTA) and S = Q K^T is issued with the A operand in TMEM: the other per-tile operand that never
+// changes leaves the shared-memory port (16 of the remaining 48 KB per 64-key tile).
+template <int D, int BN, int DR = D, int PACKED = 1, bool PT = false, bool SB = false, bool QT = false>
 __global__ void __launch_bounds__(kAttnThreads, AttnCfg<D, BN, SB>::kOcc)
 attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   static_assert(DR == D || (D == 64 && DR == 32), "head dim 32 rides on the 64-column tiles");
   static_assert(!SB || PT, "the single S buffer holds P as well");
+  static_assert(!QT || (D == 64 && AttnCfg<D, BN, SB>::kOCol + D + D / 2 <= AttnCfg<D, BN, SB>::kTmemCols),
+                "Q in TMEM: 64-column kernels, D / 2 more columns");
+  constexpr int kQCol = AttnCfg<D, BN, SB>::kOCol + D;   // Q (QT) at [kOCol + D, kOCol + D + D / 2)
   using Cfg = AttnCfg<D, BN, SB>;
   // buffer index / mbarrier phase parity of tile j: two buffers alternate (a barrier completes every second tile), one
   // buffer completes a phase per tile
@@ -196,6 +203,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   const uint32_t p_full = s_empty + 16;              // [2]
   const uint32_t pv_done = p_full + 16;              // [2]: PV of even / odd tiles (one per P buffer)
   const uint32_t tmem_slot = pv_done + 16;
+  const uint32_t q_tmem = tmem_slot + 8;             // QT: the softmax warps have copied Q into TMEM (128 arrivals)
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -219,6 +227,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
     ptx::mbar_init(p_full + 8, 128);
     ptx::mbar_init(pv_done, 1);
     ptx::mbar_init(pv_done + 8, 1);
+    ptx::mbar_init(q_tmem, 128);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -291,14 +300,22 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
 #pragma unroll
         for (int k = 0; k < DR / 16; ++k) {
           const int kk = k + kk0;
-          ptx::umma_bf16_lohi(tS, q_lo + (uint32_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
-                              k_lo + (uint32_t)(((kk >> 2) * Cfg::kKVSub + (kk & 3) * 32) >> 4), khi, khi, idesc_s,
-                              k > 0 ? 1u : 0u);
+          if constexpr (QT) {
+            ptx::umma_bf16_ts(tS, tmem + kQCol + kk * 8,
+                              (static_cast<uint64_t>(khi) << 32) |
+                                  static_cast<uint64_t>(k_lo + (uint32_t)(((kk >> 2) * Cfg::kKVSub + (kk & 3) * 32) >> 4)),
+                              idesc_s, k > 0 ? 1u : 0u);
+          } else {
+            ptx::umma_bf16_lohi(tS, q_lo + (uint32_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
+                                k_lo + (uint32_t)(((kk >> 2) * Cfg::kKVSub + (kk & 3) * 32) >> 4), khi, khi, idesc_s,
+                                k > 0 ? 1u : 0u);
+          }
         }
         ptx::umma_commit(s_full + 8 * bf(j));
         ptx::umma_commit(k_empty + 8 * s);   // K_j is free once S_j retires
       };
-      ptx::mbar_wait(q_full, 0, 13);
+      if constexpr (QT) ptx::mbar_wait(q_tmem, 0, 13);
+      else ptx::mbar_wait(q_full, 0, 13);
       issue_s(0);
       for (int j = 0; j < ntiles; ++j) {
         if (!SB && j + 1 < ntiles) issue_s(j + 1);
@@ -335,6 +352,24 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
     float m_used = -INFINITY;  // reference max (log2 domain) the running sums are expressed against
     float l_sum = 0.f;
     uint8_t* p_base = smem_gen + (p_smem - smem_base);
+    if constexpr (QT) {
+      // this thread's query row: 8 x 16 bytes out of the SWIZZLE_128B landing zone (chunk c of row r sits at
+      // r * 128 + ((c ^ (r & 7)) << 4)) -> 32 words of bf16 pairs in K order -> TMEM lane `row`
+      ptx::mbar_wait(q_full, 0, 24);
+      const uint8_t* q_gen = smem_gen + (q_smem - smem_base) + row * 128;
+      uint32_t qw[2][16];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 v = *reinterpret_cast<const uint4*>(q_gen + ((c ^ (row & 7)) << 4));
+        qw[c >> 2][(c & 3) * 4 + 0] = v.x; qw[c >> 2][(c & 3) * 4 + 1] = v.y;
+        qw[c >> 2][(c & 3) * 4 + 2] = v.z; qw[c >> 2][(c & 3) * 4 + 3] = v.w;
+      }
+      ptx::tmem_st16(tmem + lane_off + kQCol, qw[0]);
+      ptx::tmem_st16(tmem + lane_off + kQCol + 16, qw[1]);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(q_tmem);
+    }
 
 #ifdef B200LDM_ATTN_TRACE
     const bool tr = a.trace != nullptr && lane == 0 && qd == 0;
@@ -871,6 +906,8 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
   // B200LDM_ATTN_SB: 1 = single S buffer + P through TMEM, three CTAs per SM (head dim 32 / 64 with 64-key tiles only)
   static const int ptmem = [] { const char* e = getenv("B200LDM_ATTN_PTMEM"); return e ? atoi(e) : kAttnPTmemDefault; }();
   static const int sbuf = [] { const char* e = getenv("B200LDM_ATTN_SB"); return e ? atoi(e) : kAttnSBDefault; }();
+  // B200LDM_ATTN_QTMEM: 1 = Q in TMEM as well (S issued with the A operand in TMEM); needs PTMEM, 64-column kernels
+  static const int qtmem = [] { const char* e = getenv("B200LDM_ATTN_QTMEM"); return e ? atoi(e) : kAttnQTmemDefault; }();
   // B200LDM_ATTN_SMEM_PAD=<bytes>: extra dynamic shared memory per CTA (experiments: forces fewer CTAs per SM)
   static const int smem_pad = [] { const char* e = getenv("B200LDM_ATTN_SMEM_PAD"); return e ? atoi(e) : 0; }();
 #define B2_ATTN_LAUNCH(MODE, PTM, SBF)                                                                         \
@@ -887,6 +924,15 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
         case 4: B2_ATTN_LAUNCH(4, true, true); break;
         default: B2_ATTN_LAUNCH(1, true, true); break;
       }
+      B2_LAUNCH_CHECK();
+      return B200LDM_OK;
+    }
+  }
+  if constexpr (D == 64 && BN == 64) {
+    if (ptmem && qtmem) {
+      using QCfg = AttnCfg<D, BN, false>;
+      B2_SET_SMEM_ONCE(QCfg::kSmem + smem_pad, attention_tc_kernel<D, BN, DR, 1, true, false, true>);
+      attention_tc_kernel<D, BN, DR, 1, true, false, true><<<grid, kAttnThreads, QCfg::kSmem + smem_pad, st>>>(maps, a);
       B2_LAUNCH_CHECK();
       return B200LDM_OK;
     }
