@@ -45,6 +45,7 @@ constexpr int kAttnPackedDefault = 1;   // B200LDM_ATTN_PACKED (see launch_atten
 constexpr int kAttnPTmemDefault = 1;    // B200LDM_ATTN_PTMEM: P through TMEM for the 64-column kernels (+6 %, measured); the
                                         // wider heads (tensor-bound, one CTA per SM) show no difference and keep shared memory
 constexpr int kAttnSBDefault = 0;       // B200LDM_ATTN_SB
+constexpr int kAttnWideTmemDefault = 0;  // B200LDM_ATTN_WIDE_TMEM: head dim 128 / 256 one-tile kernel: 1 = P in TMEM, 2 = P and Q
 constexpr int kAttnQTmemDefault = 1;    // B200LDM_ATTN_QTMEM: Q in TMEM too (+3-4 % on top of P in TMEM, measured)
 constexpr int kAttnStaggerDefault = 0;  // B200LDM_ATTN_STAGGER: start offset (cycles) of every second CTA of an SM
 
@@ -168,8 +169,8 @@ __global__ void __launch_bounds__(kAttnThreads, AttnCfg<D, BN, SB>::kOcc)
 attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   static_assert(DR == D || (D == 64 && DR == 32), "head dim 32 rides on the 64-column tiles");
   static_assert(!SB || PT, "the single S buffer holds P as well");
-  static_assert(!QT || (D == 64 && AttnCfg<D, BN, SB>::kOCol + D + D / 2 <= AttnCfg<D, BN, SB>::kTmemCols),
-                "Q in TMEM: 64-column kernels, D / 2 more columns");
+  static_assert(!QT || (PT && AttnCfg<D, BN, SB>::kOCol + D + D / 2 <= AttnCfg<D, BN, SB>::kTmemCols),
+                "Q in TMEM: D / 2 more columns (head dim 256 with 64-key tiles fills all 512)");
   constexpr int kQCol = AttnCfg<D, BN, SB>::kOCol + D;   // Q (QT) at [kOCol + D, kOCol + D + D / 2)
   using Cfg = AttnCfg<D, BN, SB>;
   // buffer index / mbarrier phase parity of tile j: two buffers alternate (a barrier completes every second tile), one
@@ -356,16 +357,19 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       // this thread's query row: 8 x 16 bytes out of the SWIZZLE_128B landing zone (chunk c of row r sits at
       // r * 128 + ((c ^ (r & 7)) << 4)) -> 32 words of bf16 pairs in K order -> TMEM lane `row`
       ptx::mbar_wait(q_full, 0, 24);
-      const uint8_t* q_gen = smem_gen + (q_smem - smem_base) + row * 128;
-      uint32_t qw[2][16];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint4 v = *reinterpret_cast<const uint4*>(q_gen + ((c ^ (row & 7)) << 4));
-        qw[c >> 2][(c & 3) * 4 + 0] = v.x; qw[c >> 2][(c & 3) * 4 + 1] = v.y;
-        qw[c >> 2][(c & 3) * 4 + 2] = v.z; qw[c >> 2][(c & 3) * 4 + 3] = v.w;
+      for (int sub = 0; sub < D / 64; ++sub) {     // one 64-column sub-tile of Q = 32 TMEM columns
+        const uint8_t* q_gen = smem_gen + (q_smem - smem_base) + sub * 16384 + row * 128;
+        uint32_t qw[2][16];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 v = *reinterpret_cast<const uint4*>(q_gen + ((c ^ (row & 7)) << 4));
+          qw[c >> 2][(c & 3) * 4 + 0] = v.x; qw[c >> 2][(c & 3) * 4 + 1] = v.y;
+          qw[c >> 2][(c & 3) * 4 + 2] = v.z; qw[c >> 2][(c & 3) * 4 + 3] = v.w;
+        }
+        ptx::tmem_st16(tmem + lane_off + kQCol + sub * 32, qw[0]);
+        ptx::tmem_st16(tmem + lane_off + kQCol + sub * 32 + 16, qw[1]);
       }
-      ptx::tmem_st16(tmem + lane_off + kQCol, qw[0]);
-      ptx::tmem_st16(tmem + lane_off + kQCol + 16, qw[1]);
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(q_tmem);
@@ -956,7 +960,19 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
       }
     }
   } else {
-    if (ptmem > 1) { if (packed == 0) B2_ATTN_LAUNCH(0, true, false); else B2_ATTN_LAUNCH(1, true, false); }   // =2: forced
+    // wider heads: P (and Q) in TMEM when the columns are there - head dim 256 with 64-key tiles uses all 512
+    // (S 2 x 64, O 256, Q 128); B200LDM_ATTN_WIDE_TMEM=0 keeps both operands in shared memory
+    static const int wide = [] { const char* e = getenv("B200LDM_ATTN_WIDE_TMEM"); return e ? atoi(e) : kAttnWideTmemDefault; }();
+    if constexpr (AttnCfg<D, BN, false>::kOCol + D + D / 2 <= AttnCfg<D, BN, false>::kTmemCols) {
+      if (wide == 2) {
+        using QCfg = AttnCfg<D, BN, false>;
+        B2_SET_SMEM_ONCE(QCfg::kSmem + smem_pad, attention_tc_kernel<D, BN, DR, 1, true, false, true>);
+        attention_tc_kernel<D, BN, DR, 1, true, false, true><<<grid, kAttnThreads, QCfg::kSmem + smem_pad, st>>>(maps, a);
+        B2_LAUNCH_CHECK();
+        return B200LDM_OK;
+      }
+    }
+    if (wide >= 1) { if (packed == 0) B2_ATTN_LAUNCH(0, true, false); else B2_ATTN_LAUNCH(1, true, false); }
     else { if (packed == 0) B2_ATTN_LAUNCH(0, false, false); else B2_ATTN_LAUNCH(1, false, false); }
   }
 #undef B2_ATTN_LAUNCH
