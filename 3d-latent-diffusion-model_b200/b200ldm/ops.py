@@ -174,7 +174,8 @@ def conv3d(x, w_packed, bias, cout: int, ksize: int = 3, stride: int = 1, pad_lo
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
     splits = 1
-    if defer and ws is not None and out is None and not out_f32 and DEFER_FINALIZE:
+    if defer and ws is not None and out is None and not out_f32 and DEFER_FINALIZE and Do * Ho * Wo <= GN_SMALL_MAX_S:
+        # (larger tensors: the finalize pass of the conv call itself also accumulates the GroupNorm chunk sums)
         splits = lib.b200ldm_conv3d_splits(C.byref(p))
         p.defer_finalize = 1 if splits > 1 else 0
     cstats = None

@@ -9,6 +9,7 @@ void set_conv_trace(void* p);
 void set_conv_trace2(void* p);
 void set_attn_trace(void* p);
 void set_conv_kernel(int k);
+void set_conv_splits(int s);
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -84,6 +85,13 @@ int b200ldm_debug_set_conv_trace(void* buf) {
 /* debug only (not in the public header): pin the conv kernel like B200LDM_CONV_KERNEL does (-1 = measured / model) */
 int b200ldm_debug_set_conv_kernel(int k) {
   b200ldm::set_conv_kernel(k);
+  return B200LDM_OK;
+}
+
+/* debug only (not in the public header): force a split-K factor on the one-CTA-per-tile kernel like B200LDM_CONV_SPLITS
+   does (0 = measured / model) */
+int b200ldm_debug_set_conv_splits(int s) {
+  b200ldm::set_conv_splits(s);
   return B200LDM_OK;
 }
 

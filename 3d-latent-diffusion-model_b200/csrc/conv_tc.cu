@@ -350,6 +350,45 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
         }
       }
       if (issuer) ptx::tma_store_wait_read0();  // smem must outlive the bulk reads
+    } else if (BN >= 64 && a.slab_tma) {
+      // ---- split-K partial sums (fp32, no bias / temb / residual): one thread owns one accumulator row, so direct
+      // stores hand the LSU 32 different lines per instruction (~16 K cycles for a 256 x 256 tile).  Instead the tile is
+      // staged in 32-channel SWIZZLE_128B groups ([128 rows][128 B]) in the dead main-loop stages and leaves through TMA
+      // stores into slab `zsplit` (the fp32 map folds the slab index into the sample coordinate).
+      constexpr int G32 = BN >= 64 ? BN / 32 : 2;   // (the BN = 16 instance never takes this branch)
+      constexpr int kAvail = (STAGES * Cfg::kStageBytes / 16384) / MT;
+      constexpr int SLOTS = kAvail < G32 ? kAvail : G32;
+      static_assert(SLOTS >= 2, "slab staging slots");
+      if (mt != MT - 1) ptx::mbar_wait(tmem_full_bar + 8 * (MT - 1), 0, 4);   // the last MMAs still read the final stage
+      const uint32_t stg = smem_base + (uint32_t)mt * (SLOTS * 16384);
+      uint8_t* stg_gen = smem_gen + (size_t)mt * (SLOTS * 16384);
+      const bool issuer = (((warp - 2) & 3) == 0) && lane == 0;
+      const int gmax = min(G32, (a.Cout - co0 + 31) / 32);
+#pragma unroll 1
+      for (int g = 0; g < gmax; ++g) {
+        const int slot = g % SLOTS;
+        uint32_t rr[2][16];
+        ptx::tmem_ld16(tacc + (uint32_t)(g * 32), rr[0]);
+        ptx::tmem_ld16(tacc + (uint32_t)(g * 32 + 16), rr[1]);
+        if (g >= SLOTS) {   // slot reuse: the store of group g - SLOTS must have read the buffer out
+          if (issuer) ptx::tma_store_wait_read<SLOTS - 1>();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
+        }
+        ptx::tmem_ld_wait();
+        uint8_t* rowp = stg_gen + (size_t)slot * 16384 + (size_t)row * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(rowp + ((c ^ (row & 7)) << 4)) =
+              make_uint4(rr[c >> 2][(c & 3) * 4], rr[c >> 2][(c & 3) * 4 + 1], rr[c >> 2][(c & 3) * 4 + 2],
+                         rr[c >> 2][(c & 3) * 4 + 3]);
+        ptx::fence_proxy_async();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
+        if (issuer) {
+          ptx::tma_store_5d(&maps.y[0], stg + slot * 16384, co0 + g * 32, w0, h0, d0, zsplit * a.N + n0);
+          ptx::tma_store_commit();
+        }
+      }
+      if (issuer) ptx::tma_store_wait_read0();
     } else
 #pragma unroll 1
     for (int c = 0; c < BN; c += 16) {
@@ -488,6 +527,25 @@ static int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, i
   return B200LDM_OK;
 }
 
+// fp32 split-K slabs [splits][N][Do][Ho][Wo][Cout] as ONE 5-D map (C, W, H, D, splits * N): 32-channel (128-byte) boxes
+static int make_slab_map(CUtensorMap* m, const void* base, int C, int W, int H, int D, int NS, int tw, int th, int td,
+                         int tn) {
+  auto enc = get_encode_fn();
+  if (!enc) return fail(B200LDM_CUDA_ERROR, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)NS};
+  const uint64_t sW = (uint64_t)C * 4, sH = sW * W, sD = sH * H, sN = sD * D;
+  cuuint64_t strides[4] = {sW, sH, sD, sN};  // bytes
+  cuuint32_t box[5] = {32, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)td, (cuuint32_t)tn};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(B200LDM_BAD_SHAPE, "cuTensorMapEncodeTiled(slab) failed: %d dims=(%d,%d,%d,%d,%d) box=(32,%d,%d,%d,%d)",
+                (int)r, C, W, H, D, NS, tw, th, td, tn);
+  return B200LDM_OK;
+}
+
 static int make_weight_map(CUtensorMap* m, const void* base, int Cin, int Cout_rows, int taps, int bn) {
   auto enc = get_encode_fn();
   if (!enc) return fail(B200LDM_CUDA_ERROR, "cuTensorMapEncodeTiled entry point unavailable");
@@ -586,6 +644,86 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int S, long
   }
 }
 
+// The same finalize that also accumulates the GroupNorm chunk sums of the tensor it writes - (sum, sumsq) per 8 channels
+// and sample of the bf16-rounded values, like the TMA epilogues of the unsplit kernels - so a split-K conv needs no
+// statistics pass either.  grid = (blocks per sample, N): a block owns a contiguous row range of ONE sample, sums into
+// shared-memory fp32 accumulators and issues one fp64 atomic pair per chunk.
+__global__ void splitk_finalize_stats_kernel(const float* __restrict__ ws, int S, long long slab, int Cout,
+                                             long long vox_per_sample, const float* __restrict__ bias,
+                                             const float* __restrict__ temb, int temb_stride,
+                                             const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ y,
+                                             double* __restrict__ chunk_stats) {
+  extern __shared__ float fs_csum[];   // [Cout/8][2]
+  const int cpr = Cout >> 3;           // 8-channel chunks per row
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * cpr; i += blockDim.x) fs_csum[i] = 0.f;
+  __syncthreads();
+  const long long r0 = vox_per_sample * blockIdx.x / gridDim.x, r1 = vox_per_sample * (blockIdx.x + 1) / gridDim.x;
+  const long long v0 = r0 * cpr, v1 = r1 * cpr;
+  for (long long i = v0 + threadIdx.x; i < v1; i += blockDim.x) {
+    const long long r = i / cpr;
+    const int k = (int)(i - r * cpr), c = k * 8;
+    const size_t off = (size_t)(n * vox_per_sample + r) * Cout + c;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    for (int z = 0; z < S; ++z) {
+      float f[8];
+      Vec8<float>::load(ws + (size_t)z * slab + off, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += f[e];
+    }
+    if (bias) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += __ldg(bias + c + e);
+    }
+    if (temb) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += __ldg(temb + (size_t)(temb_stride ? n : 0) * temb_stride + c + e);
+    }
+    if (residual) {
+      float f[8];
+      Vec8<__nv_bfloat16>::load(residual + off, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += f[e];
+    }
+    Vec8<__nv_bfloat16>::store(y + off, v);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float x = __bfloat162float(__float2bfloat16_rn(v[e]));   // statistics of the tensor as stored
+      s1 += x;
+      s2 = fmaf(x, x, s2);
+    }
+    atomicAdd(&fs_csum[2 * k], s1);
+    atomicAdd(&fs_csum[2 * k + 1], s2);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * cpr; i += blockDim.x)
+    atomicAdd(chunk_stats + (size_t)n * 2 * cpr + i, (double)fs_csum[i]);
+}
+
+static int launch_finalize(const b200ldm_conv3d_params* p, int splits, long long M_total, cudaStream_t st) {
+  const long long vps = (long long)p->Do * p->Ho * p->Wo;
+  if (p->chunk_stats) {
+    int bps = ceil_div(2 * sm_count(), p->N);
+    if (bps > vps / 4) bps = (int)(vps / 4);
+    if (bps < 1) bps = 1;
+    splitk_finalize_stats_kernel<<<dim3((unsigned)bps, (unsigned)p->N), 256, (size_t)(p->Cout / 8) * 2 * sizeof(float), st>>>(
+        reinterpret_cast<const float*>(p->workspace), splits, M_total * p->Cout, p->Cout, vps, p->bias, p->temb,
+        p->temb_stride, reinterpret_cast<const __nv_bfloat16*>(p->residual), reinterpret_cast<__nv_bfloat16*>(p->y),
+        p->chunk_stats);
+  } else {
+    const long long vecs = M_total * (p->Cout / 8);
+    const unsigned blocks = (unsigned)std::min<long long>((vecs + 255) / 256, (long long)sm_count() * 16);
+    splitk_finalize_kernel<<<blocks, 256, 0, st>>>(
+        reinterpret_cast<const float*>(p->workspace), splits, M_total * p->Cout, M_total, p->Cout, vps, p->bias, p->temb,
+        p->temb_stride, reinterpret_cast<const __nv_bfloat16*>(p->residual), reinterpret_cast<__nv_bfloat16*>(p->y));
+  }
+  B2_LAUNCH_CHECK();
+  return B200LDM_OK;
+}
+
 static unsigned long long* g_conv_trace = nullptr;
 void set_conv_trace(void* p) { g_conv_trace = reinterpret_cast<unsigned long long*>(p); }
 
@@ -597,6 +735,11 @@ static const int g_force_mt = [] {
 static const int g_legacy_epilogue = [] {
   const char* e = getenv("B200LDM_CONV_LEGACY_EPILOGUE");
   return e ? atoi(e) : 0;
+}();
+// B200LDM_CONV_SLAB_TMA=0: split-K slabs by direct per-row stores (the round-1 epilogue) instead of smem + TMA stores
+static const int g_slab_tma = [] {
+  const char* e = getenv("B200LDM_CONV_SLAB_TMA");
+  return e ? atoi(e) : 1;
 }();
 static const int g_force_cl = [] {
   const char* e = getenv("B200LDM_CONV_CL");
@@ -619,13 +762,15 @@ static const int g_halo = [] {
 }();
 void set_conv_kernel(int k) { g_tc2 = k; }   // tests: exercise every kernel in one process (b200ldm_debug_set_conv_kernel)
 
-static const int g_force_splits = [] {
+static int g_force_splits = [] {
   const char* e = getenv("B200LDM_CONV_SPLITS");
   return e ? atoi(e) : 0;
 }();
+void set_conv_splits(int s) { g_force_splits = s; }   // tests (b200ldm_debug_set_conv_splits): force a split-K factor
 
 struct ConvPlan {
   int bn, n_tiles, tn, td, th, tw, nb_n, nb_d, nb_h, nb_w, m_tiles, mt, cl, splits;
+  int bn0;     // the default Cout tile (the widest that divides Cout); bn < bn0 only by a measured choice
   int tc2;     // kernel: 0 one CTA per tile, 1 persistent CTA pairs (conv_tc2.cu), 2 persistent single CTAs (conv_tcp.cu),
                // 3 persistent W-halo kernel (conv_halo.cu), 4 conv_tcp.cu with two epilogue warp sets
   int tc2_ok;  // the problem is eligible for the persistent kernels
@@ -697,6 +842,21 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
   else if (p->Cout <= 64) pl.bn = 64;
   else if (p->Cout <= 128) pl.bn = 128;
   else pl.bn = 256;
+  pl.bn0 = pl.bn;
+  // the choice this plan follows: forced (tuning runs), remembered (measured), or none yet (cost model below)
+  int choice_in = -1;
+  if (force_tc2 >= 0) choice_in = force_tc2;
+  else if (g_tc2 < 0) {
+    std::lock_guard<std::mutex> lk(g_choice_mu);
+    auto it = g_choice.find(conv_key(p));
+    if (it != g_choice.end()) choice_in = it->second;
+  }
+  if (choice_in >= 0) {
+    // a narrower Cout tile (bits 20..21: 1 = 64, 2 = 128) gives launches that cannot fill the chip more CTAs with
+    // shorter epilogues: the 1x1x1 projections of the 5^3 / 10^3 levels
+    const int code = (choice_in >> 20) & 3, alt = code == 1 ? 64 : code == 2 ? 128 : 0;
+    if (alt && alt < pl.bn && p->Cout % alt == 0) pl.bn = alt;
+  }
   pl.n_tiles = ceil_div(p->Cout, pl.bn);
   // M tiles enumerate output voxels; with the fused upsample they enumerate LOW-RES voxels (x 8 phases in grid.z)
   const int eD = p->upsample2x ? p->D : p->Do, eH = p->upsample2x ? p->H : p->Ho, eW = p->upsample2x ? p->W : p->Wo;
@@ -759,12 +919,7 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
       const double t2 = ceil_div(work, SMS) * (main_loop > epi ? main_loop : epi) + 3000.0 + epi;
       choice = (g_tc2 > 0) ? g_tc2 : (t2 < best ? 2 : 0);
     }
-    if (force_tc2 >= 0) choice = force_tc2;
-    else if (g_tc2 < 0) {
-      std::lock_guard<std::mutex> lk(g_choice_mu);
-      auto it = g_choice.find(conv_key(p));
-      if (it != g_choice.end()) choice = it->second;
-    }
+    if (choice_in >= 0) choice = choice_in;
     pl.tc2 = tma_epi ? (choice & 15) : 0;
     // kernel 3 (conv_halo.cu): its own tile geometry - one sample, 16 lines of 8 voxels
     pl.halo_ok = (tma_epi && pl.bn <= 128 && p->ksize == 3 && p->stride == 1 && p->pad_lo == 1 && !p->upsample2x &&
@@ -779,7 +934,7 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
     }
     if (pl.tc2) { pl.mt = 1; pl.cl = 1; pl.splits = 1; }
     else {
-      const int sp = (choice >> 4) & 255, mt = (choice >> 12) & 15, cl = choice >> 16;
+      const int sp = (choice >> 4) & 255, mt = (choice >> 12) & 15, cl = (choice >> 16) & 15;
       if (mt == 1 || mt == 2) pl.mt = mt;
       if (sp >= 1 && (sp == 1 || split_ok)) { pl.splits = sp; pl.cl = sp > 1 ? 1 : pl.cl; }
       if ((cl == 1 || cl == 2) && pl.splits == 1 && (cl == 1 || (pl.bn >= 128 && !p->skip_x))) pl.cl = cl;
@@ -797,11 +952,16 @@ static int chunk_width_of(const b200ldm_conv3d_params* p) { return p->chunk_widt
 static bool plan_emits_width(const ConvPlan& pl, int cw) {
   return cw == 8 || ((cw == 2 || cw == 4) && pl.bn <= 128 && (pl.tc2 == 2 || pl.tc2 == 3));
 }
+// a split-K plan emits the (8-channel) chunk sums from its finalize pass - unless that pass is left to the caller
+static bool split_emits_stats(const b200ldm_conv3d_params* p) {
+  return chunk_width_of(p) == 8 && !p->defer_finalize && !p->out_f32 && p->Cout % 64 == 0 && p->Cout <= 8192;
+}
 int conv3d_tcgen05_emits_chunk_stats(const b200ldm_conv3d_params* p) {
   if (p->dtype != B200LDM_BF16 || p->C1 % 64 || p->C2 % 64 || p->Cout % 64 || p->out_f32 || p->gn_stats) return 0;
   if (g_legacy_epilogue) return 0;
   const ConvPlan pl = plan_conv(p);
-  return (pl.splits == 1 && pl.tn == 1 && pl.bn >= 64 && plan_emits_width(pl, chunk_width_of(p))) ? 1 : 0;
+  if (pl.splits > 1) return split_emits_stats(p) ? 1 : 0;   // from the finalize kernel (splitk_finalize_stats_kernel)
+  return (pl.tn == 1 && pl.bn >= 64 && plan_emits_width(pl, chunk_width_of(p))) ? 1 : 0;
 }
 
 // A measurement is pending for this problem: tuning is on, nothing is pinned, the problem has more than one candidate
@@ -916,7 +1076,7 @@ int conv3d_tcgen05_tune(const b200ldm_conv3d_params* p, cudaStream_t st) {
       // time the candidates on the caller's own buffers (the result is the same tensor every time): the cost model's
       // plan, the persistent kernel, and - for launches that cannot fill the chip - other split-K factors / tile
       // heights of the one-CTA-per-tile kernel
-      int choices[24], nc = 0;
+      int choices[48], nc = 0;
       choices[nc++] = 0;
       if (pl.tc2_ok) choices[nc++] = 2;
       if (pl.halo_ok && g_halo) choices[nc++] = 3;
@@ -933,6 +1093,16 @@ int conv3d_tcgen05_tune(const b200ldm_conv3d_params* p, cudaStream_t st) {
             choices[nc++] = (sp << 4) | (mt << 12);
           }
       }
+      if (pl.tc2_ok && pl.ctas1 < SMS && !p->upsample2x) {
+        // narrower Cout tiles for launches that leave SMs idle (more CTAs, a quarter / half of the epilogue each)
+        for (int code = 1; code <= 2; ++code) {
+          const int alt = code == 1 ? 64 : 128;
+          if (alt >= pl.bn0 || p->Cout % alt) continue;
+          choices[nc++] = (code << 20) | (1 << 12);
+          choices[nc++] = (code << 20) | (2 << 12);
+          choices[nc++] = (code << 20) | 2;
+        }
+      }
       const long long M_total = (long long)p->N * p->Do * p->Ho * p->Wo;
       float ms_best = 1e30f, ms0 = 0.f, ms_tcp = 0.f;
       int best = 0;
@@ -945,8 +1115,9 @@ int conv3d_tcgen05_tune(const b200ldm_conv3d_params* p, cudaStream_t st) {
         if (cp.splits > 1 && (!p->workspace || p->workspace_bytes < (long long)cp.splits * M_total * p->Cout * 4)) continue;
         b200ldm_conv3d_params q = *p;
         // statistics are accumulated by atomics: tuning launches must not add to the caller's buffer
-        if (cp.splits > 1 || cp.tn != 1 || cp.bn < 64 || !plan_emits_width(cp, chunk_width_of(p)) || p->Cout % 64 ||
-            p->out_f32 || p->gn_stats || g_legacy_epilogue)
+        if (cp.splits > 1 ? !split_emits_stats(p)
+                          : (cp.tn != 1 || cp.bn < 64 || !plan_emits_width(cp, chunk_width_of(p)) || p->Cout % 64 ||
+                             p->out_f32 || p->gn_stats || g_legacy_epilogue))
           q.chunk_stats = nullptr;
         for (int rep = 0; rep < 3 && rc == B200LDM_OK; ++rep) {
           if (rep == 1) cudaEventRecord(e0, st);
@@ -971,7 +1142,9 @@ int conv3d_tcgen05_tune(const b200ldm_conv3d_params* p, cudaStream_t st) {
                         "best %.3f ms = kernel %d splits %d mt %d cl %d (%d candidates)\n",
                 p->C1, p->C2, p->Cout, p->ksize, p->stride, p->upsample2x ? " up" : "", p->residual ? " +res" : "",
                 p->skip_x ? " +skip" : "", p->N, p->Do, p->Ho, p->Wo, ms0 / 2, ms_tcp / 2, ms_best / 2, best & 15,
-                (best >> 4) & 255, (best >> 12) & 15, best >> 16, nc);
+                (best >> 4) & 255, (best >> 12) & 15, (best >> 16) & 15, nc);
+      if (getenv("B200LDM_CONV_AUTOTUNE_LOG") && (best >> 20))
+        fprintf(stderr, "b200ldm autotune:   ... with Cout tile %d\n", ((best >> 20) & 3) == 1 ? 64 : 128);
     }
   }
   return B200LDM_OK;
@@ -1064,11 +1237,20 @@ static int conv3d_run_plan(const b200ldm_conv3d_params* p, const ConvPlan& pl, c
   // coalesced TMA-store epilogue whenever the output is bf16 in whole 64-channel groups
   a.tma_epilogue = (!a.out_f32 && p->Cout % 64 == 0 && !p->gn_stats && bn >= 64 && g_legacy_epilogue == 0) ? 1 : 0;
   if (a.up) B2_REQUIRE(a.tma_epilogue, B200LDM_BAD_SHAPE, "fused upsample conv needs the TMA epilogue");
-  a.chunk_stats = p->chunk_stats;
+  a.chunk_stats = pl.splits > 1 ? nullptr : p->chunk_stats;   // split-K: the finalize pass accumulates them
   a.cw = chunk_width_of(p);
-  if (p->chunk_stats)
-    B2_REQUIRE(a.tma_epilogue && pl.tn == 1 && pl.splits == 1 && plan_emits_width(pl, a.cw), B200LDM_BAD_ARG,
+  if (p->chunk_stats && pl.splits > 1)
+    B2_REQUIRE(split_emits_stats(p), B200LDM_BAD_ARG,
+               "conv3d: chunk_stats not available for this split-K problem (ask b200ldm_conv3d_emits_chunk_stats first)");
+  if (p->chunk_stats && pl.splits == 1)
+    B2_REQUIRE(a.tma_epilogue && pl.tn == 1 && plan_emits_width(pl, a.cw), B200LDM_BAD_ARG,
                "conv3d: chunk_stats not available for this problem (ask b200ldm_conv3d_emits_chunk_stats first)");
+  // split-K partial sums through smem + TMA stores (conv3d_tc_kernel only; a box never straddles two slabs)
+  a.slab_tma = (pl.splits > 1 && !pl.tc2 && p->Cout % 64 == 0 && bn >= 64 && p->N % a.tn == 0 && g_slab_tma) ? 1 : 0;
+  if (a.slab_tma) {
+    rc = make_slab_map(&maps.y[0], p->workspace, p->Cout, p->Wo, p->Ho, p->Do, p->N * pl.splits, a.tw, a.th, a.td, a.tn);
+    if (rc) return rc;
+  }
   if (a.tma_epilogue) {
     const uint64_t Co = p->Cout, Wo = p->Wo, Ho = p->Ho, Do = p->Do;
     if (!a.up) {
@@ -1137,14 +1319,7 @@ static int conv3d_run_plan(const b200ldm_conv3d_params* p, const ConvPlan& pl, c
   }
   if (rc || pl.splits == 1) return rc;
   if (p->defer_finalize) return B200LDM_OK;   // the caller sums the slabs (b200ldm_conv3d_finalize / groupnorm_small_slabs)
-  const long long vecs = M_total * (p->Cout / 8);
-  const unsigned blocks = (unsigned)std::min<long long>((vecs + 255) / 256, (long long)sm_count() * 16);
-  splitk_finalize_kernel<<<blocks, 256, 0, st>>>(
-      reinterpret_cast<const float*>(p->workspace), pl.splits, M_total * p->Cout, M_total, p->Cout,
-      (long long)p->Do * p->Ho * p->Wo, p->bias, p->temb, p->temb_stride,
-      reinterpret_cast<const __nv_bfloat16*>(p->residual), reinterpret_cast<__nv_bfloat16*>(p->y));
-  B2_LAUNCH_CHECK();
-  return B200LDM_OK;
+  return launch_finalize(p, pl.splits, M_total, st);
 }
 
 }  // namespace b200ldm

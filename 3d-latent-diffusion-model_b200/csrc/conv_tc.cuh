@@ -37,6 +37,8 @@ struct ConvTcArgs {
   long long slab_elems;       // elements per fp32 slab (N*Do*Ho*Wo*Cout)
   int ashift;                 // experiment: A sub-tile base shifted by ashift*128 bytes (swizzle-phase probe)
   int tma_epilogue;           // 1: stage the tile in smem and TMA-store it (bf16, Cout % 64 == 0, no GN partials)
+  int slab_tma;               // 1: split-K partial sums leave as fp32 32-channel groups through smem + TMA stores (maps.y[0]
+                              //    is an fp32 map over all slabs, sample coordinate = z * N + n)
   unsigned long long* trace;  // debug: per-CTA clock64 stamps (b200ldm_debug_set_conv_trace), else nullptr
   int work_x, work_y, work_z; // conv_tc2: M pair-tiles, Cout tiles, upsample phases of the persistent work list
 };

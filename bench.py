@@ -15,7 +15,9 @@ Default workload (N = 1 .. 8, weak scaling, one replica + one batch per GPU):
   gather over NCCL) - the other half of BASELINE.json's metric (--no-sampling skips it, --sampling-T shortens it).
   Every throughput fraction is quoted twice: on ALGORITHMIC FLOPs and on EXECUTED FLOPs (`frac_executed`:
   the convs behind a nearest-x2 up-sampling run 8 of their 27 taps); the `sampling` object has its own `e2e` (host noise
-  in, gathered volumes back in pinned host memory) and `roofline`.
+  in, gathered volumes back in pinned host memory) and `roofline`.  "other_configs" carries BASELINE.json configs[3]
+  (DDIM 50 steps at a 40^3 latent -> 160^3, 4 volumes per GPU) and configs[4] (AutoencoderKL encode + decode at
+  96^3 .. 192^3), each resident and e2e (--no-extra skips them).
 `--workload sample_32g`: that sampling workload alone as the headline line (--T steps, --latent edge, --batch volumes per
   call; `--scaling strong --total-volumes 64` shares BASELINE configs[2]'s 64 volumes between the GPUs).
 `--impl reference`: the CPU oracle (pure-PyTorch restatement of the MONAI path; the reference itself is not
@@ -125,6 +127,28 @@ def decoder_flops(kw, latent_sp, taps_up=27):
             sp = tuple(2 * v for v in sp)
             f += _conv_f(cout, cout, sp, taps_up)
     return f + _conv_f(cout, kw["out_channels"], sp)
+
+
+def encoder_flops(kw, image_sp):
+    """FLOPs of AutoencoderKL.encode for ONE volume (MONAI Encoder: conv_in, per level res blocks (+ attention) and a
+    stride-2 conv between levels, optional non-local trio, conv to the latent channels, the two 1x1x1 quant convs)"""
+    ch, att = list(kw["channels"]), list(kw["attention_levels"])
+    L = len(ch)
+    nres = kw["num_res_blocks"]
+    nres = list(nres) if isinstance(nres, (list, tuple)) else [nres] * L
+    sp, lc = tuple(image_sp), kw["latent_channels"]
+    f = _conv_f(kw["in_channels"], ch[0], sp)
+    cout = ch[0]
+    for i in range(L):
+        cin, cout = cout, ch[i]
+        for j in range(nres[i]):
+            f += _res_f(cin if j == 0 else cout, cout, sp) + (_attn_f(cout, sp) if att[i] else 0.0)
+        if i != L - 1:
+            sp = tuple((v + 1) // 2 for v in sp)
+            f += _conv_f(cout, cout, sp)
+    if kw.get("with_encoder_nonlocal_attn", True):
+        f += 2 * _res_f(cout, cout, sp) + _attn_f(cout, sp)
+    return f + _conv_f(cout, lc, sp) + 2 * _conv_f(lc, lc, sp, 1)
 
 
 def executed_fraction_unet(kw, spatial):
@@ -442,6 +466,11 @@ def bench_unet_step(args, rank, world, local):
         sampling = run_sampling(rank, world, local, args.sampling_T, 20, reps=1, warm=1, batch=BATCH,
                                 total=BATCH * world)
 
+    extra = None
+    if not args.no_extra:
+        torch.cuda.empty_cache()
+        extra = run_big_configs(rank, world, local)
+
     if rank != 0:
         return
     cpu = None
@@ -460,7 +489,8 @@ def bench_unet_step(args, rank, world, local):
             "e2e": {"value": e2e_value, "unit": "volume-steps/s", "h2d_bytes_per_step": nbytes,
                     "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
             "gpu_launches": per_graph * args.steps, "launches_per_step": per_graph,
-            "roofline": roof, "kernel_breakdown": breakdown, "sampling": sampling, "cpu_baseline": cpu,
+            "roofline": roof, "kernel_breakdown": breakdown, "sampling": sampling, "other_configs": extra,
+            "cpu_baseline": cpu,
             "clocks": clk.summary()}
     print(json.dumps(line))
 
@@ -547,6 +577,92 @@ def run_sampling(rank, world, local, T, latent, reps, warm, batch=BATCH, total=N
     return out
 
 
+def run_big_configs(rank, world, local, ddim_batch=4, edges=(96, 128, 160, 192)):
+    """BASELINE.json configs[3] and configs[4] per GPU, through the public API (weak scaling: every rank does the same):
+    * `ddim50_40`: DDIM 50-step sampling with the config_train_32g UNet at a 40^3 latent + AutoencoderKL decode to 160^3,
+      `ddim_batch` volumes per GPU (configs[3]: 32 volumes over 8 GPUs) - the attention-heavy path (L = 8000 / 1000 tokens
+      in the UNet, L = 64 000 with 256-channel heads in the decoder);
+    * `ae_sweep`: AutoencoderKL `reconstruct` (encode -> mu -> decode) of one volume per GPU at each edge.
+    Each with a device-resident number and an e2e number (pinned host input, result back in pinned host memory)."""
+    import b200ldm
+    dev = torch.device("cuda", local)
+    pk = peaks()
+    unet = seeded_init(b200ldm.DiffusionModelUNet(**UNET_32G, precision="bf16"), 1234).to(dev).eval()
+    ae = seeded_init(b200ldm.AutoencoderKL(**AE_32G, precision="bf16"), 4321).to(dev).eval()
+    out = {}
+    # ---- configs[3]
+    sched = b200ldm.DDIMScheduler(**SCHED)
+    sched.set_timesteps(50)
+    inf = b200ldm.LatentDiffusionInferer(sched, 1.0)
+    g = torch.Generator().manual_seed(11 + rank)
+    lat = (16, 40, 40, 40)
+    x_host = torch.randn((ddim_batch,) + lat, generator=g).pin_memory()
+    c_host = torch.randn((ddim_batch,) + lat, generator=g).pin_memory()
+    v_host = torch.empty((ddim_batch, 1, 160, 160, 160)).pin_memory()
+    x_dev, c_dev = x_host.to(dev), c_host.to(dev)
+
+    def sample(x, c):
+        return inf.sample(input_noise=x, autoencoder_model=ae, diffusion_model=unet, scheduler=sched, conditioning=c,
+                          mode="concat", verbose=False)
+
+    def ddim_e2e():
+        v_host.copy_(sample(x_host.to(dev, non_blocking=True), c_host.to(dev, non_blocking=True)), non_blocking=True)
+
+    sample(x_dev, c_dev)                       # convs measured, loop + decode graphs captured
+    with ClockSampler(local) as clk:
+        ms = timed_region(lambda: sample(x_dev, c_dev), 2, world) / 2
+    ddim_e2e()
+    ms_e2e = timed_region(ddim_e2e, 1, world)
+    flop = ddim_batch * (50 * FLOP_UNET_32G[40] + FLOP_DEC_32G[40])
+    fx = ddim_batch * (50 * FLOP_UNET_32G[40] * executed_fraction_unet(UNET_32G, (40,) * 3)
+                       + decoder_flops(AE_32G, (40,) * 3, 8))
+    out["ddim50_40"] = {
+        "metric": "generated_volumes_per_sec", "value": world * ddim_batch / (ms * 1e-3), "unit": "volumes/s",
+        "ms_per_batch": ms, "batch_per_gpu": ddim_batch,
+        "workload": f"DDIM 50-step sampling (config_train_32g UNet, concat conditioning) at a 40^3 latent + AutoencoderKL "
+                    f"decode to 160^3, {ddim_batch} volumes per GPU x {world} GPU(s) (BASELINE.json configs[3])",
+        "tflops_algorithmic": flop / (ms * 1e-3) / 1e12, "frac_of_sustained_peak": flop / (ms * 1e-3) / 1e12 / pk["bf16_sustained"],
+        "tflops_executed": fx / (ms * 1e-3) / 1e12, "frac_executed": fx / (ms * 1e-3) / 1e12 / pk["bf16_sustained"],
+        "e2e": {"value": world * ddim_batch / (ms_e2e * 1e-3), "unit": "volumes/s", "ms_per_batch": ms_e2e,
+                "h2d_bytes_per_step": (x_host.numel() + c_host.numel()) * 4, "d2h_bytes_per_step": v_host.numel() * 4},
+        "parity": "tests/test_gpu_long.py::test_cfg4_ddim_50_steps_40cubed_vs_oracle (40.3 dB, profiles/r02_long_parity)",
+        "clocks": clk.summary()}
+    del x_dev, c_dev, v_host
+    inf.clear_cache() if hasattr(inf, "clear_cache") else None
+    torch.cuda.empty_cache()
+    # ---- configs[4]
+    sweep = []
+    for edge in edges:
+        vol_host = torch.rand((1, 1, edge, edge, edge), generator=g).pin_memory()
+        rec_host = torch.empty_like(vol_host).pin_memory()
+        vol = vol_host.to(dev)
+
+        def e2e_rec():
+            rec_host.copy_(ae.reconstruct(vol_host.to(dev, non_blocking=True)), non_blocking=True)
+
+        ae.reconstruct(vol)
+        ae.reconstruct(vol)
+        reps = 5 if edge <= 128 else 3
+        ms = timed_region(lambda: ae.reconstruct(vol), reps, world) / reps
+        e2e_rec()
+        ms_e2e = timed_region(e2e_rec, reps, world) / reps
+        fa = encoder_flops(AE_32G, (edge,) * 3) + decoder_flops(AE_32G, (edge // 4,) * 3, 27)
+        fe = encoder_flops(AE_32G, (edge,) * 3) + decoder_flops(AE_32G, (edge // 4,) * 3, 8)
+        sweep.append({"edge": edge, "ms": ms, "volumes_per_s": world / (ms * 1e-3),
+                      "tflops_algorithmic": fa / (ms * 1e-3) / 1e12, "tflops_executed": fe / (ms * 1e-3) / 1e12,
+                      "frac_executed": fe / (ms * 1e-3) / 1e12 / pk["bf16_sustained"],
+                      "e2e_ms": ms_e2e, "e2e_volumes_per_s": world / (ms_e2e * 1e-3),
+                      "h2d_bytes_per_step": vol_host.numel() * 4, "d2h_bytes_per_step": rec_host.numel() * 4})
+        del vol, vol_host, rec_host
+        torch.cuda.empty_cache()
+    out["ae_sweep"] = {"metric": "autoencoder_reconstruct_volumes_per_sec", "unit": "volumes/s",
+                       "workload": f"AutoencoderKL (config_train_32g) encode + decode of one volume per GPU x {world} GPU(s), "
+                                   "bf16 (BASELINE.json configs[4])",
+                       "parity": "tests/test_gpu_long.py::test_cfg5_autoencoder_reconstruct_vs_oracle (96^3 / 128^3: 53.7 / 54.5 dB)",
+                       "sizes": sweep}
+    return out
+
+
 def bench_sample(args, rank, world, local):
     total = args.total_volumes if args.scaling == "strong" else args.batch * world
     sm = run_sampling(rank, world, local, args.T, args.latent, args.steps, max(1, args.warmup), batch=args.batch,
@@ -582,6 +698,8 @@ def main():
     ap.add_argument("--total-volumes", type=int, default=64, help="sample_32g --scaling strong (BASELINE configs[2]: 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sampling", action="store_true", help="skip the volumes/s leg of the default workload")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the BASELINE configs[3] (DDIM-50 @ 40^3) and configs[4] (AutoencoderKL sweep) legs")
     ap.add_argument("--sampling-T", type=int, default=1000, help="DDPM steps of the volumes/s leg (reference: 1000)")
     args = ap.parse_args()
     if args.steps is None:

@@ -456,6 +456,53 @@ def test_split_k_finalize_fused_into_groupnorm(case):
     assert y3.pending is None and torch.equal(n3, n4)
 
 
+@pytest.mark.parametrize("splits", [2, 3, 8])
+@pytest.mark.parametrize("slab_case", [(8, (5, 5, 5), 256, 0, 512, 3), (2, (10, 10, 10), 128, 64, 256, 3), (8, (4, 4, 4), 128, 0, 192, 3),
+                                       (3, (3, 5, 2), 256, 0, 64, 1), (5, (4, 4, 4), 64, 64, 320, 3)],
+                         ids=lambda c: f"N{c[0]}_{'x'.join(map(str, c[1]))}_C{c[2]}+{c[3]}->{c[4]}_k{c[5]}")
+def test_split_k_slabs_by_tma_and_finalize_with_statistics(slab_case, splits):
+    """Split-K forced on the one-CTA-per-tile kernel: the fp32 partial sums leave through smem + TMA stores (one map over
+    all slabs; boxes with batch folded in - 4^3, N % tn != 0 falls back to direct stores), the finalize pass adds bias /
+    time embedding / residual AND accumulates the GroupNorm chunk sums of the bf16 tensor it writes."""
+    import ctypes
+    from b200ldm import _lib, ops
+    lib = _lib.load()
+    lib.b200ldm_debug_set_conv_kernel.argtypes = [ctypes.c_int]
+    lib.b200ldm_debug_set_conv_splits.argtypes = [ctypes.c_int]
+    N, sp, C1, C2, Cout, k = slab_case
+    C = C1 + C2
+    x = q(rnd((N, C) + sp, 71), torch.bfloat16)
+    w = q(rnd((Cout, C, k, k, k), 72) * (C * k ** 3) ** -0.5, torch.bfloat16)
+    b, temb = 0.1 * rnd((Cout,), 73), 0.1 * rnd((N, Cout), 74)
+    ref = F.conv3d(x.double(), w.double(), b.double(), padding=k // 2) + temb.double()[:, :, None, None, None]
+    res = q(rnd(tuple(ref.shape), 75), torch.bfloat16)
+    ref = ref + res.double()
+    xa = to_act(x[:, :C1], torch.bfloat16)
+    x2a = to_act(x[:, C1:], torch.bfloat16) if C2 else None
+    wp = ops.repack_conv_weight(w.to(DEV), Cout, C, torch.bfloat16, C1 if C2 else None, C1 if C2 else None)
+    lib.b200ldm_debug_set_conv_kernel(0)
+    lib.b200ldm_debug_set_conv_splits(splits)
+    try:
+        y = ops.conv3d(xa, wp, b.to(DEV), Cout, ksize=k, stride=1, pad_lo=k // 2, x2=x2a, temb=temb.to(DEV),
+                       temb_stride=Cout, residual=to_act(res, torch.bfloat16), want_stats=True)
+    finally:
+        lib.b200ldm_debug_set_conv_kernel(-1)
+        lib.b200ldm_debug_set_conv_splits(0)
+    assert relerr(from_act(y, Cout), ref) <= 1e-2
+    cs = getattr(y, "cstats", None)
+    yf = from_act(y, Cout).double()
+    if (C // 64) * k ** 3 >= splits:               # the factor was applicable (at least one k-iteration per slab)
+        assert cs is not None                      # accumulated by the finalize pass of the same b200ldm_conv3d call
+    if cs is not None:
+        want = torch.stack([yf.reshape(N, Cout // 8, 8, -1).sum(dim=(2, 3)), (yf ** 2).reshape(N, Cout // 8, 8, -1).sum(dim=(2, 3))], dim=-1)
+        assert relerr(cs.reshape(N, Cout // 8, 2).cpu(), want) <= 1e-4
+    # the GroupNorm that follows normalises from those sums alone
+    gamma, beta = (1 + 0.1 * rnd((Cout,), 76)).to(DEV), (0.1 * rnd((Cout,), 77)).to(DEV)
+    got = ops.groupnorm(y, gamma, beta, 32, 1e-6, True)
+    gref = F.silu(F.group_norm(yf, 32, gamma.double().cpu(), beta.double().cpu(), 1e-6))
+    assert relerr(from_act(got, Cout), gref) <= 1e-2
+
+
 def test_conv3d_rejects_bad_arguments():
     from b200ldm import ops
     x = torch.zeros((1, 4, 4, 4, 48), dtype=torch.bfloat16, device=DEV)
