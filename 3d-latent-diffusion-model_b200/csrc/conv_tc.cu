@@ -93,7 +93,7 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
   if (CL > 1) ptx::cluster_sync();  // peers' barriers exist before anyone multicasts into / arrives on them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  unsigned long long* trc = a.trace ? a.trace + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  unsigned long long* trc = a.trace ? a.trace + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
   if (trc && threadIdx.x == 0) trc[0] = clock64();
 
   if (warp == 0) {

@@ -338,6 +338,28 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def cpu_oracle_cfg1(threads):
+    """BASELINE.json configs[0] exactly, on the host cores: config_train_32g UNet + AutoencoderKL, ONE 16^3 latent (64^3
+    volume), 10 DDPM steps + decode (the inference.py flow, concat conditioning), fp32 oracle, single shot after one
+    warm-up UNet step.  5.54 TFLOP of algorithmic work."""
+    import oracle
+    torch.set_num_threads(threads)
+    unet = oracle.randomize_parameters(oracle.DiffusionModelUNet(**UNET_32G), 1234).eval()
+    ae = oracle.randomize_parameters(oracle.AutoencoderKL(**AE_32G), 4321).eval()
+    sched = oracle.DDPMScheduler(**SCHED)
+    sched.set_timesteps(10)
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn((1, 16, 16, 16, 16), generator=g)
+    c = torch.randn((1, 16, 16, 16, 16), generator=g)
+    with torch.no_grad():
+        unet(torch.cat([x, c], 1), torch.tensor([900.0]))           # warm-up step (allocator, oneDNN primitives)
+        t0 = time.perf_counter()
+        oracle.LatentDiffusionInferer(sched, 1.0).sample(x, ae, unet, sched, conditioning=c, mode="concat", verbose=False)
+        dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": "volumes/s", "seconds_per_volume": dt, "cores": threads, "kind": "port",
+            "sample": "the whole of configs[0]: 1 volume, 10 DDPM steps at a 16^3 latent + decode to 64^3, single shot"}
+
+
 # ---------------------------------------------------------------------------------------------- GPU workloads
 def profile_eager_steps(body, n_prof=8, n_heat=8):
     """per-kernel CUDA events (on the launching stream) around every launch of `n_prof` eager steps; returns
@@ -476,6 +498,9 @@ def bench_unet_step(args, rank, world, local):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_oracle_unet_step(os.cpu_count() or 1, budget_s=30.0, n_timed=1, n_warm=1)
+        if extra is not None:
+            # the reference's own CPU-runnable case, timed on the same host cores next to the GPU's number for it
+            extra["cfg1_default_inference"]["cpu_baseline"] = cpu_oracle_cfg1(os.cpu_count() or 1)
     step_s = ms / args.steps * 1e-3
     step_tf = FLOP_PER_VOLUME_STEP_16G * BATCH / step_s / 1e12
     fx = executed_fraction_unet(UNET_16G, LATENT_16G)
@@ -590,6 +615,31 @@ def run_big_configs(rank, world, local, ddim_batch=4, edges=(96, 128, 160, 192))
     unet = seeded_init(b200ldm.DiffusionModelUNet(**UNET_32G, precision="bf16"), 1234).to(dev).eval()
     ae = seeded_init(b200ldm.AutoencoderKL(**AE_32G, precision="bf16"), 4321).to(dev).eval()
     out = {}
+    # ---- configs[0] on the GPU: the reference's own CPU-runnable case (inference.py defaults), latency of one volume
+    s10 = b200ldm.DDPMScheduler(**SCHED)
+    s10.set_timesteps(10)
+    inf10 = b200ldm.LatentDiffusionInferer(s10, 1.0)
+    g1 = torch.Generator().manual_seed(42)
+    x1_host = torch.randn((1, 16, 16, 16, 16), generator=g1).pin_memory()
+    c1_host = torch.randn((1, 16, 16, 16, 16), generator=g1).pin_memory()
+    v1_host = torch.empty((1, 1, 64, 64, 64)).pin_memory()
+
+    def cfg1_e2e():
+        v1_host.copy_(inf10.sample(input_noise=x1_host.to(dev, non_blocking=True), autoencoder_model=ae, diffusion_model=unet,
+                                   scheduler=s10, conditioning=c1_host.to(dev, non_blocking=True), mode="concat",
+                                   verbose=False), non_blocking=True)
+
+    cfg1_e2e()
+    cfg1_e2e()
+    ms1 = timed_region(cfg1_e2e, 10, world) / 10
+    out["cfg1_default_inference"] = {
+        "metric": "generated_volumes_per_sec", "value": world * 1e3 / ms1, "unit": "volumes/s", "ms_per_volume": ms1,
+        "workload": "config_train_32g UNet + AutoencoderKL, ONE 16^3 latent -> 64^3 volume, 10 DDPM steps + decode through "
+                    "LatentDiffusionInferer.sample, host noise in / host volume out inside the timed region "
+                    "(BASELINE.json configs[0]; 5.54 TFLOP algorithmic)",
+        "tflops_algorithmic": (10 * FLOP_UNET_32G[16] + FLOP_DEC_32G[16]) / (ms1 * 1e-3) / 1e12,
+        "h2d_bytes_per_step": (x1_host.numel() + c1_host.numel()) * 4, "d2h_bytes_per_step": v1_host.numel() * 4,
+        "parity": "tests/test_gpu_models.py::test_cfg1_default_config_sampling_psnr (>= 40 dB vs the CPU oracle)"}
     # ---- configs[3]
     sched = b200ldm.DDIMScheduler(**SCHED)
     sched.set_timesteps(50)

@@ -31,4 +31,6 @@ vals = [t[:, 1] - t[:, 0], t[:, 2] - t[:, 1], t[:, 3] - t[:, 2], t[:, 4] - t[:, 
 for n, v in zip(names, vals):
     print(f"{n:36s} mean {v.mean():10.0f}  p10 {v.quantile(0.1):10.0f}  p90 {v.quantile(0.9):10.0f} cycles")
 iters = 27 * C // 64
+sp = int(os.environ.get("SPLITS", "1"))
+iters = iters // sp
 print("iters", iters, "ideal MMA cycles per CTA (MT=2,BN=256):", iters * 8 * 128, " mainloop/ideal:", ((t[:, 2] - t[:, 1]).mean() / (iters * 8 * 128)).item())

@@ -14,6 +14,9 @@ for f in sys.argv[1:]:
                 print('   sampling', round(sm['value'], 3), 'volumes/s', round(sm['ms_per_batch'], 1), 'ms; e2e', round(sm['e2e']['value'], 3), 'frac_executed', round(sm.get('frac_executed', 0), 3))
             oc = d.get('other_configs')
             if oc:
+                c1 = oc.get('cfg1_default_inference')
+                if c1:
+                    print('   cfg1', round(c1['ms_per_volume'], 1), 'ms per volume e2e;', 'cpu', c1.get('cpu_baseline', {}).get('seconds_per_volume'), 's')
                 dd = oc['ddim50_40']
                 print('   ddim50_40', round(dd['value'], 3), 'volumes/s', round(dd['ms_per_batch'], 1), 'ms; e2e', round(dd['e2e']['value'], 3), 'frac_executed', round(dd['frac_executed'], 3))
                 for r in oc['ae_sweep']['sizes']:
