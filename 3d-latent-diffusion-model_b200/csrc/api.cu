@@ -10,6 +10,7 @@ void set_conv_trace2(void* p);
 void set_attn_trace(void* p);
 void set_conv_kernel(int k);
 void set_conv_splits(int s);
+void set_conv_trace_sk(void* p);
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -78,6 +79,7 @@ int b200ldm_check_device(void) {
 int b200ldm_debug_set_conv_trace(void* buf) {
   b200ldm::set_conv_trace(buf);
   b200ldm::set_conv_trace2(buf);
+  b200ldm::set_conv_trace_sk(buf);
   b200ldm::set_attn_trace(buf);
   return B200LDM_OK;
 }

@@ -760,6 +760,11 @@ static const int g_halo = [] {
   const char* e = getenv("B200LDM_CONV_HALO");
   return e ? atoi(e) : 1;
 }();
+// B200LDM_CONV_STREAMK=0 keeps the stream-K kernel (conv_sk.cu, kernel 5) out of the measured candidates
+static const int g_stream_k = [] {
+  const char* e = getenv("B200LDM_CONV_STREAMK");
+  return e ? atoi(e) : 1;
+}();
 void set_conv_kernel(int k) { g_tc2 = k; }   // tests: exercise every kernel in one process (b200ldm_debug_set_conv_kernel)
 
 static int g_force_splits = [] {
@@ -775,6 +780,7 @@ struct ConvPlan {
                // 3 persistent W-halo kernel (conv_halo.cu), 4 conv_tcp.cu with two epilogue warp sets
   int tc2_ok;  // the problem is eligible for the persistent kernels
   int halo_ok; // ... and for the W-halo kernel
+  int sk_ok;   // ... and for the stream-K kernel (conv_sk.cu, kernel 5)
   int split_ok, ctas1, iters;   // split-K allowed; CTAs of the one-CTA-per-tile kernel at splits = 1 (mt = 1); k-iterations
 };
 
@@ -832,6 +838,7 @@ static void remember_choice(const ConvKey& key, int choice) {
 // A choice is kernel | splits << 4 | mt << 12 | cl << 16 (splits / mt / cluster size only for kernel 0; 0 = the cost
 // model's value).
 // force_tc2: -1 = remembered measurement, else cost model; >= 0 = that choice (tuning runs).
+static int chunk_width_of(const b200ldm_conv3d_params* p) { return p->chunk_width ? p->chunk_width : 8; }
 static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
   ConvPlan pl{};
   const int SMS = sm_count();
@@ -924,6 +931,8 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
     // kernel 3 (conv_halo.cu): its own tile geometry - one sample, 16 lines of 8 voxels
     pl.halo_ok = (tma_epi && pl.bn <= 128 && p->ksize == 3 && p->stride == 1 && p->pad_lo == 1 && !p->upsample2x &&
                   p->Wo >= 4) ? 1 : 0;
+    pl.sk_ok = (tma_epi && pl.bn0 == 256 && !p->upsample2x && chunk_width_of(p) == 8 && g_stream_k) ? 1 : 0;
+    if (pl.tc2 == 5 && !(pl.sk_ok && pl.bn == 256)) pl.tc2 = 0;
     if (pl.tc2 == 3 && !pl.halo_ok) pl.tc2 = 0;
     if (pl.tc2 == 4 && pl.bn != 256) pl.tc2 = 2;   // the wide-epilogue variant exists for the 128 x 256 tile only
     if (pl.tc2 == 3) {
@@ -947,7 +956,6 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
 }
 
 // 1 when this exact problem runs the TMA epilogue with one sample per tile and no split-K, i.e. can emit chunk stats
-static int chunk_width_of(const b200ldm_conv3d_params* p) { return p->chunk_width ? p->chunk_width : 8; }
 // chunk sums finer than 8 channels exist in the persistent kernels (conv_tcp.cu, conv_halo.cu) with Cout tiles <= 128
 static bool plan_emits_width(const ConvPlan& pl, int cw) {
   return cw == 8 || ((cw == 2 || cw == 4) && pl.bn <= 128 && (pl.tc2 == 2 || pl.tc2 == 3));
@@ -1007,15 +1015,19 @@ int conv3d_splitk_finalize(const float* slabs, int splits, long long M, int Cout
 long long conv3d_tcgen05_workspace_bytes(const b200ldm_conv3d_params* p) {
   if (p->dtype != B200LDM_BF16 || p->C1 % 64 || p->C2 % 64 || p->Cout % 8) return 0;
   const ConvPlan pl = plan_conv(p);
+  if (pl.tc2 == 5) return conv_sk_workspace_bytes(conv_sk_grid(pl.m_tiles, pl.n_tiles, pl.iters));
   int splits = pl.splits;
   const int SMS = sm_count();
-  if (pl.split_ok && pl.ctas1 < SMS && pl.iters >= 16 && tune_pending(p, pl)) {
+  long long sk = 0;
+  const bool pending = tune_pending(p, pl);
+  if (pending && pl.sk_ok) sk = conv_sk_workspace_bytes(conv_sk_grid(pl.m_tiles, pl.n_tiles, pl.iters));   // a candidate
+  if (pl.split_ok && pl.ctas1 < SMS && pl.iters >= 16 && pending) {
     // b200ldm_conv3d_tune measures split factors up to 16 (those that keep >= 8 k-iterations per CTA)
     for (int sp = 16; sp > splits; --sp)
       if (pl.iters / sp >= 8 && (long long)pl.m_tiles * pl.n_tiles * sp <= 2 * SMS) { splits = sp; break; }
   }
-  if (splits <= 1) return 0;
-  return (long long)splits * p->N * p->Do * p->Ho * p->Wo * p->Cout * 4;
+  const long long slabs = splits <= 1 ? 0 : (long long)splits * p->N * p->Do * p->Ho * p->Wo * p->Cout * 4;
+  return slabs > sk ? slabs : sk;
 }
 
 static int conv3d_run_plan(const b200ldm_conv3d_params* p, const ConvPlan& pl, cudaStream_t st);
@@ -1081,6 +1093,9 @@ int conv3d_tcgen05_tune(const b200ldm_conv3d_params* p, cudaStream_t st) {
       if (pl.tc2_ok) choices[nc++] = 2;
       if (pl.halo_ok && g_halo) choices[nc++] = 3;
       if (pl.tc2_ok && pl.bn == 256) choices[nc++] = 4;   // persistent kernel with two epilogue warp sets
+      if (pl.sk_ok && p->workspace &&
+          p->workspace_bytes >= conv_sk_workspace_bytes(conv_sk_grid(pl.m_tiles, pl.n_tiles, pl.iters)))
+        choices[nc++] = 5;                                // stream-K
       if (pl.tc2_ok && getenv("B200LDM_CONV_TUNE_PAIRS")) choices[nc++] = 1;   // CTA pairs: measured slower almost everywhere
       // (2-CTA weight-multicast variants were candidates for big launches for a while: they never won by the 2 %
       // margin, and the one intermittent launch failure of the round happened with them in the set - left out)
@@ -1128,7 +1143,9 @@ int conv3d_tcgen05_tune(const b200ldm_conv3d_params* p, cudaStream_t st) {
         if (rc == B200LDM_OK && cudaEventSynchronize(e1) == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
         if (choices[c] == 0) ms0 = ms;
         if (choices[c] == 2) ms_tcp = ms;
-        if (ms < ms_best * 0.98f) { ms_best = ms; best = choices[c]; }   // a later candidate must win by 2 %
+        // a later candidate must win by 2 %; stream-K by 4 %: it occupies every SM, so launches that share the GPU with
+        // a concurrent stream (the sub-batch branches of the sampling graph) lose what it gains in isolation
+        if (ms < ms_best * ((choices[c] & 15) == 5 ? 0.96f : 0.98f)) { ms_best = ms; best = choices[c]; }
       }
       cudaEventDestroy(e0);
       cudaEventDestroy(e1);
@@ -1280,6 +1297,11 @@ static int conv3d_run_plan(const b200ldm_conv3d_params* p, const ConvPlan& pl, c
     rc = make_weight_map(&maps.w, p->w, Cin, cout_rows, taps, bn);
     if (rc) return rc;
     return launch_conv_halo(maps, a, bn, m_tiles, n_tiles, st);
+  }
+  if (pl.tc2 == 5 && conv_sk_supported(bn, a)) {
+    rc = make_weight_map(&maps.w, p->w, Cin, cout_rows, taps, bn);
+    if (rc) return rc;
+    return launch_conv_sk(maps, a, m_tiles, n_tiles, pl.iters, p->workspace, p->workspace_bytes, st);
   }
   if ((pl.tc2 == 2 || pl.tc2 == 4) && conv_tcp_supported(bn, a)) {
     rc = make_weight_map(&maps.w, p->w, Cin, cout_rows, taps, bn);

@@ -41,6 +41,8 @@ struct ConvTcArgs {
                               //    is an fp32 map over all slabs, sample coordinate = z * N + n)
   unsigned long long* trace;  // debug: per-CTA clock64 stamps (b200ldm_debug_set_conv_trace), else nullptr
   int work_x, work_y, work_z; // conv_tc2: M pair-tiles, Cout tiles, upsample phases of the persistent work list
+  void* sk_ws;                // conv_sk.cu: workspace = [flags, sk_flag_bytes][one 256 KB partial-tile slot per CTA]
+  int sk_flag_bytes;
 };
 
 constexpr int kABytes = 128 * 128;  // one M sub-tile: 128 rows x 64 bf16
@@ -64,5 +66,13 @@ int launch_conv_tcp(const ConvTcMaps& maps, const ConvTcArgs& a, int bn, int m_t
 bool conv_halo_supported(int bn, const ConvTcArgs& a);
 void choose_halo_tile(int Do, int Ho, int* td, int* th);
 int launch_conv_halo(const ConvTcMaps& maps, const ConvTcArgs& a, int bn, int m_tiles, int n_tiles, cudaStream_t st);
+
+// conv_sk.cu: stream-K kernel for the 256 x 256 tile (one CTA per SM runs an equal share of ALL k-iterations; partial
+// tiles are exchanged through the caller's workspace inside the launch - no finalize pass)
+bool conv_sk_supported(int bn, const ConvTcArgs& a);
+int conv_sk_grid(int m_tiles, int n_tiles, int iters);
+long long conv_sk_workspace_bytes(int grid);
+int launch_conv_sk(const ConvTcMaps& maps, ConvTcArgs a, int m_tiles, int n_tiles, int iters, void* ws, long long ws_bytes,
+                   cudaStream_t st);
 
 }  // namespace b200ldm

@@ -302,7 +302,7 @@ def test_tap_gather_fp32_exact():
     assert torch.allclose(y, want, atol=1e-5, rtol=1e-5)
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 2, 3, 4], ids=["tile_per_cta", "cta_pairs", "persistent", "w_halo", "persistent_wide_epi"])
+@pytest.mark.parametrize("kernel", [0, 1, 2, 3, 4, 5], ids=["tile_per_cta", "cta_pairs", "persistent", "w_halo", "persistent_wide_epi", "stream_k"])
 @pytest.mark.parametrize("case", [(2, (9, 11, 7), 128, 0, 256, 3, 1), (1, (8, 8, 8), 64, 64, 64, 3, 1), (2, (6, 10, 6), 64, 0, 128, 3, 2),
                                   (3, (5, 5, 5), 256, 0, 512, 1, 1), (1, (18, 22, 14), 64, 0, 64, 3, 1),
                                   (8, (4, 4, 4), 128, 0, 192, 3, 1), (5, (3, 4, 2), 64, 64, 320, 3, 1),
@@ -501,6 +501,64 @@ def test_split_k_slabs_by_tma_and_finalize_with_statistics(slab_case, splits):
     got = ops.groupnorm(y, gamma, beta, 32, 1e-6, True)
     gref = F.silu(F.group_norm(yf, 32, gamma.double().cpu(), beta.double().cpu(), 1e-6))
     assert relerr(from_act(got, Cout), gref) <= 1e-2
+
+
+@pytest.mark.parametrize("sk_case", [(8, (10, 10, 10), 256, 0, 256, 3, 1, 0), (8, (20, 20, 20), 64, 0, 256, 3, 1, 0),
+                                     (3, (9, 11, 7), 128, 128, 512, 3, 1, 128), (2, (12, 10, 8), 128, 0, 256, 3, 2, 0),
+                                     (1, (1, 1, 1000), 256, 0, 768, 1, 1, 0), (8, (5, 5, 5), 512, 0, 256, 3, 1, 0)],
+                         ids=lambda c: f"N{c[0]}_{'x'.join(map(str, c[1]))}_C{c[2]}+{c[3]}->{c[4]}_k{c[5]}s{c[6]}_skip{c[7]}")
+def test_conv3d_stream_k(sk_case):
+    """conv_sk.cu pinned: every CTA runs an equal share of ALL k-iterations, tiles cut by a span boundary are completed
+    through partial tiles in the workspace (contributor -> owner inside the launch).  Shapes with several CTAs per tile,
+    whole tiles between two partial ones, two sources + fused skip conv, stride 2, a 1x1x1 projection; bias + time
+    embedding + residual + GroupNorm chunk sums on the owner's epilogue; repeated launches reuse the (self-cleaning)
+    flags; bitwise repeatable."""
+    import ctypes
+    from b200ldm import _lib, ops
+    lib = _lib.load()
+    lib.b200ldm_debug_set_conv_kernel.argtypes = [ctypes.c_int]
+    N, sp, C1, C2, Cout, k, stride, Cs = sk_case
+    C = C1 + C2
+    x = q(rnd((N, C) + sp, 31), torch.bfloat16)
+    w = q(rnd((Cout, C, k, k, k), 32) * (C * k ** 3) ** -0.5, torch.bfloat16)
+    b, temb = 0.1 * rnd((Cout,), 33), 0.1 * rnd((N, Cout), 34)
+    pad = k // 2
+    ref = F.conv3d(x.double(), w.double(), b.double(), stride=stride, padding=pad) + temb.double()[:, :, None, None, None]
+    res = q(rnd(tuple(ref.shape), 35), torch.bfloat16) if stride == 1 else None
+    if res is not None:
+        ref = ref + res.double()
+    skip = None
+    if Cs:
+        sx = q(rnd((N, Cs) + sp, 36), torch.bfloat16)
+        sw = q(rnd((Cout, Cs, 1, 1, 1), 37) * Cs ** -0.5, torch.bfloat16)
+        ref = ref + F.conv3d(sx.double(), sw.double())
+        skip = (to_act(sx, torch.bfloat16), None, ops.repack_conv_weight(sw.to(DEV), Cout, Cs, torch.bfloat16))
+    xa = to_act(x[:, :C1], torch.bfloat16)
+    x2a = to_act(x[:, C1:], torch.bfloat16) if C2 else None
+    wp = ops.repack_conv_weight(w.to(DEV), Cout, C, torch.bfloat16, C1 if C2 else None, C1 if C2 else None)
+    kw = dict(ksize=k, stride=stride, pad_lo=pad, x2=x2a, temb=temb.to(DEV), temb_stride=Cout,
+              residual=None if res is None else to_act(res, torch.bfloat16), want_stats=True, skip=skip)
+    lib.b200ldm_debug_set_conv_kernel(5)
+    try:
+        ys = [ops.conv3d(xa, wp, b.to(DEV), Cout, **kw) for _ in range(3)]
+        torch.cuda.synchronize()
+    finally:
+        lib.b200ldm_debug_set_conv_kernel(-1)
+    y = ys[0]
+    assert relerr(from_act(y, Cout), ref) <= 1e-2
+    assert torch.equal(ys[1], y) and torch.equal(ys[2], y)
+    cs = getattr(y, "cstats", None)
+    if cs is not None:
+        yf = from_act(y, Cout).double()
+        want = torch.stack([yf.reshape(N, Cout // 8, 8, -1).sum(dim=(2, 3)), (yf ** 2).reshape(N, Cout // 8, 8, -1).sum(dim=(2, 3))], dim=-1)
+        assert relerr(cs.reshape(N, Cout // 8, 2).cpu(), want) <= 1e-4
+    # against the one-CTA-per-tile kernel: same products, different summation order of the fp32 partial tiles
+    lib.b200ldm_debug_set_conv_kernel(0)
+    try:
+        y0 = ops.conv3d(xa, wp, b.to(DEV), Cout, **kw)
+    finally:
+        lib.b200ldm_debug_set_conv_kernel(-1)
+    assert relerr(y.float(), y0.float()) <= 8e-3
 
 
 def test_conv3d_rejects_bad_arguments():
