@@ -72,6 +72,10 @@ SIGNATURES = {
     "b200ldm_groupnorm_small": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _f32, _i32, _i32, _vp]),
     "b200ldm_fill_zero": (C.c_int, [_vp, _sz, _vp]),
     "b200ldm_attention": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _f32, _i32, _i32, _vp]),
+    "b200ldm_attention_workspace_bytes": (C.c_int64, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "b200ldm_attention_ws": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _f32, _i32, _i32, _vp, _i64, _vp]),
+    "b200ldm_cross_attention_ws": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _f32, _i32, _i32,
+                                             _vp, _i64, _vp]),
     "b200ldm_cross_attention": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _f32, _i32, _i32,
                                           _vp]),
     "b200ldm_layernorm": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _vp]),

@@ -324,9 +324,13 @@ def attention(qkv, heads: int, head_dim: int, scale: float, engine: int = ENGINE
     o = torch.empty((B, L, Cc), dtype=qkv.dtype, device=qkv.device)
     es = qkv.element_size()
     base = qkv.data_ptr()
+    # scratch for splitting the key range of the last, partial wave of query tiles (0 when that gains nothing)
+    ws_bytes = lib.b200ldm_attention_workspace_bytes(B, heads, L, L, head_dim, dtype_code(qkv.dtype), engine)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=qkv.device) if ws_bytes > 0 else None
     ev = PROFILER.start() if PROFILER is not None else None
-    _lib.check(lib.b200ldm_attention(base, base + Cc * es, base + 2 * Cc * es, o.data_ptr(), B, heads, L, head_dim,
-                                     C3, float(scale), dtype_code(qkv.dtype), engine, _stream()), "attention")
+    _lib.check(lib.b200ldm_attention_ws(base, base + Cc * es, base + 2 * Cc * es, o.data_ptr(), B, heads, L, head_dim,
+                                        C3, float(scale), dtype_code(qkv.dtype), engine, _ptr(ws), ws_bytes, _stream()),
+               "attention")
     if ev is not None:
         PROFILER.stop("attention", f"B{B} H{heads} L{L} d{head_dim}", 4.0 * B * heads * L * L * head_dim, ev)
     return o

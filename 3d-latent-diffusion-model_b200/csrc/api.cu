@@ -11,6 +11,7 @@ void set_attn_trace(void* p);
 void set_conv_kernel(int k);
 void set_conv_splits(int s);
 void set_conv_trace_sk(void* p);
+void set_attn_split(int s);
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -94,6 +95,13 @@ int b200ldm_debug_set_conv_kernel(int k) {
    does (0 = measured / model) */
 int b200ldm_debug_set_conv_splits(int s) {
   b200ldm::set_conv_splits(s);
+  return B200LDM_OK;
+}
+
+/* debug only (not in the public header): attention split-KV factor for the partial wave like B200LDM_ATTN_SPLIT
+   (-1 = planner, 0 = never, n >= 2 = force) */
+int b200ldm_debug_set_attn_split(int s) {
+  b200ldm::set_attn_split(s);
   return B200LDM_OK;
 }
 

@@ -91,15 +91,24 @@ static int launch_attention_simt(const void* q, const void* k, const void* v, vo
 }
 
 int attention_tcgen05(const void* q, const void* k, const void* v, void* o, int B, int H, int L, int Lk, int d,
-                      long long ld, long long ldkv, float scale, cudaStream_t st);
+                      long long ld, long long ldkv, float scale, void* ws, long long ws_bytes, cudaStream_t st);
+long long attention_tcgen05_workspace_bytes(int B, int H, int L, int Lk, int d);
 bool attention_tcgen05_supported(int d);
 
 }  // namespace b200ldm
 
-extern "C" int b200ldm_cross_attention(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t H,
-                                       int32_t Lq, int32_t Lk, int32_t d, int64_t ldq, int64_t ldkv, float scale,
-                                       int32_t dtype, int32_t engine, b200ldm_stream stream) {
+extern "C" int64_t b200ldm_attention_workspace_bytes(int32_t B, int32_t H, int32_t Lq, int32_t Lk, int32_t d, int32_t dtype,
+                                                     int32_t engine) {
+  if (dtype != B200LDM_BF16 || (engine != B200LDM_ENGINE_AUTO && engine != B200LDM_ENGINE_TCGEN05)) return 0;
+  return b200ldm::attention_tcgen05_workspace_bytes(B, H, Lq, Lk, d);
+}
+
+extern "C" int b200ldm_cross_attention_ws(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t H,
+                                          int32_t Lq, int32_t Lk, int32_t d, int64_t ldq, int64_t ldkv, float scale,
+                                          int32_t dtype, int32_t engine, void* workspace, int64_t workspace_bytes,
+                                          b200ldm_stream stream) {
   using namespace b200ldm;
+  B2_REQUIRE(!workspace || aligned16(workspace), B200LDM_BAD_ALIGN, "attention: workspace must be 16-byte aligned");
   B2_REQUIRE(q && k && v && o, B200LDM_BAD_ARG, "attention: null pointer");
   B2_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0 && d > 0 && ldq >= (int64_t)H * d && ldkv >= (int64_t)H * d,
              B200LDM_BAD_SHAPE, "attention: bad shape");
@@ -114,15 +123,28 @@ extern "C" int b200ldm_cross_attention(const void* q, const void* k, const void*
   cudaStream_t st = (cudaStream_t)stream;
   if (engine == B200LDM_ENGINE_TCGEN05) {
     B2_REQUIRE(dtype == B200LDM_BF16, B200LDM_BAD_ARG, "tcgen05 attention needs bf16");
-    return attention_tcgen05(q, k, v, o, B, H, Lq, Lk, d, ldq, ldkv, scale, st);
+    return attention_tcgen05(q, k, v, o, B, H, Lq, Lk, d, ldq, ldkv, scale, workspace, workspace_bytes, st);
   }
   if (dtype == B200LDM_BF16) return launch_attention_simt<__nv_bfloat16>(q, k, v, o, B, H, Lq, Lk, d, ldq, ldkv, scale, st);
   if (dtype == B200LDM_F32) return launch_attention_simt<float>(q, k, v, o, B, H, Lq, Lk, d, ldq, ldkv, scale, st);
   return fail(B200LDM_BAD_ARG, "bad dtype %d", dtype);
 }
 
+extern "C" int b200ldm_cross_attention(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t H,
+                                       int32_t Lq, int32_t Lk, int32_t d, int64_t ldq, int64_t ldkv, float scale,
+                                       int32_t dtype, int32_t engine, b200ldm_stream stream) {
+  return b200ldm_cross_attention_ws(q, k, v, o, B, H, Lq, Lk, d, ldq, ldkv, scale, dtype, engine, nullptr, 0, stream);
+}
+
 extern "C" int b200ldm_attention(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t H, int32_t L,
                                  int32_t d, int64_t ld, float scale, int32_t dtype, int32_t engine,
                                  b200ldm_stream stream) {
-  return b200ldm_cross_attention(q, k, v, o, B, H, L, L, d, ld, ld, scale, dtype, engine, stream);
+  return b200ldm_cross_attention_ws(q, k, v, o, B, H, L, L, d, ld, ld, scale, dtype, engine, nullptr, 0, stream);
+}
+
+extern "C" int b200ldm_attention_ws(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t H, int32_t L,
+                                    int32_t d, int64_t ld, float scale, int32_t dtype, int32_t engine, void* workspace,
+                                    int64_t workspace_bytes, b200ldm_stream stream) {
+  return b200ldm_cross_attention_ws(q, k, v, o, B, H, L, L, d, ld, ld, scale, dtype, engine, workspace, workspace_bytes,
+                                    stream);
 }

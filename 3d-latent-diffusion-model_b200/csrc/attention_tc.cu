@@ -31,6 +31,13 @@ struct AttnArgs {
   unsigned long long* trace;  // debug (b200ldm_debug_set_conv_trace): per-CTA cycle counters of the softmax warps
   int dbg;                    // debug: bit0 = exp2 replaced by a multiply (is the MUFU pipe the limiter?)
   int stagger;                // cycles the softmax warps of every second CTA of an SM wait before their first tile (0: off)
+  // split-KV for the last, partial wave of query tiles (one-query-tile kernel; b200ldm_attention_ws): the 1-D grid holds
+  // `split_t0` whole tiles followed by (tiles - split_t0) * nsplit parts.  A part runs a contiguous range of the key tiles
+  // and leaves its un-normalised O (fp32), reference max and row sum in the workspace; attention_merge_kernel combines.
+  int tiles_x;                // query tiles per (batch, head)
+  int split_t0, nsplit;       // nsplit <= 1: no tile is split
+  float* part_o;              // [part unit][D / 4][128] float4: O, column quad major (a warp stores 512 contiguous bytes)
+  float* part_ml;             // [part unit][2][128]: reference max (log2 domain), row sum
 };
 
 // CTAs that have started on each SM so far (only its parity is used): two CTAs of the one-query-tile kernel share an
@@ -209,9 +216,19 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int ntiles = (a.Lk + BN - 1) / BN;
+  // 1-D grid: whole query tiles first (linear tile id = x + tiles_x * (h + H * b)), then the parts of the split tiles
+  int tile_id = (int)blockIdx.x, part = 0, nparts = 1;
+  if (a.nsplit > 1 && tile_id >= a.split_t0) {
+    const int u = tile_id - a.split_t0;
+    tile_id = a.split_t0 + u / a.nsplit;
+    part = u - (u / a.nsplit) * a.nsplit;
+    nparts = a.nsplit;
+  }
+  const int q0 = (tile_id % a.tiles_x) * 128;
+  const int h = (tile_id / a.tiles_x) % a.H, b = tile_id / (a.tiles_x * a.H);
+  const int ntiles_all = (a.Lk + BN - 1) / BN;
+  const int jbase = (int)((long long)ntiles_all * part / nparts);               // first key tile of this part
+  const int ntiles = (int)((long long)ntiles_all * (part + 1) / nparts) - jbase;  // key tiles of this part (>= 1)
   const int colh = h * DR;                    // this head's first column in the [.., H * DR] projections
   const int col0 = DR == D ? colh : (colh & ~63);   // first column of the TMA boxes
   const int kk0 = DR == D ? 0 : ((colh & 63) >> 4); // first 16-column K-slice of this head inside the box
@@ -256,7 +273,8 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         ptx::mbar_expect_tx(k_full + 8 * s, Cfg::kKVBytes);
 #pragma unroll
         for (int sub = 0; sub < D / 64; ++sub)
-          ptx::tma_load_3d(k_smem + s * Cfg::kKVBytes + sub * Cfg::kKVSub, &maps.k, k_full + 8 * s, col0 + sub * 64, j * BN, b);
+          ptx::tma_load_3d(k_smem + s * Cfg::kKVBytes + sub * Cfg::kKVSub, &maps.k, k_full + 8 * s, col0 + sub * 64,
+                           (jbase + j) * BN, b);
       };
       auto load_v = [&](int j) {
         const int s = j % STAGES;
@@ -264,7 +282,8 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         ptx::mbar_expect_tx(v_full + 8 * s, Cfg::kKVBytes);
 #pragma unroll
         for (int sub = 0; sub < D / 64; ++sub)
-          ptx::tma_load_3d(v_smem + s * Cfg::kKVBytes + sub * Cfg::kKVSub, &maps.v, v_full + 8 * s, col0 + sub * 64, j * BN, b);
+          ptx::tma_load_3d(v_smem + s * Cfg::kKVBytes + sub * Cfg::kKVSub, &maps.v, v_full + 8 * s, col0 + sub * 64,
+                           (jbase + j) * BN, b);
       };
       load_k(0);   // K runs one tile ahead of V: its stage frees first and S needs it first
       for (int j = 0; j < ntiles; ++j) {
@@ -408,7 +427,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       if constexpr (!PT) ptx::mbar_arrive(s_empty + 8 * (j & 1));  // S buffer may be overwritten by tile j+2
       if (tr) { t1 = clock64(); tc[1] += t1 - t0; t0 = t1; }
 
-      const int kvalid = a.Lk - j * BN;  // keys in this tile that exist
+      const int kvalid = a.Lk - (jbase + j) * BN;  // keys in this tile that exist
       if (kvalid < BN) {                // last tile only (warp-uniform)
 #pragma unroll
         for (int i = 0; i < BN; ++i)
@@ -520,7 +539,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       if (tr) { t1 = clock64(); tc[5] += t1 - t0; }
     }
     if (tr) {
-      const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      const size_t cta = blockIdx.x;
       if (cta < 1024) {
         unsigned long long* o = a.trace + cta * 2 * 8;
         for (int i = 0; i < 6; ++i) o[i] = (unsigned long long)tc[i];
@@ -532,9 +551,28 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
     ptx::mbar_wait(pv_done + 8 * bf(ntiles - 1), ph(ntiles - 1), 22);
     ptx::tc_fence_after();
     const int qi = q0 + row;
+    const uint32_t tO = tmem + lane_off + Cfg::kOCol + (uint32_t)(colh - col0);   // this head's columns of O
+    if (nparts > 1) {
+      // a part of a split tile: O stays un-normalised (fp32) next to its reference max and row sum
+      const size_t unit = (size_t)blockIdx.x - (size_t)a.split_t0;
+      float4* po = reinterpret_cast<float4*>(a.part_o) + unit * (size_t)(DR / 4) * 128 + row;
+#pragma unroll
+      for (int c = 0; c < DR; c += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld16(tO + c, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+          __stcg(po + (size_t)(c / 4 + j4) * 128,
+                 make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]), __uint_as_float(r[4 * j4 + 2]),
+                             __uint_as_float(r[4 * j4 + 3])));
+      }
+      a.part_ml[unit * 256 + row] = m_used;
+      a.part_ml[unit * 256 + 128 + row] = l_sum;
+      ptx::tc_fence_before();
+    } else {
     const float inv = 1.0f / l_sum;
     __nv_bfloat16* orow = a.o + ((size_t)b * a.L + (qi < a.L ? qi : 0)) * ((size_t)a.H * DR) + colh;
-    const uint32_t tO = tmem + lane_off + Cfg::kOCol + (uint32_t)(colh - col0);   // this head's columns of O
 #pragma unroll
     for (int c = 0; c < DR; c += 16) {
       uint32_t r[16];
@@ -551,6 +589,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       }
     }
     ptx::tc_fence_before();
+    }
   }
   __syncthreads();
   if (warp == 1) {
@@ -890,9 +929,84 @@ static int make_qkv_map(CUtensorMap* m, const void* base, int cols, int L, int B
   return B200LDM_OK;
 }
 
+// ---- split-KV of the last, partial wave (one-query-tile kernels).  T query tiles on `slots` = SMs x CTAs/SM: the first
+// floor(T / slots) * slots tiles run whole; the rest (rem < slots) would be one more wave with SMs idle, so each of them
+// is cut into `nsplit` key ranges (rem * nsplit parts = a few short rounds) and merged by attention_merge_kernel.
+struct AttnSplit {
+  int t0, nsplit;   // nsplit <= 1: nothing is split
+};
+static int g_attn_split = [] {
+  const char* e = getenv("B200LDM_ATTN_SPLIT");   // 0: never split; n >= 2: force that factor on the partial wave
+  return e ? atoi(e) : -1;
+}();
+void set_attn_split(int s) { g_attn_split = s; }   // tests (b200ldm_debug_set_attn_split); -1 = planner
+static AttnSplit plan_attn_split(long long T, int slots, int ntiles_kv) {
+  AttnSplit sp{(int)T, 1};
+  if (g_attn_split == 0 || T > (1ll << 30)) return sp;
+  const long long full = T / slots, rem = T - full * slots;
+  if (rem == 0) return sp;
+  // time in key-tile units, calibrated on the AutoencoderKL attention (d = 256, L = 13824 / 32768 / 64000 with and without
+  // the split, profiles/r02_attention/split_kv.log): a CTA costs its key tiles + ~32 more (prologue, Q load, pipeline
+  // ramp, epilogue), the merge launch ~10
+  const double kOvh = 32.0, kMerge = 10.0;
+  const double now = (double)(full + 1) * (ntiles_kv + kOvh);
+  double best = now;
+  for (int s = 2; s <= 8; ++s) {
+    if (ntiles_kv / s < 1) break;
+    if (g_attn_split >= 2 && s != g_attn_split) continue;
+    const double rounds = (double)((rem * s + slots - 1) / slots);
+    const double t = (double)full * (ntiles_kv + kOvh) + rounds * ((double)ntiles_kv / s + kOvh) + kMerge;
+    if (t < best || (g_attn_split >= 2 && sp.nsplit == 1)) { best = t; sp.nsplit = s; }
+  }
+  if (g_attn_split < 2 && best > now * 0.96) sp.nsplit = 1;   // not worth a second launch below 4 %
+  if (sp.nsplit > 1) sp.t0 = (int)(full * slots);
+  return sp;
+}
+static long long attn_split_workspace_bytes(long long T, const AttnSplit& sp, int dr) {
+  if (sp.nsplit <= 1) return 0;
+  return (T - sp.t0) * sp.nsplit * ((long long)dr * 128 * 4 + 2 * 128 * 4);
+}
+
+// out[q][c] = sum_p O_p[q][c] 2^(m_p - m) / sum_p l_p 2^(m_p - m),  m = max_p m_p.  One CTA per split tile, thread =
+// (column quad, row) like the partial layout.
+__global__ void attention_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml,
+                                       __nv_bfloat16* __restrict__ o, int t0, int nsplit, int tiles_x, int H, int L, int dr) {
+  const int tile = t0 + (int)blockIdx.x;
+  const int q0 = (tile % tiles_x) * 128, h = (tile / tiles_x) % H, b = tile / (tiles_x * H);
+  const size_t unit0 = (size_t)blockIdx.x * nsplit;
+  __shared__ float w[8][128];   // per part and row: 2^(m_p - m) / l
+  for (int row = threadIdx.x; row < 128; row += blockDim.x) {
+    float m = -INFINITY;
+    for (int p = 0; p < nsplit; ++p) m = fmaxf(m, part_ml[(unit0 + p) * 256 + row]);
+    float l = 0.f;
+    for (int p = 0; p < nsplit; ++p) {
+      const float e = exp2f(part_ml[(unit0 + p) * 256 + row] - m);
+      w[p][row] = e;
+      l += part_ml[(unit0 + p) * 256 + 128 + row] * e;
+    }
+    const float inv = 1.0f / l;
+    for (int p = 0; p < nsplit; ++p) w[p][row] *= inv;
+  }
+  __syncthreads();
+  const int quads = dr / 4;
+  for (int i = threadIdx.x; i < quads * 128; i += blockDim.x) {
+    const int row = i & 127, cq = i >> 7;
+    if (q0 + row >= L) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < nsplit; ++p) {
+      const float4 f = __ldcg(reinterpret_cast<const float4*>(part_o) + ((unit0 + p) * (size_t)quads + cq) * 128 + row);
+      const float ww = w[p][row];
+      acc.x = fmaf(f.x, ww, acc.x); acc.y = fmaf(f.y, ww, acc.y); acc.z = fmaf(f.z, ww, acc.z); acc.w = fmaf(f.w, ww, acc.w);
+    }
+    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(o + ((size_t)b * L + q0 + row) * ((size_t)H * dr) + (size_t)h * dr + cq * 4);
+    dst[0] = __floats2bfloat162_rn(acc.x, acc.y);
+    dst[1] = __floats2bfloat162_rn(acc.z, acc.w);
+  }
+}
+
 template <int D, int BN, int DR = D>
 static int launch_attention_tc(const void* q, const void* k, const void* v, void* o, int B, int H, int L, int Lk,
-                               long long ld, long long ldkv, float scale, cudaStream_t st) {
+                               long long ld, long long ldkv, float scale, void* ws, long long ws_bytes, cudaStream_t st) {
   using Cfg = AttnCfg<D, BN>;
   AttnMaps maps;
   int rc;
@@ -902,10 +1016,28 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
   static const int dbg = [] { const char* e = getenv("B200LDM_ATTN_DBG"); return e ? atoi(e) : 0; }();
   static const int stagger = [] { const char* e = getenv("B200LDM_ATTN_STAGGER"); return e ? atoi(e) : kAttnStaggerDefault; }();
   AttnArgs a{H, L, DR, Lk, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(o), g_attn_trace, dbg, stagger};
+  a.tiles_x = ceil_div(L, 128);
+  const long long T = (long long)a.tiles_x * H * B;
+  B2_REQUIRE(T < (1ll << 31) / 8, B200LDM_BAD_SHAPE, "attention: too many query tiles (%lld)", T);
+  AttnSplit sp = plan_attn_split(T, sm_count() * Cfg::kOcc, ceil_div(Lk, BN));
+  if (!ws || ws_bytes < attn_split_workspace_bytes(T, sp, DR)) sp = AttnSplit{(int)T, 1};   // no scratch: whole tiles
+  a.split_t0 = sp.t0; a.nsplit = sp.nsplit;
+  if (sp.nsplit > 1) {
+    a.part_o = reinterpret_cast<float*>(ws);
+    a.part_ml = a.part_o + (size_t)(T - sp.t0) * sp.nsplit * DR * 128;
+  }
   // B200LDM_ATTN_PACKED: 0 = scalar softmax loop, 1 = two-wide fp32 instructions, 2 .. 5 = + 1 .. 4 of every 8 score
   // pairs through the polynomial exp2 (head dim 32 / 64 only: the wider heads are tensor-bound); default: measured best
   static const int packed = [] { const char* e = getenv("B200LDM_ATTN_PACKED"); return e ? atoi(e) : kAttnPackedDefault; }();
-  dim3 grid((unsigned)ceil_div(L, 128), (unsigned)H, (unsigned)B);
+  dim3 grid((unsigned)(sp.t0 + (T - sp.t0) * sp.nsplit), 1, 1);
+  // the merge pass of the split tiles, queued behind the attention kernel by every return path below
+  auto merge = [&]() -> int {
+    if (sp.nsplit > 1) {
+      attention_merge_kernel<<<(unsigned)(T - sp.t0), 256, 0, st>>>(a.part_o, a.part_ml, a.o, sp.t0, sp.nsplit, a.tiles_x, H, L, DR);
+      B2_LAUNCH_CHECK();
+    }
+    return B200LDM_OK;
+  };
   // B200LDM_ATTN_PTMEM: 1 = P through TMEM (A operand of the PV MMA from TMEM), 0 = P through shared memory;
   // B200LDM_ATTN_SB: 1 = single S buffer + P through TMEM, three CTAs per SM (head dim 32 / 64 with 64-key tiles only)
   static const int ptmem = [] { const char* e = getenv("B200LDM_ATTN_PTMEM"); return e ? atoi(e) : kAttnPTmemDefault; }();
@@ -929,7 +1061,7 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
         default: B2_ATTN_LAUNCH(1, true, true); break;
       }
       B2_LAUNCH_CHECK();
-      return B200LDM_OK;
+      return merge();
     }
   }
   if constexpr (D == 64 && BN == 64) {
@@ -938,7 +1070,7 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
       B2_SET_SMEM_ONCE(QCfg::kSmem + smem_pad, attention_tc_kernel<D, BN, DR, 1, true, false, true>);
       attention_tc_kernel<D, BN, DR, 1, true, false, true><<<grid, kAttnThreads, QCfg::kSmem + smem_pad, st>>>(maps, a);
       B2_LAUNCH_CHECK();
-      return B200LDM_OK;
+      return merge();
     }
   }
   if constexpr (D == 64) {
@@ -969,7 +1101,7 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
         B2_SET_SMEM_ONCE(QCfg::kSmem + smem_pad, attention_tc_kernel<D, BN, DR, 1, true, false, true>);
         attention_tc_kernel<D, BN, DR, 1, true, false, true><<<grid, kAttnThreads, QCfg::kSmem + smem_pad, st>>>(maps, a);
         B2_LAUNCH_CHECK();
-        return B200LDM_OK;
+        return merge();
       }
     }
     if (wide >= 1) { if (packed == 0) B2_ATTN_LAUNCH(0, true, false); else B2_ATTN_LAUNCH(1, true, false); }
@@ -977,7 +1109,7 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
   }
 #undef B2_ATTN_LAUNCH
   B2_LAUNCH_CHECK();
-  return B200LDM_OK;
+  return merge();
 }
 
 template <int D, int BN, int OCC>
@@ -1007,8 +1139,20 @@ static const int g_attn_v = [] {
 
 bool attention_tcgen05_supported(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
 
+// scratch that lets the launch split the key range of its last, partial wave of query tiles (0: nothing to gain)
+long long attention_tcgen05_workspace_bytes(int B, int H, int L, int Lk, int d) {
+  if (!attention_tcgen05_supported(d) || B <= 0 || H <= 0 || L <= 0 || Lk <= 0) return 0;
+  if (d == 128 && L > 128 && Lk > 128 && g_attn_v != 1) return 0;   // ping-pong kernel: no split
+  const long long T = (long long)ceil_div(L, 128) * H * B;
+  const int bn = (d == 256 || Lk > 128) ? 64 : 128;
+  if (d == 128) return 0;
+  const int occ = (d <= 64 && bn == 64) ? 2 : 1;
+  const AttnSplit sp = plan_attn_split(T, sm_count() * occ, ceil_div(Lk, bn));
+  return attn_split_workspace_bytes(T, sp, d);
+}
+
 int attention_tcgen05(const void* q, const void* k, const void* v, void* o, int B, int H, int L, int Lk, int d,
-                      long long ld, long long ldkv, float scale, cudaStream_t st) {
+                      long long ld, long long ldkv, float scale, void* ws, long long ws_bytes, cudaStream_t st) {
   B2_REQUIRE(attention_tcgen05_supported(d), B200LDM_BAD_SHAPE,
              "tcgen05 attention supports head dim 32/64/128/256 (got %d)", d);
   B2_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && ld % 8 == 0 && ldkv % 8 == 0,
@@ -1025,12 +1169,12 @@ int attention_tcgen05(const void* q, const void* k, const void* v, void* o, int 
     if (d == 64) return launch_attention_tc2<64, 128, 1>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
     return launch_attention_tc2<128, 64, 1>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
   }
-  if (d == 32 && Lk > 128) return launch_attention_tc<64, 64, 32>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
-  if (d == 32) return launch_attention_tc<64, 128, 32>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
-  if (d == 64 && Lk > 128) return launch_attention_tc<64, 64>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
-  if (d == 64) return launch_attention_tc<64, 128>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
-  if (d == 128) return launch_attention_tc<128, 128>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
-  return launch_attention_tc<256, 64>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, st);
+  if (d == 32 && Lk > 128) return launch_attention_tc<64, 64, 32>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, ws, ws_bytes, st);
+  if (d == 32) return launch_attention_tc<64, 128, 32>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, ws, ws_bytes, st);
+  if (d == 64 && Lk > 128) return launch_attention_tc<64, 64>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, ws, ws_bytes, st);
+  if (d == 64) return launch_attention_tc<64, 128>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, ws, ws_bytes, st);
+  if (d == 128) return launch_attention_tc<128, 128>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, nullptr, 0, st);
+  return launch_attention_tc<256, 64>(q, k, v, o, B, H, L, Lk, ld, ldkv, scale, ws, ws_bytes, st);
 }
 
 }  // namespace b200ldm

@@ -138,10 +138,13 @@ int b200ldm_conv3d(const b200ldm_conv3d_params* p, b200ldm_stream stream);
 int b200ldm_conv3d_tune(const b200ldm_conv3d_params* p, b200ldm_stream stream);
 int b200ldm_conv3d_tune_pending(const b200ldm_conv3d_params* p);
 /* bytes of `workspace` this exact problem needs (0 for most shapes; > 0 when the planner splits K over CTAs
- * because the output has too few tiles to fill 148 SMs).  Pure host arithmetic, no CUDA call. */
+ * because the output has too few tiles to fill 148 SMs - fp32 slabs [splits][M][Cout] - or runs the stream-K kernel -
+ * flags + one 256 KB partial-tile slot per SM; the workspace needs no initialisation and may be reused by the next
+ * call on the same stream).  Pure host arithmetic, no CUDA call. */
 int64_t b200ldm_conv3d_workspace_bytes(const b200ldm_conv3d_params* p);
-/* 1 if this exact problem can accumulate `chunk_stats` in its epilogue (bf16 tensor-core path, Cout % 64 == 0,
- * one sample per tile, no split-K), else 0.  Pure host arithmetic. */
+/* 1 if this exact problem can accumulate `chunk_stats` (bf16 tensor-core path, Cout % 64 == 0): in its epilogue (one
+ * sample per tile) or, for a split-K plan with 8-channel chunks and defer_finalize = 0, in its finalize pass; else 0.
+ * Pure host arithmetic. */
 int b200ldm_conv3d_emits_chunk_stats(const b200ldm_conv3d_params* p);
 /* split-K factor this exact problem runs with right now (1 = no split; the remembered measured choice, else the cost
  * model).  Pure host arithmetic. */
@@ -226,6 +229,21 @@ int b200ldm_attention(const void* q, const void* k, const void* v, void* o, int3
 int b200ldm_cross_attention(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t H, int32_t Lq,
                             int32_t Lk, int32_t d, int64_t ldq, int64_t ldkv, float scale, int32_t dtype,
                             int32_t engine, b200ldm_stream stream);
+
+/* The same two calls with caller-owned scratch.  With one CTA per 128-query tile, a launch whose tile count is not a
+ * multiple of the resident CTA count ends in a partial wave with SMs idle (AutoencoderKL attention at 160^3: 500 tiles on
+ * 148 SMs = 3.4 waves, 4 run).  Given `workspace` >= b200ldm_attention_workspace_bytes(...) the launch cuts the key range
+ * of the tiles of that last wave into parts (un-normalised O, reference max and row sum per part in the workspace) and
+ * merges them in a second, small launch; with workspace = NULL it runs whole tiles exactly like the calls above.
+ * b200ldm_attention_workspace_bytes returns 0 when splitting gains nothing for the shape.  No initialisation needed. */
+int64_t b200ldm_attention_workspace_bytes(int32_t B, int32_t H, int32_t Lq, int32_t Lk, int32_t d, int32_t dtype,
+                                          int32_t engine);
+int b200ldm_attention_ws(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t H, int32_t L, int32_t d,
+                         int64_t ld, float scale, int32_t dtype, int32_t engine, void* workspace,
+                         int64_t workspace_bytes, b200ldm_stream stream);
+int b200ldm_cross_attention_ws(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t H, int32_t Lq,
+                               int32_t Lk, int32_t d, int64_t ldq, int64_t ldkv, float scale, int32_t dtype,
+                               int32_t engine, void* workspace, int64_t workspace_bytes, b200ldm_stream stream);
 
 /* Token-major helpers of MONAI DiffusionUNetTransformerBlock (replace nn.LayerNorm and the
  * GEGLU gate of MLPBlock(act="GEGLU")):

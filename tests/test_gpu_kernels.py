@@ -654,6 +654,41 @@ def test_attention_tcgen05_bf16(case):
     assert e <= 1e-2, e
 
 
+@pytest.mark.parametrize("factor", [-1, 2, 3, 5, 8])
+@pytest.mark.parametrize("case", [(1, 1, 4500, 256), (1, 1, 20000, 256), (2, 3, 1100, 64), (1, 5, 700, 32), (3, 1, 333, 256)],
+                         ids=lambda c: f"B{c[0]}H{c[1]}L{c[2]}d{c[3]}")
+def test_attention_split_kv_of_the_partial_wave(case, factor):
+    """b200ldm_attention_ws: with scratch, the query tiles of the last (partial) wave run as `factor` key ranges each
+    (un-normalised O + reference max + row sum per part) and a merge launch combines them.  Forced factors on shapes
+    whose tile count is below / above one wave, ragged last query and key tiles, head dims 32 / 64 / 256; factor -1 = the
+    planner's own decision (L = 20000, d = 256: 157 tiles on 148 SMs).  Same result as whole tiles to bf16 round-off."""
+    import ctypes
+    from b200ldm import _lib, ops
+    lib = _lib.load()
+    lib.b200ldm_debug_set_attn_split.argtypes = [ctypes.c_int]
+    B, H, L, d = case
+    qkv = q(rnd((B, L, 3 * H * d), 28), torch.bfloat16)
+    qkv[:, L // 2:, H * d: 2 * H * d] *= 2.5          # later keys dominate: the parts end with different reference maxima
+    dev_qkv = q(qkv, torch.bfloat16).to(DEV).to(torch.bfloat16)
+    lib.b200ldm_debug_set_attn_split(0)
+    try:
+        whole = ops.attention(dev_qkv, H, d, d ** -0.5, engine=ops.ENGINE_TCGEN05)
+        lib.b200ldm_debug_set_attn_split(factor)
+        ws = lib.b200ldm_attention_workspace_bytes(B, H, L, L, d, _lib.BF16, ops.ENGINE_TCGEN05)
+        l0 = ops.launch_count()
+        split = ops.attention(dev_qkv, H, d, d ** -0.5, engine=ops.ENGINE_TCGEN05)
+        launches = ops.launch_count() - l0
+    finally:
+        lib.b200ldm_debug_set_attn_split(-1)
+    bn = 64 if (d == 256 or L > 128) else 128
+    if (factor >= 2 and -(-L // bn) >= factor) or case == (1, 1, 20000, 256):
+        assert ws > 0, ws
+    assert launches == (2 if ws > 0 else 1), (ws, launches)     # attention (+ merge)
+    assert relerr(split.float(), whole.float()) <= 6e-3
+    if L <= 1200:
+        assert relerr(split.float(), _att_ref(q(qkv, torch.bfloat16), H, d)) <= 1e-2
+
+
 def test_attention_auto_engine_never_falls_back_to_simt():
     """north_star: no silent CUDA-core fallback on the bf16 product path.  ENGINE_AUTO with a head
     dim that has no tcgen05 instance raises; head dim 32 runs on tcgen05 and agrees with the explicit engine."""
