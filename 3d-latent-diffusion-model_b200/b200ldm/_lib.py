@@ -84,6 +84,7 @@ SIGNATURES = {
     "b200ldm_tap_gather": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
                                      C.POINTER(SchedParams), _vp]),
     "b200ldm_upsample_nearest2x": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "b200ldm_pack_taps": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200ldm_ncdhw_to_ndhwc": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _vp]),
     "b200ldm_ndhwc_to_ncdhw": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _i32, _i32, _vp]),
     "b200ldm_silu_f32": (C.c_int, [_vp, _vp, _i64, _vp]),

@@ -34,6 +34,9 @@ FUSE_UPSAMPLE = os.environ.get("B200LDM_FUSE_UPSAMPLE", "1") != "0"
 # narrow-output 3x3x3 convs (Cout <= 16) as a 1x1x1 tensor-core GEMM over stacked taps + a gather (ops.tap_gather):
 # the direct kernel re-reads its input 27 times for 16 output columns (0.58 ms for the UNet's out conv, 135 TFLOP/s)
 TAP_EXPAND = os.environ.get("B200LDM_TAP_EXPAND", "1") != "0"
+# narrow-INPUT 3x3x3 convs (Cin <= 2: the AutoencoderKL's conv_in) as ops.pack_taps + a 1x1x1 GEMM: one k-iteration instead
+# of 27 over a zero-padded 64-channel input (0.93 -> ~0.3 ms at 160^3)
+TAP_PACK = os.environ.get("B200LDM_TAP_PACK", "1") != "0"
 # DiffusionModelUNet.forward (the public module call) replays a cached CUDA graph from the second call of a signature on
 FORWARD_GRAPH = os.environ.get("B200LDM_FORWARD_GRAPH", "1") != "0"
 # sub-batch streams of the top UNet level inside the captured forward graph (see forward_ndhwc(split=...))
@@ -120,6 +123,20 @@ class Conv(nn.Module):
             return self._run_tap_expanded(x, sched, out)
         if sched is not None:
             raise RuntimeError("the fused scheduler update needs the stacked-tap output conv (Conv.tap_expanded)")
+        if self.tap_packed(x) and x2 is None and gn_stats is None and not out_f32:
+            # 1 or 2 input channels: the 27 taps become the channels of ONE k-iteration (ops.pack_taps) instead of 27
+            # k-iterations over a zero-padded 64-channel input
+            def build():
+                wm = self.weight.detach().float().permute(0, 2, 3, 4, 1).reshape(self.cout, 27 * self.cin)  # [co][t*cin+c]
+                wk = ops.repack_conv_weight(wm.contiguous(), self.cout_phys, 64, x.dtype)
+                bb = torch.zeros(self.cout_phys, dtype=torch.float32, device=wm.device)
+                bb[: self.cout] = self.bias.detach().float()
+                return wk, bb
+
+            wk, bb = self._cache.get(("tappack", x.dtype), (self.weight, self.bias), build)
+            return ops.conv3d(ops.pack_taps(x, self.cin), wk, bb, self.cout_phys, 1, 1, 0, 0, temb=temb,
+                              temb_stride=temb_stride, residual=residual, want_stats=want_stats, out=out,
+                              cstats_out=cstats_out, stats_width=self.stats_width(), defer=defer)
         if x2 is None:
             w, b = self.packed(x.dtype, cin_phys=x.shape[-1])
         else:
@@ -129,6 +146,11 @@ class Conv(nn.Module):
                           out_f32=out_f32, want_stats=want_stats, out=out, cstats_out=cstats_out,
                           stats_width=self.stats_width(), defer=defer)
 
+
+    def tap_packed(self, x) -> bool:
+        """True when this conv runs as ops.pack_taps + a 1x1x1 GEMM for activations like `x` (AutoencoderKL conv_in)"""
+        return (TAP_PACK and self.cin <= 2 and self.ksize == 3 and self.stride == 1 and self.pad_lo == 1
+                and self.pad_hi == 1 and x.dtype == torch.bfloat16)
 
     def tap_expanded(self, x) -> bool:
         """True when this conv runs as a 1x1x1 GEMM over stacked taps + ops.tap_gather for activations like `x`."""
@@ -1125,7 +1147,9 @@ class AutoencoderKL(nn.Module):
     @torch.no_grad()
     def encode(self, x):
         dt = _PREC[self.precision]
-        mu, logvar = self.encode_ndhwc(ops.to_ndhwc(x, _pad64(self.in_channels), dt))
+        # a tap-packed conv_in reads its 1 or 2 input channels with any row stride: 8 channels (16 bytes) instead of 64
+        narrow = self.encoder.blocks[0].conv.tap_packed(torch.empty(0, dtype=dt))
+        mu, logvar = self.encode_ndhwc(ops.to_ndhwc(x, 8 if narrow else _pad64(self.in_channels), dt))
         z, sigma = ops.ae_sampling(mu, logvar, None)  # z == mu (fp32), sigma = exp(clamp(logvar)/2)
         return ops.to_ncdhw(z, self.latent_channels), ops.to_ncdhw(sigma, self.latent_channels)
 

@@ -427,6 +427,21 @@ def upsample_nearest2x(x):
     return y
 
 
+def pack_taps(x: torch.Tensor, cin: int) -> torch.Tensor:
+    """[N,D,H,W,Cp] (first `cin` <= 2 channels real) -> [N,D,H,W,64]: channel t * cin + c = x at tap t of the 3x3x3
+    neighbourhood (zero padding), so that the conv becomes ONE 64-wide k-iteration (b200ldm_pack_taps)."""
+    _need_cuda(x)
+    N, D, H, W, Cp = x.shape
+    assert x.is_contiguous() and cin in (1, 2) and Cp >= cin
+    y = torch.empty((N, D, H, W, 64), dtype=x.dtype, device=x.device)
+    ev = PROFILER.start() if PROFILER is not None else None
+    _lib.check(_lib.load().b200ldm_pack_taps(_ptr(x), y.data_ptr(), N, D, H, W, Cp, cin, dtype_code(x.dtype), _stream()),
+               "pack_taps")
+    if ev is not None:
+        PROFILER.stop("pack_taps", f"cin{cin} S{D * H * W}", float(N * D * H * W) * (27 * cin + 64) * x.element_size(), ev)
+    return y
+
+
 def to_ndhwc(src: torch.Tensor, c_dst: int, dtype: torch.dtype, out: torch.Tensor | None = None, c_offset: int = 0):
     """NCDHW fp32 -> NDHWC `dtype`, channels [c_offset, c_offset+C) of a c_dst-wide (zero padded) buffer."""
     _need_cuda(src)

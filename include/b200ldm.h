@@ -275,6 +275,14 @@ int b200ldm_tap_gather(const void* z, const float* bias, void* y, int32_t N, int
 int b200ldm_upsample_nearest2x(const void* x, void* y, int32_t N, int32_t D, int32_t H, int32_t W,
                                int32_t C, int32_t dtype, b200ldm_stream stream);
 
+/* First half of a 3x3x3 / stride 1 / pad 1 conv with 1 or 2 input channels (AutoencoderKL `conv_in`,
+ * 3d_ldm/config/config_train_32g.json:9-10: in_channels 1): y[v][t * cin + c] = x[v + shift(t)][c] for the 27 taps t
+ * (zero outside the volume, zero for channels >= 27 * cin); x: NDHWC with row stride Cp elements, y: NDHWC with 64
+ * channels.  The conv itself then runs as b200ldm_conv3d with ksize 1 over y and weights [Cout][27 * cin] (tap major):
+ * one k-iteration instead of 27 zero-padded ones. */
+int b200ldm_pack_taps(const void* x, void* y, int32_t N, int32_t D, int32_t H, int32_t W, int32_t Cp, int32_t cin,
+                      int32_t dtype, b200ldm_stream stream);
+
 /* layout bridges between the MONAI surface (NCDHW fp32) and the engine (NDHWC, channel padded) */
 int b200ldm_ncdhw_to_ndhwc(const float* src, void* dst, int32_t N, int32_t C, int64_t S, int32_t C_dst,
                            int32_t c_offset, int32_t dtype, b200ldm_stream stream);

@@ -561,6 +561,42 @@ def test_conv3d_stream_k(sk_case):
     assert relerr(y.float(), y0.float()) <= 8e-3
 
 
+@pytest.mark.parametrize("case", [(2, (9, 11, 7), 1, 64, 8), (1, (16, 12, 20), 2, 64, 64), (3, (4, 5, 6), 1, 128, 16)],
+                         ids=lambda c: f"N{c[0]}_{'x'.join(map(str, c[1]))}_cin{c[2]}->{c[3]}_Cp{c[4]}")
+def test_narrow_input_conv_as_packed_taps(case):
+    """AutoencoderKL conv_in (1 or 2 input channels): ops.pack_taps puts the 27 taps of a voxel's neighbourhood into one
+    64-channel row (zero padding at the borders), the conv runs as ONE 1x1x1 k-iteration with tap-major weights - same
+    products as the 27-tap conv over the zero-padded input, against fp64 F.conv3d and against the regular kernel."""
+    from b200ldm import nets, ops
+    N, sp, cin, cout, Cp = case
+    x = q(rnd((N, cin) + sp, 41), torch.bfloat16)
+    conv = nets.Conv(cin, cout).to(DEV)
+    with torch.no_grad():
+        conv.weight.copy_(q(rnd((cout, cin, 3, 3, 3), 42) * (cin * 27) ** -0.5, torch.bfloat16))
+        conv.bias.copy_(0.1 * rnd((cout,), 43))
+    ref = F.conv3d(x.double(), conv.weight.detach().double().cpu(), conv.bias.detach().double().cpu(), padding=1)
+    xa = ops.to_ndhwc(x.to(DEV), Cp, torch.bfloat16)
+    packed = ops.pack_taps(xa, cin)
+    # the packed tensor itself: channel t * cin + c = x at tap t
+    xp = F.pad(x, (1, 1, 1, 1, 1, 1))
+    D, H, W = sp
+    want = torch.zeros((N, D, H, W, 64))
+    for t in range(27):
+        kd, kh, kw = t // 9, (t // 3) % 3, t % 3
+        want[..., t * cin:(t + 1) * cin] = xp[:, :, kd:kd + D, kh:kh + H, kw:kw + W].permute(0, 2, 3, 4, 1)
+    assert torch.equal(packed.float().cpu(), want)
+    assert conv.tap_packed(xa)
+    y = conv.run(xa, want_stats=True)
+    assert relerr(from_act(y, cout), ref) <= 1e-2
+    keep = nets.TAP_PACK
+    nets.TAP_PACK = False
+    try:
+        y0 = conv.run(ops.to_ndhwc(x.to(DEV), 64, torch.bfloat16))
+    finally:
+        nets.TAP_PACK = keep
+    assert relerr(y.float(), y0.float()) <= 8e-3
+
+
 def test_conv3d_rejects_bad_arguments():
     from b200ldm import ops
     x = torch.zeros((1, 4, 4, 4, 48), dtype=torch.bfloat16, device=DEV)
