@@ -10,6 +10,7 @@ void set_conv_trace2(void* p);
 void set_attn_trace(void* p);
 void set_conv_kernel(int k);
 void set_conv_splits(int s);
+void set_conv_choice(int c);
 void set_conv_trace_sk(void* p);
 void set_attn_split(int s);
 
@@ -95,6 +96,12 @@ int b200ldm_debug_set_conv_kernel(int k) {
    does (0 = measured / model) */
 int b200ldm_debug_set_conv_splits(int s) {
   b200ldm::set_conv_splits(s);
+  return B200LDM_OK;
+}
+
+/* debug only (not in the public header): force one tuner candidate (choice code, see conv_tc.cu) on every conv; -1 = off */
+int b200ldm_debug_set_conv_choice(int c) {
+  b200ldm::set_conv_choice(c);
   return B200LDM_OK;
 }
 

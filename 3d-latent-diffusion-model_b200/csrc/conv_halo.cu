@@ -233,6 +233,8 @@ conv3d_halo_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) 
     const int rw = t % a.tw; t /= a.tw;
     const int rh = t % a.th; t /= a.th;
     const int rd = t;
+    double* s_dst = nullptr;   // GroupNorm chunk sums: cross-tile fp64 accumulator of this thread's entry
+    double s_acc = 0.0;
     for (int wk = blockIdx.x; wk < total; wk += gridDim.x, ++tile) {
       const int x = wk % work_x, co0 = (wk / work_x) * BN;
       const HaloTile c = halo_box(a, x * MT + mt);
@@ -362,12 +364,22 @@ conv3d_halo_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) 
       }
       if (do_stats) {
         if (row < gmax * 16 * ns && c.n0 < a.N) {
-          const int k = row >> 1, which = row & 1;   // chunk k of this Cout tile, 0 = sum / 1 = sumsq
-          atomicAdd(a.chunk_stats + ((size_t)c.n0 * (a.Cout / a.cw) + co0 / a.cw + k) * 2 + which, (double)csum[row]);
+          // entry `row` of this tile's sums (chunk row >> 1 of the Cout tile, 0 = sum / 1 = sumsq) joins this thread's
+          // fp64 accumulator; the global atomic is issued only when its target changes (another sample / Cout tile) or
+          // after the last tile: a CTA of a batch-1 AutoencoderKL conv walks ~200 tiles of ONE sample, and 2 M atomics
+          // on the same 64 addresses (four L2 lines) cost more than the statistics themselves
+          double* dst = a.chunk_stats + ((size_t)c.n0 * (a.Cout / a.cw) + co0 / a.cw + (row >> 1)) * 2 + (row & 1);
+          if (dst != s_dst) {
+            if (s_dst) atomicAdd(s_dst, s_acc);
+            s_dst = dst;
+            s_acc = 0.0;
+          }
+          s_acc += (double)csum[row];
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");   // csum is re-zeroed at the top of the next tile
       }
     }
+    if (s_dst) atomicAdd(s_dst, s_acc);
     if (issuer) ptx::tma_store_wait_all();   // smem must outlive the bulk reads
     ptx::tc_fence_before();
   }

@@ -383,7 +383,9 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
                          rr[c >> 2][(c & 3) * 4 + 3]);
         ptx::fence_proxy_async();
         asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
-        if (issuer) {
+        // (a sub-tile past the end - odd tile count with MT = 2 - decodes to n0 >= N: in the bf16 epilogue the TMA unit
+        // clips it, but here the slab index is folded into the sample coordinate, so it would land in slab z + 1)
+        if (issuer && n0 < a.N) {
           ptx::tma_store_5d(&maps.y[0], stg + slot * 16384, co0 + g * 32, w0, h0, d0, zsplit * a.N + n0);
           ptx::tma_store_commit();
         }
@@ -771,7 +773,11 @@ static int g_force_splits = [] {
   const char* e = getenv("B200LDM_CONV_SPLITS");
   return e ? atoi(e) : 0;
 }();
-void set_conv_splits(int s) { g_force_splits = s; }   // tests (b200ldm_debug_set_conv_splits): force a split-K factor
+void set_conv_splits(int s) { g_force_splits = s; }
+// tests (b200ldm_debug_set_conv_choice): run exactly one candidate of the tuner - a choice code (kernel | splits << 4 |
+// mt << 12 | cl << 16 | Cout-tile code << 20) - for every problem; -1 = off
+static int g_force_choice = -1;
+void set_conv_choice(int c) { g_force_choice = c; }   // tests (b200ldm_debug_set_conv_splits): force a split-K factor
 
 struct ConvPlan {
   int bn, n_tiles, tn, td, th, tw, nb_n, nb_d, nb_h, nb_w, m_tiles, mt, cl, splits;
@@ -852,6 +858,7 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
   pl.bn0 = pl.bn;
   // the choice this plan follows: forced (tuning runs), remembered (measured), or none yet (cost model below)
   int choice_in = -1;
+  if (force_tc2 < 0 && g_force_choice >= 0) force_tc2 = g_force_choice;
   if (force_tc2 >= 0) choice_in = force_tc2;
   else if (g_tc2 < 0) {
     std::lock_guard<std::mutex> lk(g_choice_mu);
@@ -945,7 +952,8 @@ static ConvPlan plan_conv(const b200ldm_conv3d_params* p, int force_tc2 = -1) {
     else {
       const int sp = (choice >> 4) & 255, mt = (choice >> 12) & 15, cl = (choice >> 16) & 15;
       if (mt == 1 || mt == 2) pl.mt = mt;
-      if (sp >= 1 && (sp == 1 || split_ok)) { pl.splits = sp; pl.cl = sp > 1 ? 1 : pl.cl; }
+      // (every slab needs at least one k-iteration: an empty slab would never complete its accumulator barrier)
+      if (sp >= 1 && (sp == 1 || (split_ok && iters / sp >= 1))) { pl.splits = sp; pl.cl = sp > 1 ? 1 : pl.cl; }
       if ((cl == 1 || cl == 2) && pl.splits == 1 && (cl == 1 || (pl.bn >= 128 && !p->skip_x))) pl.cl = cl;
     }
   }
@@ -976,7 +984,7 @@ int conv3d_tcgen05_emits_chunk_stats(const b200ldm_conv3d_params* p) {
 // (persistent kernels and / or split-K factors) and no choice has been remembered yet.
 static bool tune_pending(const b200ldm_conv3d_params* p, const ConvPlan& pl) {
   const bool splittable = pl.split_ok && pl.ctas1 < sm_count() && pl.iters >= 16;
-  if (!g_autotune || g_tc2 >= 0 || !(pl.tc2_ok || splittable)) return false;
+  if (!g_autotune || g_tc2 >= 0 || g_force_choice >= 0 || !(pl.tc2_ok || splittable)) return false;
   std::lock_guard<std::mutex> lk(g_choice_mu);
   return g_choice.count(conv_key(p)) == 0;
 }

@@ -233,6 +233,8 @@ conv3d_tcp_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
     const int rh = t % a.th; t /= a.th;
     const int rd = t % a.td; t /= a.td;
     const int rn = t;
+    double* s_dst = nullptr;   // GroupNorm chunk sums: cross-tile fp64 accumulator of this thread's entry
+    double s_acc = 0.0;
     for (int wk = blockIdx.x; wk < total; wk += gridDim.x, ++tile) {
       int x, co0, phase;
       tcp_decode_work(a, wk, BN, &x, &co0, &phase);
@@ -378,11 +380,21 @@ conv3d_tcp_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
       if (do_stats) {
         asm volatile("bar.sync %0, 128;" ::"r"(1 + es) : "memory");
         if (row < gmax * 16 * ns && ((row / (16 * ns)) % EW) == half && c.n0 < a.N) {
-          const int k = row >> 1, which = row & 1;   // chunk k of this Cout tile, 0 = sum / 1 = sumsq
-          atomicAdd(a.chunk_stats + ((size_t)c.n0 * (a.Cout / a.cw) + co0 / a.cw + k) * 2 + which, (double)csum[row]);
+          // entry `row` of this tile's sums (chunk row >> 1 of the Cout tile, 0 = sum / 1 = sumsq) joins this thread's
+          // fp64 accumulator; the global atomic is issued only when its target changes (another sample / Cout tile) or
+          // after the last tile: a CTA of a batch-1 AutoencoderKL conv walks ~200 tiles of ONE sample, and 2 M atomics
+          // on the same 64 addresses (four L2 lines) cost more than the statistics themselves
+          double* dst = a.chunk_stats + ((size_t)c.n0 * (a.Cout / a.cw) + co0 / a.cw + (row >> 1)) * 2 + (row & 1);
+          if (dst != s_dst) {
+            if (s_dst) atomicAdd(s_dst, s_acc);
+            s_dst = dst;
+            s_acc = 0.0;
+          }
+          s_acc += (double)csum[row];
         }
       }
     }
+    if (s_dst) atomicAdd(s_dst, s_acc);
     if (issuer) ptx::tma_store_wait_all();   // smem must outlive the bulk reads
     ptx::tc_fence_before();
   }

@@ -597,6 +597,65 @@ def test_narrow_input_conv_as_packed_taps(case):
     assert relerr(y.float(), y0.float()) <= 8e-3
 
 
+CAND_CASES = [(2, (6, 8, 4), 64, 0, 64, 3, 1, 0), (2, (3, 4, 2), 128, 0, 128, 3, 1, 0), (2, (3, 4, 2), 128, 128, 128, 3, 1, 256),
+              (2, (6, 8, 4), 64, 128, 64, 3, 1, 192), (2, (6, 8, 4), 64, 0, 64, 3, 2, 0), (2, (1, 1, 24), 128, 0, 384, 1, 1, 0),
+              (8, (5, 5, 5), 256, 0, 512, 3, 1, 0), (3, (10, 10, 10), 128, 0, 256, 3, 1, 0), (1, (9, 11, 7), 256, 0, 256, 1, 1, 0)]
+
+
+@pytest.mark.parametrize("case", CAND_CASES, ids=lambda c: f"N{c[0]}_{'x'.join(map(str, c[1]))}_C{c[2]}+{c[3]}->{c[4]}_k{c[5]}s{c[6]}_skip{c[7]}")
+def test_conv3d_every_tuner_candidate(case):
+    """b200ldm_conv3d_tune picks among candidates by TIME; every one of them must be RIGHT.  Each choice code the tuner
+    can build (kernel 0 / 2 / 3 / 4 / 5, split-K factor x tile height, narrower Cout tile x tile height / persistent) is
+    forced in turn on shapes of the tiny and the real UNets (a candidate that does not apply falls back to the plan it
+    would fall back to in the tuner): output vs fp64 F.conv3d, GroupNorm chunk sums vs the stored tensor."""
+    import ctypes
+    from b200ldm import _lib, ops
+    lib = _lib.load()
+    lib.b200ldm_debug_set_conv_choice.argtypes = [ctypes.c_int]
+    N, sp, C1, C2, Cout, k, stride, Cs = case
+    C = C1 + C2
+    x = q(rnd((N, C) + sp, 51), torch.bfloat16)
+    w = q(rnd((Cout, C, k, k, k), 52) * (C * k ** 3) ** -0.5, torch.bfloat16)
+    b, temb = 0.1 * rnd((Cout,), 53), 0.1 * rnd((N, Cout), 54)
+    pad = k // 2
+    ref = F.conv3d(x.double(), w.double(), b.double(), stride=stride, padding=pad) + temb.double()[:, :, None, None, None]
+    res = q(rnd(tuple(ref.shape), 55), torch.bfloat16) if (stride == 1 and not Cs) else None
+    if res is not None:
+        ref = ref + res.double()
+    skip = None
+    if Cs:
+        sx = q(rnd((N, Cs) + sp, 56), torch.bfloat16)
+        sw = q(rnd((Cout, Cs, 1, 1, 1), 57) * Cs ** -0.5, torch.bfloat16)
+        ref = ref + F.conv3d(sx.double(), sw.double())
+        skip = (to_act(sx, torch.bfloat16), None, ops.repack_conv_weight(sw.to(DEV), Cout, Cs, torch.bfloat16))
+    xa = to_act(x[:, :C1], torch.bfloat16)
+    x2a = to_act(x[:, C1:], torch.bfloat16) if C2 else None
+    wp = ops.repack_conv_weight(w.to(DEV), Cout, C, torch.bfloat16, C1 if C2 else None, C1 if C2 else None)
+    kw = dict(ksize=k, stride=stride, pad_lo=pad, x2=x2a, temb=temb.to(DEV), temb_stride=Cout,
+              residual=None if res is None else to_act(res, torch.bfloat16), want_stats=True, skip=skip)
+    codes = [0, 2, 3, 4, 5]
+    codes += [(sp_ << 4) | (mt << 12) for mt in (1, 2) for sp_ in (1, 2, 3, 4, 6, 8, 12, 16)]
+    codes += [(bc << 20) | v for bc in (1, 2) for v in (1 << 12, 2 << 12, 2)]
+    bad = []
+    for code in codes:
+        lib.b200ldm_debug_set_conv_choice(code)
+        try:
+            y = ops.conv3d(xa, wp, b.to(DEV), Cout, **kw)
+            torch.cuda.synchronize()
+        finally:
+            lib.b200ldm_debug_set_conv_choice(-1)
+        e = relerr(from_act(y, Cout), ref)
+        cs = getattr(y, "cstats", None)
+        es = 0.0
+        if cs is not None:
+            yf = from_act(y, Cout).double()
+            want = torch.stack([yf.reshape(N, Cout // 8, 8, -1).sum(dim=(2, 3)), (yf ** 2).reshape(N, Cout // 8, 8, -1).sum(dim=(2, 3))], dim=-1)
+            es = relerr(cs.reshape(N, Cout // 8, 2).cpu(), want)
+        if not (e <= 1e-2 and es <= 1e-4):
+            bad.append((hex(code), float(e), float(es)))
+    assert not bad, bad
+
+
 def test_conv3d_rejects_bad_arguments():
     from b200ldm import ops
     x = torch.zeros((1, 4, 4, 4, 48), dtype=torch.bfloat16, device=DEV)
