@@ -356,8 +356,17 @@ def cpu_oracle_cfg1(threads):
         t0 = time.perf_counter()
         oracle.LatentDiffusionInferer(sched, 1.0).sample(x, ae, unet, sched, conditioning=c, mode="concat", verbose=False)
         dt = time.perf_counter() - t0
-    return {"value": 1.0 / dt, "unit": "volumes/s", "seconds_per_volume": dt, "cores": threads, "kind": "port",
-            "sample": "the whole of configs[0]: 1 volume, 10 DDPM steps at a 16^3 latent + decode to 64^3, single shot"}
+    out = {"value": 1.0 / dt, "unit": "volumes/s", "seconds_per_volume": dt, "cores": threads, "kind": "port",
+           "sample": "the whole of configs[0]: 1 volume, 10 DDPM steps at a 16^3 latent + decode to 64^3, single shot"}
+    if threads > 4:
+        # the reference's own setting (3d_ldm/inference.py:58: torch.set_num_threads(4)); SURVEY.md 8d asks for both
+        torch.set_num_threads(4)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            oracle.LatentDiffusionInferer(sched, 1.0).sample(x, ae, unet, sched, conditioning=c, mode="concat", verbose=False)
+            out["seconds_per_volume_4_threads"] = time.perf_counter() - t0
+        torch.set_num_threads(threads)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- GPU workloads
