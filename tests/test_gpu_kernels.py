@@ -6,6 +6,7 @@ bf16 tensor-core engine.  For bf16 the reference is evaluated in fp64 on the bf1
 the only differences left are accumulation order and the final bf16 rounding (tight 1e-2 bound).
 """
 import math
+import os
 
 import pytest
 import torch
@@ -345,6 +346,7 @@ def test_conv3d_every_tensor_core_kernel(case, kernel):
         assert relerr(cs.reshape(N, Cout // 8, 2).cpu(), want) <= 1e-4
 
 
+@pytest.mark.skipif(os.environ.get("B200LDM_CONV_AUTOTUNE", "1") == "0", reason="tuning disabled by B200LDM_CONV_AUTOTUNE=0")
 def test_conv3d_tuning_is_an_explicit_entry_point():
     """ABI contract (SURVEY.md 8b threading row): b200ldm_conv3d never measures or synchronises -
     it is capture-safe even for a problem signature nothing has been measured for; measuring is b200ldm_conv3d_tune,
