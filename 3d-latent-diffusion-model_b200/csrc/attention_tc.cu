@@ -171,9 +171,16 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // QT: the query tile lives in TMEM too (D / 2 columns of bf16 pairs next to O; the softmax warps copy it there from the TMA
 // landing zone once per CTA) and S = Q K^T is issued with the A operand in TMEM: the other per-tile operand that never
 // changes leaves the shared-memory port (16 of the remaining 48 KB per 64-key tile).
-template <int D, int BN, int DR = D, int PACKED = 1, bool PT = false, bool SB = false, bool QT = false>
-__global__ void __launch_bounds__(kAttnThreads, AttnCfg<D, BN, SB>::kOcc)
+// TI: TWO MMA-issuing threads - warp 1 issues S = Q K^T, a seventh warp issues O += P V.  The head-dim-256 kernel was bound
+// by its single issuing thread (clock64 trace, round 2: 1730 cycles per key tile - 866 to issue the 16 S instructions and
+// their 2 commits, 343 for PV, ~125 for each of 4 barrier waits even when they are already complete - against 1280 cycles
+// of tensor work).  With two threads neither exceeds the tensor time.  tcgen05.commit only covers the MMAs of the
+// committing thread, so s_full(j) no longer implies that PV(j-2) has retired: the softmax warps wait for pv_done
+// before they overwrite a P buffer.
+template <int D, int BN, int DR = D, int PACKED = 1, bool PT = false, bool SB = false, bool QT = false, bool TI = false>
+__global__ void __launch_bounds__(kAttnThreads + (TI ? 32 : 0), AttnCfg<D, BN, SB>::kOcc)
 attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
+  static_assert(!TI || (!SB && !PT && !QT), "two issuing threads: the shared-memory P / Q variant only");
   static_assert(DR == D || (D == 64 && DR == 32), "head dim 32 rides on the 64-column tiles");
   static_assert(!SB || PT, "the single S buffer holds P as well");
   static_assert(!QT || (PT && AttnCfg<D, BN, SB>::kOCol + D + D / 2 <= AttnCfg<D, BN, SB>::kTmemCols),
@@ -291,8 +298,8 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         load_v(j);
       }
     }
-  } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
+  } else if (warp == 1 || (TI && warp == 6)) {
+    // =========================== MMA issuer(s) ===========================
     if (lane == 0) {
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, BN);
       constexpr uint32_t idesc_o = ptx::umma_idesc_bf16_bmn(128, D);
@@ -304,9 +311,19 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       const uint32_t p_lo0 = ptx::umma_desc_lo_sw128(p_smem);
       // V: MN-major SWIZZLE_128B, LBO = one 64-column block (kKVSub), SBO = 1024
       const uint32_t v_lo0 = ((v_smem & 0x3FFFFu) >> 4) | ((uint32_t)((Cfg::kKVSub >> 4) & 0x3FFF) << 16);
+#ifdef B200LDM_ATTN_TRACE
+      const bool mtr = a.trace != nullptr;
+#else
+      constexpr bool mtr = false;
+#endif
+      long long mc[6] = {0, 0, 0, 0, 0, 0};   // wait K | wait S buffer | issue S | wait V | wait P | issue PV
+      long long mt0 = 0;
+      auto tick = [&](int i) { if (mtr) { const long long t = clock64(); mc[i] += t - mt0; mt0 = t; } };
       auto issue_s = [&](int j) {
         const int s = j % STAGES;
+        if (mtr) mt0 = clock64();
         ptx::mbar_wait(k_full + 8 * s, (uint32_t)(j / STAGES) & 1u, 11);
+        tick(0);
         if (!SB && j >= 2) {
           // S_j overwrites the buffer of tile j - 2: free once the softmax warps hold S_{j-2} in registers - or, with P
           // aliased onto it (PT), once PV_{j-2} has consumed that P.  (SB: S_j is issued right behind PV_{j-1}, the
@@ -315,6 +332,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
           else ptx::mbar_wait(s_empty + 8 * (j & 1), (uint32_t)((j >> 1) - 1) & 1u, 12);
         }
         ptx::tc_fence_after();
+        tick(1);
         const uint32_t k_lo = k_lo0 + (uint32_t)s * (uint32_t)(Cfg::kKVBytes >> 4);
         const uint32_t tS = tmem + Cfg::kSCol0 + bf(j) * BN;
 #pragma unroll
@@ -333,16 +351,16 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         }
         ptx::umma_commit(s_full + 8 * bf(j));
         ptx::umma_commit(k_empty + 8 * s);   // K_j is free once S_j retires
+        tick(2);
       };
-      if constexpr (QT) ptx::mbar_wait(q_tmem, 0, 13);
-      else ptx::mbar_wait(q_full, 0, 13);
-      issue_s(0);
-      for (int j = 0; j < ntiles; ++j) {
-        if (!SB && j + 1 < ntiles) issue_s(j + 1);
+      auto issue_pv = [&](int j) {
         const int s = j % STAGES;
+        if (mtr) mt0 = clock64();
         ptx::mbar_wait(v_full + 8 * s, (uint32_t)(j / STAGES) & 1u, 16);
+        tick(3);
         ptx::mbar_wait(p_full + 8 * bf(j), ph(j), 14);
         ptx::tc_fence_after();
+        tick(4);
         const uint32_t v_lo = v_lo0 + (uint32_t)s * (uint32_t)(Cfg::kKVBytes >> 4);
         const uint32_t p_lo = p_lo0 + (uint32_t)(j & 1) * (uint32_t)(Cfg::kPBytes >> 4);
         const uint32_t tO = tmem + Cfg::kOCol;
@@ -361,7 +379,28 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         }
         ptx::umma_commit(v_empty + 8 * s);   // V_j is free once PV_j retires
         ptx::umma_commit(pv_done + 8 * bf(j));
-        if (SB && j + 1 < ntiles) issue_s(j + 1);   // queued right behind PV_j: it overwrites the P that PV_j reads
+        tick(5);
+      };
+      if (!TI || warp == 1) {
+        if constexpr (QT) ptx::mbar_wait(q_tmem, 0, 13);
+        else ptx::mbar_wait(q_full, 0, 13);
+      }
+      if constexpr (TI) {
+        if (warp == 1) { for (int j = 0; j < ntiles; ++j) issue_s(j); }   // throttled by K stages and s_empty
+        else { for (int j = 0; j < ntiles; ++j) issue_pv(j); }
+      } else {
+        issue_s(0);
+        for (int j = 0; j < ntiles; ++j) {
+          if (!SB && j + 1 < ntiles) issue_s(j + 1);
+          issue_pv(j);
+          if (SB && j + 1 < ntiles) issue_s(j + 1);   // queued right behind PV_j: it overwrites the P that PV_j reads
+        }
+      }
+      if (mtr && blockIdx.x < 1024) {
+        unsigned long long* o = a.trace + (size_t)blockIdx.x * 2 * 8 + 8;
+        for (int i = 0; i < 6; ++i)
+          if (mc[i]) o[i] = (unsigned long long)mc[i];
+        o[6] = (unsigned long long)ntiles;
       }
     }
   } else {
@@ -458,6 +497,10 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       // ~900-cycle MMA round trip behind every tile.  O itself is only touched when the lazy rescale fires.
       // (no pv_done wait for the P buffer: tcgen05.commit covers every earlier MMA of the issuing thread, S_j was issued
       // after PV_{j-2}, so s_full(j) - waited for above - already implies that PV_{j-2} has retired and P(j & 1) is free)
+      if constexpr (TI) {
+        // two issuing threads: s_full(j) says nothing about PV(j-2) any more - P(j & 1) is free once that PV has retired
+        if (j >= 2) ptx::mbar_wait(pv_done + 8 * bf(j), ph(j - 2), 25);
+      }
       if (tr) { t1 = clock64(); tc[3] += t1 - t0; t0 = t1; }
       if (any_need) {
         if (need) {
@@ -1100,6 +1143,18 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
         using QCfg = AttnCfg<D, BN, false>;
         B2_SET_SMEM_ONCE(QCfg::kSmem + smem_pad, attention_tc_kernel<D, BN, DR, 1, true, false, true>);
         attention_tc_kernel<D, BN, DR, 1, true, false, true><<<grid, kAttnThreads, QCfg::kSmem + smem_pad, st>>>(maps, a);
+        B2_LAUNCH_CHECK();
+        return merge();
+      }
+    }
+    // head dim 256: two MMA-issuing threads (B200LDM_ATTN_TWO_ISSUERS=0: one) - the single thread was the bound
+    static const int two = [] { const char* e = getenv("B200LDM_ATTN_TWO_ISSUERS"); return e ? atoi(e) : 1; }();
+    if constexpr (D == 256) {
+      if (two && wide == 0 && packed != 0) {
+        using TCfg = AttnCfg<D, BN, false>;
+        B2_SET_SMEM_ONCE(TCfg::kSmem + smem_pad, attention_tc_kernel<D, BN, DR, 1, false, false, false, true>);
+        attention_tc_kernel<D, BN, DR, 1, false, false, false, true>
+            <<<grid, kAttnThreads + 32, TCfg::kSmem + smem_pad, st>>>(maps, a);
         B2_LAUNCH_CHECK();
         return merge();
       }
