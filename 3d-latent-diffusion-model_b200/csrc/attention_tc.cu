@@ -54,6 +54,7 @@ constexpr int kAttnPTmemDefault = 1;    // B200LDM_ATTN_PTMEM: P through TMEM fo
 constexpr int kAttnSBDefault = 0;       // B200LDM_ATTN_SB
 constexpr int kAttnWideTmemDefault = 0;  // B200LDM_ATTN_WIDE_TMEM: head dim 128 / 256 one-tile kernel: 1 = P in TMEM, 2 = P and Q
 constexpr int kAttnQTmemDefault = 1;    // B200LDM_ATTN_QTMEM: Q in TMEM too (+3-4 % on top of P in TMEM, measured)
+constexpr int kAttnTwoIssuersDefault = 1;  // B200LDM_ATTN_TWO_ISSUERS (see launch_attention_tc)
 constexpr int kAttnStaggerDefault = 0;  // B200LDM_ATTN_STAGGER: start offset (cycles) of every second CTA of an SM
 
 // SB: ONE S buffer (with P aliased onto it, i.e. PT) instead of two: BN + D = 128 TMEM columns and no P tiles in shared
@@ -180,7 +181,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 template <int D, int BN, int DR = D, int PACKED = 1, bool PT = false, bool SB = false, bool QT = false, bool TI = false>
 __global__ void __launch_bounds__(kAttnThreads + (TI ? 32 : 0), AttnCfg<D, BN, SB>::kOcc)
 attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
-  static_assert(!TI || (!SB && !PT && !QT), "two issuing threads: the shared-memory P / Q variant only");
+  static_assert(!TI || !SB, "two issuing threads need the two S buffers");
   static_assert(DR == D || (D == 64 && DR == 32), "head dim 32 rides on the 64-column tiles");
   static_assert(!SB || PT, "the single S buffer holds P as well");
   static_assert(!QT || (PT && AttnCfg<D, BN, SB>::kOCol + D + D / 2 <= AttnCfg<D, BN, SB>::kTmemCols),
@@ -497,8 +498,10 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       // ~900-cycle MMA round trip behind every tile.  O itself is only touched when the lazy rescale fires.
       // (no pv_done wait for the P buffer: tcgen05.commit covers every earlier MMA of the issuing thread, S_j was issued
       // after PV_{j-2}, so s_full(j) - waited for above - already implies that PV_{j-2} has retired and P(j & 1) is free)
-      if constexpr (TI) {
-        // two issuing threads: s_full(j) says nothing about PV(j-2) any more - P(j & 1) is free once that PV has retired
+      if constexpr (TI && !PT) {
+        // two issuing threads: s_full(j) says nothing about PV(j-2) any more - the shared-memory buffer P(j & 1) is free
+        // once that PV has retired.  (P in TMEM: P(j) replaces S(j) in place, and S(j) was only issued after the S thread
+        // itself waited for pv_done(j-2).)
         if (j >= 2) ptx::mbar_wait(pv_done + 8 * bf(j), ph(j - 2), 25);
       }
       if (tr) { t1 = clock64(); tc[3] += t1 - t0; t0 = t1; }
@@ -1107,6 +1110,18 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
       return merge();
     }
   }
+  // B200LDM_ATTN_TWO_ISSUERS: 0 = one MMA-issuing thread everywhere, 1 = two for head dim 256 (measured +10 %), 2 = two for
+  // the head-dim-32 / 64 kernel with P and Q in TMEM as well
+  static const int two_d64 = [] { const char* e = getenv("B200LDM_ATTN_TWO_ISSUERS"); return e ? atoi(e) : kAttnTwoIssuersDefault; }();
+  if constexpr (D == 64 && BN == 64) {
+    if (ptmem && qtmem && two_d64 >= 2) {
+      using QCfg = AttnCfg<D, BN, false>;
+      B2_SET_SMEM_ONCE(QCfg::kSmem + smem_pad, attention_tc_kernel<D, BN, DR, 1, true, false, true, true>);
+      attention_tc_kernel<D, BN, DR, 1, true, false, true, true><<<grid, kAttnThreads + 32, QCfg::kSmem + smem_pad, st>>>(maps, a);
+      B2_LAUNCH_CHECK();
+      return merge();
+    }
+  }
   if constexpr (D == 64 && BN == 64) {
     if (ptmem && qtmem) {
       using QCfg = AttnCfg<D, BN, false>;
@@ -1148,7 +1163,7 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
       }
     }
     // head dim 256: two MMA-issuing threads (B200LDM_ATTN_TWO_ISSUERS=0: one) - the single thread was the bound
-    static const int two = [] { const char* e = getenv("B200LDM_ATTN_TWO_ISSUERS"); return e ? atoi(e) : 1; }();
+    static const int two = [] { const char* e = getenv("B200LDM_ATTN_TWO_ISSUERS"); return e ? atoi(e) : kAttnTwoIssuersDefault; }();
     if constexpr (D == 256) {
       if (two && wide == 0 && packed != 0) {
         using TCfg = AttnCfg<D, BN, false>;
