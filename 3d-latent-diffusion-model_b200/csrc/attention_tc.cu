@@ -54,6 +54,7 @@ constexpr int kAttnPTmemDefault = 1;    // B200LDM_ATTN_PTMEM: P through TMEM fo
 constexpr int kAttnSBDefault = 0;       // B200LDM_ATTN_SB
 constexpr int kAttnWideTmemDefault = 0;  // B200LDM_ATTN_WIDE_TMEM: head dim 128 / 256 one-tile kernel: 1 = P in TMEM, 2 = P and Q
 constexpr int kAttnQTmemDefault = 1;    // B200LDM_ATTN_QTMEM: Q in TMEM too (+3-4 % on top of P in TMEM, measured)
+constexpr int kAttnW2Default = 0;          // B200LDM_ATTN_W2 (see launch_attention_tc)
 constexpr int kAttnTwoIssuersDefault = 1;  // B200LDM_ATTN_TWO_ISSUERS (see launch_attention_tc)
 constexpr int kAttnStaggerDefault = 0;  // B200LDM_ATTN_STAGGER: start offset (cycles) of every second CTA of an SM
 
@@ -178,9 +179,18 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // of tensor work).  With two threads neither exceeds the tensor time.  tcgen05.commit only covers the MMAs of the
 // committing thread, so s_full(j) no longer implies that PV(j-2) has retired: the softmax warps wait for pv_done
 // before they overwrite a P buffer.
-template <int D, int BN, int DR = D, int PACKED = 1, bool PT = false, bool SB = false, bool QT = false, bool TI = false>
-__global__ void __launch_bounds__(kAttnThreads + (TI ? 32 : 0), AttnCfg<D, BN, SB>::kOcc)
+// W2: TWO softmax warpgroups - warps 2..5 take the first half of a tile's keys, warps 6..9 the second half of the same rows
+// (a TMEM lane quarter belongs to warp % 4, so both warps of a pair may read the same rows).  The row maxima meet in shared
+// memory once per tile (a 64-thread named barrier per lane quarter); reference max and rescale decisions are then identical
+// in both halves, the row sums are combined in the epilogue.  Four instead of two softmax warps per scheduler (two CTAs
+// per SM) to hide the per-warp serial latency that bounds the head-dim-64 kernel (profiles/r02_attention_experiments.md).
+template <int D, int BN, int DR = D, int PACKED = 1, bool PT = false, bool SB = false, bool QT = false, bool TI = false,
+          bool W2 = false>
+__global__ void __launch_bounds__(kAttnThreads + (TI ? 32 : 0) + (W2 ? 128 : 0), AttnCfg<D, BN, SB>::kOcc)
 attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
+  static_assert(!W2 || (BN % 64 == 0 && DR % 32 == 0 && !SB), "two softmax warpgroups: 32-column halves");
+  constexpr int kTiWarp = W2 ? 10 : 6;          // the PV-issuing warp of TI
+  constexpr int kSmxThreads = W2 ? 256 : 128;   // threads that arrive on s_empty / p_full
   static_assert(!TI || !SB, "two issuing threads need the two S buffers");
   static_assert(DR == D || (D == 64 && DR == 32), "head dim 32 rides on the 64-column tiles");
   static_assert(!SB || PT, "the single S buffer holds P as well");
@@ -248,9 +258,9 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       ptx::mbar_init(k_full + 8 * s, 1); ptx::mbar_init(k_empty + 8 * s, 1);
       ptx::mbar_init(v_full + 8 * s, 1); ptx::mbar_init(v_empty + 8 * s, 1);
     }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(s_full + 8 * s, 1); ptx::mbar_init(s_empty + 8 * s, 128); }
-    ptx::mbar_init(p_full, 128);
-    ptx::mbar_init(p_full + 8, 128);
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(s_full + 8 * s, 1); ptx::mbar_init(s_empty + 8 * s, kSmxThreads); }
+    ptx::mbar_init(p_full, kSmxThreads);
+    ptx::mbar_init(p_full + 8, kSmxThreads);
     ptx::mbar_init(pv_done, 1);
     ptx::mbar_init(pv_done + 8, 1);
     ptx::mbar_init(q_tmem, 128);
@@ -299,7 +309,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         load_v(j);
       }
     }
-  } else if (warp == 1 || (TI && warp == 6)) {
+  } else if (warp == 1 || (TI && warp == kTiWarp)) {
     // =========================== MMA issuer(s) ===========================
     if (lane == 0) {
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, BN);
@@ -409,10 +419,19 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    const int half = W2 ? ((warp - 2) >> 2) : 0;   // which half of a tile's keys (and of the O columns) this thread owns
+    constexpr int NW = W2 ? BN / 2 : BN;           // scores per thread and tile
+    const int coff = half * NW;                    // first key column of this thread inside the tile
     float m_used = -INFINITY;  // reference max (log2 domain) the running sums are expressed against
     float l_sum = 0.f;
     uint8_t* p_base = smem_gen + (p_smem - smem_base);
-    if constexpr (QT) {
+    // W2 exchange area behind the barriers: row maxima [tile parity][half][128], row sums [half][128]
+    // (head dim 256 has 1792 bytes left: ONE maxima buffer, protected by a second barrier per tile, which the row sums
+    // reuse in the epilogue)
+    constexpr bool kXD = Cfg::kSmem + 3072 <= 232448 / Cfg::kOcc;
+    float* xmax = reinterpret_cast<float*>(smem_gen + (bar - smem_base) + 256);
+    float* xsum = kXD ? xmax + 2 * 2 * 128 : xmax;
+    if (QT && half == 0) {
       // this thread's query row: 8 x 16 bytes out of the SWIZZLE_128B landing zone (chunk c of row r sits at
       // r * 128 + ((c ^ (r & 7)) << 4)) -> 32 words of bf16 pairs in K order -> TMEM lane `row`
       ptx::mbar_wait(q_full, 0, 24);
@@ -452,14 +471,14 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       ptx::tc_fence_after();
       if (tr) { t1 = clock64(); tc[0] += t1 - t0; t0 = t1; }
       const uint32_t tS = tmem + lane_off + Cfg::kSCol0 + bf(j) * BN;
-      float sv[BN];  // RAW scores; the softmax scale is folded into the exp2 FFMA below
+      float sv[NW];  // RAW scores; the softmax scale is folded into the exp2 FFMA below
       {
-        uint32_t r[BN / 32][32];   // every load in flight before the single wait
+        uint32_t r[NW / 32][32];   // every load in flight before the single wait
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) ptx::tmem_ld32(tS + c * 32, r[c]);
+        for (int c = 0; c < NW / 32; ++c) ptx::tmem_ld32(tS + coff + c * 32, r[c]);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c)
+        for (int c = 0; c < NW / 32; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i) sv[c * 32 + i] = __uint_as_float(r[c][i]);
       }
@@ -470,24 +489,34 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       const int kvalid = a.Lk - (jbase + j) * BN;  // keys in this tile that exist
       if (kvalid < BN) {                // last tile only (warp-uniform)
 #pragma unroll
-        for (int i = 0; i < BN; ++i)
-          if (i >= kvalid) sv[i] = -INFINITY;
+        for (int i = 0; i < NW; ++i)
+          if (coff + i >= kvalid) sv[i] = -INFINITY;
       }
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 chains: no 128-deep dependency
       if constexpr (PACKED != 0) {
 #pragma unroll
-        for (int i = 0; i < BN; i += 8) {
+        for (int i = 0; i < NW; i += 8) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) mx4[u] = fmax3(mx4[u], sv[i + u], sv[i + 4 + u]);
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < BN; i += 4) {
+        for (int i = 0; i < NW; i += 4) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], sv[i + u]);
         }
       }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * a.scale_log2;  // scale > 0
+      float mx_raw = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      if constexpr (W2) {
+        // the other half of this row: exchange through shared memory (buffer = tile parity: the next write to it comes
+        // after the barrier of tile j + 1, which the partner only passes once it has read this one)
+        float* xm = xmax + (kXD ? (j & 1) * 256 : 0);
+        xm[half * 128 + row] = mx_raw;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+        mx_raw = fmaxf(mx_raw, xm[(half ^ 1) * 128 + row]);
+        if constexpr (!kXD) asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");   // read before the next tile's write
+      }
+      const float mx = mx_raw * a.scale_log2;  // scale > 0
       // lazy rescale: keep the old reference unless the max grew by more than 2^8 (warp-uniform decision)
       const bool need = mx > m_used + 8.0f;
       const bool any_need = __any_sync(0xffffffffu, need);
@@ -514,9 +543,9 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         if (j > 0) {
           ptx::mbar_wait(pv_done + 8 * bf(j - 1), ph(j - 1), 23);  // PV_{j-1} retired: O is ours
           ptx::tc_fence_after();
-          const uint32_t tO = tmem + lane_off + Cfg::kOCol;
+          const uint32_t tO = tmem + lane_off + Cfg::kOCol + (uint32_t)(W2 ? half * (D / 2) : 0);   // W2: this half's columns
 #pragma unroll
-          for (int c = 0; c < D; c += 16) {
+          for (int c = 0; c < (W2 ? D / 2 : D); c += 16) {
             uint32_t r[16];
             ptx::tmem_ld16(tO + c, r);
             ptx::tmem_ld_wait();
@@ -557,9 +586,9 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         return *reinterpret_cast<const uint32_t*>(&hb);
       };
       if constexpr (PT) {
-        const uint32_t tP = tmem + lane_off + Cfg::kSCol0 + bf(j) * BN;   // over the columns S_j was read from
+        const uint32_t tP = tmem + lane_off + Cfg::kSCol0 + bf(j) * BN + (uint32_t)(coff / 2);   // over the columns S_j was read from
 #pragma unroll
-        for (int c32 = 0; c32 < BN / 32; ++c32) {
+        for (int c32 = 0; c32 < NW / 32; ++c32) {
           uint32_t pw[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) pw[e] = exp_pair(c32 * 16 + e);
@@ -568,10 +597,11 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         ptx::tmem_st_wait();
       } else {
 #pragma unroll
-        for (int c8 = 0; c8 < BN / 8; ++c8) {
+        for (int c8l = 0; c8l < NW / 8; ++c8l) {
           uint32_t pk[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) pk[e] = exp_pair(c8 * 4 + e);
+          for (int e = 0; e < 4; ++e) pk[e] = exp_pair(c8l * 4 + e);
+          const int c8 = coff / 8 + c8l;   // 16-byte chunk of the whole tile row
           const int sub = c8 >> 3, cc = c8 & 7;
           uint4* dst = reinterpret_cast<uint4*>(p_gen + sub * 16384 + row * 128 + ((cc ^ (row & 7)) << 4));
           *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -597,13 +627,21 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
     ptx::mbar_wait(pv_done + 8 * bf(ntiles - 1), ph(ntiles - 1), 22);
     ptx::tc_fence_after();
     const int qi = q0 + row;
-    const uint32_t tO = tmem + lane_off + Cfg::kOCol + (uint32_t)(colh - col0);   // this head's columns of O
+    if constexpr (W2) {
+      // the row sums of the two key halves meet here (the reference max is already common)
+      xsum[half * 128 + row] = l_sum;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+      l_sum += xsum[(half ^ 1) * 128 + row];
+    }
+    constexpr int DRH = W2 ? DR / 2 : DR;          // O columns this thread writes out
+    const int ocol = W2 ? half * DRH : 0;          // ... starting here inside the head
+    const uint32_t tO = tmem + lane_off + Cfg::kOCol + (uint32_t)(colh - col0 + ocol);   // this head's columns of O
     if (nparts > 1) {
       // a part of a split tile: O stays un-normalised (fp32) next to its reference max and row sum
       const size_t unit = (size_t)blockIdx.x - (size_t)a.split_t0;
-      float4* po = reinterpret_cast<float4*>(a.part_o) + unit * (size_t)(DR / 4) * 128 + row;
+      float4* po = reinterpret_cast<float4*>(a.part_o) + unit * (size_t)(DR / 4) * 128 + (size_t)(ocol / 4) * 128 + row;
 #pragma unroll
-      for (int c = 0; c < DR; c += 16) {
+      for (int c = 0; c < DRH; c += 16) {
         uint32_t r[16];
         ptx::tmem_ld16(tO + c, r);
         ptx::tmem_ld_wait();
@@ -613,14 +651,16 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
                  make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]), __uint_as_float(r[4 * j4 + 2]),
                              __uint_as_float(r[4 * j4 + 3])));
       }
-      a.part_ml[unit * 256 + row] = m_used;
-      a.part_ml[unit * 256 + 128 + row] = l_sum;
+      if (half == 0) {
+        a.part_ml[unit * 256 + row] = m_used;
+        a.part_ml[unit * 256 + 128 + row] = l_sum;
+      }
       ptx::tc_fence_before();
     } else {
     const float inv = 1.0f / l_sum;
-    __nv_bfloat16* orow = a.o + ((size_t)b * a.L + (qi < a.L ? qi : 0)) * ((size_t)a.H * DR) + colh;
+    __nv_bfloat16* orow = a.o + ((size_t)b * a.L + (qi < a.L ? qi : 0)) * ((size_t)a.H * DR) + colh + ocol;
 #pragma unroll
-    for (int c = 0; c < DR; c += 16) {
+    for (int c = 0; c < DRH; c += 16) {
       uint32_t r[16];
       ptx::tmem_ld16(tO + c, r);
       ptx::tmem_ld_wait();
@@ -1113,6 +1153,20 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
   // B200LDM_ATTN_TWO_ISSUERS: 0 = one MMA-issuing thread everywhere, 1 = two for head dim 256 (measured +10 %), 2 = two for
   // the head-dim-32 / 64 kernel with P and Q in TMEM as well
   static const int two_d64 = [] { const char* e = getenv("B200LDM_ATTN_TWO_ISSUERS"); return e ? atoi(e) : kAttnTwoIssuersDefault; }();
+  // B200LDM_ATTN_W2=1: two softmax warpgroups per CTA (each thread owns half of a tile's keys) for the head-dim-32 / 64
+  // kernel with P and Q in TMEM
+  static const int w2 = [] { const char* e = getenv("B200LDM_ATTN_W2"); return e ? atoi(e) : kAttnW2Default; }();
+  if constexpr (D == 64 && BN == 64) {
+    if (ptmem && qtmem && w2) {
+      using QCfg = AttnCfg<D, BN, false>;
+      constexpr int kSm = QCfg::kSmem + 3072;   // + the exchange area of the two halves
+      static_assert(kSm <= 232448 / QCfg::kOcc, "smem budget with the exchange area");
+      B2_SET_SMEM_ONCE(kSm + smem_pad, attention_tc_kernel<D, BN, DR, 1, true, false, true, false, true>);
+      attention_tc_kernel<D, BN, DR, 1, true, false, true, false, true><<<grid, kAttnThreads + 128, kSm + smem_pad, st>>>(maps, a);
+      B2_LAUNCH_CHECK();
+      return merge();
+    }
+  }
   if constexpr (D == 64 && BN == 64) {
     if (ptmem && qtmem && two_d64 >= 2) {
       using QCfg = AttnCfg<D, BN, false>;
@@ -1164,6 +1218,18 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
     }
     // head dim 256: two MMA-issuing threads (B200LDM_ATTN_TWO_ISSUERS=0: one) - the single thread was the bound
     static const int two = [] { const char* e = getenv("B200LDM_ATTN_TWO_ISSUERS"); return e ? atoi(e) : kAttnTwoIssuersDefault; }();
+    if constexpr (D == 256) {
+      if (two && w2 && wide == 0 && packed != 0) {   // two issuing threads AND two softmax warpgroups
+        using TCfg = AttnCfg<D, BN, false>;
+        constexpr int kSm = TCfg::kSmem + (TCfg::kSmem + 3072 <= 232448 / TCfg::kOcc ? 3072 : 1024);
+        static_assert(kSm <= 232448 / TCfg::kOcc, "smem budget with the exchange area");
+        B2_SET_SMEM_ONCE(kSm + smem_pad, attention_tc_kernel<D, BN, DR, 1, false, false, false, true, true>);
+        attention_tc_kernel<D, BN, DR, 1, false, false, false, true, true>
+            <<<grid, kAttnThreads + 32 + 128, kSm + smem_pad, st>>>(maps, a);
+        B2_LAUNCH_CHECK();
+        return merge();
+      }
+    }
     if constexpr (D == 256) {
       if (two && wide == 0 && packed != 0) {
         using TCfg = AttnCfg<D, BN, false>;
