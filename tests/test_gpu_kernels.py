@@ -658,6 +658,38 @@ def test_conv3d_every_tuner_candidate(case):
     assert not bad, bad
 
 
+def test_conv3d_stream_k_under_concurrent_streams():
+    """forward progress of the stream-K kernel when several of its launches share the GPU: owners poll the flags of
+    contributors that may not be resident yet; CTAs are dispatched in order and a contribution is always posted before its
+    CTA waits for anything, so every launch completes (scripts/stress_streamk.py runs 200 rounds) - and bit for bit equal
+    to the launch that had the GPU to itself."""
+    import ctypes
+    from b200ldm import _lib, ops
+    lib = _lib.load()
+    lib.b200ldm_debug_set_conv_kernel.argtypes = [ctypes.c_int]
+    probs = []
+    for N, sp, C, Cout in [(8, (10, 10, 10), 256, 256), (4, (20, 20, 20), 256, 256), (8, (5, 5, 5), 512, 512)]:
+        x = to_act(q(rnd((N, C) + sp, 61), torch.bfloat16), torch.bfloat16)
+        w = ops.repack_conv_weight((q(rnd((Cout, C, 3, 3, 3), 62), torch.bfloat16) * (C * 27) ** -0.5).to(DEV), Cout, C, torch.bfloat16)
+        probs.append((x, w, torch.zeros(Cout, device=DEV), Cout))
+    lib.b200ldm_debug_set_conv_kernel(5)
+    try:
+        refs = [ops.conv3d(x, w, b, co) for x, w, b, co in probs]
+        torch.cuda.synchronize()
+        streams = [torch.cuda.Stream() for _ in range(3)]
+        for it in range(30):
+            outs = []
+            for si, st in enumerate(streams):
+                with torch.cuda.stream(st):
+                    k = (it + si) % len(probs)
+                    x, w, b, co = probs[k]
+                    outs.append((k, ops.conv3d(x, w, b, co)))
+            torch.cuda.synchronize()
+            assert all(torch.equal(y, refs[k]) for k, y in outs)
+    finally:
+        lib.b200ldm_debug_set_conv_kernel(-1)
+
+
 def test_conv3d_rejects_bad_arguments():
     from b200ldm import ops
     x = torch.zeros((1, 4, 4, 4, 48), dtype=torch.bfloat16, device=DEV)
