@@ -380,6 +380,15 @@ def test_bench_reference_arm_contract():
     assert abs(bench_mod.unet_flops(bench_mod.UNET_32G, (20, 20, 20)) / 914.5e9 - 1) < 2e-3
     assert abs(bench_mod.decoder_flops(bench_mod.AE_32G, (20, 20, 20)) / 1799.7e9 - 1) < 2e-3
     assert 0.93 < bench_mod.executed_fraction_unet(bench_mod.UNET_16G, bench_mod.LATENT_16G) < 0.95
+    # ... and the AutoencoderKL sweep of configs[4] (SURVEY.md 8d cfg 5: enc 1.75 / 5.42 / 14.7 / 35.9 TF, dec 3.27 / 9.03 /
+    # 21.7 / 48.1 TF per volume at 96^3 / 128^3 / 160^3 / 192^3), the other sizes of the UNet and the decoder
+    for edge, enc, dec in ((96, 1.75e12, 3.27e12), (128, 5.42e12, 9.03e12), (160, 14.7e12, 21.7e12), (192, 35.9e12, 48.1e12)):
+        assert abs(bench_mod.encoder_flops(bench_mod.AE_32G, (edge,) * 3) / enc - 1) < 5e-3
+        assert abs(bench_mod.decoder_flops(bench_mod.AE_32G, (edge // 4,) * 3) / dec - 1) < 5e-3
+    for lat, f in bench_mod.FLOP_UNET_32G.items():
+        assert abs(bench_mod.unet_flops(bench_mod.UNET_32G, (lat,) * 3) / f - 1) < 2e-3
+    for lat, f in bench_mod.FLOP_DEC_32G.items():
+        assert abs(bench_mod.decoder_flops(bench_mod.AE_32G, (lat,) * 3) / f - 1) < 2e-3
     r1 = subprocess.run([sys.executable, bench, "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                         capture_output=True, text=True, env={**env, "RANK": "1", "WORLD_SIZE": "2"}, timeout=600)
     assert r1.returncode == 0 and not [l for l in r1.stdout.splitlines() if l.startswith("{")]
