@@ -1053,8 +1053,10 @@ static long long attn_split_workspace_bytes(long long T, const AttnSplit& sp, in
   return (T - sp.t0) * sp.nsplit * ((long long)dr * 128 * 4 + 2 * 128 * 4);
 }
 
-// out[q][c] = sum_p O_p[q][c] 2^(m_p - m) / sum_p l_p 2^(m_p - m),  m = max_p m_p.  One CTA per split tile, thread =
-// (column quad, row) like the partial layout.
+// out[q][c] = sum_p O_p[q][c] 2^(m_p - m) / sum_p l_p 2^(m_p - m),  m = max_p m_p.  grid = (split tiles, column slices):
+// a CTA merges 128 rows x (dr / 4 / gridDim.y) column quads, thread = (column quad, row) like the partial layout.  (One
+// CTA per tile ran at 0.9 TB/s - 61 us for the 56 MB of a 128^3 reconstruct, ncu r02af; the partial tiles are read once,
+// so the launch just needs enough CTAs in flight.)
 __global__ void attention_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml,
                                        __nv_bfloat16* __restrict__ o, int t0, int nsplit, int tiles_x, int H, int L, int dr) {
   const int tile = t0 + (int)blockIdx.x;
@@ -1075,7 +1077,9 @@ __global__ void attention_merge_kernel(const float* __restrict__ part_o, const f
   }
   __syncthreads();
   const int quads = dr / 4;
-  for (int i = threadIdx.x; i < quads * 128; i += blockDim.x) {
+  const int qper = (quads + (int)gridDim.y - 1) / (int)gridDim.y, q_lo = (int)blockIdx.y * qper;
+  const int q_hi = q_lo + qper < quads ? q_lo + qper : quads;
+  for (int i = q_lo * 128 + threadIdx.x; i < q_hi * 128; i += blockDim.x) {
     const int row = i & 127, cq = i >> 7;
     if (q0 + row >= L) continue;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1119,7 +1123,8 @@ static int launch_attention_tc(const void* q, const void* k, const void* v, void
   // the merge pass of the split tiles, queued behind the attention kernel by every return path below
   auto merge = [&]() -> int {
     if (sp.nsplit > 1) {
-      attention_merge_kernel<<<(unsigned)(T - sp.t0), 256, 0, st>>>(a.part_o, a.part_ml, a.o, sp.t0, sp.nsplit, a.tiles_x, H, L, DR);
+      attention_merge_kernel<<<dim3((unsigned)(T - sp.t0), (unsigned)(DR >= 64 ? 8 : 4)), 256, 0, st>>>(
+          a.part_o, a.part_ml, a.o, sp.t0, sp.nsplit, a.tiles_x, H, L, DR);
       B2_LAUNCH_CHECK();
     }
     return B200LDM_OK;
